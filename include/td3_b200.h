@@ -1,0 +1,200 @@
+/*
+ * td3_b200.h -- C ABI of libtd3b200.so: the B200-native (sm_100a) TD3 update hot path.
+ *
+ * The reference (yannikkellerde/TD3) has no FFI: its boundary is a duck-typed Python
+ * object surface.  This header is the boundary a maintainer of the
+ * reference binds with ctypes (INTEGRATION.md shows the stub); every entry point names
+ * the reference code it replaces.  Conventions:
+ *   - plain C types only; device memory is BORROWED (the caller -- PyTorch in the
+ *     shipped host layer -- owns every allocation, so state_dict() views stay valid);
+ *   - every call takes the CUDA stream to launch on (cudaStream_t passed as void*),
+ *     never synchronises the host, and returns 0 on success or a negative td3_status;
+ *     the message is available from td3_last_error() (thread-local);
+ *   - all floating-point data is IEEE fp32, indices are int64.
+ */
+#ifndef TD3_B200_H_
+#define TD3_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TD3_ABI_VERSION 1
+#define TD3_MAX_LINEAR 8          /* linear layers per network, incl. the output layer */
+#define TD3_MAX_SEGMENTS 16       /* destination segments of one replay row */
+
+typedef enum td3_status {
+  TD3_OK = 0,
+  TD3_ERR_INVALID = -1,           /* bad argument (ValueError on the Python side) */
+  TD3_ERR_CUDA = -2,              /* a CUDA runtime call failed (RuntimeError) */
+  TD3_ERR_STATE = -3,             /* call order / plan missing */
+  TD3_ERR_UNSUPPORTED = -4
+} td3_status;
+
+typedef enum td3_norm { TD3_NORM_NONE = 0, TD3_NORM_LAYER = 1 } td3_norm;
+typedef enum td3_variant { TD3_VARIANT_FEATURED = 0, TD3_VARIANT_PARTICLES = 1 } td3_variant;
+typedef enum td3_rng_mode {
+  TD3_RNG_PHILOX = 0,             /* on-device Philox4x32-10 indices + noise */
+  TD3_RNG_INJECTED = 1            /* indices / N(0,1) draws supplied by the caller (parity mode) */
+} td3_rng_mode;
+
+/* ----------------------------------------------------------------------------------- */
+/* Packed network layout.  One network = one contiguous fp32 buffer whose tensors sit   */
+/* at the offsets below, in the reference's nn.Module.parameters() order, each          */
+/* reference-shaped and contiguous (so the host exposes them as state_dict views).      */
+/* Replaces: Actor/Q (TD3_featured.py:15-81), Actor/Q_network (TD3_particles.py:19-119) */
+/* ----------------------------------------------------------------------------------- */
+typedef struct td3_net_layout {
+  int32_t n_linear;                        /* len(self.linears) */
+  int32_t dims[TD3_MAX_LINEAR + 1];        /* dims[0] = trunk input width, dims[n_linear] = output width */
+  int64_t w_off[TD3_MAX_LINEAR];           /* linears.i.weight  [dims[i+1], dims[i]] row-major */
+  int64_t b_off[TD3_MAX_LINEAR];           /* linears.i.bias    [dims[i+1]] */
+  int64_t ln_g_off[TD3_MAX_LINEAR];        /* lnorms.i.weight   [dims[i+1]]   (norm == layer) */
+  int64_t ln_b_off[TD3_MAX_LINEAR];        /* lnorms.i.bias */
+  /* particle-set encoder (TD3_particles.py:29-32,53-58); unused for the featured variant */
+  int32_t enc_hidden;                      /* 256 = conv1 out channels */
+  int32_t enc_out;                         /* 128 = conv2 out channels */
+  int64_t c1w_off, c1b_off;                /* conv1.weight [enc_hidden,1,1,D], conv1.bias */
+  int64_t c2w_off, c2b_off;                /* conv2.weight [enc_out,enc_hidden,1], conv2.bias */
+  int64_t ln_in_g_off, ln_in_b_off;        /* lnorm1.weight/bias [dims[0]] (norm == layer) */
+  int64_t n_floats;                        /* padded size of this network in the packed buffer */
+} td3_net_layout;
+
+/* The five packed buffers of one network family (online, target, grad, Adam moments). */
+typedef struct td3_param_set {
+  float* params;      /* online network   (actor or critic = [q1 | q2]) */
+  float* target;      /* target network, same layout */
+  float* grad;        /* gradient of the last backward, same layout */
+  float* exp_avg;     /* Adam first moment  (torch.optim.Adam state "exp_avg") */
+  float* exp_avg_sq;  /* Adam second moment (state "exp_avg_sq") */
+} td3_param_set;
+
+/* Agent configuration.  Replaces TD3_base.__init__ (TD3_base.py:7-24) and the TD3
+ * constructors (TD3_featured.py:100-110, TD3_particles.py:139-151). */
+typedef struct td3_agent_config {
+  int32_t variant;                 /* td3_variant */
+  int32_t norm;                    /* td3_norm */
+  int32_t n_q;                     /* 2 = clipped double Q (CDQ), 1 = single critic (TD3_particles.py:131) */
+  int32_t state_dim;               /* featured: S.  particles: F (feature vector width) */
+  int32_t action_dim;              /* A */
+  int32_t n_particles;             /* particles: N (0 for featured) */
+  int32_t particle_dim;            /* particles: D */
+  int32_t clamp_target_action;     /* featured 1 (TD3_featured.py:135-137), particles 0 (TD3_particles.py:179-181) */
+  int32_t n_agents;                /* independent agents stepped in lock-step in one launch (>= 1) */
+  int32_t reserved0;
+  float max_action;                /* actor output scale; particles actor ignores it (TD3_particles.py:68-69) -> pass 1 */
+  float discount, tau, policy_noise, noise_clip;
+  float lr_actor, lr_critic, beta1, beta2, adam_eps;
+  int32_t policy_freq;
+  int32_t reserved1;
+  uint64_t seed;                   /* Philox key */
+  td3_net_layout actor;            /* layout of ONE actor */
+  td3_net_layout q;                /* layout of ONE Q network; the critic buffer is n_q of them back to back */
+} td3_agent_config;
+
+/* Device-resident replay buffer view: array-of-rows, one transition per row.
+ * Row = [state | action | next_state | reward | not_done] (featured) or
+ *       [feat | particles | action | next_feat | next_particles | reward | not_done] (particles),
+ * fp32, row_stride floats apart.  Replaces the five/seven float64 NumPy arrays of
+ * my_replay_buffer.py:16-22,81-85 (fp32 round-to-nearest at add == FloatTensor(float64) at sample). */
+typedef struct td3_replay_view {
+  const float* rows;
+  int64_t row_stride;              /* floats between consecutive rows (multiple of 4) */
+  int64_t row_floats;              /* payload floats per row */
+  int64_t max_size;
+  int64_t size;                    /* rows currently valid: sampling is uniform over [0, size) */
+  int64_t agent_stride;            /* floats between the buffers of consecutive agents (n_agents > 1) */
+} td3_replay_view;
+
+typedef struct td3_agent td3_agent;      /* opaque */
+
+/* ---- library ---------------------------------------------------------------------- */
+int td3_abi_version(void);
+/* sizeof(td3_net_layout, td3_param_set, td3_agent_config, td3_replay_view): binding self-check. */
+void td3_struct_sizes(int64_t* out4);
+const char* td3_last_error(void);
+/* SM count / name of the current device; fails (TD3_ERR_CUDA) when no sm_100 device is present. */
+int td3_device_info(int* sm_count, int* cc_major, int* cc_minor, char* name, int name_len);
+
+/* ---- replay buffer (my_replay_buffer.py) ------------------------------------------ */
+/* add(): copy n packed fp32 rows from (pinned) host memory into rows[ptr .. ptr+n) with
+ * ring wrap-around.  Replaces ReplayBuffer_*.add (my_replay_buffer.py:46-56,109-117); the
+ * caller advances ptr/size exactly as :55-56. */
+int rb_add_rows(float* rows, int64_t row_stride, int64_t row_floats, int64_t max_size, int64_t ptr,
+                const float* host_rows, int64_t n_rows, void* stream);
+/* sample() given indices: out segment k receives columns [seg_off[k], seg_off[k]+seg_len[k]) of
+ * row idx[b] at dst[k] + b*dst_ld[k].  Replaces the fancy-index gather + FloatTensor cast +
+ * H2D of my_replay_buffer.py:61-69,122-128; bit-exact for identical indices. */
+int rb_sample_indices(const td3_replay_view* rb, const int64_t* idx_dev, int64_t batch, int32_t n_seg,
+                      const int64_t* seg_off, const int64_t* seg_len, float* const* dst, const int64_t* dst_ld,
+                      void* stream);
+/* np.random.randint(0, size, batch) replaced by Philox4x32-10 (my_replay_buffer.py:59,120):
+ * idx[b] = mulhi64(philox(seed; stream_id, step, b), size). */
+int rb_philox_indices(int64_t* idx_dev, int64_t batch, int64_t size, uint64_t seed, uint64_t stream_id,
+                      uint64_t step, void* stream);
+
+/* ---- elementwise optimiser kernels over packed buffers ----------------------------- */
+/* torch.optim.Adam.step (TD3_featured.py:153,164) on n floats, t = step number (1-based), and
+ * optionally the Polyak update target = tau*p + (1-tau)*target (TD3_featured.py:167-171) fused in.
+ * target == NULL -> Adam only.  grad == NULL -> Polyak only. */
+int adam_polyak_step(float* params, const float* grad, float* exp_avg, float* exp_avg_sq, float* target,
+                     int64_t n, int64_t t, float lr, float beta1, float beta2, float eps, float tau, void* stream);
+
+/* ---- agent ------------------------------------------------------------------------- */
+int td3_agent_create(const td3_agent_config* cfg, td3_agent** out);
+int td3_agent_destroy(td3_agent* agent);
+/* Bind the packed parameter buffers (borrowed). */
+int td3_agent_bind_params(td3_agent* agent, const td3_param_set* actor, const td3_param_set* critic);
+/* Bind the small persistent device state block (borrowed, zero-initialised by the caller):
+ *   u64[0] sampling step (Philox counter)   u64[1] critic Adam step   u64[2] actor Adam step
+ *   u64[3] live replay size                 u64[4..15] reserved
+ *   then fp32: critic_loss[n_agents], actor_loss[n_agents]  (last update's losses; the reference never
+ *   reads them back -- TD3_featured.py:148,159 -- they exist for tests and metrics).
+ * n_bytes >= 128 + 8*n_agents.  The Adam steps are what torch.optim.Adam keeps in state["step"]. */
+int td3_agent_bind_state(td3_agent* agent, void* state_dev, int64_t n_bytes);
+/* Workspace (activations, batch staging) for a given batch size, in floats. */
+int64_t td3_agent_workspace_floats(const td3_agent* agent, int64_t batch);
+/* Bind the workspace and build the launch plan for `batch`.  Drops captured graphs. */
+int td3_agent_plan(td3_agent* agent, int64_t batch, float* workspace, int64_t workspace_floats, void* stream);
+/* Offset (floats) and length of a named workspace region ("q", "target_q", "critic_loss",
+ * "next_action", "indices", "noise_in", "indices_in", ...): test / metric read-back and injection. */
+int td3_agent_region(const td3_agent* agent, const char* name, int64_t* offset, int64_t* n_floats);
+
+/* `iterations` full TD3 updates (TD3_featured.py:123-171 / TD3_particles.py:167-224), each:
+ * sample -> target step -> twin-critic fwd/bwd + Adam -> every policy_freq-th call actor step +
+ * Polyak.  total_it is the reference's counter BEFORE the first of these updates.  In
+ * TD3_RNG_INJECTED mode the caller has filled the regions "indices_in" (int64 [n_agents][batch]) and
+ * "noise_in" (N(0,1) draws, fp32 [n_agents][batch][A]) and iterations must be 1.  CUDA-graph replay unless use_graph == 0. */
+int td3_train_n(td3_agent* agent, const td3_replay_view* rb, int64_t total_it, int32_t iterations,
+                int32_t rng_mode, int32_t use_graph, void* stream);
+/* The phases of one update, launched individually (no graph): parity tests and the DP critic
+ * (gradient all-reduce between critic_backward and critic_apply). */
+int td3_sample_batch(td3_agent* agent, const td3_replay_view* rb, int32_t rng_mode, void* stream);
+int td3_target_step(td3_agent* agent, void* stream);      /* TD3_featured.py:129-142 */
+int td3_critic_step(td3_agent* agent, int32_t apply, void* stream);  /* :145-153 (apply=0: stop after backward) */
+int td3_critic_apply(td3_agent* agent, void* stream);     /* Adam on the critic (:153) */
+int td3_actor_step(td3_agent* agent, int32_t apply, void* stream);   /* :159-164 */
+int td3_actor_apply(td3_agent* agent, void* stream);      /* actor Adam + Polyak of both targets (:164-171) */
+/* Loss normaliser for data-parallel critics: gradients are scaled by 1/(global_batch) instead of 1/batch. */
+int td3_agent_set_global_batch(td3_agent* agent, int64_t global_batch);
+
+/* B=small inference on caller buffers (device pointers):
+ * actor(x)  -> select_action (TD3_featured.py:113-115, TD3_particles.py:153-157)
+ * critic(x,u) -> eval_q      (TD3_featured.py:117-121, TD3_particles.py:159-164)
+ * which: 0 = online net, 1 = target net; agent_index selects one of n_agents.  particles == NULL for
+ * the featured variant.  batch must not exceed the planned batch.  q_out is [n_q][batch][q_width].
+ * These reuse the training workspace (nothing in it persists between updates). */
+int td3_actor_forward(td3_agent* agent, int32_t which, int32_t agent_index, const float* state, const float* particles,
+                      int64_t batch, float* action_out, void* stream);
+int td3_critic_forward(td3_agent* agent, int32_t which, int32_t agent_index, const float* state, const float* particles,
+                       const float* action, int64_t batch, float* q_out, void* stream);
+
+/* Number of kernel launches issued by this library since load (bench.py "gpu_launches"). */
+int64_t td3_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TD3_B200_H_ */

@@ -1,0 +1,101 @@
+"""TD3 with plain-MLP actor/critics on feature observations -- B200-native drop-in for the
+reference's TD3_featured (TD3_featured.py:15-171).
+
+Same constructor keywords and methods; extra keyword-only options:
+  actor_widths / q_widths   hidden widths (defaults = the fork's hard-coded (500,400,300)/(500,400,200),
+                            TD3_featured.py:19,54; BASELINE's "400-300" is widths=(400,300) for both)
+  rng                       "device": Philox indices + noise generated on the GPU (default)
+                            "host":   np.random.randint + torch.randn on the host, i.e. the reference's
+                                      own random streams (seed-for-seed comparable with a CPU reference run)
+  seed                      Philox key for rng="device" (default: drawn from torch's global generator)
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _lib
+from .TD3_base import TD3_base
+from .packing import MlpActor, MlpCritic, PackedFamily, net_layout
+
+device = torch.device("cuda" if torch.cuda.is_available() else "cpu")
+
+Actor, Critic = MlpActor, MlpCritic
+
+
+class TD3(TD3_base):
+    def __init__(self, obs_space, action_space, max_action=1, lr=1e-4, norm=None, CDQ=True, *,
+                 actor_widths=(500, 400, 300), q_widths=(500, 400, 200), rng="device", seed=None, **kwargs):
+        _lib.require_cuda()
+        S, A = obs_space.shape[0], action_space.shape[0]
+        # Build on the CPU with torch's default initialisers in the reference's construction order
+        # (actor, then critic q1, q2; TD3_featured.py:101-106) so that torch.manual_seed(s) gives the
+        # same initial weights as the reference; targets start as copies (deepcopy at :102,107).
+        actor = MlpActor(S, A, max_action, norm, actor_widths)
+        actor_t = _clone_shell(actor)
+        critic = MlpCritic(S, A, norm, q_widths)
+        critic_t = _clone_shell(critic)
+        super(TD3, self).__init__(max_action=max_action, **kwargs)      # :110 (CDQ accepted and ignored, :100)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        fam_a = PackedFamily(actor, actor_t, [""], dev)
+        fam_c = PackedFamily(critic, critic_t, ["q1", "q2"], dev)
+        self.actor, self.actor_target, self.critic, self.critic_target = actor, actor_t, critic, critic_t
+        for m, w in ((actor, 0), (actor_t, 1), (critic, 0), (critic_t, 1)):
+            m._attach(self, w)
+        cfg = _lib.AgentConfig()
+        cfg.variant, cfg.norm = _lib.VARIANT_FEATURED, (_lib.NORM_LAYER if norm == "layer" else _lib.NORM_NONE)
+        cfg.n_q, cfg.state_dim, cfg.action_dim = 2, S, A
+        cfg.n_particles = cfg.particle_dim = 0
+        cfg.clamp_target_action, cfg.n_agents = 1, 1
+        cfg.max_action, cfg.discount, cfg.tau = float(self.max_action), float(self.discount), float(self.tau)
+        cfg.policy_noise, cfg.noise_clip = float(self.policy_noise), float(self.noise_clip)
+        cfg.lr_actor = cfg.lr_critic = float(lr)
+        cfg.beta1, cfg.beta2, cfg.adam_eps = 0.9, 0.999, 1e-8
+        cfg.policy_freq = int(self.policy_freq)
+        cfg.seed = int(torch.randint(0, 2**62, (1,)).item()) if seed is None else int(seed)
+        cfg.actor, cfg.q = net_layout(actor), net_layout(critic.q1)
+        self.CDQ = CDQ
+        self._engine_init(cfg, fam_a, fam_c, lr, rng)
+
+    # ------------------------------------------------------------------ B=1 API (TD3_featured.py:113-121)
+    def select_action(self, state):
+        state = torch.as_tensor(np.asarray(state, dtype=np.float32).reshape(1, -1), device=self._device)
+        return self._actor_forward(0, state).cpu().numpy().flatten()
+
+    def eval_q(self, state, action):
+        state = torch.as_tensor(np.asarray(state, dtype=np.float32).reshape(1, -1), device=self._device)
+        action = torch.as_tensor(np.asarray(action, dtype=np.float32).reshape(1, -1), device=self._device)
+        return [q.cpu().numpy().flatten() for q in self._critic_forward(0, state, action)]
+
+    def _actor_forward(self, which, state, particles=None):
+        state = state.to(self._device, torch.float32).contiguous()
+        B = state.shape[0]
+        self._ensure_plan(max(B, self._planned_batch))
+        out = torch.empty(B, self._cfg.action_dim, device=self._device)
+        _lib.check(self._lib.td3_actor_forward(self._handle, which, 0, state.data_ptr(), None, B, out.data_ptr(),
+                                               _lib.stream_ptr()))
+        return out
+
+    def _critic_forward(self, which, state, action, particles=None):
+        state = state.to(self._device, torch.float32).contiguous()
+        action = action.to(self._device, torch.float32).contiguous()
+        B = state.shape[0]
+        self._ensure_plan(max(B, self._planned_batch))
+        out = torch.empty(self._cfg.n_q, B, 1, device=self._device)
+        _lib.check(self._lib.td3_critic_forward(self._handle, which, 0, state.data_ptr(), None, action.data_ptr(), B,
+                                                out.data_ptr(), _lib.stream_ptr()))
+        return [out[i] for i in range(self._cfg.n_q)]
+
+    # ------------------------------------------------------------------ the hot path (TD3_featured.py:123-171)
+    def train(self, replay_buffer, batch_size=100, *, iterations=1, indices=None, noise=None, use_graph=True):
+        """One TD3 update (``iterations`` of them back to back when given), entirely on the device:
+        sample -> target step -> twin-critic step -> every policy_freq-th update actor step + Polyak.
+        Returns None and never synchronises the host, like the reference.  ``indices`` ([batch] ints) and
+        ``noise`` ([batch, A] N(0,1) draws) replace the two random draws for parity tests."""
+        self._train_common(replay_buffer, batch_size, iterations, indices, noise, use_graph)
+
+
+def _clone_shell(module):
+    """Fresh shell of the same architecture without consuming the global RNG (the reference deep-copies)."""
+    import copy
+    return copy.deepcopy(module)

@@ -1,0 +1,1358 @@
+// engine.cu -- host side of libtd3b200.so: builds the launch plan of one TD3 update
+// (TD3_featured.py:123-171 / TD3_particles.py:167-224) as a list of "stages" (stage.cuh),
+// captures it into CUDA graphs and exposes the C ABI declared in include/td3_b200.h.
+//
+// No CPU fallback exists anywhere in this file: every entry point launches sm_100a kernels
+// or fails with an error code.
+#include "../../include/td3_b200.h"
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "misc.cuh"
+#include "stage.cuh"
+
+using namespace td3;
+
+namespace {
+
+thread_local std::string g_err;
+std::atomic<long long> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                           \
+  do {                                                                                           \
+    cudaError_t e_ = (expr);                                                                     \
+    if (e_ != cudaSuccess) return fail(TD3_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e_));   \
+  } while (0)
+
+inline long long round_up(long long v, long long m) { return (v + m - 1) / m * m; }
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// ------------------------------------------------------------------------------------
+// launch list
+// ------------------------------------------------------------------------------------
+struct Launch {
+  enum Kind { STAGE, GATHER, LOSS, EW, COUNTER } kind = STAGE;
+  StageParams stage{};
+  GatherParams gather{};
+  LossParams loss{};
+  EwParams ew{};
+  unsigned long long* counter = nullptr;
+  int grid_x = 1, grid_y = 1;
+};
+
+int run_launch(const Launch& L, cudaStream_t s) {
+  switch (L.kind) {
+    case Launch::STAGE:
+      if (L.stage.total_tiles <= 0) return TD3_OK;
+      stage_kernel<<<L.stage.total_tiles, kStageThreads, 0, s>>>(L.stage);
+      break;
+    case Launch::GATHER:
+      gather_kernel<<<dim3(L.grid_x, L.grid_y), 256, 0, s>>>(L.gather);
+      break;
+    case Launch::LOSS:
+      loss_kernel<<<L.grid_x, 256, 0, s>>>(L.loss);
+      break;
+    case Launch::EW:
+      adam_polyak_kernel<<<L.grid_x, kEwThreads, 0, s>>>(L.ew);
+      break;
+    case Launch::COUNTER:
+      counter_add_kernel<<<1, 32, 0, s>>>(L.counter, 1ull);
+      break;
+  }
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  CUDA_TRY(cudaGetLastError());
+  return TD3_OK;
+}
+
+// A stage under construction: problems that may run concurrently.
+using ProblemList = std::vector<Problem>;
+
+Problem blank_problem(int kind) {
+  Problem p;
+  memset(&p, 0, sizeof(p));
+  p.kind = kind;
+  p.groups_inner = 1;
+  p.c_dups = 1;
+  p.ksplit = 1;
+  return p;
+}
+
+struct GroupShape { int n_outer, n_inner; };
+
+Problem make_gemm(int M, int N, int K, const float* A, int lda, bool a_rc, const float* B, int ldb, bool b_rc, float* C,
+                  int ldc, int epi) {
+  Problem p = blank_problem(PK_GEMM);
+  p.epi = epi;
+  p.M = M; p.N = N; p.K = K;
+  p.A = A; p.lda = lda; p.a_rc = a_rc;
+  p.B = B; p.ldb = ldb; p.b_rc = b_rc;
+  p.C = C; p.ldc = ldc;
+  return p;
+}
+
+void finalize_problem(Problem& p, GroupShape gs) {
+  p.groups_inner = gs.n_inner;
+  const int groups = gs.n_outer * gs.n_inner;
+  switch (p.kind) {
+    case PK_GEMM: {
+      p.tiles_m = (p.M + kBM - 1) / kBM;
+      p.tiles_n = (p.N + kBN - 1) / kBN;
+      p.tiles_per_group = p.tiles_m * p.tiles_n * p.ksplit;
+      auto ok4 = [](long long v) { return (v & 3) == 0; };
+      p.a_vec = aligned16(p.A) && ok4(p.lda) && ok4(p.a_go) && ok4(p.a_gi) && ok4(p.a_rc ? p.K : p.M);
+      p.b_vec = aligned16(p.B) && ok4(p.ldb) && ok4(p.b_go) && ok4(p.b_gi) && ok4(p.b_rc ? p.K : p.N);
+      break;
+    }
+    case PK_LN_FWD:
+    case PK_LN_BWD_ROWS:
+      p.tiles_per_group = (p.M + 7) / 8;
+      break;
+    case PK_LN_BWD_COLS:
+      p.tiles_per_group = (p.N + 31) / 32;
+      break;
+    case PK_POOL_FWD:
+      p.tiles_n = (p.N + 31) / 32;
+      p.tiles_per_group = p.M * p.tiles_n;
+      break;
+    case PK_POOL_BWD:
+      p.tiles_per_group = (int)(((long long)p.M * p.K + 7) / 8);
+      break;
+    case PK_REDUCE_SPLITS:
+      p.tiles_per_group = (p.M + 1023) / 1024;
+      break;
+    case PK_NEG_MEAN:
+      p.tiles_per_group = 1;
+      break;
+  }
+  p.tile_count = p.tiles_per_group * groups;
+}
+
+int emit_stage(std::vector<Launch>& seq, const ProblemList& probs) {
+  // split into chunks of kMaxProblemsPerStage (they stay independent, so extra launches are still correct)
+  size_t i = 0;
+  while (i < probs.size()) {
+    Launch L;
+    L.kind = Launch::STAGE;
+    int n = 0, tiles = 0;
+    while (i < probs.size() && n < kMaxProblemsPerStage) {
+      Problem p = probs[i++];
+      if (p.tile_count <= 0) continue;
+      p.tile_begin = tiles;
+      tiles += p.tile_count;
+      L.stage.p[n++] = p;
+    }
+    L.stage.n_problems = n;
+    L.stage.total_tiles = tiles;
+    if (n > 0) seq.push_back(L);
+  }
+  return TD3_OK;
+}
+
+// merge several per-pass stage sequences so that stage s of every pass shares one launch
+std::vector<ProblemList> zip_stages(const std::vector<std::vector<ProblemList>>& passes) {
+  size_t depth = 0;
+  for (auto& p : passes) depth = std::max(depth, p.size());
+  std::vector<ProblemList> out(depth);
+  for (auto& p : passes)
+    for (size_t s = 0; s < p.size(); ++s) out[s].insert(out[s].end(), p[s].begin(), p[s].end());
+  return out;
+}
+
+// ------------------------------------------------------------------------------------
+// workspace
+// ------------------------------------------------------------------------------------
+struct Bump {
+  float* base = nullptr;
+  long long used = 0;
+  std::map<std::string, std::pair<long long, long long>> regions;
+  float* take(long long n, const char* name = nullptr) {
+    n = std::max<long long>(n, 1);
+    const long long off = used;
+    used += round_up(n, 64);
+    if (name) regions[name] = {off, n};
+    return base ? base + off : nullptr;
+  }
+};
+
+// Activations of one forward pass over `groups` networks of identical shape.
+struct PassBuf {
+  float* x0 = nullptr; int ld0 = 0; long long x0_go = 0, x0_gi = 0;    // trunk input [B, ld0]
+  float* x0n = nullptr; float* mean0 = nullptr; float* rstd0 = nullptr; // input LayerNorm (lnorm1)
+  long long x0n_go = 0, x0n_gi = 0;
+  float* r[TD3_MAX_LINEAR] = {};      // relu(z_l)            [B, w_l]
+  float* n[TD3_MAX_LINEAR] = {};      // LN(relu(z_l))        (norm == layer)
+  float* mean[TD3_MAX_LINEAR] = {};
+  float* rstd[TD3_MAX_LINEAR] = {};
+  long long h_go[TD3_MAX_LINEAR] = {}, h_gi[TD3_MAX_LINEAR] = {};
+  long long s_go = 0, s_gi = 0;       // strides of the [B] statistics
+  const float* P = nullptr; long long P_go = 0;       // particles [B*N, D]
+  float* h1 = nullptr; float* h2 = nullptr;           // encoder activations
+  long long h1_go = 0, h1_gi = 0, h2_go = 0, h2_gi = 0;
+};
+
+struct OutSpec {
+  float* out = nullptr; int ld = 0; long long go = 0, gi = 0;
+  int epi = EPI_BIAS;
+  float* aux0 = nullptr; int ldaux = 0; long long aux0_go = 0, aux0_gi = 0;
+  float f0 = 1.f, f1 = 0.f;
+  int dups = 1; long long dup_stride = 0;
+};
+
+struct ParamRef {   // packed parameters of `n_inner` networks per agent
+  const float* base = nullptr;
+  long long go = 0, gi = 0;
+};
+
+struct GradRef {
+  float* base = nullptr;
+  long long go = 0, gi = 0;
+};
+
+}  // namespace
+
+struct td3_agent {
+  td3_agent_config cfg{};
+  td3_param_set actor{}, critic{};
+  bool params_bound = false;
+  unsigned long long* state_u64 = nullptr;   // [0] sample step [1] critic Adam t [2] actor Adam t [3] rb size
+  float* state_f32 = nullptr;                // critic_loss[n_agents], actor_loss[n_agents]
+  long long batch = 0, global_batch = 0;
+  Bump ws;
+  long long ws_floats = 0;
+
+  // --- workspace pointers (valid after plan) ---
+  int ld_a = 0, ld_q = 0, in_a = 0, in_q = 0, qw = 1;
+  float *xa = nullptr, *xa2 = nullptr, *xq = nullptr, *xq2 = nullptr, *xpi = nullptr, *xapi = nullptr;
+  long long xa_go = 0, xq_go = 0, xq_gi = 0, xpi_go = 0;
+  float *P = nullptr, *P2 = nullptr;
+  float *r = nullptr, *nd = nullptr, *eps = nullptr, *noise_in = nullptr;
+  long long *idx = nullptr, *idx_in = nullptr;
+  float *q = nullptr, *tq = nullptr, *y = nullptr, *dq = nullptr, *q_pi = nullptr, *dq_pi = nullptr, *tanh_y = nullptr;
+  PassBuf pb_at, pb_ct, pb_c, pb_a, pb_q1;
+
+  std::vector<Launch> seq_sample, seq_target, seq_critic_fb, seq_critic_apply, seq_actor_fb, seq_actor_apply;
+  const float* plan_rows = nullptr;
+  long long plan_row_stride = 0, plan_rb_agent_stride = 0;
+  int plan_rng_mode = -1;
+
+  struct Graphs {
+    cudaGraphExec_t critic_only = nullptr, with_actor = nullptr;
+    long long nodes_critic_only = 0, nodes_with_actor = 0;     // kernels per replay (launch accounting)
+    const float* rows = nullptr;
+    long long row_stride = 0;
+    int rng_mode = -1;
+  } graphs;
+  long long last_rb_size = -1;
+  cudaStream_t cap_stream = nullptr;         // capture happens here: the caller's stream may be the legacy stream
+};
+
+namespace {
+
+void drop_graphs(td3_agent* a) {
+  if (a->graphs.critic_only) cudaGraphExecDestroy(a->graphs.critic_only);
+  if (a->graphs.with_actor) cudaGraphExecDestroy(a->graphs.with_actor);
+  a->graphs = td3_agent::Graphs{};
+}
+
+// ------------------------------------------------------------------------------------
+// forward pass builder
+// ------------------------------------------------------------------------------------
+void set_groups(Problem& p, long long a_go, long long a_gi, long long b_go, long long b_gi, long long c_go, long long c_gi) {
+  p.a_go = a_go; p.a_gi = a_gi; p.b_go = b_go; p.b_gi = b_gi; p.c_go = c_go; p.c_gi = c_gi;
+}
+
+std::vector<ProblemList> build_forward(const td3_agent_config& cfg, const td3_net_layout& net, ParamRef W, GroupShape gs,
+                                       int B, const PassBuf& pb, const OutSpec& out, int pool_dups = 1,
+                                       long long pool_dup_stride = 0) {
+  std::vector<ProblemList> st;
+  const bool ln = cfg.norm == TD3_NORM_LAYER;
+  const bool enc = cfg.variant == TD3_VARIANT_PARTICLES;
+  const int L = net.n_linear;
+  if (enc) {
+    const int rows = B * cfg.n_particles;
+    // conv1 == per-particle linear D -> enc_hidden (TD3_particles.py:29,54)
+    Problem e1 = make_gemm(rows, net.enc_hidden, cfg.particle_dim, pb.P, cfg.particle_dim, true, W.base + net.c1w_off,
+                           cfg.particle_dim, true, pb.h1, net.enc_hidden, EPI_BIAS_RELU);
+    set_groups(e1, pb.P_go, 0, W.go, W.gi, pb.h1_go, pb.h1_gi);
+    e1.bias = W.base + net.c1b_off; e1.bias_go = W.go; e1.bias_gi = W.gi;
+    finalize_problem(e1, gs);
+    st.push_back({e1});
+    // conv2 (1x1) == linear enc_hidden -> enc_out (:30,56)
+    Problem e2 = make_gemm(rows, net.enc_out, net.enc_hidden, pb.h1, net.enc_hidden, true, W.base + net.c2w_off,
+                           net.enc_hidden, true, pb.h2, net.enc_out, EPI_BIAS_RELU);
+    set_groups(e2, pb.h1_go, pb.h1_gi, W.go, W.gi, pb.h2_go, pb.h2_gi);
+    e2.bias = W.base + net.c2b_off; e2.bias_go = W.go; e2.bias_gi = W.gi;
+    finalize_problem(e2, gs);
+    st.push_back({e2});
+    // avg_pool over particles + relu, written into the first enc_out columns of the trunk input (:57-59)
+    Problem pl = blank_problem(PK_POOL_FWD);
+    pl.M = B; pl.N = net.enc_out; pl.K = cfg.n_particles;
+    pl.A = pb.h2; pl.lda = net.enc_out; pl.a_go = pb.h2_go; pl.a_gi = pb.h2_gi;
+    pl.C = pb.x0; pl.ldc = pb.ld0; pl.c_go = pb.x0_go; pl.c_gi = pb.x0_gi;
+    pl.c_dups = pool_dups; pl.c_dup_stride = pool_dup_stride;
+    finalize_problem(pl, gs);
+    st.push_back({pl});
+  }
+  const float* in = pb.x0;
+  int ld_in = pb.ld0;
+  long long in_go = pb.x0_go, in_gi = pb.x0_gi;
+  if (enc && ln) {   // lnorm1 on the concatenated input (:60-61)
+    Problem p = blank_problem(PK_LN_FWD);
+    p.M = B; p.N = net.dims[0];
+    p.A = pb.x0; p.lda = pb.ld0; p.a_go = pb.x0_go; p.a_gi = pb.x0_gi;
+    p.B = W.base + net.ln_in_g_off; p.b_go = W.go; p.b_gi = W.gi;
+    p.bias = W.base + net.ln_in_b_off; p.bias_go = W.go; p.bias_gi = W.gi;
+    p.C = pb.x0n; p.ldc = pb.ld0; p.c_go = pb.x0n_go; p.c_gi = pb.x0n_gi;
+    p.aux2 = pb.mean0; p.aux3 = pb.rstd0; p.aux2_go = p.aux3_go = pb.s_go; p.aux2_gi = p.aux3_gi = pb.s_gi;
+    p.f0 = 1e-5f;
+    finalize_problem(p, gs);
+    st.push_back({p});
+    in = pb.x0n; in_go = pb.x0n_go; in_gi = pb.x0n_gi;
+  }
+  for (int l = 0; l < L; ++l) {
+    const int K = net.dims[l], N = net.dims[l + 1];
+    const bool last = l == L - 1;
+    Problem g = make_gemm(B, N, K, in, ld_in, true, W.base + net.w_off[l], K, true, last ? out.out : pb.r[l],
+                          last ? out.ld : N, last ? out.epi : EPI_BIAS_RELU);
+    set_groups(g, in_go, in_gi, W.go, W.gi, last ? out.go : pb.h_go[l], last ? out.gi : pb.h_gi[l]);
+    g.bias = W.base + net.b_off[l]; g.bias_go = W.go; g.bias_gi = W.gi;
+    if (last) {
+      g.aux0 = out.aux0; g.ldaux = out.ldaux; g.aux0_go = out.aux0_go; g.aux0_gi = out.aux0_gi;
+      g.f0 = out.f0; g.f1 = out.f1;
+      g.c_dups = out.dups; g.c_dup_stride = out.dup_stride;
+    }
+    finalize_problem(g, gs);
+    st.push_back({g});
+    if (last) break;
+    in = pb.r[l]; ld_in = N; in_go = pb.h_go[l]; in_gi = pb.h_gi[l];
+    if (ln) {   // post-ReLU LayerNorm (TD3_featured.py:44-46)
+      Problem p = blank_problem(PK_LN_FWD);
+      p.M = B; p.N = N;
+      p.A = pb.r[l]; p.lda = N; p.a_go = pb.h_go[l]; p.a_gi = pb.h_gi[l];
+      p.B = W.base + net.ln_g_off[l]; p.b_go = W.go; p.b_gi = W.gi;
+      p.bias = W.base + net.ln_b_off[l]; p.bias_go = W.go; p.bias_gi = W.gi;
+      p.C = pb.n[l]; p.ldc = N; p.c_go = pb.h_go[l]; p.c_gi = pb.h_gi[l];
+      p.aux2 = pb.mean[l]; p.aux3 = pb.rstd[l]; p.aux2_go = p.aux3_go = pb.s_go; p.aux2_gi = p.aux3_gi = pb.s_gi;
+      p.f0 = 1e-5f;
+      finalize_problem(p, gs);
+      st.push_back({p});
+      in = pb.n[l];
+    }
+  }
+  return st;
+}
+
+// ------------------------------------------------------------------------------------
+// backward pass builder.  dout = d(loss)/d(network output) [B, w_L] (ld = ld_dout).
+//   want_dw : write parameter gradients into G (same layout as the parameters)
+//   dx0_mode: 0 none, 1 d(input columns [col0, col0+ncols)) -> dx0 (epilogue dx0_epi)
+// Scratch: dz[2] ping-pong [groups][B*maxw], dn [groups][B*maxw].
+// ------------------------------------------------------------------------------------
+struct BwdScratch {
+  float* dz[2] = {nullptr, nullptr};
+  float* dn = nullptr;
+  long long go = 0, gi = 0;          // strides of dz/dn
+  float* dx0_full = nullptr; long long dx0_full_go = 0, dx0_full_gi = 0;   // [B, ld0] (encoder / lnorm1 path)
+  float* dh2 = nullptr; float* dh1 = nullptr; long long dh2_go = 0, dh2_gi = 0, dh1_go = 0, dh1_gi = 0;
+  float* part = nullptr; long long part_go = 0, part_gi = 0;               // split-K partials
+  long long part_cap = 0;
+};
+
+struct Dx0Spec {
+  int mode = 0;
+  int col0 = 0, ncols = 0;
+  float* out = nullptr; int ld = 0; long long go = 0, gi = 0;
+  int epi = EPI_STORE;
+  float* aux0 = nullptr; int ldaux = 0; long long aux0_go = 0, aux0_gi = 0;
+  float f0 = 1.f;
+};
+
+int choose_ksplit(int tiles, int groups, int K) {
+  if (K <= 2048) return 1;
+  int want = std::max(1, 592 / std::max(1, tiles * groups));
+  int cap = std::max(1, K / 512);
+  return std::max(1, std::min(std::min(want, cap), 128));
+}
+
+std::vector<ProblemList> build_backward(const td3_agent_config& cfg, const td3_net_layout& net, ParamRef W, GradRef G,
+                                        GroupShape gs, int B, const PassBuf& pb, const float* dout, int ld_dout,
+                                        long long dout_go, long long dout_gi, bool want_dw, const Dx0Spec& dx0,
+                                        const BwdScratch& sc) {
+  std::vector<ProblemList> st;
+  const bool ln = cfg.norm == TD3_NORM_LAYER;
+  const bool enc = cfg.variant == TD3_VARIANT_PARTICLES;
+  const int L = net.n_linear;
+  const int groups = gs.n_outer * gs.n_inner;
+  const float* dz = dout;
+  int ld_dz = ld_dout;
+  long long dz_go = dout_go, dz_gi = dout_gi;
+  int pp = 0;
+  for (int l = L - 1; l >= 0; --l) {
+    const int K = net.dims[l], N = net.dims[l + 1];
+    ProblemList stage;
+    // input activation of layer l
+    const float* in; int ld_in; long long in_go, in_gi;
+    if (l == 0) {
+      const bool lnin = enc && ln;
+      in = lnin ? pb.x0n : pb.x0; ld_in = pb.ld0;
+      in_go = lnin ? pb.x0n_go : pb.x0_go; in_gi = lnin ? pb.x0n_gi : pb.x0_gi;
+    } else {
+      in = ln ? pb.n[l - 1] : pb.r[l - 1]; ld_in = K; in_go = pb.h_go[l - 1]; in_gi = pb.h_gi[l - 1];
+    }
+    if (want_dw) {   // dW_l[n,k] = sum_b dz[b,n] in[b,k] ; db_l[n] = sum_b dz[b,n]
+      Problem p = make_gemm(N, K, B, dz, ld_dz, false, in, ld_in, false, G.base + net.w_off[l], K, EPI_STORE);
+      set_groups(p, dz_go, dz_gi, in_go, in_gi, G.go, G.gi);
+      p.aux1 = G.base + net.b_off[l]; p.aux1_go = G.go; p.aux1_gi = G.gi;
+      finalize_problem(p, gs);
+      stage.push_back(p);
+    }
+    if (l > 0) {     // d(in_l) = dz . W_l
+      const bool mask_now = !ln;
+      float* dst = mask_now ? sc.dz[pp] : sc.dn;
+      Problem p = make_gemm(B, K, N, dz, ld_dz, true, W.base + net.w_off[l], K, false, dst, K,
+                            mask_now ? EPI_RELU_MASK : EPI_STORE);
+      set_groups(p, dz_go, dz_gi, W.go, W.gi, sc.go, sc.gi);
+      if (mask_now) { p.aux0 = pb.r[l - 1]; p.ldaux = K; p.aux0_go = pb.h_go[l - 1]; p.aux0_gi = pb.h_gi[l - 1]; }
+      finalize_problem(p, gs);
+      stage.push_back(p);
+      st.push_back(stage);
+      if (ln) {      // through LayerNorm then ReLU
+        ProblemList s2;
+        Problem rr = blank_problem(PK_LN_BWD_ROWS);
+        rr.epi = EPI_RELU_MASK;
+        rr.M = B; rr.N = K;
+        rr.A = sc.dn; rr.lda = K; rr.a_go = sc.go; rr.a_gi = sc.gi;
+        rr.B = W.base + net.ln_g_off[l - 1]; rr.b_go = W.go; rr.b_gi = W.gi;
+        rr.aux0 = pb.r[l - 1]; rr.ldaux = K; rr.aux0_go = pb.h_go[l - 1]; rr.aux0_gi = pb.h_gi[l - 1];
+        rr.aux2 = pb.mean[l - 1]; rr.aux3 = pb.rstd[l - 1];
+        rr.aux2_go = rr.aux3_go = pb.s_go; rr.aux2_gi = rr.aux3_gi = pb.s_gi;
+        rr.C = sc.dz[pp]; rr.ldc = K; rr.c_go = sc.go; rr.c_gi = sc.gi;
+        finalize_problem(rr, gs);
+        s2.push_back(rr);
+        if (want_dw) {
+          Problem cc = blank_problem(PK_LN_BWD_COLS);
+          cc.M = B; cc.N = K;
+          cc.A = sc.dn; cc.lda = K; cc.a_go = sc.go; cc.a_gi = sc.gi;
+          cc.aux0 = pb.r[l - 1]; cc.ldaux = K; cc.aux0_go = pb.h_go[l - 1]; cc.aux0_gi = pb.h_gi[l - 1];
+          cc.aux2 = pb.mean[l - 1]; cc.aux3 = pb.rstd[l - 1];
+          cc.aux2_go = cc.aux3_go = pb.s_go; cc.aux2_gi = cc.aux3_gi = pb.s_gi;
+          cc.C = G.base + net.ln_g_off[l - 1]; cc.c_go = G.go; cc.c_gi = G.gi;
+          cc.aux1 = G.base + net.ln_b_off[l - 1]; cc.aux1_go = G.go; cc.aux1_gi = G.gi;
+          finalize_problem(cc, gs);
+          s2.push_back(cc);
+        }
+        st.push_back(s2);
+      }
+      dz = sc.dz[pp]; ld_dz = K; dz_go = sc.go; dz_gi = sc.gi;
+      pp ^= 1;
+      continue;
+    }
+    // ---- l == 0 : gradient w.r.t. the trunk input ----
+    const bool lnin = enc && ln;
+    const bool need_enc_bwd = enc && want_dw;
+    const bool need_full = lnin || need_enc_bwd;
+    if (!need_full && dx0.mode == 1) {
+      // only a column slice of d(x0) is needed (the action columns): slice W_0
+      Problem p = make_gemm(B, dx0.ncols, N, dz, ld_dz, true, W.base + net.w_off[0] + dx0.col0, K, false, dx0.out, dx0.ld,
+                            dx0.epi);
+      set_groups(p, dz_go, dz_gi, W.go, W.gi, dx0.go, dx0.gi);
+      p.aux0 = dx0.aux0; p.ldaux = dx0.ldaux; p.aux0_go = dx0.aux0_go; p.aux0_gi = dx0.aux0_gi; p.f0 = dx0.f0;
+      finalize_problem(p, gs);
+      stage.push_back(p);
+      st.push_back(stage);
+      break;
+    }
+    if (need_full || dx0.mode == 1) {
+      float* dst = lnin ? sc.dn : sc.dx0_full;
+      const int ldd = lnin ? K : pb.ld0;
+      Problem p = make_gemm(B, K, N, dz, ld_dz, true, W.base + net.w_off[0], K, false, dst, ldd, EPI_STORE);
+      set_groups(p, dz_go, dz_gi, W.go, W.gi, lnin ? sc.go : sc.dx0_full_go, lnin ? sc.gi : sc.dx0_full_gi);
+      finalize_problem(p, gs);
+      stage.push_back(p);
+    }
+    if (!stage.empty()) st.push_back(stage);
+    if (lnin) {
+      ProblemList s2;
+      Problem rr = blank_problem(PK_LN_BWD_ROWS);
+      rr.epi = EPI_STORE;
+      rr.M = B; rr.N = K;
+      rr.A = sc.dn; rr.lda = K; rr.a_go = sc.go; rr.a_gi = sc.gi;
+      rr.B = W.base + net.ln_in_g_off; rr.b_go = W.go; rr.b_gi = W.gi;
+      rr.aux0 = pb.x0; rr.ldaux = pb.ld0; rr.aux0_go = pb.x0_go; rr.aux0_gi = pb.x0_gi;
+      rr.aux2 = pb.mean0; rr.aux3 = pb.rstd0; rr.aux2_go = rr.aux3_go = pb.s_go; rr.aux2_gi = rr.aux3_gi = pb.s_gi;
+      rr.C = sc.dx0_full; rr.ldc = pb.ld0; rr.c_go = sc.dx0_full_go; rr.c_gi = sc.dx0_full_gi;
+      finalize_problem(rr, gs);
+      s2.push_back(rr);
+      if (want_dw) {
+        Problem cc = blank_problem(PK_LN_BWD_COLS);
+        cc.M = B; cc.N = K;
+        cc.A = sc.dn; cc.lda = K; cc.a_go = sc.go; cc.a_gi = sc.gi;
+        cc.aux0 = pb.x0; cc.ldaux = pb.ld0; cc.aux0_go = pb.x0_go; cc.aux0_gi = pb.x0_gi;
+        cc.aux2 = pb.mean0; cc.aux3 = pb.rstd0; cc.aux2_go = cc.aux3_go = pb.s_go; cc.aux2_gi = cc.aux3_gi = pb.s_gi;
+        cc.C = G.base + net.ln_in_g_off; cc.c_go = G.go; cc.c_gi = G.gi;
+        cc.aux1 = G.base + net.ln_in_b_off; cc.aux1_go = G.go; cc.aux1_gi = G.gi;
+        finalize_problem(cc, gs);
+        s2.push_back(cc);
+      }
+      st.push_back(s2);
+    }
+    if (need_enc_bwd) {
+      const int rows = B * cfg.n_particles;
+      const int H = net.enc_hidden, O = net.enc_out, D = cfg.particle_dim;
+      // dH2 = dpool/N gated by both ReLUs (:56-57)
+      Problem pbk = blank_problem(PK_POOL_BWD);
+      pbk.M = B; pbk.N = O; pbk.K = cfg.n_particles;
+      pbk.A = sc.dx0_full; pbk.lda = pb.ld0; pbk.a_go = sc.dx0_full_go; pbk.a_gi = sc.dx0_full_gi;
+      pbk.aux0 = pb.x0; pbk.ldaux = pb.ld0; pbk.aux0_go = pb.x0_go; pbk.aux0_gi = pb.x0_gi;
+      pbk.aux1 = pb.h2; pbk.ldb = O; pbk.aux1_go = pb.h2_go; pbk.aux1_gi = pb.h2_gi;
+      pbk.C = sc.dh2; pbk.ldc = O; pbk.c_go = sc.dh2_go; pbk.c_gi = sc.dh2_gi;
+      finalize_problem(pbk, gs);
+      st.push_back({pbk});
+      // conv2: dW2 = dH2^T H1 (split-K over B*N), dH1 = (dH2 W2) * (H1 > 0)
+      const int tiles2 = ((O + 31) / 32) * ((H + 31) / 32);
+      const int ks2 = choose_ksplit(tiles2, groups, rows);
+      Problem dw2 = make_gemm(O, H, rows, sc.dh2, O, false, pb.h1, H, false, ks2 > 1 ? sc.part : G.base + net.c2w_off, H,
+                              EPI_STORE);
+      dw2.ksplit = ks2; dw2.c_split = (long long)O * H;
+      set_groups(dw2, sc.dh2_go, sc.dh2_gi, pb.h1_go, pb.h1_gi, ks2 > 1 ? sc.part_go : G.go, ks2 > 1 ? sc.part_gi : G.gi);
+      dw2.aux1 = ks2 > 1 ? sc.part + (long long)ks2 * O * H : G.base + net.c2b_off;
+      dw2.aux1_go = ks2 > 1 ? sc.part_go : G.go; dw2.aux1_gi = ks2 > 1 ? sc.part_gi : G.gi;
+      finalize_problem(dw2, gs);
+      Problem dx2 = make_gemm(rows, H, O, sc.dh2, O, true, W.base + net.c2w_off, H, false, sc.dh1, H, EPI_RELU_MASK);
+      set_groups(dx2, sc.dh2_go, sc.dh2_gi, W.go, W.gi, sc.dh1_go, sc.dh1_gi);
+      dx2.aux0 = pb.h1; dx2.ldaux = H; dx2.aux0_go = pb.h1_go; dx2.aux0_gi = pb.h1_gi;
+      finalize_problem(dx2, gs);
+      st.push_back({dw2, dx2});
+      ProblemList s3;
+      if (ks2 > 1) {
+        Problem r1 = blank_problem(PK_REDUCE_SPLITS);
+        r1.M = O * H; r1.K = ks2; r1.c_split = (long long)O * H;
+        r1.A = sc.part; r1.a_go = sc.part_go; r1.a_gi = sc.part_gi;
+        r1.C = G.base + net.c2w_off; r1.c_go = G.go; r1.c_gi = G.gi;
+        finalize_problem(r1, gs);
+        s3.push_back(r1);
+        Problem r2 = blank_problem(PK_REDUCE_SPLITS);
+        r2.M = O; r2.K = ks2; r2.c_split = O;
+        r2.A = sc.part + (long long)ks2 * O * H; r2.a_go = sc.part_go; r2.a_gi = sc.part_gi;
+        r2.C = G.base + net.c2b_off; r2.c_go = G.go; r2.c_gi = G.gi;
+        finalize_problem(r2, gs);
+        s3.push_back(r2);
+      }
+      // conv1: dW1 = dH1^T P (split-K), second half of the partial buffer
+      const int tiles1 = ((H + 31) / 32) * ((D + 31) / 32);
+      const int ks1 = choose_ksplit(tiles1, groups, rows);
+      float* part1 = sc.part + (long long)ks2 * (O * H + O);
+      Problem dw1 = make_gemm(H, D, rows, sc.dh1, H, false, pb.P, D, false, ks1 > 1 ? part1 : G.base + net.c1w_off, D,
+                              EPI_STORE);
+      dw1.ksplit = ks1; dw1.c_split = (long long)H * D;
+      set_groups(dw1, sc.dh1_go, sc.dh1_gi, pb.P_go, 0, ks1 > 1 ? sc.part_go : G.go, ks1 > 1 ? sc.part_gi : G.gi);
+      dw1.aux1 = ks1 > 1 ? part1 + (long long)ks1 * H * D : G.base + net.c1b_off;
+      dw1.aux1_go = ks1 > 1 ? sc.part_go : G.go; dw1.aux1_gi = ks1 > 1 ? sc.part_gi : G.gi;
+      finalize_problem(dw1, gs);
+      s3.push_back(dw1);
+      st.push_back(s3);
+      if (ks1 > 1) {
+        ProblemList s4;
+        Problem r1 = blank_problem(PK_REDUCE_SPLITS);
+        r1.M = H * D; r1.K = ks1; r1.c_split = (long long)H * D;
+        r1.A = part1; r1.a_go = sc.part_go; r1.a_gi = sc.part_gi;
+        r1.C = G.base + net.c1w_off; r1.c_go = G.go; r1.c_gi = G.gi;
+        finalize_problem(r1, gs);
+        s4.push_back(r1);
+        Problem r2 = blank_problem(PK_REDUCE_SPLITS);
+        r2.M = H; r2.K = ks1; r2.c_split = H;
+        r2.A = part1 + (long long)ks1 * H * D; r2.a_go = sc.part_go; r2.a_gi = sc.part_gi;
+        r2.C = G.base + net.c1b_off; r2.c_go = G.go; r2.c_gi = G.gi;
+        finalize_problem(r2, gs);
+        s4.push_back(r2);
+        st.push_back(s4);
+      }
+    }
+  }
+  return st;
+}
+
+long long partial_floats(const td3_agent_config& cfg, const td3_net_layout& net, int B) {
+  if (cfg.variant != TD3_VARIANT_PARTICLES) return 1;
+  const long long H = net.enc_hidden, O = net.enc_out, D = cfg.particle_dim;
+  return 128 * (O * H + O) + 128 * (H * D + H);
+}
+
+// allocate the activations of a pass
+void alloc_pass(Bump& ws, const td3_agent_config& cfg, const td3_net_layout& net, GroupShape gs, int B, PassBuf& pb,
+                bool own_x0, bool need_enc_acts) {
+  const int groups = gs.n_outer * gs.n_inner;
+  const bool ln = cfg.norm == TD3_NORM_LAYER;
+  const bool enc = cfg.variant == TD3_VARIANT_PARTICLES;
+  if (own_x0) {
+    pb.ld0 = (int)round_up(net.dims[0], 4);
+    pb.x0 = ws.take((long long)groups * B * pb.ld0);
+    pb.x0_gi = (long long)B * pb.ld0;
+    pb.x0_go = pb.x0_gi * gs.n_inner;
+  }
+  pb.s_gi = B; pb.s_go = (long long)B * gs.n_inner;
+  if (enc && ln) {
+    pb.x0n = ws.take((long long)groups * B * pb.ld0);
+    pb.x0n_gi = (long long)B * pb.ld0; pb.x0n_go = pb.x0n_gi * gs.n_inner;
+    pb.mean0 = ws.take((long long)groups * B);
+    pb.rstd0 = ws.take((long long)groups * B);
+  }
+  for (int l = 0; l + 1 < net.n_linear; ++l) {
+    const long long w = net.dims[l + 1];
+    pb.h_gi[l] = B * w; pb.h_go[l] = B * w * gs.n_inner;
+    pb.r[l] = ws.take(groups * B * w);
+    if (ln) {
+      pb.n[l] = ws.take(groups * B * w);
+      pb.mean[l] = ws.take((long long)groups * B);
+      pb.rstd[l] = ws.take((long long)groups * B);
+    }
+  }
+  if (enc && need_enc_acts) {
+    const long long rows = (long long)B * cfg.n_particles;
+    pb.h1_gi = rows * net.enc_hidden; pb.h1_go = pb.h1_gi * gs.n_inner;
+    pb.h2_gi = rows * net.enc_out; pb.h2_go = pb.h2_gi * gs.n_inner;
+    pb.h1 = ws.take(groups * rows * net.enc_hidden);
+    pb.h2 = ws.take(groups * rows * net.enc_out);
+  }
+}
+
+void alloc_bwd(Bump& ws, const td3_agent_config& cfg, const td3_net_layout& net, GroupShape gs, int B, BwdScratch& sc,
+               bool enc_bwd) {
+  const int groups = gs.n_outer * gs.n_inner;
+  long long maxw = 4;
+  for (int l = 0; l <= net.n_linear; ++l) maxw = std::max<long long>(maxw, round_up(net.dims[l], 4));
+  sc.gi = B * maxw; sc.go = sc.gi * gs.n_inner;
+  sc.dz[0] = ws.take(groups * B * maxw);
+  sc.dz[1] = ws.take(groups * B * maxw);
+  sc.dn = ws.take(groups * B * maxw);
+  const long long ld0 = round_up(net.dims[0], 4);
+  sc.dx0_full_gi = B * ld0; sc.dx0_full_go = sc.dx0_full_gi * gs.n_inner;
+  sc.dx0_full = ws.take(groups * B * ld0);
+  if (cfg.variant == TD3_VARIANT_PARTICLES && enc_bwd) {
+    const long long rows = (long long)B * cfg.n_particles;
+    sc.dh2_gi = rows * net.enc_out; sc.dh2_go = sc.dh2_gi * gs.n_inner;
+    sc.dh1_gi = rows * net.enc_hidden; sc.dh1_go = sc.dh1_gi * gs.n_inner;
+    sc.dh2 = ws.take(groups * rows * net.enc_out);
+    sc.dh1 = ws.take(groups * rows * net.enc_hidden);
+    sc.part_cap = partial_floats(cfg, net, B);
+    sc.part_gi = sc.part_cap; sc.part_go = sc.part_cap * gs.n_inner;
+    sc.part = ws.take(groups * sc.part_cap);
+  }
+}
+
+// out[b, j] = epi(in[b, j]) for a [B, ncols] column slice, expressed as a product with a tiny identity matrix so
+// that it reuses the GEMM tile path and its epilogues (only the particles + LayerNorm actor step needs it).
+Problem make_slice(int B, int ncols, const float* in, int ld_in, const float* eye, float* out, int ld_out, int epi) {
+  Problem p = make_gemm(B, ncols, ncols, in, ld_in, true, eye, ncols, false, out, ld_out, epi);
+  return p;
+}
+
+int plan_agent(td3_agent* a, long long batch) {
+  const td3_agent_config& c = a->cfg;
+  const int B = (int)batch, nA = c.n_agents, nq = c.n_q;
+  const bool enc = c.variant == TD3_VARIANT_PARTICLES;
+  const bool ln = c.norm == TD3_NORM_LAYER;
+  const GroupShape g_actor{nA, 1}, g_crit{nA, nq}, g_q1{nA, 1};
+  Bump& ws = a->ws;
+  ws.used = 0;
+  ws.regions.clear();
+  const int A = c.action_dim, S = c.state_dim, E = enc ? c.actor.enc_out : 0;
+  a->in_a = c.actor.dims[0];
+  a->in_q = c.q.dims[0];
+  a->qw = c.q.dims[c.q.n_linear];
+  a->ld_a = (int)round_up(a->in_a, 4);
+  a->ld_q = (int)round_up(a->in_q, 4);
+  const int ld_q = a->ld_q, ld_a = a->ld_a, qw = a->qw;
+  if (a->in_a != E + S || a->in_q != E + S + A)
+    return fail(TD3_ERR_INVALID, "layout dims[0] (%d,%d) inconsistent with enc_out+state_dim(+action_dim) (%d,%d)",
+                a->in_a, a->in_q, E + S, E + S + A);
+
+  // ---- batch staging ----
+  a->idx = reinterpret_cast<long long*>(ws.take(2LL * nA * B, "indices"));
+  a->idx_in = reinterpret_cast<long long*>(ws.take(2LL * nA * B, "indices_in"));
+  a->noise_in = ws.take((long long)nA * B * A, "noise_in");
+  a->eps = ws.take((long long)nA * B * A, "eps");
+  a->r = ws.take((long long)nA * B, "reward");
+  a->nd = ws.take((long long)nA * B, "not_done");
+  // trunk inputs.  Q inputs are per twin only when an encoder makes the pooled columns differ.
+  const int xq_inner = enc ? nq : 1;
+  a->xq_gi = enc ? (long long)B * ld_q : 0;
+  a->xq_go = (long long)B * ld_q * xq_inner;
+  a->xq = ws.take((long long)nA * xq_inner * B * ld_q, "x_q");
+  a->xq2 = ws.take((long long)nA * xq_inner * B * ld_q, "x_q_next");
+  a->xpi_go = (long long)B * ld_q;
+  a->xpi = ws.take((long long)nA * B * ld_q, "x_q_pi");
+  if (enc) {
+    a->xa_go = (long long)B * ld_a;
+    a->xa = ws.take((long long)nA * B * ld_a, "x_actor");
+    a->xa2 = ws.take((long long)nA * B * ld_a, "x_actor_next");
+    const long long pn = (long long)B * c.n_particles * c.particle_dim;
+    a->P = ws.take(nA * pn, "particles");
+    a->P2 = ws.take(nA * pn, "particles_next");
+  }
+  a->q = ws.take((long long)nA * nq * B * qw, "q");
+  a->tq = ws.take((long long)nA * nq * B * qw, "tq");
+  a->y = ws.take((long long)nA * B * qw, "target_q");
+  a->dq = ws.take((long long)nA * nq * B * qw, "dq");
+  a->q_pi = ws.take((long long)nA * B * qw, "q_pi");
+  a->dq_pi = ws.take((long long)nA * B * qw, "dq_pi");
+  a->tanh_y = ws.take((long long)nA * B * A, "tanh_y");
+  float* da = ws.take((long long)nA * B * A, "d_action");
+  float* eye = ws.take((long long)A * A, "eye");
+
+  // ---- passes ----
+  auto share_x0 = [&](PassBuf& pb, float* x, int ld, long long go, long long gi) {
+    pb.x0 = x; pb.ld0 = ld; pb.x0_go = go; pb.x0_gi = gi;
+  };
+  PassBuf &at = a->pb_at, &ct = a->pb_ct, &cc = a->pb_c, &pa = a->pb_a, &q1 = a->pb_q1;
+  at = ct = cc = pa = q1 = PassBuf{};
+  if (enc) {
+    share_x0(at, a->xa2, ld_a, a->xa_go, 0);
+    share_x0(pa, a->xa, ld_a, a->xa_go, 0);
+    at.P = a->P2; pa.P = a->P; ct.P = a->P2; cc.P = a->P; q1.P = a->P;
+    at.P_go = pa.P_go = ct.P_go = cc.P_go = q1.P_go = (long long)B * c.n_particles * c.particle_dim;
+  } else {
+    share_x0(at, a->xq2, ld_q, a->xq_go, 0);   // actor input = first S columns of the Q input
+    share_x0(pa, a->xpi, ld_q, a->xpi_go, 0);
+  }
+  share_x0(ct, a->xq2, ld_q, a->xq_go, a->xq_gi);
+  share_x0(cc, a->xq, ld_q, a->xq_go, a->xq_gi);
+  share_x0(q1, a->xpi, ld_q, a->xpi_go, 0);
+  alloc_pass(ws, c, c.actor, g_actor, B, at, false, true);
+  alloc_pass(ws, c, c.q, g_crit, B, ct, false, true);
+  alloc_pass(ws, c, c.q, g_crit, B, cc, false, true);
+  alloc_pass(ws, c, c.actor, g_actor, B, pa, false, true);
+  alloc_pass(ws, c, c.q, g_q1, B, q1, false, true);
+  BwdScratch sc_c, sc_q1, sc_a;
+  alloc_bwd(ws, c, c.q, g_crit, B, sc_c, true);
+  alloc_bwd(ws, c, c.q, g_q1, B, sc_q1, false);
+  alloc_bwd(ws, c, c.actor, g_actor, B, sc_a, true);
+  a->ws_floats = ws.used;
+  if (!ws.base) return TD3_OK;   // sizing pass only
+
+  // ---- parameter references ----
+  const long long qn = c.q.n_floats, an = c.actor.n_floats;
+  ParamRef Wa{a->actor.params, an, 0}, Wat{a->actor.target, an, 0};
+  ParamRef Wc{a->critic.params, qn * nq, qn}, Wct{a->critic.target, qn * nq, qn};
+  ParamRef Wq1{a->critic.params, qn * nq, 0};
+  GradRef Ga{a->actor.grad, an, 0}, Gc{a->critic.grad, qn * nq, qn};
+
+  a->seq_sample.clear(); a->seq_target.clear(); a->seq_critic_fb.clear(); a->seq_critic_apply.clear();
+  a->seq_actor_fb.clear(); a->seq_actor_apply.clear();
+
+  // ---- target step (TD3_featured.py:129-142) ----
+  {
+    OutSpec o;   // next_action into the action columns of the target-critic input(s)
+    o.out = a->xq2 + E + S; o.ld = ld_q; o.go = a->xq_go; o.gi = 0;
+    o.epi = EPI_BIAS_TANH_NOISE; o.aux0 = a->eps; o.ldaux = A; o.aux0_go = (long long)B * A;
+    o.f0 = enc ? 1.f : c.max_action;
+    o.f1 = c.clamp_target_action ? c.max_action : 0.f;
+    o.dups = xq_inner; o.dup_stride = a->xq_gi;
+    auto s_at = build_forward(c, c.actor, Wat, g_actor, B, at, o);
+    OutSpec oq;
+    oq.out = a->tq; oq.ld = qw; oq.gi = (long long)B * qw; oq.go = oq.gi * nq; oq.epi = EPI_BIAS;
+    auto s_ct = build_forward(c, c.q, Wct, g_crit, B, ct, oq);
+    // the online critic forward is independent of the target path: run it alongside the target actor
+    OutSpec oc;
+    oc.out = a->q; oc.ld = qw; oc.gi = (long long)B * qw; oc.go = oc.gi * nq; oc.epi = EPI_BIAS;
+    auto s_cc = build_forward(c, c.q, Wc, g_crit, B, cc, oc);
+    for (auto& st : zip_stages({s_at, s_cc})) emit_stage(a->seq_target, st);
+    for (auto& st : s_ct) emit_stage(a->seq_target, st);
+  }
+  // ---- critic loss + backward (:145-152) ----
+  {
+    Launch L;
+    L.kind = Launch::LOSS;
+    L.grid_x = nA;
+    LossParams& lp = L.loss;
+    lp.q = a->q; lp.tq = a->tq; lp.r = a->r; lp.nd = a->nd; lp.y = a->y; lp.dq = a->dq; lp.loss = a->state_f32;
+    lp.batch = B; lp.width = qw; lp.ldq = qw; lp.n_q = nq;
+    lp.q_gi = (long long)B * qw; lp.q_go = lp.q_gi * nq; lp.y_go = (long long)B * qw; lp.r_go = B;
+    lp.discount = c.discount;
+    lp.inv_norm = 1.f / (float)((a->global_batch > 0 ? a->global_batch : batch) * qw);
+    lp.counters = a->state_u64;
+    a->seq_critic_fb.push_back(L);
+    Dx0Spec none;
+    auto s_b = build_backward(c, c.q, Wc, Gc, g_crit, B, cc, a->dq, qw, (long long)B * qw * nq, (long long)B * qw, true,
+                              none, sc_c);
+    for (auto& st : s_b) emit_stage(a->seq_critic_fb, st);
+  }
+  // ---- critic Adam (:153) ----
+  {
+    Launch L;
+    L.kind = Launch::EW;
+    EwParams& e = L.ew;
+    e.n_ranges = 1;
+    e.beta1 = c.beta1; e.beta2 = c.beta2; e.eps = c.adam_eps; e.tau = c.tau;
+    EwRange& r = e.r[0];
+    r.p = a->critic.params; r.g = a->critic.grad; r.m = a->critic.exp_avg; r.v = a->critic.exp_avg_sq; r.tgt = nullptr;
+    r.n = qn * nq * nA; r.blk_begin = 0; r.t_ptr = a->state_u64 + 1; r.lr = c.lr_critic; r.do_adam = 1; r.do_polyak = 0;
+    L.grid_x = (int)((r.n + kEwPerBlock - 1) / kEwPerBlock);
+    a->seq_critic_apply.push_back(L);
+  }
+  // ---- actor step (:159-163): actor fwd, Q1 fwd with the stepped critic, -mean, backward ----
+  {
+    OutSpec o;
+    o.out = a->xpi + E + S; o.ld = ld_q; o.go = a->xpi_go; o.gi = 0;
+    o.epi = EPI_BIAS_TANH; o.aux0 = a->tanh_y; o.ldaux = A; o.aux0_go = (long long)B * A;
+    o.f0 = enc ? 1.f : c.max_action;
+    auto s_a = build_forward(c, c.actor, Wa, g_actor, B, pa, o);
+    for (auto& st : s_a) emit_stage(a->seq_actor_fb, st);
+    OutSpec oq;
+    oq.out = a->q_pi; oq.ld = qw; oq.go = (long long)B * qw; oq.epi = EPI_BIAS;
+    auto s_q = build_forward(c, c.q, Wq1, g_q1, B, q1, oq);
+    for (auto& st : s_q) emit_stage(a->seq_actor_fb, st);
+    // actor_loss = -mean(Q1) (read-back only) + bump the actor Adam step counter
+    {
+      Problem nm = blank_problem(PK_NEG_MEAN);
+      nm.M = B; nm.N = qw; nm.A = a->q_pi; nm.lda = qw; nm.a_go = (long long)B * qw;
+      nm.C = a->state_f32 + nA; nm.c_go = 1; nm.f0 = -1.f;
+      finalize_problem(nm, g_q1);
+      // first backward stage of Q1 shares the launch with the read-back
+      Dx0Spec dx;
+      dx.mode = 1; dx.col0 = E + S; dx.ncols = A;
+      const bool lnin = enc && ln;
+      dx.out = da; dx.ld = A; dx.go = (long long)B * A;
+      dx.epi = lnin ? EPI_STORE : EPI_TANH_GRAD;
+      dx.aux0 = a->tanh_y; dx.ldaux = A; dx.aux0_go = (long long)B * A; dx.f0 = enc ? 1.f : c.max_action;
+      auto s_qb = build_backward(c, c.q, Wq1, GradRef{}, g_q1, B, q1, a->dq_pi, qw, (long long)B * qw, 0, false, dx,
+                                 sc_q1);
+      if (!s_qb.empty()) s_qb[0].push_back(nm);
+      for (auto& st : s_qb) emit_stage(a->seq_actor_fb, st);
+      if (lnin) {
+        // d(action) = slice of the full input gradient, then through tanh: identity-GEMM slice
+        Problem sl = make_slice(B, A, sc_q1.dx0_full + E + S, ld_q, eye, da, A, EPI_TANH_GRAD);
+        set_groups(sl, sc_q1.dx0_full_go, 0, 0, 0, (long long)B * A, 0);
+        sl.aux0 = a->tanh_y; sl.ldaux = A; sl.aux0_go = (long long)B * A; sl.f0 = 1.f;
+        finalize_problem(sl, g_q1);
+        emit_stage(a->seq_actor_fb, {sl});
+      }
+    }
+    {
+      Launch L;
+      L.kind = Launch::COUNTER;
+      L.counter = a->state_u64 + 2;
+      a->seq_actor_fb.push_back(L);
+    }
+    Dx0Spec none;
+    auto s_ab = build_backward(c, c.actor, Wa, Ga, g_actor, B, pa, da, A, (long long)B * A, 0, true, none, sc_a);
+    for (auto& st : s_ab) emit_stage(a->seq_actor_fb, st);
+  }
+  // ---- actor Adam + Polyak of both targets (:164-171) ----
+  {
+    Launch L;
+    L.kind = Launch::EW;
+    EwParams& e = L.ew;
+    e.n_ranges = 2;
+    e.beta1 = c.beta1; e.beta2 = c.beta2; e.eps = c.adam_eps; e.tau = c.tau;
+    EwRange& r0 = e.r[0];
+    r0.p = a->critic.params; r0.tgt = a->critic.target; r0.n = qn * nq * nA; r0.blk_begin = 0;
+    r0.do_adam = 0; r0.do_polyak = 1;
+    const long long b0 = (r0.n + kEwPerBlock - 1) / kEwPerBlock;
+    EwRange& r1 = e.r[1];
+    r1.p = a->actor.params; r1.g = a->actor.grad; r1.m = a->actor.exp_avg; r1.v = a->actor.exp_avg_sq;
+    r1.tgt = a->actor.target; r1.n = an * nA; r1.blk_begin = b0; r1.t_ptr = a->state_u64 + 2; r1.lr = c.lr_actor;
+    r1.do_adam = 1; r1.do_polyak = 1;
+    L.grid_x = (int)(b0 + (r1.n + kEwPerBlock - 1) / kEwPerBlock);
+    a->seq_actor_apply.push_back(L);
+  }
+  // constant buffers: dq_pi = -1/(B*qw) (d(-mean)/dQ1), identity for the slice problem
+  {
+    std::vector<float> h((size_t)nA * B * qw, -1.f / (float)((a->global_batch > 0 ? a->global_batch : batch) * qw));
+    cudaMemcpy(a->dq_pi, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice);
+    std::vector<float> I((size_t)A * A, 0.f);
+    for (int i = 0; i < A; ++i) I[(size_t)i * A + i] = 1.f;
+    cudaMemcpy(eye, I.data(), I.size() * sizeof(float), cudaMemcpyHostToDevice);
+  }
+  a->batch = batch;
+  a->plan_rows = nullptr;
+  a->plan_rng_mode = -1;
+  drop_graphs(a);
+  return TD3_OK;
+}
+
+// (re)build the sampling launch for a replay view / rng mode
+int plan_sample(td3_agent* a, const td3_replay_view* rb, int rng_mode) {
+  if (a->plan_rows == rb->rows && a->plan_row_stride == rb->row_stride && a->plan_rng_mode == rng_mode &&
+      a->plan_rb_agent_stride == rb->agent_stride && !a->seq_sample.empty())
+    return TD3_OK;
+  const td3_agent_config& c = a->cfg;
+  const int B = (int)a->batch, nA = c.n_agents, nq = c.n_q;
+  const bool enc = c.variant == TD3_VARIANT_PARTICLES;
+  const int A = c.action_dim, S = c.state_dim, E = enc ? c.actor.enc_out : 0;
+  const int ld_q = a->ld_q, ld_a = a->ld_a;
+  Launch L;
+  L.kind = Launch::GATHER;
+  GatherParams& G = L.gather;
+  memset(&G, 0, sizeof(G));
+  G.rows = rb->rows; G.row_stride = rb->row_stride; G.rb_agent_stride = rb->agent_stride;
+  G.size = 0; G.size_ptr = a->state_u64 + 3;
+  G.batch = B; G.n_agents = nA; G.rng_mode = rng_mode;
+  G.idx_in = a->idx_in; G.idx_out = a->idx; G.step_ptr = a->state_u64; G.seed = c.seed;
+  G.eps_out = a->eps; G.noise_in = a->noise_in; G.action_dim = A;
+  G.policy_noise = c.policy_noise; G.noise_clip = c.noise_clip;
+  int n = 0;
+  auto seg = [&](int off, int len, float* dst, int ld, long long astride) {
+    G.seg_off[n] = off; G.seg_len[n] = len; G.dst[n] = dst; G.dst_ld[n] = ld; G.dst_agent_stride[n] = astride; ++n;
+  };
+  const int xq_inner = enc ? nq : 1;
+  if (!enc) {
+    // row = [s | a | s2 | r | nd]
+    seg(0, S, a->xq, ld_q, a->xq_go);
+    seg(0, S, a->xpi, ld_q, a->xpi_go);
+    seg(S, A, a->xq + S, ld_q, a->xq_go);
+    seg(S + A, S, a->xq2, ld_q, a->xq_go);
+    seg(2 * S + A, 1, a->r, 1, B);
+    seg(2 * S + A + 1, 1, a->nd, 1, B);
+  } else {
+    // row = [f | particles | a | f2 | particles2 | r | nd]
+    const int PN = c.n_particles * c.particle_dim;
+    const int o_f = 0, o_p = S, o_a = S + PN, o_f2 = o_a + A, o_p2 = o_f2 + S, o_r = o_p2 + PN;
+    seg(o_f, S, a->xa + E, ld_a, a->xa_go);
+    seg(o_f, S, a->xpi + E, ld_q, a->xpi_go);
+    for (int g = 0; g < xq_inner; ++g) seg(o_f, S, a->xq + g * a->xq_gi + E, ld_q, a->xq_go);
+    for (int g = 0; g < xq_inner; ++g) seg(o_a, A, a->xq + g * a->xq_gi + E + S, ld_q, a->xq_go);
+    seg(o_f2, S, a->xa2 + E, ld_a, a->xa_go);
+    for (int g = 0; g < xq_inner; ++g) seg(o_f2, S, a->xq2 + g * a->xq_gi + E, ld_q, a->xq_go);
+    seg(o_p, PN, a->P, PN, (long long)B * PN);
+    seg(o_p2, PN, a->P2, PN, (long long)B * PN);
+    seg(o_r, 1, a->r, 1, B);
+    seg(o_r + 1, 1, a->nd, 1, B);
+  }
+  if (n > kMaxSeg) return fail(TD3_ERR_INVALID, "too many gather segments (%d)", n);
+  G.n_seg = n;
+  const long long jobs = (long long)nA * B;
+  L.grid_x = (int)((jobs + 7) / 8);
+  L.grid_y = rb->row_floats > 2048 ? (int)std::min<long long>(32, (rb->row_floats + 2047) / 2048) : 1;
+  G.slices = L.grid_y;
+  a->seq_sample.clear();
+  a->seq_sample.push_back(L);
+  a->plan_rows = rb->rows; a->plan_row_stride = rb->row_stride; a->plan_rng_mode = rng_mode;
+  a->plan_rb_agent_stride = rb->agent_stride;
+  return TD3_OK;
+}
+
+int run_seq(const std::vector<Launch>& seq, cudaStream_t s) {
+  for (const Launch& L : seq) {
+    int rc = run_launch(L, s);
+    if (rc != TD3_OK) return rc;
+  }
+  return TD3_OK;
+}
+
+__global__ void set_u64_kernel(unsigned long long* p, unsigned long long v) { *p = v; }
+
+int check_ready(td3_agent* a, bool need_plan = true) {
+  if (!a) return fail(TD3_ERR_INVALID, "null agent");
+  if (!a->params_bound || !a->state_u64) return fail(TD3_ERR_STATE, "td3_agent_bind_params/bind_state not called");
+  if (need_plan && (a->batch <= 0 || !a->ws.base)) return fail(TD3_ERR_STATE, "td3_agent_plan not called");
+  return TD3_OK;
+}
+
+int check_rb(td3_agent* a, const td3_replay_view* rb) {
+  if (!rb || !rb->rows) return fail(TD3_ERR_INVALID, "null replay view");
+  if (rb->size <= 0) return fail(TD3_ERR_INVALID, "cannot sample from an empty replay buffer (size=%lld)", (long long)rb->size);
+  const td3_agent_config& c = a->cfg;
+  long long want = c.variant == TD3_VARIANT_PARTICLES
+                       ? 2LL * (c.state_dim + (long long)c.n_particles * c.particle_dim) + c.action_dim + 2
+                       : 2LL * c.state_dim + c.action_dim + 2;
+  if (rb->row_floats != want) return fail(TD3_ERR_INVALID, "replay row has %lld floats, agent expects %lld", (long long)rb->row_floats, want);
+  return TD3_OK;
+}
+
+int sync_rb_size(td3_agent* a, const td3_replay_view* rb, cudaStream_t s) {
+  if (a->last_rb_size != rb->size) {
+    set_u64_kernel<<<1, 1, 0, s>>>(a->state_u64 + 3, (unsigned long long)rb->size);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    CUDA_TRY(cudaGetLastError());
+    a->last_rb_size = rb->size;
+  }
+  return TD3_OK;
+}
+
+int capture(td3_agent* a, bool with_actor, cudaGraphExec_t* out, long long* n_nodes) {
+  cudaGraph_t graph = nullptr;
+  const long long launches_before = g_launches.load();
+  if (!a->cap_stream) CUDA_TRY(cudaStreamCreateWithFlags(&a->cap_stream, cudaStreamNonBlocking));
+  cudaStream_t s = a->cap_stream;
+  CUDA_TRY(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+  int rc = run_seq(a->seq_sample, s);
+  if (rc == TD3_OK) rc = run_seq(a->seq_target, s);
+  if (rc == TD3_OK) rc = run_seq(a->seq_critic_fb, s);
+  if (rc == TD3_OK) rc = run_seq(a->seq_critic_apply, s);
+  if (rc == TD3_OK && with_actor) rc = run_seq(a->seq_actor_fb, s);
+  if (rc == TD3_OK && with_actor) rc = run_seq(a->seq_actor_apply, s);
+  cudaError_t e = cudaStreamEndCapture(s, &graph);
+  *n_nodes = g_launches.load() - launches_before;            // captured, not executed: move to per-replay accounting
+  g_launches.fetch_sub(*n_nodes, std::memory_order_relaxed);
+  if (rc != TD3_OK) {
+    if (graph) cudaGraphDestroy(graph);
+    return rc;
+  }
+  if (e != cudaSuccess) return fail(TD3_ERR_CUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(e));
+  e = cudaGraphInstantiate(out, graph, 0);
+  cudaGraphDestroy(graph);
+  if (e != cudaSuccess) return fail(TD3_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e));
+  return TD3_OK;
+}
+
+}  // namespace
+
+// ====================================================================================
+// C ABI
+// ====================================================================================
+extern "C" {
+
+int td3_abi_version(void) { return TD3_ABI_VERSION; }
+void td3_struct_sizes(int64_t* out) {   // lets a foreign-language binding check its struct mirrors at load time
+  out[0] = (int64_t)sizeof(td3_net_layout);
+  out[1] = (int64_t)sizeof(td3_param_set);
+  out[2] = (int64_t)sizeof(td3_agent_config);
+  out[3] = (int64_t)sizeof(td3_replay_view);
+}
+const char* td3_last_error(void) { return g_err.c_str(); }
+int64_t td3_launch_count(void) { return g_launches.load(); }
+
+int td3_device_info(int* sm_count, int* cc_major, int* cc_minor, char* name, int name_len) {
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  cudaDeviceProp p;
+  CUDA_TRY(cudaGetDeviceProperties(&p, dev));
+  if (sm_count) *sm_count = p.multiProcessorCount;
+  if (cc_major) *cc_major = p.major;
+  if (cc_minor) *cc_minor = p.minor;
+  if (name && name_len > 0) {
+    strncpy(name, p.name, name_len - 1);
+    name[name_len - 1] = 0;
+  }
+  if (p.major != 10) return fail(TD3_ERR_UNSUPPORTED, "libtd3b200 is built for sm_100a only; device is sm_%d%d", p.major, p.minor);
+  return TD3_OK;
+}
+
+int rb_add_rows(float* rows, int64_t row_stride, int64_t row_floats, int64_t max_size, int64_t ptr, const float* host_rows,
+                int64_t n_rows, void* stream) {
+  if (!rows || !host_rows || n_rows < 0 || ptr < 0 || ptr >= max_size || n_rows > max_size || row_floats > row_stride)
+    return fail(TD3_ERR_INVALID, "rb_add_rows: bad arguments (ptr=%lld n=%lld max=%lld)", (long long)ptr, (long long)n_rows, (long long)max_size);
+  cudaStream_t s = (cudaStream_t)stream;
+  const int64_t first = std::min<int64_t>(n_rows, max_size - ptr);
+  // host rows are packed row_floats apart; device rows row_stride apart
+  if (first > 0)
+    CUDA_TRY(cudaMemcpy2DAsync(rows + ptr * row_stride, row_stride * sizeof(float), host_rows, row_floats * sizeof(float),
+                               row_floats * sizeof(float), first, cudaMemcpyHostToDevice, s));
+  if (n_rows > first)
+    CUDA_TRY(cudaMemcpy2DAsync(rows, row_stride * sizeof(float), host_rows + first * row_floats, row_floats * sizeof(float),
+                               row_floats * sizeof(float), n_rows - first, cudaMemcpyHostToDevice, s));
+  return TD3_OK;
+}
+
+int rb_sample_indices(const td3_replay_view* rb, const int64_t* idx_dev, int64_t batch, int32_t n_seg, const int64_t* seg_off,
+                      const int64_t* seg_len, float* const* dst, const int64_t* dst_ld, void* stream) {
+  if (!rb || !rb->rows || !idx_dev || batch <= 0 || n_seg <= 0 || n_seg > kMaxSeg)
+    return fail(TD3_ERR_INVALID, "rb_sample_indices: bad arguments");
+  static unsigned long long* zero_step = nullptr;
+  if (!zero_step) {
+    CUDA_TRY(cudaMalloc(&zero_step, sizeof(unsigned long long)));
+    CUDA_TRY(cudaMemset(zero_step, 0, sizeof(unsigned long long)));
+  }
+  static long long* idx_scratch = nullptr;
+  static int64_t idx_cap = 0;
+  if (idx_cap < batch) {
+    if (idx_scratch) cudaFree(idx_scratch);
+    CUDA_TRY(cudaMalloc(&idx_scratch, batch * sizeof(long long)));
+    idx_cap = batch;
+  }
+  Launch L;
+  L.kind = Launch::GATHER;
+  GatherParams& G = L.gather;
+  memset(&G, 0, sizeof(G));
+  G.rows = rb->rows; G.row_stride = rb->row_stride; G.size = rb->size;
+  G.batch = (int)batch; G.n_agents = 1; G.rng_mode = 1; G.n_seg = n_seg;
+  for (int i = 0; i < n_seg; ++i) {
+    G.seg_off[i] = (int)seg_off[i]; G.seg_len[i] = (int)seg_len[i]; G.dst[i] = dst[i]; G.dst_ld[i] = (int)dst_ld[i];
+  }
+  G.idx_in = reinterpret_cast<const long long*>(idx_dev);
+  G.idx_out = idx_scratch;
+  G.step_ptr = zero_step;
+  G.action_dim = 0;
+  L.grid_x = (int)((batch + 7) / 8);
+  L.grid_y = rb->row_floats > 2048 ? (int)std::min<long long>(32, (rb->row_floats + 2047) / 2048) : 1;
+  G.slices = L.grid_y;
+  return run_launch(L, (cudaStream_t)stream);
+}
+
+int rb_philox_indices(int64_t* idx_dev, int64_t batch, int64_t size, uint64_t seed, uint64_t stream_id, uint64_t step,
+                      void* stream) {
+  if (!idx_dev || batch <= 0) return fail(TD3_ERR_INVALID, "rb_philox_indices: bad arguments");
+  if (size <= 0) return fail(TD3_ERR_INVALID, "cannot sample from an empty replay buffer (size=%lld)", (long long)size);
+  philox_indices_kernel<<<(unsigned)((batch + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<long long*>(idx_dev), batch, size, seed, (unsigned)stream_id, step);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  CUDA_TRY(cudaGetLastError());
+  return TD3_OK;
+}
+
+int adam_polyak_step(float* params, const float* grad, float* exp_avg, float* exp_avg_sq, float* target, int64_t n, int64_t t,
+                     float lr, float beta1, float beta2, float eps, float tau, void* stream) {
+  if (!params || n <= 0) return fail(TD3_ERR_INVALID, "adam_polyak_step: bad arguments");
+  if (!grad && !target) return fail(TD3_ERR_INVALID, "adam_polyak_step: nothing to do (grad and target both NULL)");
+  if (grad && (!exp_avg || !exp_avg_sq || t < 1)) return fail(TD3_ERR_INVALID, "adam_polyak_step: Adam needs moments and t >= 1");
+  Launch L;
+  L.kind = Launch::EW;
+  EwParams& e = L.ew;
+  e.n_ranges = 1;
+  e.beta1 = (double)beta1; e.beta2 = (double)beta2; e.eps = (double)eps; e.tau = (double)tau;
+  EwRange& r = e.r[0];
+  r.p = params; r.g = grad; r.m = exp_avg; r.v = exp_avg_sq; r.tgt = target; r.n = n; r.blk_begin = 0;
+  r.t_ptr = nullptr; r.t_val = t; r.lr = (double)lr; r.do_adam = grad != nullptr; r.do_polyak = target != nullptr;
+  L.grid_x = (int)((n + kEwPerBlock - 1) / kEwPerBlock);
+  return run_launch(L, (cudaStream_t)stream);
+}
+
+int td3_agent_create(const td3_agent_config* cfg, td3_agent** out) {
+  if (!cfg || !out) return fail(TD3_ERR_INVALID, "td3_agent_create: null argument");
+  if (cfg->n_q < 1 || cfg->n_q > 2) return fail(TD3_ERR_INVALID, "n_q must be 1 or 2");
+  if (cfg->n_agents < 1) return fail(TD3_ERR_INVALID, "n_agents must be >= 1");
+  if (cfg->actor.n_linear < 1 || cfg->actor.n_linear > TD3_MAX_LINEAR || cfg->q.n_linear < 1 || cfg->q.n_linear > TD3_MAX_LINEAR)
+    return fail(TD3_ERR_INVALID, "n_linear out of range");
+  if (cfg->policy_freq < 1) return fail(TD3_ERR_INVALID, "policy_freq must be >= 1");
+  if (cfg->variant == TD3_VARIANT_PARTICLES && (cfg->n_particles < 1 || cfg->particle_dim < 1))
+    return fail(TD3_ERR_INVALID, "particles variant needs n_particles, particle_dim >= 1");
+  if (cfg->actor.dims[cfg->actor.n_linear] != cfg->action_dim) return fail(TD3_ERR_INVALID, "actor output width != action_dim");
+  td3_agent* a = new td3_agent();
+  a->cfg = *cfg;
+  *out = a;
+  return TD3_OK;
+}
+
+int td3_agent_destroy(td3_agent* agent) {
+  if (!agent) return TD3_OK;
+  drop_graphs(agent);
+  if (agent->cap_stream) cudaStreamDestroy(agent->cap_stream);
+  delete agent;
+  return TD3_OK;
+}
+
+int td3_agent_bind_params(td3_agent* a, const td3_param_set* actor, const td3_param_set* critic) {
+  if (!a || !actor || !critic) return fail(TD3_ERR_INVALID, "td3_agent_bind_params: null argument");
+  const td3_param_set* sets[2] = {actor, critic};
+  for (auto* s : sets)
+    if (!s->params || !s->target || !s->grad || !s->exp_avg || !s->exp_avg_sq || !aligned16(s->params) || !aligned16(s->target) ||
+        !aligned16(s->grad) || !aligned16(s->exp_avg) || !aligned16(s->exp_avg_sq))
+      return fail(TD3_ERR_INVALID, "td3_agent_bind_params: null or misaligned (16 B) buffer");
+  a->actor = *actor;
+  a->critic = *critic;
+  a->params_bound = true;
+  a->batch = 0;
+  drop_graphs(a);
+  return TD3_OK;
+}
+
+int td3_agent_bind_state(td3_agent* a, void* state_dev, int64_t n_bytes) {
+  if (!a || !state_dev) return fail(TD3_ERR_INVALID, "td3_agent_bind_state: null argument");
+  const int64_t need = 16 * 8 + 2 * (int64_t)a->cfg.n_agents * 4;
+  if (n_bytes < need) return fail(TD3_ERR_INVALID, "state buffer too small: %lld < %lld bytes", (long long)n_bytes, (long long)need);
+  a->state_u64 = reinterpret_cast<unsigned long long*>(state_dev);
+  a->state_f32 = reinterpret_cast<float*>(a->state_u64 + 16);
+  a->batch = 0;
+  a->last_rb_size = -1;
+  drop_graphs(a);
+  return TD3_OK;
+}
+
+int64_t td3_agent_workspace_floats(const td3_agent* agent, int64_t batch) {
+  if (!agent || batch <= 0) return -1;
+  td3_agent tmp;
+  tmp.cfg = agent->cfg;
+  tmp.ws.base = nullptr;
+  if (plan_agent(&tmp, batch) != TD3_OK) return -1;
+  return tmp.ws_floats;
+}
+
+int td3_agent_plan(td3_agent* a, int64_t batch, float* workspace, int64_t workspace_floats, void* stream) {
+  int rc = check_ready(a, false);
+  if (rc != TD3_OK) return rc;
+  if (batch <= 0 || !workspace || !aligned16(workspace)) return fail(TD3_ERR_INVALID, "td3_agent_plan: bad batch/workspace");
+  const int64_t need = td3_agent_workspace_floats(a, batch);
+  if (need < 0) return TD3_ERR_INVALID;
+  if (workspace_floats < need) return fail(TD3_ERR_INVALID, "workspace too small: %lld < %lld floats", (long long)workspace_floats, (long long)need);
+  CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+  a->ws.base = workspace;
+  rc = plan_agent(a, batch);
+  if (rc != TD3_OK) a->batch = 0;
+  return rc;
+}
+
+int td3_agent_region(const td3_agent* a, const char* name, int64_t* offset, int64_t* n_floats) {
+  if (!a || !name) return fail(TD3_ERR_INVALID, "td3_agent_region: null argument");
+  auto it = a->ws.regions.find(name);
+  if (it == a->ws.regions.end()) return fail(TD3_ERR_INVALID, "unknown workspace region '%s'", name);
+  if (offset) *offset = it->second.first;
+  if (n_floats) *n_floats = it->second.second;
+  return TD3_OK;
+}
+
+int td3_agent_set_global_batch(td3_agent* a, int64_t global_batch) {
+  if (!a || global_batch < 0) return fail(TD3_ERR_INVALID, "td3_agent_set_global_batch: bad argument");
+  a->global_batch = global_batch;
+  if (a->batch > 0 && a->ws.base) return plan_agent(a, a->batch);
+  return TD3_OK;
+}
+
+int td3_sample_batch(td3_agent* a, const td3_replay_view* rb, int32_t rng_mode, void* stream) {
+  int rc = check_ready(a);
+  if (rc == TD3_OK) rc = check_rb(a, rb);
+  if (rc == TD3_OK) rc = plan_sample(a, rb, rng_mode);
+  if (rc == TD3_OK) rc = sync_rb_size(a, rb, (cudaStream_t)stream);
+  if (rc == TD3_OK) rc = run_seq(a->seq_sample, (cudaStream_t)stream);
+  return rc;
+}
+
+int td3_target_step(td3_agent* a, void* stream) {
+  int rc = check_ready(a);
+  return rc == TD3_OK ? run_seq(a->seq_target, (cudaStream_t)stream) : rc;
+}
+
+int td3_critic_step(td3_agent* a, int32_t apply, void* stream) {
+  int rc = check_ready(a);
+  if (rc == TD3_OK) rc = run_seq(a->seq_critic_fb, (cudaStream_t)stream);
+  if (rc == TD3_OK && apply) rc = run_seq(a->seq_critic_apply, (cudaStream_t)stream);
+  return rc;
+}
+
+int td3_critic_apply(td3_agent* a, void* stream) {
+  int rc = check_ready(a);
+  return rc == TD3_OK ? run_seq(a->seq_critic_apply, (cudaStream_t)stream) : rc;
+}
+
+int td3_actor_step(td3_agent* a, int32_t apply, void* stream) {
+  int rc = check_ready(a);
+  if (rc == TD3_OK) rc = run_seq(a->seq_actor_fb, (cudaStream_t)stream);
+  if (rc == TD3_OK && apply) rc = run_seq(a->seq_actor_apply, (cudaStream_t)stream);
+  return rc;
+}
+
+int td3_actor_apply(td3_agent* a, void* stream) {
+  int rc = check_ready(a);
+  return rc == TD3_OK ? run_seq(a->seq_actor_apply, (cudaStream_t)stream) : rc;
+}
+
+int td3_train_n(td3_agent* a, const td3_replay_view* rb, int64_t total_it, int32_t iterations, int32_t rng_mode, int32_t use_graph,
+                void* stream) {
+  int rc = check_ready(a);
+  if (rc == TD3_OK) rc = check_rb(a, rb);
+  if (rc != TD3_OK) return rc;
+  if (iterations < 1) return fail(TD3_ERR_INVALID, "iterations must be >= 1");
+  if (rng_mode == TD3_RNG_INJECTED && iterations != 1)
+    return fail(TD3_ERR_INVALID, "injected indices/noise cover exactly one update: iterations must be 1");
+  cudaStream_t s = (cudaStream_t)stream;
+  rc = plan_sample(a, rb, rng_mode);
+  if (rc == TD3_OK) rc = sync_rb_size(a, rb, s);
+  if (rc != TD3_OK) return rc;
+  if (use_graph) {
+    auto& g = a->graphs;
+    if (g.rows != rb->rows || g.row_stride != rb->row_stride || g.rng_mode != rng_mode || !g.critic_only) {
+      drop_graphs(a);
+      rc = capture(a, false, &g.critic_only, &g.nodes_critic_only);
+      if (rc == TD3_OK) rc = capture(a, true, &g.with_actor, &g.nodes_with_actor);
+      if (rc != TD3_OK) { drop_graphs(a); return rc; }
+      g.rows = rb->rows; g.row_stride = rb->row_stride; g.rng_mode = rng_mode;
+    }
+  }
+  for (int it = 0; it < iterations; ++it) {
+    const int64_t step_no = total_it + it + 1;                      // self.total_it += 1 (TD3_featured.py:124)
+    const bool policy_step = (step_no % a->cfg.policy_freq) == 0;   // :156
+    if (use_graph) {
+      CUDA_TRY(cudaGraphLaunch(policy_step ? a->graphs.with_actor : a->graphs.critic_only, s));
+      g_launches.fetch_add(policy_step ? a->graphs.nodes_with_actor : a->graphs.nodes_critic_only, std::memory_order_relaxed);
+    } else {
+      rc = run_seq(a->seq_sample, s);
+      if (rc == TD3_OK) rc = run_seq(a->seq_target, s);
+      if (rc == TD3_OK) rc = run_seq(a->seq_critic_fb, s);
+      if (rc == TD3_OK) rc = run_seq(a->seq_critic_apply, s);
+      if (rc == TD3_OK && policy_step) rc = run_seq(a->seq_actor_fb, s);
+      if (rc == TD3_OK && policy_step) rc = run_seq(a->seq_actor_apply, s);
+      if (rc != TD3_OK) return rc;
+    }
+  }
+  return TD3_OK;
+}
+
+// ---- small-batch inference on caller buffers ------------------------------------------
+static int copy_cols(float* dst, int ld, const float* src, int w, int64_t rows, cudaStream_t s) {
+  CUDA_TRY(cudaMemcpy2DAsync(dst, (size_t)ld * sizeof(float), src, (size_t)w * sizeof(float), (size_t)w * sizeof(float),
+                             (size_t)rows, cudaMemcpyDeviceToDevice, s));
+  return TD3_OK;
+}
+
+int td3_actor_forward(td3_agent* a, int32_t which, int32_t agent_index, const float* state, const float* particles,
+                      int64_t batch, float* action_out, void* stream) {
+  int rc = check_ready(a);
+  if (rc != TD3_OK) return rc;
+  const td3_agent_config& c = a->cfg;
+  if (!state || !action_out || batch < 1 || batch > a->batch || agent_index < 0 || agent_index >= c.n_agents)
+    return fail(TD3_ERR_INVALID, "td3_actor_forward: bad arguments (batch %lld, planned %lld)", (long long)batch, (long long)a->batch);
+  const bool enc = c.variant == TD3_VARIANT_PARTICLES;
+  if (enc && !particles) return fail(TD3_ERR_INVALID, "td3_actor_forward: particles required");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int E = enc ? c.actor.enc_out : 0, S = c.state_dim, A = c.action_dim;
+  PassBuf pb = a->pb_a;                    // agent 0's slot of the online-actor activations
+  rc = copy_cols(pb.x0 + E, pb.ld0, state, S, batch, s);
+  if (rc != TD3_OK) return rc;
+  if (enc)
+    CUDA_TRY(cudaMemcpyAsync(const_cast<float*>(pb.P), particles, sizeof(float) * batch * c.n_particles * c.particle_dim,
+                             cudaMemcpyDeviceToDevice, s));
+  ParamRef W{(which ? a->actor.target : a->actor.params) + (long long)agent_index * c.actor.n_floats, 0, 0};
+  OutSpec o;
+  o.out = action_out; o.ld = A; o.epi = EPI_BIAS_TANH; o.aux0 = a->tanh_y; o.ldaux = A;
+  o.f0 = enc ? 1.f : c.max_action;
+  std::vector<Launch> seq;
+  for (auto& st : build_forward(c, c.actor, W, GroupShape{1, 1}, (int)batch, pb, o)) emit_stage(seq, st);
+  return run_seq(seq, s);
+}
+
+int td3_critic_forward(td3_agent* a, int32_t which, int32_t agent_index, const float* state, const float* particles,
+                       const float* action, int64_t batch, float* q_out, void* stream) {
+  int rc = check_ready(a);
+  if (rc != TD3_OK) return rc;
+  const td3_agent_config& c = a->cfg;
+  if (!state || !action || !q_out || batch < 1 || batch > a->batch || agent_index < 0 || agent_index >= c.n_agents)
+    return fail(TD3_ERR_INVALID, "td3_critic_forward: bad arguments (batch %lld, planned %lld)", (long long)batch, (long long)a->batch);
+  const bool enc = c.variant == TD3_VARIANT_PARTICLES;
+  if (enc && !particles) return fail(TD3_ERR_INVALID, "td3_critic_forward: particles required");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int E = enc ? c.q.enc_out : 0, S = c.state_dim, A = c.action_dim, nq = c.n_q, qw = a->qw;
+  PassBuf pb = a->pb_c;
+  const int copies = enc ? nq : 1;
+  for (int g = 0; g < copies; ++g) {
+    rc = copy_cols(pb.x0 + g * pb.x0_gi + E, pb.ld0, state, S, batch, s);
+    if (rc == TD3_OK) rc = copy_cols(pb.x0 + g * pb.x0_gi + E + S, pb.ld0, action, A, batch, s);
+    if (rc != TD3_OK) return rc;
+  }
+  if (enc)
+    CUDA_TRY(cudaMemcpyAsync(const_cast<float*>(pb.P), particles, sizeof(float) * batch * c.n_particles * c.particle_dim,
+                             cudaMemcpyDeviceToDevice, s));
+  ParamRef W{(which ? a->critic.target : a->critic.params) + (long long)agent_index * c.q.n_floats * nq, 0, c.q.n_floats};
+  OutSpec o;
+  o.out = q_out; o.ld = qw; o.gi = batch * qw; o.epi = EPI_BIAS;
+  std::vector<Launch> seq;
+  for (auto& st : build_forward(c, c.q, W, GroupShape{1, nq}, (int)batch, pb, o)) emit_stage(seq, st);
+  return run_seq(seq, s);
+}
+
+}  // extern "C"
