@@ -1,0 +1,365 @@
+#!/usr/bin/env python
+"""bench.py -- TD3 gradient updates/sec (batch 256), BASELINE.json's metric.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2]
+
+A "step" is one complete TD3 update: sample 256 transitions from the replay buffer, target step,
+twin-critic forward/backward + Adam, and on every policy_freq-th step the actor update + Polyak
+(TD3_featured.py:123-171).  Default workload = BASELINE configs[1] ("cfg2"): S=17, A=6, 400-300 MLPs,
+batch 256, 1M-row device-resident replay buffer, one agent per GPU.
+
+  value  updates/s with everything resident in HBM (K updates queued as CUDA-graph replays, CUDA-event
+         timed, max over ranks).
+  e2e    the same metric through the public Python API the reference's main.py loop uses, per step:
+         replay_buffer.add(one host transition -> pinned -> H2D), policy.train(replay_buffer, 256),
+         and a synchronous D2H read of the critic loss.
+  --impl reference times the CPU oracle port of the reference (oracle/td3_oracle.py, torch CPU ops --
+         /root/reference is not present on the GPU box) on the host cores with the same config.
+With N > 1 (torchrun) every rank runs an independent agent/seed on its own GPU (weak scaling, no
+data-path collective: SURVEY.md 8e); value = total updates of all ranks / max-over-ranks time.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: description of the synthetic job
+    "cfg1": dict(kind="featured", S=17, A=6, aw=(400, 300), qw=(400, 300), norm=None, B=100, rows=10_000),
+    "cfg2": dict(kind="featured", S=17, A=6, aw=(400, 300), qw=(400, 300), norm=None, B=256, rows=1_000_000),
+    "cfg3": dict(kind="featured", S=17, A=6, aw=(500, 400, 300), qw=(500, 400, 200), norm=None, B=256, rows=1_000_000),
+    "cfg3_layer": dict(kind="featured", S=17, A=6, aw=(500, 400, 300), qw=(500, 400, 200), norm="layer", B=256,
+                       rows=1_000_000),
+    "cfg4": dict(kind="particles", F=8, N=1024, D=6, A=3, norm=None, B=256, rows=8192),
+    "cfg4_layer": dict(kind="particles", F=8, N=1024, D=6, A=3, norm="layer", B=256, rows=8192),
+}
+HYPER = dict(discount=0.99, tau=0.005, policy_noise=0.2, noise_clip=0.5, policy_freq=2)
+
+
+def algorithmic_per_update(w):
+    """(GFLOP, MB) per update averaged over the policy_freq cycle -- SURVEY.md 8d formulas."""
+    pf = HYPER["policy_freq"]
+    B = w["B"]
+
+    def macs(dims):
+        return sum(dims[i] * dims[i + 1] for i in range(len(dims) - 1))
+
+    def nparams(dims):
+        return sum(dims[i] * dims[i + 1] + dims[i + 1] for i in range(len(dims) - 1))
+    if w["kind"] == "featured":
+        da = [w["S"], *w["aw"], w["A"]]
+        dq = [w["S"] + w["A"], *w["qw"], 1]
+        Wa, Wq, Wa0, Wq0, E, Eb = macs(da), macs(dq), da[0] * da[1], dq[0] * dq[1], 0, 0
+        Pa, Pc = nparams(da), 2 * nparams(dq)
+        if w["norm"] == "layer":
+            Pa += 2 * sum(w["aw"])
+            Pc += 4 * sum(w["qw"])
+        row_bytes = (2 * w["S"] + w["A"] + 2) * 4
+    else:
+        da = [128 + w["F"], 500, 400, 300, w["A"]]
+        dq = [128 + w["F"] + w["A"], 500, 400, 300, w["A"]]
+        Wa, Wq, Wa0, Wq0 = macs(da), macs(dq), da[0] * da[1], dq[0] * dq[1]
+        E = w["N"] * w["D"] * 256 + w["N"] * 256 * 128
+        Eb = w["N"] * w["D"] * 256 + 2 * w["N"] * 256 * 128
+        enc_p = w["D"] * 256 + 256 + 256 * 128 + 128
+        Pa, Pc = nparams(da) + enc_p, 2 * (nparams(dq) + enc_p)
+        row_bytes = (2 * (w["F"] + w["N"] * w["D"]) + w["A"] + 2) * 4
+    critic = 2 * B * ((Wa + E) + 2 * (Wq + E) + 2 * (Wq + E) + 2 * (2 * Wq - Wq0 + Eb))
+    actor = 2 * B * ((Wa + E) + (Wq + E) + Wq + (2 * Wa - Wa0 + Eb))
+    flops = critic + actor / pf
+    nbytes = 28 * Pc + (28 * Pa + 12 * (Pa + Pc)) / pf + 2 * row_bytes * B
+    return flops / 1e9, nbytes / 1e6
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return dict(hbm=float(p["hbm_gbs"]), bf16=float(p["bf16_tflops"]), bf16_sustained=float(p["bf16_tflops_sustained"]),
+                    source="measured (MEASURED_PEAKS.json)")
+    except Exception:
+        return dict(hbm=6650.0, bf16=1590.0, bf16_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+# --------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """Polls NVML for SM clock + throttle reasons during the timed region."""
+
+    BAD = {0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown"}
+    NOTE = {0x4: "sw_power_cap"}
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz, self._stop = [], set(), None, threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+        self.t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                r = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for bit, name in {**self.BAD, **self.NOTE}.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.01)
+
+    def __enter__(self):
+        if self.nv:
+            self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self.nv:
+            self.t.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+# --------------------------------------------------------------------------- builders
+def build_ours(w, seed, rows=None):
+    import torch
+    from oracle import td3_oracle as O              # synthetic-data generator only (inputs, not the measured path)
+    rows = rows or w["rows"]
+    if w["kind"] == "featured":
+        from td3_b200.TD3_featured import TD3
+        from td3_b200.my_replay_buffer import ReplayBuffer_featured
+        obs, act = O.Space(w["S"]), O.Space(w["A"])
+        torch.manual_seed(seed)
+        agent = TD3(obs, act, lr=1e-4, norm=w["norm"], actor_widths=w["aw"], q_widths=w["qw"], seed=seed + 1, max_action=1,
+                    **HYPER)
+        rb = ReplayBuffer_featured(obs, act, max_size=rows)
+        rb.add_batch(**O.synthetic_transitions_featured(rows, w["S"], w["A"], seed=0))
+    else:
+        from td3_b200.TD3_particles import TD3
+        from td3_b200.my_replay_buffer import ReplayBuffer_particles
+        obs, act = (O.Space(w["F"]), O.Space(w["N"], w["D"])), O.Space(w["A"])
+        torch.manual_seed(seed)
+        agent = TD3(obs, act, lr=1e-4, norm=w["norm"], seed=seed + 1, **HYPER)
+        rb = ReplayBuffer_particles(obs, act, max_size=rows)
+        rb.add_batch(**O.synthetic_transitions_particles(rows, w["F"], w["N"], w["D"], w["A"], seed=0))
+    return agent, rb
+
+
+def build_oracle(w, seed, rows):
+    import torch
+    from oracle import td3_oracle as O
+    torch.manual_seed(seed)
+    if w["kind"] == "featured":
+        obs, act = O.Space(w["S"]), O.Space(w["A"])
+        agent = O.TD3Featured(obs, act, lr=1e-4, norm=w["norm"], actor_widths=w["aw"], q_widths=w["qw"], max_action=1, **HYPER)
+        rb = O.ReplayFeatured(obs, act, rows)
+        O.fill_featured(rb, O.synthetic_transitions_featured(rows, w["S"], w["A"], seed=0))
+    else:
+        obs, act = (O.Space(w["F"]), O.Space(w["N"], w["D"])), O.Space(w["A"])
+        agent = O.TD3Particles(obs, act, lr=1e-4, norm=w["norm"], **HYPER)
+        rb = O.ReplayParticles(obs, act, rows)
+        O.fill_particles(rb, O.synthetic_transitions_particles(rows, w["F"], w["N"], w["D"], w["A"], seed=0))
+    return agent, rb
+
+
+def time_cpu(w, steps, warmup, threads_list, rows):
+    """Reference arm / cpu_baseline: oracle port on the host cores; best over thread counts."""
+    import numpy as np
+    import torch
+    best = None
+    for th in threads_list:
+        torch.set_num_threads(th)
+        agent, rb = build_oracle(w, 0, rows)
+        np.random.seed(7)
+        torch.manual_seed(7)
+        for _ in range(warmup):
+            agent.train(rb, w["B"])
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            agent.train(rb, w["B"])
+        dt = time.perf_counter() - t0
+        ups = steps / dt
+        if best is None or ups > best[0]:
+            best = (ups, th, dt)
+    return best
+
+
+def cpu_sample_size(w):
+    # ~10-30 s of CPU work in total
+    return (5, 1) if w["kind"] == "particles" else (150, 15)
+
+
+# --------------------------------------------------------------------------- main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=200)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    w = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    K, W = args.steps, max(args.warmup, 3)
+    gflop, mbytes = algorithmic_per_update(w)
+    config = {"workload": f"{args.workload}: " + (
+        f"TD3_{w['kind']} S={w['S']} A={w['A']} actor {w['aw']} critic {w['qw']} norm={w['norm']}" if w["kind"] == "featured"
+        else f"TD3_particles F={w['F']} N={w['N']} D={w['D']} A={w['A']} norm={w['norm']}"),
+        "batch": w["B"], "replay_rows": w["rows"], "policy_freq": HYPER["policy_freq"], "agents_per_gpu": 1,
+        "algorithmic_gflop_per_update": round(gflop, 4), "algorithmic_mb_per_update": round(mbytes, 3),
+        "l2": "inputs larger than L2: the replay buffer (192 MB at 1M rows) is sampled uniformly at random every step; "
+              "the parameters are re-used across steps by the algorithm itself"}
+
+    ncpu = os.cpu_count() or 1
+    threads_list = sorted({1, min(4, ncpu), ncpu})
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        cpu_rows = min(w["rows"], 100_000)            # float64 host buffer; sampling cost does not depend on rows
+        steps = min(K, 300 if w["kind"] == "featured" else 5)
+        warm = min(W, 30 if w["kind"] == "featured" else 1)
+        ups, th, dt = time_cpu(w, steps, warm, threads_list, cpu_rows)
+        line = {"impl": "reference", "metric": "TD3 gradient updates/sec (batch 256)", "value": ups, "unit": "updates/s",
+                "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": 1000.0 / ups, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": ups, "unit": "updates/s", "cores": th, "kind": "port",
+                                 "sample": f"{steps} updates after {warm} warm-up, oracle port of the reference "
+                                           f"(torch {__import__('torch').__version__} CPU), best of threads {threads_list}, "
+                                           f"os.cpu_count()={ncpu}"},
+                "e2e": {"value": ups, "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    agent, rb = build_ours(w, seed=100 + rank)
+    lib = agent._lib
+    B = w["B"]
+    peaks = measured_peaks()
+
+    # ---------------- device-resident throughput ----------------
+    agent.train(rb, B, iterations=W)
+    barrier()
+    launches0 = lib.td3_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clk:
+        barrier()
+        ev0.record()
+        agent.train(rb, B, iterations=K)
+        ev1.record()
+        barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = lib.td3_launch_count() - launches0
+    clocks = clk.summary()
+
+    # ---------------- end to end through the public API ----------------
+    rs = np.random.RandomState(1234 + rank)
+    if w["kind"] == "featured":
+        new_rows = [(rs.standard_normal(w["S"]), rs.uniform(-1, 1, w["A"]), rs.standard_normal(w["S"]),
+                     float(rs.standard_normal()), 0.0) for _ in range(64)]
+    else:
+        new_rows = [((rs.standard_normal(w["F"]), rs.standard_normal((w["N"], w["D"])).astype(np.float32)),
+                     rs.uniform(-1, 1, w["A"]),
+                     (rs.standard_normal(w["F"]), rs.standard_normal((w["N"], w["D"])).astype(np.float32)),
+                     float(rs.standard_normal()), 0.0) for _ in range(8)]
+    loss_host = torch.zeros(1).pin_memory()
+    Ke = min(K, 2000)
+
+    def e2e_step(i):
+        rb.add(*new_rows[i % len(new_rows)])                       # host transition -> pinned slot -> H2D
+        agent.train(rb, B)                                          # the call main.py:269 makes
+        loss_host.copy_(agent.last_critic_loss, non_blocking=True)  # D2H of the step's result
+        torch.cuda.current_stream().synchronize()
+        return float(loss_host[0])
+
+    for i in range(min(W, 50)):
+        e2e_step(i)
+    with ClockSampler(local_rank) as clk2:
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(Ke):
+            e2e_step(i)
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
+        barrier()
+    clocks_e2e = clk2.summary()
+
+    # ---------------- reduce over ranks ----------------
+    if world > 1:
+        t = torch.tensor([ms, e2e_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_s = float(t[0]), float(t[1])
+    value = world * K / (ms / 1000.0)
+    e2e = world * Ke / e2e_s
+    t_update_us = ms * 1000.0 / K
+
+    line = {"metric": "TD3 gradient updates/sec (batch 256)", "value": value, "unit": "updates/s", "n_gpus": world,
+            "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": config, "clocks": clocks,
+            "e2e": {"value": e2e, "unit": "updates/s", "h2d_bytes_per_step": int(rb.row_floats * 4), "d2h_bytes_per_step": 4,
+                    "steps": Ke, "clocks": clocks_e2e,
+                    "what": "rb.add(host row) + policy.train(rb, 256) + synchronous D2H of the critic loss, per step"},
+            "gpu_launches": int(launches)}
+
+    if rank == 0:
+        hbm_floor_us = mbytes * 1e6 / (peaks["hbm"] * 1e9) * 1e6
+        tf32_peak = peaks["bf16_sustained"] / 2.0
+        tensor_floor_us = gflop * 1e9 / (tf32_peak * 1e12) * 1e6
+        bound = "hbm" if hbm_floor_us >= tensor_floor_us else "tensor"
+        if bound == "hbm":
+            achieved, peak, unit = mbytes * 1e6 / (t_update_us * 1e-6) / 1e9, peaks["hbm"], "GB/s"
+        else:
+            achieved, peak, unit = gflop * 1e9 / (t_update_us * 1e-6) / 1e12, tf32_peak, "TFLOP/s"
+        line["roofline"] = {
+            "bound": bound, "achieved": achieved, "peak": peak, "unit": unit, "frac": achieved / peak, "traffic": None,
+            "kernel": "td3::stage_kernel (every GEMM/LayerNorm stage of one update; averaged over the policy_freq cycle)",
+            "per": "update", "us_per_update": t_update_us, "hbm_floor_us": hbm_floor_us, "tensor_floor_us": tensor_floor_us,
+            "peak_source": peaks["source"],
+            "note": "single-agent MLP updates are bound by the ~20-stage dependency chain (launch/sync latency), not by "
+                    "HBM or tensor throughput (SURVEY.md 8d); frac is reported against the binding floor anyway"}
+        if not args.no_cpu_baseline:
+            steps_cpu, warm_cpu = cpu_sample_size(w)
+            ups, th, dt = time_cpu(w, steps_cpu, warm_cpu, threads_list, min(w["rows"], 100_000))
+            line["cpu_baseline"] = {"value": ups, "unit": "updates/s", "cores": th, "kind": "port",
+                                    "sample": f"{steps_cpu} updates after {warm_cpu} warm-up of the same workload, oracle "
+                                              f"port of the reference on torch CPU, best of threads {threads_list}, "
+                                              f"os.cpu_count()={ncpu}"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -85,8 +85,10 @@ typedef struct td3_agent_config {
   int32_t n_agents;                /* independent agents stepped in lock-step in one launch (>= 1) */
   int32_t reserved0;
   float max_action;                /* actor output scale; particles actor ignores it (TD3_particles.py:68-69) -> pass 1 */
-  float discount, tau, policy_noise, noise_clip;
-  float lr_actor, lr_critic, beta1, beta2, adam_eps;
+  float discount, policy_noise, noise_clip;   /* used as fp32 scalars against fp32 tensors, as torch casts them */
+  /* Python-float (double) hyper-parameters: torch derives 1-beta1, 1-beta2, 1-tau and the bias corrections in
+   * double before casting to fp32, so they must arrive un-rounded for <= 2 ulp Adam parity. */
+  double tau, lr_actor, lr_critic, beta1, beta2, adam_eps;
   int32_t policy_freq;
   int32_t reserved1;
   uint64_t seed;                   /* Philox key */
@@ -140,7 +142,7 @@ int rb_philox_indices(int64_t* idx_dev, int64_t batch, int64_t size, uint64_t se
  * optionally the Polyak update target = tau*p + (1-tau)*target (TD3_featured.py:167-171) fused in.
  * target == NULL -> Adam only.  grad == NULL -> Polyak only. */
 int adam_polyak_step(float* params, const float* grad, float* exp_avg, float* exp_avg_sq, float* target,
-                     int64_t n, int64_t t, float lr, float beta1, float beta2, float eps, float tau, void* stream);
+                     int64_t n, int64_t t, double lr, double beta1, double beta2, double eps, double tau, void* stream);
 
 /* ---- agent ------------------------------------------------------------------------- */
 int td3_agent_create(const td3_agent_config* cfg, td3_agent** out);

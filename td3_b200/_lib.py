@@ -46,9 +46,9 @@ class AgentConfig(C.Structure):
         ("variant", C.c_int32), ("norm", C.c_int32), ("n_q", C.c_int32), ("state_dim", C.c_int32),
         ("action_dim", C.c_int32), ("n_particles", C.c_int32), ("particle_dim", C.c_int32),
         ("clamp_target_action", C.c_int32), ("n_agents", C.c_int32), ("reserved0", C.c_int32),
-        ("max_action", C.c_float), ("discount", C.c_float), ("tau", C.c_float), ("policy_noise", C.c_float),
-        ("noise_clip", C.c_float), ("lr_actor", C.c_float), ("lr_critic", C.c_float), ("beta1", C.c_float),
-        ("beta2", C.c_float), ("adam_eps", C.c_float),
+        ("max_action", C.c_float), ("discount", C.c_float), ("policy_noise", C.c_float), ("noise_clip", C.c_float),
+        ("tau", C.c_double), ("lr_actor", C.c_double), ("lr_critic", C.c_double), ("beta1", C.c_double),
+        ("beta2", C.c_double), ("adam_eps", C.c_double),
         ("policy_freq", C.c_int32), ("reserved1", C.c_int32),
         ("seed", C.c_uint64),
         ("actor", NetLayout), ("q", NetLayout),
@@ -60,7 +60,7 @@ class ReplayView(C.Structure):
                 ("size", C.c_int64), ("agent_stride", C.c_int64)]
 
 
-_vp, _i32, _i64, _u64, _f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64, C.c_float
+_vp, _i32, _i64, _u64, _f32, _f64 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64, C.c_float, C.c_double
 _P = C.POINTER
 
 # name -> (restype, argtypes); mirrors include/td3_b200.h one to one
@@ -72,7 +72,7 @@ SIGNATURES = {
     "rb_add_rows": (C.c_int, [_vp, _i64, _i64, _i64, _i64, _vp, _i64, _vp]),
     "rb_sample_indices": (C.c_int, [_P(ReplayView), _vp, _i64, _i32, _P(_i64), _P(_i64), _P(_vp), _P(_i64), _vp]),
     "rb_philox_indices": (C.c_int, [_vp, _i64, _i64, _u64, _u64, _u64, _vp]),
-    "adam_polyak_step": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _f32, _f32, _f32, _f32, _f32, _vp]),
+    "adam_polyak_step": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _f64, _f64, _f64, _f64, _f64, _vp]),
     "td3_agent_create": (C.c_int, [_P(AgentConfig), _P(_vp)]),
     "td3_agent_destroy": (C.c_int, [_vp]),
     "td3_agent_bind_params": (C.c_int, [_vp, _P(ParamSet), _P(ParamSet)]),

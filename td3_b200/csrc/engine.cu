@@ -1108,7 +1108,7 @@ int rb_philox_indices(int64_t* idx_dev, int64_t batch, int64_t size, uint64_t se
 }
 
 int adam_polyak_step(float* params, const float* grad, float* exp_avg, float* exp_avg_sq, float* target, int64_t n, int64_t t,
-                     float lr, float beta1, float beta2, float eps, float tau, void* stream) {
+                     double lr, double beta1, double beta2, double eps, double tau, void* stream) {
   if (!params || n <= 0) return fail(TD3_ERR_INVALID, "adam_polyak_step: bad arguments");
   if (!grad && !target) return fail(TD3_ERR_INVALID, "adam_polyak_step: nothing to do (grad and target both NULL)");
   if (grad && (!exp_avg || !exp_avg_sq || t < 1)) return fail(TD3_ERR_INVALID, "adam_polyak_step: Adam needs moments and t >= 1");
@@ -1116,10 +1116,10 @@ int adam_polyak_step(float* params, const float* grad, float* exp_avg, float* ex
   L.kind = Launch::EW;
   EwParams& e = L.ew;
   e.n_ranges = 1;
-  e.beta1 = (double)beta1; e.beta2 = (double)beta2; e.eps = (double)eps; e.tau = (double)tau;
+  e.beta1 = beta1; e.beta2 = beta2; e.eps = eps; e.tau = tau;
   EwRange& r = e.r[0];
   r.p = params; r.g = grad; r.m = exp_avg; r.v = exp_avg_sq; r.tgt = target; r.n = n; r.blk_begin = 0;
-  r.t_ptr = nullptr; r.t_val = t; r.lr = (double)lr; r.do_adam = grad != nullptr; r.do_polyak = target != nullptr;
+  r.t_ptr = nullptr; r.t_val = t; r.lr = lr; r.do_adam = grad != nullptr; r.do_polyak = target != nullptr;
   L.grid_x = (int)((n + kEwPerBlock - 1) / kEwPerBlock);
   return run_launch(L, (cudaStream_t)stream);
 }
