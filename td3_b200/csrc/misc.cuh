@@ -84,14 +84,14 @@ struct GatherParams {
   float policy_noise, noise_clip;
 };
 
-__global__ void __launch_bounds__(256) gather_kernel(const __grid_constant__ GatherParams G) {
+__device__ __forceinline__ void gather_body(const GatherParams& G, int bx, int by) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
-  const long long job = (long long)blockIdx.x * warps_per_block + warp;   // (agent, b)
+  const long long job = (long long)bx * warps_per_block + warp;   // (agent, b)
   if (job >= (long long)G.n_agents * G.batch) return;
   const int agent = (int)(job / G.batch), b = (int)(job - (long long)agent * G.batch);
-  const unsigned long long step = *G.step_ptr;
-  const long long size = G.size_ptr ? (long long)*G.size_ptr : G.size;
+  const unsigned long long step = __ldcg(G.step_ptr);
+  const long long size = G.size_ptr ? (long long)__ldcg(G.size_ptr) : G.size;
   long long idx;
   if (G.rng_mode == 0) {
     idx = philox_index(G.seed + (unsigned long long)agent * 0x9E3779B97F4A7C15ull, PHILOX_INDICES, step,
@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(256) gather_kernel(const __grid_constant__ Gat
   } else {
     idx = G.idx_in[job];
   }
-  const int slice = blockIdx.y;
+  const int slice = by;
   if (slice == 0) {
     if (lane == 0) G.idx_out[job] = idx;
     for (int a = lane; a < G.action_dim; a += 32) {
@@ -136,6 +136,10 @@ __global__ void __launch_bounds__(256) gather_kernel(const __grid_constant__ Gat
   }
 }
 
+__global__ void __launch_bounds__(256) gather_kernel(const __grid_constant__ GatherParams G) {
+  gather_body(G, blockIdx.x, blockIdx.y);
+}
+
 __global__ void philox_indices_kernel(long long* idx, long long batch, long long size, unsigned long long seed,
                                       unsigned int stream_id, unsigned long long step) {
   const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -159,9 +163,7 @@ struct LossParams {
   unsigned long long* counters;    // [0] sample step, [1] critic Adam t  (both += 1 here)
 };
 
-__global__ void __launch_bounds__(256) loss_kernel(const __grid_constant__ LossParams L) {
-  __shared__ float red[8];
-  const int agent = blockIdx.x;
+__device__ __forceinline__ void loss_body(const LossParams& L, int agent, float* red) {
   const float* q = L.q + agent * L.q_go;
   const float* tq = L.tq + agent * L.q_go;
   float* dq = L.dq + agent * L.q_go;
@@ -173,12 +175,12 @@ __global__ void __launch_bounds__(256) loss_kernel(const __grid_constant__ LossP
   for (int e = threadIdx.x; e < total; e += blockDim.x) {
     const int b = e / L.width, j = e - b * L.width;
     const size_t o = (size_t)b * L.ldq + j;
-    float t = tq[o];
-    if (L.n_q > 1) t = fminf(t, tq[L.q_gi + o]);
-    const float yy = __fadd_rn(r[b], __fmul_rn(__fmul_rn(nd[b], L.discount), t));
+    float t = __ldcg(tq + o);
+    if (L.n_q > 1) t = fminf(t, __ldcg(tq + L.q_gi + o));
+    const float yy = __fadd_rn(__ldcg(r + b), __fmul_rn(__fmul_rn(__ldcg(nd + b), L.discount), t));
     y[o] = yy;
     for (int g = 0; g < L.n_q; ++g) {
-      const float d = q[g * L.q_gi + o] - yy;
+      const float d = __ldcg(q + g * L.q_gi + o) - yy;
       dq[g * L.q_gi + o] = 2.f * L.inv_norm * d;
       acc = fmaf(d, d, acc);
     }
@@ -191,14 +193,19 @@ __global__ void __launch_bounds__(256) loss_kernel(const __grid_constant__ LossP
     for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += red[w];
     L.loss[agent] = tot * L.inv_norm;
     if (agent == 0 && L.counters) {
-      L.counters[0] += 1ull;
-      L.counters[1] += 1ull;
+      atomicAdd(L.counters + 0, 1ull);
+      atomicAdd(L.counters + 1, 1ull);
     }
   }
 }
 
+__global__ void __launch_bounds__(256) loss_kernel(const __grid_constant__ LossParams L) {
+  __shared__ float red[8];
+  loss_body(L, blockIdx.x, red);
+}
+
 __global__ void counter_add_kernel(unsigned long long* c, unsigned long long inc) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) *c += inc;
+  if (threadIdx.x == 0 && blockIdx.x == 0) atomicAdd(c, inc);
 }
 
 // ------------------------------------------------------------------------------------
@@ -229,36 +236,38 @@ struct EwParams {
 constexpr int kEwThreads = 256;
 constexpr int kEwPerBlock = kEwThreads * 8;   // 2 float4 per thread
 
-__global__ void __launch_bounds__(kEwThreads) adam_polyak_kernel(const __grid_constant__ EwParams E) {
-  __shared__ float s_step_size, s_bc2_sqrt;
+// smem2: two floats of shared scratch.  bx = block index within the launch / stage.
+__device__ __forceinline__ void adam_polyak_body(const EwParams& E, long long bx, float* smem2) {
   int ri = 0;
   for (int q = 1; q < 3; ++q)
-    if (q < E.n_ranges && (long long)blockIdx.x >= E.r[q].blk_begin) ri = q;
+    if (q < E.n_ranges && bx >= E.r[q].blk_begin) ri = q;
   const EwRange& R = E.r[ri];
+  __syncthreads();
   if (R.do_adam && threadIdx.x == 0) {
-    const double t = (double)(R.t_ptr ? (long long)*R.t_ptr : R.t_val);
+    const double t = (double)(R.t_ptr ? (long long)__ldcg(R.t_ptr) : R.t_val);
     const double bc1 = 1.0 - pow(E.beta1, t);
     const double bc2 = 1.0 - pow(E.beta2, t);
-    s_step_size = (float)(R.lr / bc1);
-    s_bc2_sqrt = (float)sqrt(bc2);
+    smem2[0] = (float)(R.lr / bc1);
+    smem2[1] = (float)sqrt(bc2);
   }
   __syncthreads();
+  const float s_step_size = smem2[0], s_bc2_sqrt = smem2[1];
   const float w1 = (float)(1.0 - E.beta1), b2 = (float)E.beta2, w2 = (float)(1.0 - E.beta2);
   const float eps = (float)E.eps, tau = (float)E.tau, omt = (float)(1.0 - E.tau);
   const float neg_step = R.do_adam ? -s_step_size : 0.f;
   const float bc2s = R.do_adam ? s_bc2_sqrt : 1.f;
-  const long long base = ((long long)blockIdx.x - R.blk_begin) * kEwPerBlock;
+  const long long base = (bx - R.blk_begin) * kEwPerBlock;
 #pragma unroll
   for (int u = 0; u < 2; ++u) {
     const long long e = base + ((long long)u * kEwThreads + threadIdx.x) * 4;
     if (e >= R.n) continue;
     if (e + 4 <= R.n) {
-      float4 p = *reinterpret_cast<float4*>(R.p + e);
+      float4 p = __ldcg(reinterpret_cast<const float4*>(R.p + e));
       float pv[4] = {p.x, p.y, p.z, p.w};
       if (R.do_adam) {
-        const float4 g4 = *reinterpret_cast<const float4*>(R.g + e);
-        float4 m4 = *reinterpret_cast<float4*>(R.m + e);
-        float4 v4 = *reinterpret_cast<float4*>(R.v + e);
+        const float4 g4 = __ldcg(reinterpret_cast<const float4*>(R.g + e));
+        float4 m4 = __ldcg(reinterpret_cast<const float4*>(R.m + e));
+        float4 v4 = __ldcg(reinterpret_cast<const float4*>(R.v + e));
         float gv[4] = {g4.x, g4.y, g4.z, g4.w}, mv[4] = {m4.x, m4.y, m4.z, m4.w}, vv[4] = {v4.x, v4.y, v4.z, v4.w};
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -272,7 +281,7 @@ __global__ void __launch_bounds__(kEwThreads) adam_polyak_kernel(const __grid_co
         *reinterpret_cast<float4*>(R.p + e) = make_float4(pv[0], pv[1], pv[2], pv[3]);
       }
       if (R.do_polyak) {
-        const float4 t4 = *reinterpret_cast<float4*>(R.tgt + e);
+        const float4 t4 = __ldcg(reinterpret_cast<const float4*>(R.tgt + e));
         float tv[4] = {t4.x, t4.y, t4.z, t4.w};
 #pragma unroll
         for (int k = 0; k < 4; ++k) tv[k] = __fadd_rn(__fmul_rn(tau, pv[k]), __fmul_rn(omt, tv[k]));
@@ -280,19 +289,24 @@ __global__ void __launch_bounds__(kEwThreads) adam_polyak_kernel(const __grid_co
       }
     } else {
       for (long long k = e; k < R.n; ++k) {
-        float pvk = R.p[k];
+        float pvk = __ldcg(R.p + k);
         if (R.do_adam) {
-          const float g = R.g[k];
-          const float m = fmaf(w1, __fsub_rn(g, R.m[k]), R.m[k]);
-          const float v = __fadd_rn(__fmul_rn(R.v[k], b2), __fmul_rn(__fmul_rn(w2, g), g));
+          const float g = __ldcg(R.g + k), m0 = __ldcg(R.m + k);
+          const float m = fmaf(w1, __fsub_rn(g, m0), m0);
+          const float v = __fadd_rn(__fmul_rn(__ldcg(R.v + k), b2), __fmul_rn(__fmul_rn(w2, g), g));
           const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(v), bc2s), eps);
           pvk = __fadd_rn(pvk, __fdiv_rn(__fmul_rn(neg_step, m), denom));
           R.m[k] = m; R.v[k] = v; R.p[k] = pvk;
         }
-        if (R.do_polyak) R.tgt[k] = __fadd_rn(__fmul_rn(tau, pvk), __fmul_rn(omt, R.tgt[k]));
+        if (R.do_polyak) R.tgt[k] = __fadd_rn(__fmul_rn(tau, pvk), __fmul_rn(omt, __ldcg(R.tgt + k)));
       }
     }
   }
+}
+
+__global__ void __launch_bounds__(kEwThreads) adam_polyak_kernel(const __grid_constant__ EwParams E) {
+  __shared__ float smem2[2];
+  adam_polyak_body(E, blockIdx.x, smem2);
 }
 
 }  // namespace td3

@@ -1,5 +1,8 @@
 """K4/K5 fused Adam + Polyak over packed buffers vs torch.optim.Adam / the reference's Polyak loop.
-Tolerance: <= 2 ulp per element per step for Adam, Polyak bit-exact."""
+Tolerance: moments <= 2 ulp (torch CPU lerp/addcmul kernels may or may not contract to fma depending on
+the vector path taken); parameters <= 2 ulp per step measured at the magnitude of the operands of the final add,
+ulp(max(|p_before|, |p_after|, lr)) -- an element that is almost cancelled by its +-lr update has a tiny value whose own
+ulp says nothing about the rounding of the add that produced it.  Polyak bit-exact."""
 import ctypes as C
 
 import numpy as np
@@ -30,15 +33,17 @@ def test_adam_matches_torch(n):
     for t in range(1, 6):
         grad = torch.randn(n, generator=g) * (10.0 ** float(torch.randint(-6, 2, (1,), generator=g)))
         ref.grad = grad.clone()
+        p_before = ref.detach().numpy().copy()
         opt.step()
         gd = grad.cuda()
         _lib.check(lib.adam_polyak_step(C.c_void_p(p.data_ptr()), C.c_void_p(gd.data_ptr()), C.c_void_p(m.data_ptr()),
                                         C.c_void_p(v.data_ptr()), None, n, t, 1e-3, 0.9, 0.999, 1e-8, 0.0, _lib.stream_ptr()))
         st = opt.state[ref]
-        assert _ulp_diff(m.cpu().numpy(), st["exp_avg"].numpy()).max() <= 1
-        assert _ulp_diff(v.cpu().numpy(), st["exp_avg_sq"].numpy()).max() <= 1
-        d = _ulp_diff(p.cpu().numpy(), ref.detach().numpy())
-        assert d.max() <= 2 * t, (t, d.max())
+        assert _ulp_diff(m.cpu().numpy(), st["exp_avg"].numpy()).max() <= 2
+        assert _ulp_diff(v.cpu().numpy(), st["exp_avg_sq"].numpy()).max() <= 2
+        got, want = p.cpu().numpy(), ref.detach().numpy()
+        scale = np.spacing(np.maximum(np.maximum(np.abs(p_before), np.abs(want)), np.float32(1e-3)))
+        assert np.all(np.abs(got - want) <= 2 * t * scale), (t, float((np.abs(got - want) / scale).max()))
 
 
 def test_polyak_bit_exact_and_fused_order():
