@@ -35,6 +35,11 @@ typedef enum td3_status {
 
 typedef enum td3_norm { TD3_NORM_NONE = 0, TD3_NORM_LAYER = 1 } td3_norm;
 typedef enum td3_variant { TD3_VARIANT_FEATURED = 0, TD3_VARIANT_PARTICLES = 1 } td3_variant;
+typedef enum td3_precision {
+  TD3_PRECISION_FP32 = 0,         /* every contraction on strict-fp32 FFMA tiles (matches the CPU reference to ~1e-6) */
+  TD3_PRECISION_TF32 = 1          /* contractions with 16-byte-copyable operands and K >= 64 on tcgen05 kind::tf32 tiles,
+                                     fp32 accumulation in tensor memory; everything else (and all storage) stays fp32 */
+} td3_precision;
 typedef enum td3_rng_mode {
   TD3_RNG_PHILOX = 0,             /* on-device Philox4x32-10 indices + noise */
   TD3_RNG_INJECTED = 1            /* indices / N(0,1) draws supplied by the caller (parity mode) */
@@ -83,7 +88,7 @@ typedef struct td3_agent_config {
   int32_t particle_dim;            /* particles: D */
   int32_t clamp_target_action;     /* featured 1 (TD3_featured.py:135-137), particles 0 (TD3_particles.py:179-181) */
   int32_t n_agents;                /* independent agents stepped in lock-step in one launch (>= 1) */
-  int32_t reserved0;
+  int32_t precision;               /* td3_precision */
   float max_action;                /* actor output scale; particles actor ignores it (TD3_particles.py:68-69) -> pass 1 */
   float discount, policy_noise, noise_clip;   /* used as fp32 scalars against fp32 tensors, as torch casts them */
   /* Python-float (double) hyper-parameters: torch derives 1-beta1, 1-beta2, 1-tau and the bias corrections in
@@ -144,6 +149,15 @@ int rb_philox_indices(int64_t* idx_dev, int64_t batch, int64_t size, uint64_t se
 int adam_polyak_step(float* params, const float* grad, float* exp_avg, float* exp_avg_sq, float* target,
                      int64_t n, int64_t t, double lr, double beta1, double beta2, double eps, double tau, void* stream);
 
+/* ---- dense contraction on its own (torch.nn.Linear / addmm / mm call sites: TD3_featured.py:39-48,73-81) ---- */
+/* C[M,N] = op(A)[M,K] . op(B)[K,N] (+ bias[N], optional ReLU).  a_rc / b_rc = 1: the operand is stored with the
+ * reduction index contiguous (A as [M,K] row-major, B as [N,K] row-major, i.e. an nn.Linear weight); 0: stored with
+ * the reduction index as the row (A as [K,M], B as [K,N]).  use_tc = 1 runs the tcgen05 TF32 tile (fails with
+ * TD3_ERR_UNSUPPORTED when the operands are not eligible), 0 the fp32 FFMA tile.  Used by the kernel tests and the
+ * GEMM roofline measurements. */
+int td3_gemm(int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, int32_t a_rc, const float* B, int64_t ldb,
+             int32_t b_rc, float* C, int64_t ldc, const float* bias, int32_t relu, int32_t use_tc, void* stream);
+
 /* ---- agent ------------------------------------------------------------------------- */
 int td3_agent_create(const td3_agent_config* cfg, td3_agent** out);
 int td3_agent_destroy(td3_agent* agent);
@@ -168,9 +182,11 @@ int td3_agent_region(const td3_agent* agent, const char* name, int64_t* offset, 
  * sample -> target step -> twin-critic fwd/bwd + Adam -> every policy_freq-th call actor step +
  * Polyak.  total_it is the reference's counter BEFORE the first of these updates.  In
  * TD3_RNG_INJECTED mode the caller has filled the regions "indices_in" (int64 [n_agents][batch]) and
- * "noise_in" (N(0,1) draws, fp32 [n_agents][batch][A]) and iterations must be 1.  CUDA-graph replay unless use_graph == 0. */
+ * "noise_in" (N(0,1) draws, fp32 [n_agents][batch][A]) and iterations must be 1.
+ * exec_mode: 2 = persistent cooperative kernel (all iterations in one launch, device-wide barriers between the
+ * dependent stages), 1 = CUDA-graph replay of one kernel per stage, 0 = plain stage-by-stage launches. */
 int td3_train_n(td3_agent* agent, const td3_replay_view* rb, int64_t total_it, int32_t iterations,
-                int32_t rng_mode, int32_t use_graph, void* stream);
+                int32_t rng_mode, int32_t exec_mode, void* stream);
 /* The phases of one update, launched individually (no graph): parity tests and the DP critic
  * (gradient all-reduce between critic_backward and critic_apply). */
 int td3_sample_batch(td3_agent* agent, const td3_replay_view* rb, int32_t rng_mode, void* stream);

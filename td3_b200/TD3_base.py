@@ -64,6 +64,10 @@ class TD3_base(object):
         if rng not in ("device", "host"):
             raise ValueError("rng must be 'device' (on-device Philox) or 'host' (reference's NumPy/torch CPU streams)")
         self.rng = rng
+        # how td3_train_n executes an update: "persistent" = one cooperative kernel walking the stage program with
+        # device-wide barriers (default), "graph" = CUDA-graph replay of one kernel per stage, "launches" = plain
+        # stage-by-stage launches (debugging)
+        self.exec_mode = os.environ.get("TD3_EXEC_MODE", "persistent")
         n_agents = cfg.n_agents
         self._state = torch.zeros(16 + n_agents, dtype=torch.int64, device=self._device)
         self._losses = self._state[16:].view(torch.float32)          # critic_loss[nA], actor_loss[nA]
@@ -126,8 +130,11 @@ class TD3_base(object):
         self._region("indices_in").view(torch.int64)[: nA * batch].copy_(idx.reshape(-1))
         self._region("noise_in")[: nA * batch * A].copy_(nz.reshape(-1))
 
+    _EXEC_MODES = {"launches": 0, "graph": 1, "persistent": 2}
+
     def _train_common(self, replay_buffer, batch_size, iterations, indices, noise, use_graph):
         batch_size, iterations = int(batch_size), int(iterations)
+        use_graph = self._EXEC_MODES[self.exec_mode] if use_graph else 0
         view = self._rb_view(replay_buffer)
         if view.size <= 0:
             raise ValueError("high <= 0")        # what np.random.randint(0, 0) raises (my_replay_buffer.py:59,120)

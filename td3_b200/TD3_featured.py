@@ -8,8 +8,12 @@ Same constructor keywords and methods; extra keyword-only options:
                             "host":   np.random.randint + torch.randn on the host, i.e. the reference's
                                       own random streams (seed-for-seed comparable with a CPU reference run)
   seed                      Philox key for rng="device" (default: drawn from torch's global generator)
+  precision                 "tf32" (default; env TD3_PRECISION): the layer GEMMs with K >= 64 run on the tcgen05 tensor
+                            cores in TF32 with fp32 accumulation; "fp32": every contraction in strict fp32 (parity mode)
 """
 from __future__ import annotations
+
+import os
 
 import numpy as np
 import torch
@@ -25,7 +29,8 @@ Actor, Critic = MlpActor, MlpCritic
 
 class TD3(TD3_base):
     def __init__(self, obs_space, action_space, max_action=1, lr=1e-4, norm=None, CDQ=True, *,
-                 actor_widths=(500, 400, 300), q_widths=(500, 400, 200), rng="device", seed=None, **kwargs):
+                 actor_widths=(500, 400, 300), q_widths=(500, 400, 200), rng="device", seed=None, precision=None,
+                 **kwargs):
         _lib.require_cuda()
         S, A = obs_space.shape[0], action_space.shape[0]
         # Build on the CPU with torch's default initialisers in the reference's construction order
@@ -52,6 +57,7 @@ class TD3(TD3_base):
         cfg.lr_actor = cfg.lr_critic = float(lr)
         cfg.beta1, cfg.beta2, cfg.adam_eps = 0.9, 0.999, 1e-8
         cfg.policy_freq = int(self.policy_freq)
+        cfg.precision = _lib.PRECISIONS[precision or os.environ.get("TD3_PRECISION", "tf32")]
         cfg.seed = int(torch.randint(0, 2**62, (1,)).item()) if seed is None else int(seed)
         cfg.actor, cfg.q = net_layout(actor), net_layout(critic.q1)
         self.CDQ = CDQ

@@ -10,6 +10,8 @@ and the [B,1] reward broadcasts against it, ``CDQ=False`` drops the second criti
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import torch
 
@@ -25,7 +27,8 @@ Actor, Critic = SetActor, SetCritic
 
 class TD3(TD3_base):
     def __init__(self, obs_space, action_space, lr=1e-4, norm=None, CDQ=True, *,
-                 actor_widths=(500, 400, 300), q_widths=(500, 400, 300), rng="device", seed=None, **kwargs):
+                 actor_widths=(500, 400, 300), q_widths=(500, 400, 300), rng="device", seed=None, precision=None,
+                 **kwargs):
         _lib.require_cuda()
         F = obs_space[0].shape[0]
         N, D = obs_space[1].shape
@@ -57,6 +60,7 @@ class TD3(TD3_base):
         cfg.lr_actor = cfg.lr_critic = float(lr)
         cfg.beta1, cfg.beta2, cfg.adam_eps = 0.9, 0.999, 1e-8
         cfg.policy_freq = int(self.policy_freq)
+        cfg.precision = _lib.PRECISIONS[precision or os.environ.get("TD3_PRECISION", "tf32")]
         cfg.seed = int(torch.randint(0, 2**62, (1,)).item()) if seed is None else int(seed)
         cfg.actor, cfg.q = net_layout(actor), net_layout(critic.q1)
         self._engine_init(cfg, fam_a, fam_c, lr, rng)

@@ -11,13 +11,15 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtd3b200.so")
+LIB_PATH = os.path.join(_HERE, os.environ.get("TD3_LIB_NAME", "libtd3b200.so"))   # TD3_LIB_NAME: debug builds
 
 TD3_MAX_LINEAR = 8
 TD3_MAX_SEGMENTS = 16
 RNG_PHILOX, RNG_INJECTED = 0, 1
 VARIANT_FEATURED, VARIANT_PARTICLES = 0, 1
 NORM_NONE, NORM_LAYER = 0, 1
+PRECISION_FP32, PRECISION_TF32 = 0, 1
+PRECISIONS = {"fp32": PRECISION_FP32, "tf32": PRECISION_TF32}
 
 
 class NetLayout(C.Structure):
@@ -45,7 +47,7 @@ class AgentConfig(C.Structure):
     _fields_ = [
         ("variant", C.c_int32), ("norm", C.c_int32), ("n_q", C.c_int32), ("state_dim", C.c_int32),
         ("action_dim", C.c_int32), ("n_particles", C.c_int32), ("particle_dim", C.c_int32),
-        ("clamp_target_action", C.c_int32), ("n_agents", C.c_int32), ("reserved0", C.c_int32),
+        ("clamp_target_action", C.c_int32), ("n_agents", C.c_int32), ("precision", C.c_int32),
         ("max_action", C.c_float), ("discount", C.c_float), ("policy_noise", C.c_float), ("noise_clip", C.c_float),
         ("tau", C.c_double), ("lr_actor", C.c_double), ("lr_critic", C.c_double), ("beta1", C.c_double),
         ("beta2", C.c_double), ("adam_eps", C.c_double),
@@ -73,6 +75,7 @@ SIGNATURES = {
     "rb_sample_indices": (C.c_int, [_P(ReplayView), _vp, _i64, _i32, _P(_i64), _P(_i64), _P(_vp), _P(_i64), _vp]),
     "rb_philox_indices": (C.c_int, [_vp, _i64, _i64, _u64, _u64, _u64, _vp]),
     "adam_polyak_step": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _f64, _f64, _f64, _f64, _f64, _vp]),
+    "td3_gemm": (C.c_int, [_i64, _i64, _i64, _vp, _i64, _i32, _vp, _i64, _i32, _vp, _i64, _vp, _i32, _i32, _vp]),
     "td3_agent_create": (C.c_int, [_P(AgentConfig), _P(_vp)]),
     "td3_agent_destroy": (C.c_int, [_vp]),
     "td3_agent_bind_params": (C.c_int, [_vp, _P(ParamSet), _P(ParamSet)]),

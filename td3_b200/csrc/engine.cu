@@ -16,8 +16,12 @@
 
 #include "misc.cuh"
 #include "stage.cuh"
+#include "tc.cuh"
+#include "persist.cuh"
 
 using namespace td3;
+
+constexpr int kMaxProgStages = 128;
 
 namespace {
 
@@ -56,12 +60,24 @@ struct Launch {
   int grid_x = 1, grid_y = 1;
 };
 
+int ensure_kernel_attrs() {
+  static bool done = false;
+  if (done) return TD3_OK;
+  CUDA_TRY(cudaFuncSetAttribute(stage_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynSmemBytes));
+  CUDA_TRY(cudaFuncSetAttribute(persistent_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynSmemBytes));
+  done = true;
+  return TD3_OK;
+}
+
 int run_launch(const Launch& L, cudaStream_t s) {
   switch (L.kind) {
-    case Launch::STAGE:
+    case Launch::STAGE: {
       if (L.stage.total_tiles <= 0) return TD3_OK;
-      stage_kernel<<<L.stage.total_tiles, kStageThreads, 0, s>>>(L.stage);
+      int rc = ensure_kernel_attrs();
+      if (rc != TD3_OK) return rc;
+      stage_kernel<<<L.stage.total_tiles, kStageThreads, kDynSmemBytes, s>>>(L.stage);
       break;
+    }
     case Launch::GATHER:
       gather_kernel<<<dim3(L.grid_x, L.grid_y), 256, 0, s>>>(L.gather);
       break;
@@ -106,19 +122,43 @@ Problem make_gemm(int M, int N, int K, const float* A, int lda, bool a_rc, const
   return p;
 }
 
+int g_sm_count = 148;
+// tensor-core policy of the plan being built: 0 = fp32 FFMA tiles only, 1 = TF32 tcgen05 tiles where eligible
+thread_local int g_tc_mode = 0;
+
 void finalize_problem(Problem& p, GroupShape gs) {
   p.groups_inner = gs.n_inner;
   const int groups = gs.n_outer * gs.n_inner;
   switch (p.kind) {
     case PK_GEMM: {
-      p.tiles_m = (p.M + kBM - 1) / kBM;
-      p.tiles_n = (p.N + kBN - 1) / kBN;
-      p.tiles_per_group = p.tiles_m * p.tiles_n * p.ksplit;
       auto ok4 = [](long long v) { return (v & 3) == 0; };
       p.a_vec = aligned16(p.A) && ok4(p.lda) && ok4(p.a_go) && ok4(p.a_gi) && ok4(p.a_rc ? p.K : p.M);
       p.b_vec = aligned16(p.B) && ok4(p.ldb) && ok4(p.b_go) && ok4(p.b_gi) && ok4(p.b_rc ? p.K : p.N);
+      p.c_vec = aligned16(p.C) && ok4(p.ldc) && ok4(p.c_go) && ok4(p.c_gi) && ok4(p.c_split) && ok4(p.c_dup_stride);
+      p.aux_vec = p.aux0 && aligned16(p.aux0) && ok4(p.ldaux) && ok4(p.aux0_go) && ok4(p.aux0_gi);
+      // tcgen05 path: both operands must be 16-byte copyable (tc.cuh stages them with cp.async.cg 16) and the
+      // reduction long enough to be worth a 128-row tile; no fused row-sum there (PK_COLSUM does the bias gradient)
+      p.use_tc = g_tc_mode && p.a_vec && p.b_vec && p.K >= 64 && !(p.aux1 && p.epi == EPI_STORE);
+      if (p.use_tc) {
+        p.tiles_m = (p.M + 127) / 128;
+        int nt = p.N <= 16 ? 16 : 32;
+        for (int cand : {64, 128}) {   // wider tiles only when there are plenty of them (A is re-read once per N tile)
+          const long long tiles = (long long)p.tiles_m * ((p.N + cand - 1) / cand) * p.ksplit * groups;
+          if (p.N > nt && tiles >= 2LL * g_sm_count) nt = cand;
+        }
+        p.tc_nt = nt;
+        p.tiles_n = (p.N + nt - 1) / nt;
+      } else {
+        p.tiles_m = (p.M + kBM - 1) / kBM;
+        p.tiles_n = (p.N + kBN - 1) / kBN;
+      }
+      p.tiles_per_group = p.tiles_m * p.tiles_n * p.ksplit;
       break;
     }
+    case PK_COLSUM:
+      p.tiles_n = (p.N + 31) / 32;
+      p.tiles_per_group = p.tiles_n * p.ksplit;
+      break;
     case PK_LN_FWD:
     case PK_LN_BWD_ROWS:
       p.tiles_per_group = (p.M + 7) / 8;
@@ -155,6 +195,7 @@ int emit_stage(std::vector<Launch>& seq, const ProblemList& probs) {
       if (p.tile_count <= 0) continue;
       p.tile_begin = tiles;
       tiles += p.tile_count;
+      if (p.kind == PK_GEMM && p.use_tc) L.stage.any_tc = 1;
       L.stage.p[n++] = p;
     }
     L.stage.n_problems = n;
@@ -259,7 +300,15 @@ struct td3_agent {
     int rng_mode = -1;
   } graphs;
   long long last_rb_size = -1;
-  cudaStream_t cap_stream = nullptr;         // capture happens here: the caller's stream may be the legacy stream
+  cudaStream_t cap_stream = nullptr;
+  // persistent-kernel programs (device copies live in the workspace region "program")
+  StageRec* prog_dev = nullptr;
+  long long* prof_dev = nullptr;
+  int n_prog_critic = 0, n_prog_policy = 0;
+  bool prog_dirty = true;
+  int persist_grid = 0;
+  unsigned int bar_count = 0;               // value of the device barrier counter once all queued launches finish
+  bool bar_reset = true;                    // zero the counter before the next launch (fresh state block)         // capture happens here: the caller's stream may be the legacy stream
 };
 
 namespace {
@@ -418,9 +467,19 @@ std::vector<ProblemList> build_backward(const td3_agent_config& cfg, const td3_n
     if (want_dw) {   // dW_l[n,k] = sum_b dz[b,n] in[b,k] ; db_l[n] = sum_b dz[b,n]
       Problem p = make_gemm(N, K, B, dz, ld_dz, false, in, ld_in, false, G.base + net.w_off[l], K, EPI_STORE);
       set_groups(p, dz_go, dz_gi, in_go, in_gi, G.go, G.gi);
-      p.aux1 = G.base + net.b_off[l]; p.aux1_go = G.go; p.aux1_gi = G.gi;
       finalize_problem(p, gs);
-      stage.push_back(p);
+      if (p.use_tc) {   // tensor-core tile: the bias gradient is a separate column-sum problem of the same stage
+        Problem cs = blank_problem(PK_COLSUM);
+        cs.N = N; cs.K = B; cs.A = dz; cs.lda = ld_dz; cs.a_go = dz_go; cs.a_gi = dz_gi;
+        cs.C = G.base + net.b_off[l]; cs.c_go = G.go; cs.c_gi = G.gi;
+        finalize_problem(cs, gs);
+        stage.push_back(p);
+        stage.push_back(cs);
+      } else {          // FFMA tile: row sums of the A operand fall out of the fragments already in registers
+        p.aux1 = G.base + net.b_off[l]; p.aux1_go = G.go; p.aux1_gi = G.gi;
+        finalize_problem(p, gs);
+        stage.push_back(p);
+      }
     }
     if (l > 0) {     // d(in_l) = dz . W_l
       const bool mask_now = !ln;
@@ -531,14 +590,26 @@ std::vector<ProblemList> build_backward(const td3_agent_config& cfg, const td3_n
                               EPI_STORE);
       dw2.ksplit = ks2; dw2.c_split = (long long)O * H;
       set_groups(dw2, sc.dh2_go, sc.dh2_gi, pb.h1_go, pb.h1_gi, ks2 > 1 ? sc.part_go : G.go, ks2 > 1 ? sc.part_gi : G.gi);
-      dw2.aux1 = ks2 > 1 ? sc.part + (long long)ks2 * O * H : G.base + net.c2b_off;
-      dw2.aux1_go = ks2 > 1 ? sc.part_go : G.go; dw2.aux1_gi = ks2 > 1 ? sc.part_gi : G.gi;
       finalize_problem(dw2, gs);
+      Problem cs2 = blank_problem(PK_COLSUM);
+      const bool dw2_tc = dw2.use_tc;
+      if (dw2_tc) {
+        cs2.N = O; cs2.K = rows; cs2.ksplit = ks2; cs2.c_split = O;
+        cs2.A = sc.dh2; cs2.lda = O; cs2.a_go = sc.dh2_go; cs2.a_gi = sc.dh2_gi;
+        cs2.C = ks2 > 1 ? sc.part + (long long)ks2 * O * H : G.base + net.c2b_off;
+        cs2.c_go = ks2 > 1 ? sc.part_go : G.go; cs2.c_gi = ks2 > 1 ? sc.part_gi : G.gi;
+        finalize_problem(cs2, gs);
+      } else {
+        dw2.aux1 = ks2 > 1 ? sc.part + (long long)ks2 * O * H : G.base + net.c2b_off;
+        dw2.aux1_go = ks2 > 1 ? sc.part_go : G.go; dw2.aux1_gi = ks2 > 1 ? sc.part_gi : G.gi;
+        finalize_problem(dw2, gs);
+      }
       Problem dx2 = make_gemm(rows, H, O, sc.dh2, O, true, W.base + net.c2w_off, H, false, sc.dh1, H, EPI_RELU_MASK);
       set_groups(dx2, sc.dh2_go, sc.dh2_gi, W.go, W.gi, sc.dh1_go, sc.dh1_gi);
       dx2.aux0 = pb.h1; dx2.ldaux = H; dx2.aux0_go = pb.h1_go; dx2.aux0_gi = pb.h1_gi;
       finalize_problem(dx2, gs);
-      st.push_back({dw2, dx2});
+      if (dw2_tc) st.push_back({dw2, dx2, cs2});
+      else st.push_back({dw2, dx2});
       ProblemList s3;
       if (ks2 > 1) {
         Problem r1 = blank_problem(PK_REDUCE_SPLITS);
@@ -672,6 +743,9 @@ int plan_agent(td3_agent* a, long long batch) {
   Bump& ws = a->ws;
   ws.used = 0;
   ws.regions.clear();
+  g_tc_mode = c.precision == TD3_PRECISION_TF32 ? 1 : 0;
+  cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, 0);
+  if (g_sm_count <= 0) g_sm_count = 148;
   const int A = c.action_dim, S = c.state_dim, E = enc ? c.actor.enc_out : 0;
   a->in_a = c.actor.dims[0];
   a->in_q = c.q.dims[0];
@@ -715,6 +789,8 @@ int plan_agent(td3_agent* a, long long batch) {
   a->tanh_y = ws.take((long long)nA * B * A, "tanh_y");
   float* da = ws.take((long long)nA * B * A, "d_action");
   float* eye = ws.take((long long)A * A, "eye");
+  a->prof_dev = reinterpret_cast<long long*>(ws.take(2LL * 2 * 128 * 3, "prof"));
+  a->prog_dev = reinterpret_cast<StageRec*>(ws.take(2LL * kMaxProgStages * (long long)(sizeof(StageRec) / 4), "program"));
 
   // ---- passes ----
   auto share_x0 = [&](PassBuf& pb, float* x, int ld, long long go, long long gi) {
@@ -883,6 +959,7 @@ int plan_agent(td3_agent* a, long long batch) {
   a->batch = batch;
   a->plan_rows = nullptr;
   a->plan_rng_mode = -1;
+  a->prog_dirty = true;
   drop_graphs(a);
   return TD3_OK;
 }
@@ -945,6 +1022,127 @@ int plan_sample(td3_agent* a, const td3_replay_view* rb, int rng_mode) {
   a->seq_sample.push_back(L);
   a->plan_rows = rb->rows; a->plan_row_stride = rb->row_stride; a->plan_rng_mode = rng_mode;
   a->plan_rb_agent_stride = rb->agent_stride;
+  a->prog_dirty = true;
+  return TD3_OK;
+}
+
+// ------------------------------------------------------------------------------------
+// persistent-kernel programs: the launch sequences re-expressed as stage records
+// ------------------------------------------------------------------------------------
+int append_records(std::vector<StageRec>& prog, const std::vector<Launch>& seq, unsigned long long** pending_counter) {
+  for (const Launch& L : seq) {
+    if (L.kind == Launch::COUNTER) {          // folded into the next record: CTA 0 bumps it on entry
+      *pending_counter = L.counter;
+      continue;
+    }
+    StageRec r;
+    memset(&r, 0, sizeof(r));
+    r.barrier_after = 1;
+    r.inc_counter = *pending_counter;
+    *pending_counter = nullptr;
+    switch (L.kind) {
+      case Launch::STAGE:
+        r.kind = SK_STAGE; r.u.st = L.stage; r.main_tiles = L.stage.total_tiles;
+        break;
+      case Launch::GATHER:
+        r.kind = SK_GATHER; r.u.g = L.gather; r.main_tiles = L.grid_x * L.grid_y; r.gather_grid_x = L.grid_x;
+        break;
+      case Launch::LOSS:
+        r.kind = SK_LOSS; r.u.l = L.loss; r.main_tiles = L.grid_x;
+        break;
+      case Launch::EW:
+        r.kind = SK_EW_ONLY; r.ew = L.ew; r.ew_tiles = L.grid_x;
+        break;
+      default: break;
+    }
+    prog.push_back(r);
+  }
+  return TD3_OK;
+}
+
+int build_programs(td3_agent* a, cudaStream_t s) {
+  if (!a->prog_dirty) return TD3_OK;
+  std::vector<StageRec> pc, pp;
+  unsigned long long* pend = nullptr;
+  for (auto* seq : {&a->seq_sample, &a->seq_target, &a->seq_critic_fb, &a->seq_critic_apply}) append_records(pc, *seq, &pend);
+  for (auto* seq : {&a->seq_sample, &a->seq_target, &a->seq_critic_fb}) append_records(pp, *seq, &pend);
+  // The critic's Adam step does not feed the actor forward (only Q1's forward, three stages later, reads the
+  // stepped critic: TD3_featured.py:153,159): it rides along with the first actor stage instead of owning a barrier.
+  const size_t first_actor = pp.size();
+  append_records(pp, a->seq_actor_fb, &pend);
+  bool merged = false;
+  if (pp.size() > first_actor && pp[first_actor].kind == SK_STAGE && a->seq_critic_apply.size() == 1 &&
+      a->seq_critic_apply[0].kind == Launch::EW) {
+    pp[first_actor].ew = a->seq_critic_apply[0].ew;
+    pp[first_actor].ew_tiles = a->seq_critic_apply[0].grid_x;
+    merged = true;
+  }
+  if (!merged) {
+    std::vector<StageRec> tmp;
+    append_records(tmp, a->seq_critic_apply, &pend);
+    pp.insert(pp.begin() + first_actor, tmp.begin(), tmp.end());
+  }
+  append_records(pp, a->seq_actor_apply, &pend);
+  if (pc.empty() || pp.empty() || (int)pc.size() > kMaxProgStages || (int)pp.size() > kMaxProgStages)
+    return fail(TD3_ERR_STATE, "persistent program has %zu / %zu stages (max %d)", pc.size(), pp.size(), kMaxProgStages);
+  // the stage after the last one of an update is the next update's gather, which touches nothing the
+  // optimiser stage touches: no barrier between them (the one after the gather covers the parameters)
+  pc.back().barrier_after = 0;
+  pp.back().barrier_after = 0;
+  CUDA_TRY(cudaMemcpyAsync(a->prog_dev, pc.data(), pc.size() * sizeof(StageRec), cudaMemcpyHostToDevice, s));
+  CUDA_TRY(cudaMemcpyAsync(a->prog_dev + kMaxProgStages, pp.data(), pp.size() * sizeof(StageRec), cudaMemcpyHostToDevice, s));
+  a->n_prog_critic = (int)pc.size();
+  a->n_prog_policy = (int)pp.size();
+  int max_tiles = 1;
+  for (auto* p : {&pc, &pp})
+    for (auto& r : *p) max_tiles = std::max(max_tiles, r.main_tiles + r.ew_tiles);
+  int rc = ensure_kernel_attrs();
+  if (rc != TD3_OK) return rc;
+  int dev = 0, sms = 0, per_sm = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, persistent_update_kernel, kStageThreads, kDynSmemBytes));
+  if (per_sm < 1) return fail(TD3_ERR_CUDA, "persistent kernel does not fit on an SM");
+  if (const char* e = getenv("TD3_PERSIST_CTAS_PER_SM")) per_sm = std::max(1, std::min(per_sm, atoi(e)));
+  a->persist_grid = std::min(sms * per_sm, max_tiles);
+  a->prog_dirty = false;
+  return TD3_OK;
+}
+
+int launch_persistent(td3_agent* a, long long total_it, int iterations, cudaStream_t s) {
+  PersistArgs args;
+  args.prog_critic = a->prog_dev;
+  args.prog_policy = a->prog_dev + kMaxProgStages;
+  args.n_critic = a->n_prog_critic;
+  args.n_policy = a->n_prog_policy;
+  args.total_it = total_it;
+  args.iterations = iterations;
+  args.policy_freq = a->cfg.policy_freq;
+  args.barrier = reinterpret_cast<unsigned int*>(a->state_u64 + 8);
+  if (a->bar_reset) {
+    CUDA_TRY(cudaMemsetAsync(args.barrier, 0, sizeof(unsigned int), s));
+    a->bar_count = 0;
+    a->bar_reset = false;
+  }
+  args.barrier_base = a->bar_count;
+  unsigned int bar_add = 0;
+  {   // barriers this launch will execute: one per stage except the last of every update
+    const long long pf = a->cfg.policy_freq;
+    const long long n_pol = (total_it + iterations) / pf - total_it / pf;
+    const long long n_bar = n_pol * (a->n_prog_policy - 1) + ((long long)iterations - n_pol) * (a->n_prog_critic - 1);
+    bar_add = (unsigned int)(n_bar * a->persist_grid);
+  }
+  static const bool want_prof = getenv("TD3_PERSIST_PROF") != nullptr;
+  args.prof = want_prof ? a->prof_dev : nullptr;
+  void* kargs[] = {&args};
+  cudaError_t e = cudaLaunchCooperativeKernel((void*)persistent_update_kernel, dim3(a->persist_grid), dim3(kStageThreads),
+                                              kargs, (size_t)kDynSmemBytes, s);
+  if (e != cudaSuccess) {
+    a->bar_reset = true;
+    return fail(TD3_ERR_CUDA, "cudaLaunchCooperativeKernel: %s", cudaGetErrorString(e));
+  }
+  a->bar_count += bar_add;
+  g_launches.fetch_add(1, std::memory_order_relaxed);
   return TD3_OK;
 }
 
@@ -1028,6 +1226,20 @@ void td3_struct_sizes(int64_t* out) {   // lets a foreign-language binding check
 }
 const char* td3_last_error(void) { return g_err.c_str(); }
 int64_t td3_launch_count(void) { return g_launches.load(); }
+#ifdef TD3_TC_DEBUG
+int td3_debug_set(int idx, int val) {
+  CUDA_TRY(cudaDeviceSynchronize());
+  CUDA_TRY(cudaMemcpyToSymbol(td3::g_tc_dbg, &val, sizeof(int), idx * sizeof(int)));
+  return TD3_OK;
+}
+#endif
+#ifdef TD3_TILE_PROF
+int td3_debug_tile_prof(long long* out) {
+  CUDA_TRY(cudaDeviceSynchronize());
+  CUDA_TRY(cudaMemcpyFromSymbol(out, td3::g_tp, sizeof(long long) * 128 * 8));
+  return TD3_OK;
+}
+#endif
 
 int td3_device_info(int* sm_count, int* cc_major, int* cc_minor, char* name, int name_len) {
   int dev = 0;
@@ -1124,6 +1336,23 @@ int adam_polyak_step(float* params, const float* grad, float* exp_avg, float* ex
   return run_launch(L, (cudaStream_t)stream);
 }
 
+int td3_gemm(int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, int32_t a_rc, const float* B, int64_t ldb, int32_t b_rc,
+             float* C, int64_t ldc, const float* bias, int32_t relu, int32_t use_tc, void* stream) {
+  if (M <= 0 || N <= 0 || K <= 0 || !A || !B || !C) return fail(TD3_ERR_INVALID, "td3_gemm: bad arguments");
+  Problem p = make_gemm((int)M, (int)N, (int)K, A, (int)lda, a_rc != 0, B, (int)ldb, b_rc != 0, C, (int)ldc,
+                        bias ? (relu ? EPI_BIAS_RELU : EPI_BIAS) : EPI_STORE);
+  p.bias = bias;
+  g_tc_mode = use_tc ? 1 : 0;
+  cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, 0);
+  finalize_problem(p, GroupShape{1, 1});
+  if (use_tc && !p.use_tc)
+    return fail(TD3_ERR_UNSUPPORTED, "td3_gemm: operands are not eligible for the tcgen05 tile (16-byte aligned rows, K >= 64, "
+                                     "reduction extent a multiple of 4)");
+  std::vector<Launch> seq;
+  emit_stage(seq, {p});
+  return run_seq(seq, (cudaStream_t)stream);
+}
+
 int td3_agent_create(const td3_agent_config* cfg, td3_agent** out) {
   if (!cfg || !out) return fail(TD3_ERR_INVALID, "td3_agent_create: null argument");
   if (cfg->n_q < 1 || cfg->n_q > 2) return fail(TD3_ERR_INVALID, "n_q must be 1 or 2");
@@ -1169,6 +1398,7 @@ int td3_agent_bind_state(td3_agent* a, void* state_dev, int64_t n_bytes) {
   if (n_bytes < need) return fail(TD3_ERR_INVALID, "state buffer too small: %lld < %lld bytes", (long long)n_bytes, (long long)need);
   a->state_u64 = reinterpret_cast<unsigned long long*>(state_dev);
   a->state_f32 = reinterpret_cast<float*>(a->state_u64 + 16);
+  a->bar_reset = true;
   a->batch = 0;
   a->last_rb_size = -1;
   drop_graphs(a);
@@ -1264,6 +1494,15 @@ int td3_train_n(td3_agent* a, const td3_replay_view* rb, int64_t total_it, int32
   rc = plan_sample(a, rb, rng_mode);
   if (rc == TD3_OK) rc = sync_rb_size(a, rb, s);
   if (rc != TD3_OK) return rc;
+  if (use_graph == 2) {            // persistent kernel: all `iterations` updates in cooperative launches
+    rc = build_programs(a, s);
+    for (int done = 0; rc == TD3_OK && done < iterations;) {
+      const int n = std::min(iterations - done, 8192);
+      rc = launch_persistent(a, total_it + done, n, s);
+      done += n;
+    }
+    return rc;
+  }
   if (use_graph) {
     auto& g = a->graphs;
     if (g.rows != rb->rows || g.row_stride != rb->row_stride || g.rng_mode != rng_mode || !g.critic_only) {
@@ -1311,6 +1550,7 @@ int td3_actor_forward(td3_agent* a, int32_t which, int32_t agent_index, const fl
   if (enc && !particles) return fail(TD3_ERR_INVALID, "td3_actor_forward: particles required");
   cudaStream_t s = (cudaStream_t)stream;
   const int E = enc ? c.actor.enc_out : 0, S = c.state_dim, A = c.action_dim;
+  g_tc_mode = 0;                           // B = 1 latency path: exact fp32 tiles
   PassBuf pb = a->pb_a;                    // agent 0's slot of the online-actor activations
   rc = copy_cols(pb.x0 + E, pb.ld0, state, S, batch, s);
   if (rc != TD3_OK) return rc;
@@ -1337,6 +1577,7 @@ int td3_critic_forward(td3_agent* a, int32_t which, int32_t agent_index, const f
   if (enc && !particles) return fail(TD3_ERR_INVALID, "td3_critic_forward: particles required");
   cudaStream_t s = (cudaStream_t)stream;
   const int E = enc ? c.q.enc_out : 0, S = c.state_dim, A = c.action_dim, nq = c.n_q, qw = a->qw;
+  g_tc_mode = 0;
   PassBuf pb = a->pb_c;
   const int copies = enc ? nq : 1;
   for (int g = 0; g < copies; ++g) {

@@ -22,7 +22,8 @@ enum ProblemKind : int {
   PK_POOL_FWD = 4,      // relu(mean over particles)  (TD3_particles.py:57)
   PK_POOL_BWD = 5,      // dH2 = dpool/N * (pool>0) * (h2>0)
   PK_REDUCE_SPLITS = 6, // C = sum_s partial[s]   (split-K second phase)
-  PK_NEG_MEAN = 7       // scalar = -mean(A)      (actor loss read-back)
+  PK_NEG_MEAN = 7,      // scalar = -mean(A)      (actor loss read-back)
+  PK_COLSUM = 8         // C[j] = sum_i A[i,j]    (bias gradient next to a tensor-core dW)
 };
 
 enum Epilogue : int {
@@ -46,7 +47,8 @@ struct Problem {
   int tile_begin, tile_count;     // [tile_begin, tile_begin + tile_count) of the stage's grid
   int ksplit;                     // >1: reduction split over CTAs, partials at C + s*c_split
   int c_dups;                     // epilogue writes C to c_dups destinations c_dup_stride apart
-  int reserved;
+  int use_tc;                     // 1: tcgen05 TF32 tile (128 x tc_nt) instead of the fp32 FFMA tile (32 x 32)
+  int tc_nt, c_vec, aux_vec;      // TC tile width; 16-byte stores to C / loads from aux0 are legal
   long long c_split, c_dup_stride;
   const float* A; const float* B; float* C; const float* bias;
   float* aux0; float* aux1; float* aux2; float* aux3;
@@ -61,6 +63,7 @@ constexpr int kMaxProblemsPerStage = 6;
 struct StageParams {
   int n_problems;
   int total_tiles;
+  int any_tc, pad;                // some problem of the stage runs on the tensor cores (TMEM must be allocated)
   Problem p[kMaxProblemsPerStage];
 };
 
@@ -68,65 +71,148 @@ constexpr int kStageThreads = 256;
 constexpr int kBM = 32, kBN = 32, kBK = 32;
 constexpr int kLd = 36;                         // smem row stride (floats): 16B aligned, conflict-free
 constexpr int kTileFloats = 32 * kLd;           // 1152
-constexpr int kSmemFloats = 4 * kTileFloats;    // double-buffered A and B: 4608 floats = 18 KB
+constexpr int kRing = 8;                        // K-chunks resident in shared memory (kRing - 1 in flight)
+constexpr int kRingFloats = kRing * 2 * kTileFloats;   // A and B rings: 18432 floats = 72 KB (dynamic)
+constexpr int kSmemFloats = kRingFloats + kTileFloats + 32;   // + epilogue operand tile (aux0) + bias strip
+constexpr int kSmemBytes = kSmemFloats * 4;
 
 // ------------------------------------------------------------------------------------
-// global -> register tile fragment.  Both layouts use the same thread map: row = tid/8,
-// col4 = (tid%8)*4.  rc: rows index the output dim, cols the reduction; oc: the opposite.
+// cp.async helpers.  Everything the update touches (activations, parameters) is also
+// WRITTEN by other CTAs of the same persistent kernel, so no load may use the
+// non-coherent path (ld.global.nc / __ldg): 16-byte copies bypass L1 (.cg), 4-byte
+// copies and plain loads rely on the acquire fence of the grid barrier.
 // ------------------------------------------------------------------------------------
-__device__ __forceinline__ float4 load_frag(const float* __restrict__ base, int ld, bool rc, bool vec,
-                                            int o0, int k0, int O, int K, int tid) {
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc, bool pred) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  const int n = pred ? 16 : 0;                  // src-size 0 -> the 16 bytes are zero-filled
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d), "l"(gsrc), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc, bool pred) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  const int n = pred ? 4 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(d), "l"(gsrc), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+// global -> shared copy of one 32x32 operand chunk.  Thread map: row = tid/8, col4 = (tid%8)*4.
+// rc: rows index the output dim, cols the reduction; oc: the opposite.  The shared image keeps the
+// global orientation (rows kLd floats apart).
+#ifdef TD3_TILE_PROF
+__device__ long long g_tp[128 * 8];
+__device__ int g_tp_stage = -1;
+#define TP(k) do { if (threadIdx.x == 0 && blockIdx.x == 0 && g_tp_stage >= 0) g_tp[g_tp_stage * 8 + (k)] = clock64(); } while (0)
+#else
+#define TP(k) do { } while (0)
+#endif
+
+struct Operand {
+  const float* base;
+  int ld, rc, vec, o0, O;
+};
+
+__device__ __forceinline__ void issue_chunk(float* dst, const Operand& op, int k0, int K, int tid) {
   const int row = tid >> 3, c4 = (tid & 7) << 2;
-  const int row_idx = rc ? o0 + row : k0 + row;
-  const int row_lim = rc ? O : K;
-  const int col_idx = rc ? k0 + c4 : o0 + c4;
-  const int col_lim = rc ? K : O;
-  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (row_idx < row_lim && col_idx < col_lim) {
-    const float* p = base + (size_t)row_idx * ld + col_idx;
-    if (vec) {
-      v = __ldg(reinterpret_cast<const float4*>(p));
-    } else {
-      v.x = __ldg(p);
-      if (col_idx + 1 < col_lim) v.y = __ldg(p + 1);
-      if (col_idx + 2 < col_lim) v.z = __ldg(p + 2);
-      if (col_idx + 3 < col_lim) v.w = __ldg(p + 3);
+  const int row_idx = op.rc ? op.o0 + row : k0 + row;
+  const int row_lim = op.rc ? op.O : K;
+  const int col_idx = op.rc ? k0 + c4 : op.o0 + c4;
+  const int col_lim = op.rc ? K : op.O;
+  float* d = dst + row * kLd + c4;
+  const bool row_ok = row_idx < row_lim;
+  const float* p = op.base + (size_t)(row_ok ? row_idx : 0) * op.ld + col_idx;
+  if (op.vec) {
+    const bool ok = row_ok && col_idx < col_lim;
+    cp_async16(d, ok ? p : op.base, ok);
+  } else {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const bool ok = row_ok && col_idx + e < col_lim;
+      cp_async4(d + e, ok ? p + e : op.base, ok);
     }
   }
-  return v;
 }
 
-__device__ __forceinline__ float apply_epilogue(const Problem& P, float v, int i, int j, const float* bias,
-                                                float* aux0) {
-  switch (P.epi) {
-    case EPI_BIAS: return v + __ldg(bias + j);
-    case EPI_BIAS_RELU: return fmaxf(v + __ldg(bias + j), 0.f);
+// Kept out of line on purpose: the update kernel runs ~20 different stages back to back, so its
+// instruction footprint (not its FLOPs) decides how long a tile takes; one copy of the epilogue.
+__device__ __noinline__ float2 apply_epilogue(int epi, float v, float bias, float aux, float f0, float f1) {
+  switch (epi) {                       // .x = output value, .y = value to store into aux0 (EPI_BIAS_TANH only)
+    case EPI_BIAS: return make_float2(v + bias, 0.f);
+    case EPI_BIAS_RELU: return make_float2(fmaxf(v + bias, 0.f), 0.f);
     case EPI_BIAS_TANH: {
-      float y = tanhf(v + __ldg(bias + j));
-      aux0[(size_t)i * P.ldaux + j] = y;
-      return P.f0 * y;
+      const float y = tanhf(v + bias);
+      return make_float2(f0 * y, y);
     }
     case EPI_BIAS_TANH_NOISE: {
-      float a = P.f0 * tanhf(v + __ldg(bias + j)) + aux0[(size_t)i * P.ldaux + j];
-      if (P.f1 > 0.f) a = fminf(fmaxf(a, -P.f1), P.f1);
-      return a;
+      float a = f0 * tanhf(v + bias) + aux;
+      if (f1 > 0.f) a = fminf(fmaxf(a, -f1), f1);
+      return make_float2(a, 0.f);
     }
-    case EPI_RELU_MASK: return aux0[(size_t)i * P.ldaux + j] > 0.f ? v : 0.f;
-    case EPI_TANH_GRAD: {
-      float y = aux0[(size_t)i * P.ldaux + j];
-      return v * P.f0 * (1.f - y * y);
+    case EPI_RELU_MASK: return make_float2(aux > 0.f ? v : 0.f, 0.f);
+    case EPI_TANH_GRAD: return make_float2(v * f0 * (1.f - aux * aux), 0.f);
+    default: return make_float2(v, 0.f);
+  }
+}
+
+// 8 reduction steps (this thread's k-group share of a 32-wide chunk) of the 4x4 micro-tile
+template <bool ARC, bool BRC>
+__device__ __forceinline__ void fma_block(const float* __restrict__ As, const float* __restrict__ Bs, int kg, int ti,
+                                          int tj, float (&acc)[4][4], float (&asum)[4], bool want_rowsum) {
+#pragma unroll
+  for (int s = 0; s < 2; ++s) {
+    const int r = kg * 8 + s * 4;
+    float a[4][4], b[4][4];
+    if (ARC) {
+#pragma unroll
+      for (int ci = 0; ci < 4; ++ci) {
+        const float4 v = *reinterpret_cast<const float4*>(As + (ti + 8 * ci) * kLd + r);
+        a[ci][0] = v.x; a[ci][1] = v.y; a[ci][2] = v.z; a[ci][3] = v.w;
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 v = *reinterpret_cast<const float4*>(As + (r + q) * kLd + ti * 4);
+        a[0][q] = v.x; a[1][q] = v.y; a[2][q] = v.z; a[3][q] = v.w;
+      }
     }
-    default: return v;
+    if (BRC) {
+#pragma unroll
+      for (int cj = 0; cj < 4; ++cj) {
+        const float4 v = *reinterpret_cast<const float4*>(Bs + (tj + 8 * cj) * kLd + r);
+        b[cj][0] = v.x; b[cj][1] = v.y; b[cj][2] = v.z; b[cj][3] = v.w;
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 v = *reinterpret_cast<const float4*>(Bs + (r + q) * kLd + tj * 4);
+        b[0][q] = v.x; b[1][q] = v.y; b[2][q] = v.z; b[3][q] = v.w;
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+      for (int ci = 0; ci < 4; ++ci)
+#pragma unroll
+        for (int cj = 0; cj < 4; ++cj) acc[ci][cj] = fmaf(a[ci][q], b[cj][q], acc[ci][cj]);
+    if (want_rowsum) {
+#pragma unroll
+      for (int ci = 0; ci < 4; ++ci) asum[ci] += (a[ci][0] + a[ci][1]) + (a[ci][2] + a[ci][3]);
+    }
   }
 }
 
 // ------------------------------------------------------------------------------------
 // One 32x32 output tile; 256 threads = 4 k-groups x (8x8 threads x 4x4 micro-tile).
+// Operand chunks stream through a kRing-deep cp.async ring so that up to kRing-1 chunks
+// (the whole reduction for K <= 224, most of it for the 400/500-wide layers) are in flight
+// at once: a tile costs about one L2 round trip plus its FFMA time instead of one round
+// trip per chunk.  One copy of everything but the 64-FFMA block (4 operand-orientation
+// variants, selected per chunk by a uniform branch).
 // ------------------------------------------------------------------------------------
-template <bool ARC, bool BRC>
 __device__ __forceinline__ void gemm_tile(const Problem& P, int tile, float* smem) {
   const int tid = threadIdx.x;
   const int kg = tid >> 6, t64 = tid & 63, ti = t64 >> 3, tj = t64 & 7;
+  TP(0);
 
   int t = tile;
   const int g = t / P.tiles_per_group;
@@ -140,12 +226,10 @@ __device__ __forceinline__ void gemm_tile(const Problem& P, int tile, float* sme
   }
   const int tm = t / P.tiles_n, tn = t - tm * P.tiles_n;
   const int i0 = tm * kBM, j0 = tn * kBN;
+  const int arc = P.a_rc, brc = P.b_rc, variant = arc * 2 + brc;
 
-  const float* __restrict__ A = P.A + go * P.a_go + gi * P.a_gi;
-  const float* __restrict__ B = P.B + go * P.b_go + gi * P.b_gi;
-  float* __restrict__ C = P.C + go * P.c_go + gi * P.c_gi + (long long)ks * P.c_split;
-  const float* bias = P.bias ? P.bias + go * P.bias_go + gi * P.bias_gi : nullptr;
-  float* aux0 = P.aux0 ? P.aux0 + go * P.aux0_go + gi * P.aux0_gi : nullptr;
+  Operand opA{P.A + go * P.a_go + gi * P.a_gi, P.lda, arc, P.a_vec, i0, P.M};
+  Operand opB{P.B + go * P.b_go + gi * P.b_gi, P.ldb, brc, P.b_vec, j0, P.N};
   float* aux1 = P.aux1 ? P.aux1 + go * P.aux1_go + gi * P.aux1_gi : nullptr;
 
   // reduction range of this CTA
@@ -166,67 +250,53 @@ __device__ __forceinline__ void gemm_tile(const Problem& P, int tile, float* sme
   float asum[4] = {0.f, 0.f, 0.f, 0.f};
   const bool want_rowsum = (aux1 != nullptr) && (P.epi == EPI_STORE) && (tn == 0);
 
-  const int srow = tid >> 3, sc4 = (tid & 7) << 2;
-  float4 fa = make_float4(0.f, 0.f, 0.f, 0.f), fb = fa;
-  if (n_chunks > 0) {
-    fa = load_frag(A, P.lda, ARC, P.a_vec, i0, k_begin, P.M, k_end, tid);
-    fb = load_frag(B, P.ldb, BRC, P.b_vec, j0, k_begin, P.N, k_end, tid);
+  // epilogue operands ride in the first commit group: the bias strip and the 32x32 tile of aux0 (ReLU mask /
+  // noise / tanh output) are in shared memory long before the epilogue wants them
+  const int epi = P.epi;
+  float* aux_s = smem + kRingFloats;
+  float* bias_s = aux_s + kTileFloats;
+  float* aux0 = P.aux0 ? P.aux0 + go * P.aux0_go + gi * P.aux0_gi : nullptr;
+  const bool aux_read = aux0 && (epi == EPI_BIAS_TANH_NOISE || epi == EPI_RELU_MASK || epi == EPI_TANH_GRAD);
+  if (aux_read) {
+    Operand opX{aux0, P.ldaux, 1, 0, i0, P.M};
+    issue_chunk(aux_s, opX, j0, P.N, tid);
   }
-  for (int c = 0; c < n_chunks; ++c) {
-    float* As = smem + (c & 1) * 2 * kTileFloats;
-    float* Bs = As + kTileFloats;
-    *reinterpret_cast<float4*>(As + srow * kLd + sc4) = fa;
-    *reinterpret_cast<float4*>(Bs + srow * kLd + sc4) = fb;
-    __syncthreads();
-    if (c + 1 < n_chunks) {
-      const int k0 = k_begin + (c + 1) * kBK;
-      fa = load_frag(A, P.lda, ARC, P.a_vec, i0, k0, P.M, k_end, tid);
-      fb = load_frag(B, P.ldb, BRC, P.b_vec, j0, k0, P.N, k_end, tid);
+  if (P.bias && tid < 32) {
+    const float* bias = P.bias + go * P.bias_go + gi * P.bias_gi;
+    const bool ok = j0 + tid < P.N;
+    cp_async4(bias_s + tid, ok ? bias + j0 + tid : bias, ok);
+  }
+  TP(1);
+  // c < 0: prologue (kRing-1 commit groups; empty ones keep the group arithmetic uniform)
+#pragma unroll 1
+  for (int c = -(kRing - 1); c < n_chunks; ++c) {
+    if (c >= 0) {
+      cp_async_wait<kRing - 2>();   // this thread's copies of chunk c have landed
+      __syncthreads();              // ... everyone's have, and chunk c-1 has been consumed by all warps
+      if (c == 0) TP(2);
     }
-#pragma unroll
-    for (int s = 0; s < 2; ++s) {
-      const int r = kg * 8 + s * 4;
-      float a[4][4], b[4][4];
-      if (ARC) {
-#pragma unroll
-        for (int ci = 0; ci < 4; ++ci) {
-          const float4 v = *reinterpret_cast<const float4*>(As + (ti + 8 * ci) * kLd + r);
-          a[ci][0] = v.x; a[ci][1] = v.y; a[ci][2] = v.z; a[ci][3] = v.w;
-        }
-      } else {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float4 v = *reinterpret_cast<const float4*>(As + (r + q) * kLd + ti * 4);
-          a[0][q] = v.x; a[1][q] = v.y; a[2][q] = v.z; a[3][q] = v.w;
-        }
-      }
-      if (BRC) {
-#pragma unroll
-        for (int cj = 0; cj < 4; ++cj) {
-          const float4 v = *reinterpret_cast<const float4*>(Bs + (tj + 8 * cj) * kLd + r);
-          b[cj][0] = v.x; b[cj][1] = v.y; b[cj][2] = v.z; b[cj][3] = v.w;
-        }
-      } else {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float4 v = *reinterpret_cast<const float4*>(Bs + (r + q) * kLd + tj * 4);
-          b[0][q] = v.x; b[1][q] = v.y; b[2][q] = v.z; b[3][q] = v.w;
-        }
-      }
-#pragma unroll
-      for (int q = 0; q < 4; ++q)
-#pragma unroll
-        for (int ci = 0; ci < 4; ++ci)
-#pragma unroll
-          for (int cj = 0; cj < 4; ++cj) acc[ci][cj] = fmaf(a[ci][q], b[cj][q], acc[ci][cj]);
-      if (want_rowsum) {
-#pragma unroll
-        for (int ci = 0; ci < 4; ++ci) asum[ci] += (a[ci][0] + a[ci][1]) + (a[ci][2] + a[ci][3]);
+    const int cn = c + kRing - 1;   // refill the slot chunk c-1 occupied
+    if (cn < n_chunks) {
+      float* Ns = smem + (cn % kRing) * 2 * kTileFloats;
+      issue_chunk(Ns, opA, k_begin + cn * kBK, k_end, tid);
+      issue_chunk(Ns + kTileFloats, opB, k_begin + cn * kBK, k_end, tid);
+    }
+    cp_async_commit();
+    if (c >= 0) {
+      const float* As = smem + (c % kRing) * 2 * kTileFloats;
+      const float* Bs = As + kTileFloats;
+      switch (variant) {
+        case 3: fma_block<true, true>(As, Bs, kg, ti, tj, acc, asum, want_rowsum); break;
+        case 2: fma_block<true, false>(As, Bs, kg, ti, tj, acc, asum, want_rowsum); break;
+        case 1: fma_block<false, true>(As, Bs, kg, ti, tj, acc, asum, want_rowsum); break;
+        default: fma_block<false, false>(As, Bs, kg, ti, tj, acc, asum, want_rowsum); break;
       }
     }
-    // the buffer written two iterations from now is this one: guard before it is overwritten
-    if (c + 2 < n_chunks || true) __syncthreads();
   }
+  TP(3);
+  cp_async_wait<0>();
+  __syncthreads();                  // all warps are done with the ring: reuse it for the reduction
+  TP(4);
 
   // ---- reduce the 4 k-groups through shared memory ----
   float* red = smem;                       // [kg][e][t64] : 4*16*64 = 4096 floats
@@ -241,26 +311,40 @@ __device__ __forceinline__ void gemm_tile(const Problem& P, int tile, float* sme
   }
   __syncthreads();
 
-  const int ci = kg;
-  const int i = i0 + (ARC ? ti + 8 * ci : ti * 4 + ci);
+  {
+    float* __restrict__ C = P.C + go * P.c_go + gi * P.c_gi + (long long)ks * P.c_split;
+    const bool has_bias = P.bias != nullptr;
+    const int ci = kg;
+    const int il = arc ? ti + 8 * ci : ti * 4 + ci;      // row / column of this thread's outputs inside the tile
+    const int i = i0 + il;
 #pragma unroll
-  for (int cj = 0; cj < 4; ++cj) {
-    const int e = ci * 4 + cj;
-    float v = (red[(0 * 16 + e) * 64 + t64] + red[(1 * 16 + e) * 64 + t64]) +
-              (red[(2 * 16 + e) * 64 + t64] + red[(3 * 16 + e) * 64 + t64]);
-    const int j = j0 + (BRC ? tj + 8 * cj : tj * 4 + cj);
-    if (i < P.M && j < P.N) {
-      v = apply_epilogue(P, v, i, j, bias, aux0);
-      for (int d = 0; d < P.c_dups; ++d) C[d * P.c_dup_stride + (size_t)i * P.ldc + j] = v;
+    for (int cj = 0; cj < 4; ++cj) {
+      const int e = ci * 4 + cj;
+      float v = (red[(0 * 16 + e) * 64 + t64] + red[(1 * 16 + e) * 64 + t64]) +
+                (red[(2 * 16 + e) * 64 + t64] + red[(3 * 16 + e) * 64 + t64]);
+      const int jl = brc ? tj + 8 * cj : tj * 4 + cj;
+      const int j = j0 + jl;
+      if (i < P.M && j < P.N) {
+        if (epi != EPI_STORE) {
+          const float2 ev = apply_epilogue(epi, v, has_bias ? bias_s[jl] : 0.f, aux_read ? aux_s[il * kLd + jl] : 0.f, P.f0, P.f1);
+          v = ev.x;
+          if (epi == EPI_BIAS_TANH) aux0[(size_t)i * P.ldaux + j] = ev.y;
+        }
+#pragma unroll 1
+        for (int d = 0; d < P.c_dups; ++d) C[d * P.c_dup_stride + (size_t)i * P.ldc + j] = v;
+      }
     }
   }
   if (want_rowsum && tid < 32) {
     const int rti = tid >> 2, rc = tid & 3;
     const float s = (sdb[(0 * 8 + rti) * 4 + rc] + sdb[(1 * 8 + rti) * 4 + rc]) +
                     (sdb[(2 * 8 + rti) * 4 + rc] + sdb[(3 * 8 + rti) * 4 + rc]);
-    const int row = i0 + (ARC ? rti + 8 * rc : rti * 4 + rc);
+    const int row = i0 + (arc ? rti + 8 * rc : rti * 4 + rc);
     if (row < P.M) aux1[(long long)ks * P.M + row] = s;
   }
+  TP(5);
+  __syncthreads();                  // the next tile of this CTA refills the ring
+  TP(6);
 }
 
 // ------------------------------------------------------------------------------------
@@ -274,8 +358,9 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 __device__ __forceinline__ void group_ptrs(const Problem& P, int g, long long& go, long long& gi) {
-  go = g / P.groups_inner;
-  gi = g - go * P.groups_inner;
+  const int o = g / P.groups_inner;      // 32-bit division: the 64-bit one is a ~200-instruction routine
+  go = o;
+  gi = g - o * P.groups_inner;
 }
 
 __device__ __forceinline__ void ln_fwd_tile(const Problem& P, int tile) {
@@ -291,16 +376,19 @@ __device__ __forceinline__ void ln_fwd_tile(const Problem& P, int tile) {
   const float* beta = P.bias + go * P.bias_go + gi * P.bias_gi;
   float* y = P.C + go * P.c_go + gi * P.c_gi + (size_t)row * P.ldc;
   float s = 0.f;
+  #pragma unroll 2
   for (int j = lane; j < P.N; j += 32) s += x[j];
   const float mean = warp_sum(s) / (float)P.N;
   float ss = 0.f;
+  #pragma unroll 2
   for (int j = lane; j < P.N; j += 32) {
     const float d = x[j] - mean;
     ss = fmaf(d, d, ss);
   }
   const float var = warp_sum(ss) / (float)P.N;
   const float rstd = 1.f / sqrtf(var + P.f0);
-  for (int j = lane; j < P.N; j += 32) y[j] = (x[j] - mean) * rstd * __ldg(gamma + j) + __ldg(beta + j);
+  #pragma unroll 2
+  for (int j = lane; j < P.N; j += 32) y[j] = (x[j] - mean) * rstd * gamma[j] + beta[j];
   if (lane == 0) {
     (P.aux2 + go * P.aux2_go + gi * P.aux2_gi)[row] = mean;
     (P.aux3 + go * P.aux3_go + gi * P.aux3_gi)[row] = rstd;
@@ -324,17 +412,19 @@ __device__ __forceinline__ void ln_bwd_rows_tile(const Problem& P, int tile) {
   const float mean = (P.aux2 + go * P.aux2_go + gi * P.aux2_gi)[row];
   const float rstd = (P.aux3 + go * P.aux3_go + gi * P.aux3_gi)[row];
   float s1 = 0.f, s2 = 0.f;
+  #pragma unroll 2
   for (int j = lane; j < P.N; j += 32) {
-    const float gdy = dy[j] * __ldg(gamma + j);
+    const float gdy = dy[j] * gamma[j];
     const float xh = (x[j] - mean) * rstd;
     s1 += gdy;
     s2 = fmaf(gdy, xh, s2);
   }
   s1 = warp_sum(s1) / (float)P.N;
   s2 = warp_sum(s2) / (float)P.N;
+  #pragma unroll 2
   for (int j = lane; j < P.N; j += 32) {
     const float xv = x[j];
-    const float gdy = dy[j] * __ldg(gamma + j);
+    const float gdy = dy[j] * gamma[j];
     const float xh = (xv - mean) * rstd;
     float d = rstd * (gdy - s1 - xh * s2);
     if (P.epi == EPI_RELU_MASK && !(xv > 0.f)) d = 0.f;
@@ -356,6 +446,7 @@ __device__ __forceinline__ void ln_bwd_cols_tile(const Problem& P, int tile, flo
   const float* rstd = P.aux3 + go * P.aux3_go + gi * P.aux3_gi;
   float dg = 0.f, db = 0.f;
   if (j < P.N) {
+    #pragma unroll 4
     for (int m = rl; m < P.M; m += 8) {
       const float d = dy[(size_t)m * P.lda + j];
       const float xh = (x[(size_t)m * P.ldaux + j] - mean[m]) * rstd[m];
@@ -376,6 +467,7 @@ __device__ __forceinline__ void ln_bwd_cols_tile(const Problem& P, int tile, flo
     (P.C + go * P.c_go + gi * P.c_gi)[j] = sg;
     (P.aux1 + go * P.aux1_go + gi * P.aux1_gi)[j] = sb;
   }
+  __syncthreads();                  // scratch is reused by this CTA's next tile
 }
 
 // ------------------------------------------------------------------------------------
@@ -394,6 +486,7 @@ __device__ __forceinline__ void pool_fwd_tile(const Problem& P, int tile, float*
   const float* h = P.A + go * P.a_go + gi * P.a_gi + (size_t)b * P.K * P.lda;
   float s = 0.f;
   if (c < P.N)
+    #pragma unroll 4
     for (int n = rl; n < P.K; n += 8) s += h[(size_t)n * P.lda + c];
   smem[rl * 32 + lane] = s;
   __syncthreads();
@@ -405,6 +498,7 @@ __device__ __forceinline__ void pool_fwd_tile(const Problem& P, int tile, float*
     float* C = P.C + go * P.c_go + gi * P.c_gi;
     for (int d = 0; d < P.c_dups; ++d) C[d * P.c_dup_stride + (size_t)b * P.ldc + c] = v;
   }
+  __syncthreads();
 }
 
 // dH2[(b*K+n), c] = (A[b,c] / K) * (aux0[b,c] > 0) * (aux1[(b*K+n), c] > 0)
@@ -424,6 +518,7 @@ __device__ __forceinline__ void pool_bwd_tile(const Problem& P, int tile) {
   const float* h2 = P.aux1 + go * P.aux1_go + gi * P.aux1_gi + (size_t)row * P.ldb;
   float* out = P.C + go * P.c_go + gi * P.c_gi + (size_t)row * P.ldc;
   const float inv = 1.f / (float)P.K;
+  #pragma unroll 2
   for (int c = lane; c < P.N; c += 32) {
     const float gate = (pool[c] > 0.f && h2[c] > 0.f) ? 1.f : 0.f;
     out[c] = dp[c] * inv * gate;
@@ -443,10 +538,39 @@ __device__ __forceinline__ void reduce_splits_tile(const Problem& P, int tile) {
     const int e = t * 1024 + u * 256 + threadIdx.x;
     if (e < P.M) {
       float s = 0.f;
+      #pragma unroll 4
       for (int k = 0; k < P.K; ++k) s += part[(long long)k * P.c_split + e];
       out[e] = s;
     }
   }
+}
+
+// C[ks*c_split + j] = sum over this slice's rows i of A[i, j]  (A [K rows, lda], N columns; tile = 32-column strip)
+__device__ __forceinline__ void colsum_tile(const Problem& P, int tile, float* smem) {
+  const int g = tile / P.tiles_per_group;
+  int t = tile - g * P.tiles_per_group;
+  long long go, gi;
+  group_ptrs(P, g, go, gi);
+  const int ks = t / P.tiles_n, strip = t - ks * P.tiles_n;
+  const int rl = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int j = strip * 32 + lane;
+  const int per = (P.K + P.ksplit - 1) / P.ksplit;
+  const int r0 = ks * per, r1 = min(P.K, r0 + per);
+  const float* a = P.A + go * P.a_go + gi * P.a_gi;
+  float s = 0.f;
+  if (j < P.N) {
+#pragma unroll 4
+    for (int r = r0 + rl; r < r1; r += 8) s += a[(size_t)r * P.lda + j];
+  }
+  smem[rl * 32 + lane] = s;
+  __syncthreads();
+  if (rl == 0 && j < P.N) {
+    float tot = 0.f;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) tot += smem[r * 32 + lane];
+    (P.C + go * P.c_go + gi * P.c_gi)[(long long)ks * P.c_split + j] = tot;
+  }
+  __syncthreads();
 }
 
 // scalar C[g] = f0 * mean(A[0..M*N)) with A [M, lda]; one CTA per group
@@ -456,6 +580,7 @@ __device__ __forceinline__ void neg_mean_tile(const Problem& P, int tile, float*
   const float* a = P.A + go * P.a_go + gi * P.a_gi;
   float s = 0.f;
   const int total = P.M * P.N;
+  #pragma unroll 1
   for (int e = threadIdx.x; e < total; e += kStageThreads) {
     const int i = e / P.N, j = e - i * P.N;
     s += a[(size_t)i * P.lda + j];
@@ -468,33 +593,7 @@ __device__ __forceinline__ void neg_mean_tile(const Problem& P, int tile, float*
     for (int w = 0; w < kStageThreads / 32; ++w) tot += smem[w];
     (P.C + go * P.c_go + gi * P.c_gi)[0] = P.f0 * tot / (float)total;
   }
-}
-
-__global__ void __launch_bounds__(kStageThreads, 2) stage_kernel(const __grid_constant__ StageParams S) {
-  __shared__ __align__(16) float smem[kSmemFloats];
-  const int tile_global = blockIdx.x;
-  int pi = 0;
-#pragma unroll
-  for (int q = 1; q < kMaxProblemsPerStage; ++q)
-    if (q < S.n_problems && tile_global >= S.p[q].tile_begin) pi = q;
-  const Problem& P = S.p[pi];
-  const int tile = tile_global - P.tile_begin;
-  switch (P.kind) {
-    case PK_GEMM:
-      if (P.a_rc && P.b_rc) gemm_tile<true, true>(P, tile, smem);
-      else if (P.a_rc && !P.b_rc) gemm_tile<true, false>(P, tile, smem);
-      else if (!P.a_rc && !P.b_rc) gemm_tile<false, false>(P, tile, smem);
-      else gemm_tile<false, true>(P, tile, smem);
-      break;
-    case PK_LN_FWD: ln_fwd_tile(P, tile); break;
-    case PK_LN_BWD_ROWS: ln_bwd_rows_tile(P, tile); break;
-    case PK_LN_BWD_COLS: ln_bwd_cols_tile(P, tile, smem); break;
-    case PK_POOL_FWD: pool_fwd_tile(P, tile, smem); break;
-    case PK_POOL_BWD: pool_bwd_tile(P, tile); break;
-    case PK_REDUCE_SPLITS: reduce_splits_tile(P, tile); break;
-    case PK_NEG_MEAN: neg_mean_tile(P, tile, smem); break;
-    default: break;
-  }
+  __syncthreads();
 }
 
 }  // namespace td3

@@ -1,0 +1,87 @@
+"""The two GEMM tiles behind every nn.Linear / addmm / mm of the update (td3_gemm in the C ABI): the strict-fp32 FFMA
+tile and the tcgen05 TF32 tile, in all four operand orientations (forward, dX, dW), against torch fp32 on the same
+inputs.  Tolerances: fp32 tile rel 1e-5 (summation order); TF32 tile |d| <= 5e-3 * sqrt(K) * rms(A) * rms(B) per element
+(10-bit mantissa operands, fp32 accumulate) -- and TF32 must be *exact* on operands that are representable in TF32."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _gemm(lib, _lib, A, a_rc, B, b_rc, M, N, K, bias=None, relu=False, use_tc=True):
+    Cm = torch.full((M, N), float("nan"), device="cuda")
+    _lib.check(lib.td3_gemm(M, N, K, A.data_ptr(), A.stride(0), int(a_rc), B.data_ptr(), B.stride(0), int(b_rc),
+                            Cm.data_ptr(), Cm.stride(0), bias.data_ptr() if bias is not None else None, int(relu),
+                            int(use_tc), _lib.stream_ptr()))
+    return Cm
+
+
+def _operands(M, N, K, a_rc, b_rc, gen, exact_tf32=False):
+    A = torch.randn((M, K) if a_rc else (K, M), generator=gen)
+    B = torch.randn((N, K) if b_rc else (K, N), generator=gen)
+    if exact_tf32:   # keep 10 mantissa bits: products are then exact in fp32 and only the summation order differs
+        A = (A.view(torch.int32) & ~0x1FFF).view(torch.float32)
+        B = (B.view(torch.int32) & ~0x1FFF).view(torch.float32)
+    Am = A if a_rc else A.t()
+    Bm = B.t() if b_rc else B
+    return A.cuda(), B.cuda(), (Am.double() @ Bm.double())
+
+
+SHAPES = [(256, 300, 400), (256, 400, 300), (128, 32, 64), (100, 6, 300), (300, 400, 256), (384, 128, 1024), (130, 20, 96)]
+
+
+@pytest.mark.parametrize("a_rc,b_rc", [(1, 1), (1, 0), (0, 0), (0, 1)])
+@pytest.mark.parametrize("M,N,K", SHAPES)
+def test_tcgen05_tile_exact_on_tf32_representable_operands(M, N, K, a_rc, b_rc):
+    from td3_b200 import _lib
+    lib = _lib.require_cuda()
+    gen = torch.Generator().manual_seed(M * 7 + N * 3 + K)
+    A, B, want = _operands(M, N, K, a_rc, b_rc, gen, exact_tf32=True)
+    eligible = A.stride(0) % 4 == 0 and B.stride(0) % 4 == 0      # rows must be 16-byte copyable (cp.async.cg 16)
+    if not eligible:
+        with pytest.raises(RuntimeError, match="not eligible"):
+            _gemm(lib, _lib, A, a_rc, B, b_rc, M, N, K)
+        return
+    got = _gemm(lib, _lib, A, a_rc, B, b_rc, M, N, K).cpu().double()
+    assert torch.isfinite(got).all()
+    err = (got - want).abs().max().item()
+    assert err <= 1e-5 * np.sqrt(K) * 4, (err,)
+
+
+@pytest.mark.parametrize("a_rc,b_rc", [(1, 1), (1, 0), (0, 0), (0, 1)])
+def test_tcgen05_tile_tf32_rounding_bound_and_epilogue(a_rc, b_rc):
+    from td3_b200 import _lib
+    lib = _lib.require_cuda()
+    M, N, K = 256, 300, 400
+    gen = torch.Generator().manual_seed(5)
+    A, B, want = _operands(M, N, K, a_rc, b_rc, gen)
+    bias = torch.randn(N, generator=gen)
+    got = _gemm(lib, _lib, A, a_rc, B, b_rc, M, N, K, bias=bias.cuda(), relu=True).cpu().double()
+    want = torch.relu(want + bias.double())
+    err = (got - want).abs().max().item()
+    assert err <= 5e-3 * np.sqrt(K), err
+    assert err > 0          # it really ran in reduced precision (otherwise the fp32 tile was measured)
+
+
+@pytest.mark.parametrize("a_rc,b_rc", [(1, 1), (1, 0), (0, 0), (0, 1)])
+@pytest.mark.parametrize("M,N,K", [(256, 300, 400), (64, 1, 300), (400, 23, 256), (37, 53, 17)])
+def test_fp32_tile_matches_torch(M, N, K, a_rc, b_rc):
+    from td3_b200 import _lib
+    lib = _lib.require_cuda()
+    gen = torch.Generator().manual_seed(M + N + K)
+    A, B, want = _operands(M, N, K, a_rc, b_rc, gen)
+    got = _gemm(lib, _lib, A, a_rc, B, b_rc, M, N, K, use_tc=False).cpu().double()
+    assert (got - want).abs().max().item() <= 1e-5 * np.sqrt(K) * 4
+
+
+def test_ineligible_operands_are_refused_not_silently_rerouted():
+    from td3_b200 import _lib
+    lib = _lib.require_cuda()
+    A = torch.randn(64, 23, device="cuda")      # rows 92 bytes apart: not 16-byte copyable
+    B = torch.randn(32, 23, device="cuda")
+    Cm = torch.empty(64, 32, device="cuda")
+    rc = lib.td3_gemm(64, 32, 23, A.data_ptr(), 23, 1, B.data_ptr(), 23, 1, Cm.data_ptr(), 32, None, 0, 1, _lib.stream_ptr())
+    assert rc == -4
