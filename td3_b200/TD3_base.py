@@ -80,8 +80,20 @@ class TD3_base(object):
         self._workspace: Optional[torch.Tensor] = None
         self._planned_batch = 0
         self._global_batch = 0
-        self.critic_optimizer = PackedAdam(critic_family, lr, lambda: self._state[1])
-        self.actor_optimizer = PackedAdam(actor_family, lr, lambda: self._state[2])
+        self.critic_optimizer = PackedAdam(critic_family, lr, lambda: self._state[1], lambda t: self._set_adam_step(0, t, lr))
+        self.actor_optimizer = PackedAdam(actor_family, lr, lambda: self._state[2], lambda t: self._set_adam_step(1, t, lr))
+
+    def _set_adam_step(self, which: int, step: int, lr: float, betas=(0.9, 0.999)):
+        """Checkpoint restore: set the device-resident Adam step and the scalars derived from it (the layout
+        adam_tick maintains: csrc/misc.cuh)."""
+        step = int(step)
+        self._state[1 + which] = step
+        pw = self._state.view(torch.float64)
+        pw[4 + 2 * which], pw[5 + 2 * which] = betas[0] ** step, betas[1] ** step
+        if step > 0:
+            sc = self._state.view(torch.float32)
+            sc[20 + 2 * which] = lr / (1.0 - betas[0] ** step)
+            sc[21 + 2 * which] = (1.0 - betas[1] ** step) ** 0.5
 
     def __del__(self):
         h = getattr(self, "_handle", None)

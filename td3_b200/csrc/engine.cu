@@ -6,7 +6,10 @@
 // or fails with an error code.
 #include "../../include/td3_b200.h"
 
+#include <cuda.h>   // CUtensorMap types only: the driver entry point is looked up at run time, nothing links libcuda
+
 #include <atomic>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -51,20 +54,22 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 // launch list
 // ------------------------------------------------------------------------------------
 struct Launch {
-  enum Kind { STAGE, GATHER, LOSS, EW, COUNTER } kind = STAGE;
+  enum Kind { STAGE, GATHER, LOSS, EW, TICK } kind = STAGE;
   StageParams stage{};
   GatherParams gather{};
   LossParams loss{};
   EwParams ew{};
-  unsigned long long* counter = nullptr;
+  AdamTick tick{};
   int grid_x = 1, grid_y = 1;
 };
 
 int ensure_kernel_attrs() {
   static bool done = false;
   if (done) return TD3_OK;
-  CUDA_TRY(cudaFuncSetAttribute(stage_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynSmemBytes));
-  CUDA_TRY(cudaFuncSetAttribute(persistent_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynSmemBytes));
+  CUDA_TRY(cudaFuncSetAttribute(stage_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynSmemBytes));
+  CUDA_TRY(cudaFuncSetAttribute(stage_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynSmemBytes));
+  CUDA_TRY(cudaFuncSetAttribute(persistent_update_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynSmemBytes));
+  CUDA_TRY(cudaFuncSetAttribute(persistent_update_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynSmemBytes));
   done = true;
   return TD3_OK;
 }
@@ -75,7 +80,8 @@ int run_launch(const Launch& L, cudaStream_t s) {
       if (L.stage.total_tiles <= 0) return TD3_OK;
       int rc = ensure_kernel_attrs();
       if (rc != TD3_OK) return rc;
-      stage_kernel<<<L.stage.total_tiles, kStageThreads, kDynSmemBytes, s>>>(L.stage);
+      if (L.stage.any_tc) stage_kernel<true><<<L.stage.total_tiles, kStageThreads, kDynSmemBytes, s>>>(L.stage);
+      else stage_kernel<false><<<L.stage.total_tiles, kStageThreads, kDynSmemBytes, s>>>(L.stage);
       break;
     }
     case Launch::GATHER:
@@ -87,8 +93,8 @@ int run_launch(const Launch& L, cudaStream_t s) {
     case Launch::EW:
       adam_polyak_kernel<<<L.grid_x, kEwThreads, 0, s>>>(L.ew);
       break;
-    case Launch::COUNTER:
-      counter_add_kernel<<<1, 32, 0, s>>>(L.counter, 1ull);
+    case Launch::TICK:
+      adam_tick_kernel<<<1, 32, 0, s>>>(L.tick);
       break;
   }
   g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -122,6 +128,94 @@ Problem make_gemm(int M, int N, int K, const float* A, int lda, bool a_rc, const
   return p;
 }
 
+// ------------------------------------------------------------------------------------
+// TMA tensor maps for the tcgen05 tile's operands (tc.cuh).  One map per (operand, group).
+// ------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// Appends `groups` maps for operand A (is_a) or B of a tensor-core GEMM problem; false when the operand cannot be
+// described to the TMA unit (rows not 16-byte aligned): the tile then stages it with cp.async instead.
+bool encode_operand_maps(const Problem& p, bool is_a, int n_outer, int n_inner, std::vector<CUtensorMap>& out) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) return false;
+  const float* base = is_a ? p.A : p.B;
+  const long long ld = is_a ? p.lda : p.ldb, go = is_a ? p.a_go : p.b_go, gi = is_a ? p.a_gi : p.b_gi;
+  const int rc = is_a ? p.a_rc : p.b_rc;
+  const long long O = is_a ? p.M : p.N;
+  if (!aligned16(base) || (ld & 3) || (go & 3) || (gi & 3) || ld <= 0) return false;
+  const size_t first = out.size();
+  for (int o = 0; o < n_outer; ++o)
+    for (int i = 0; i < n_inner; ++i) {
+      CUtensorMap m;
+      cuuint64_t gdim[2], gstride[1] = {(cuuint64_t)ld * 4};
+      cuuint32_t box[2], estr[2] = {1, 1};
+      CUtensorMapSwizzle sw;
+      if (rc) {        // memory [O rows][K cols]: K-major atoms, box = 32 reduction steps x (128 | NT) rows
+        gdim[0] = (cuuint64_t)p.K; gdim[1] = (cuuint64_t)O;
+        box[0] = 32; box[1] = is_a ? 128 : (cuuint32_t)p.tc_nt;
+        sw = CU_TENSOR_MAP_SWIZZLE_128B;
+      } else {         // memory [K rows][O cols]: MN-major atoms with 32-byte swizzle base, box = 32 MN x 32 reduction rows
+        gdim[0] = (cuuint64_t)O; gdim[1] = (cuuint64_t)p.K;
+        box[0] = 32; box[1] = 32;
+        sw = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
+      }
+      void* addr = const_cast<float*>(base + o * go + i * gi);
+      CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, addr, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                       CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) {
+        out.resize(first);
+        return false;
+      }
+      out.push_back(m);
+    }
+  return true;
+}
+
+constexpr int kMaxTensorMaps = 1024;
+
+// Give every tensor-core problem of `seqs` its maps; `dev_maps` is the device array they will be copied to.
+bool attach_tensor_maps(std::initializer_list<std::vector<Launch>*> seqs, CUtensorMap* dev_maps, std::vector<CUtensorMap>& host) {
+  bool ok_all = true;
+  for (auto* seq : seqs)
+    for (Launch& L : *seq) {
+      if (L.kind != Launch::STAGE) continue;
+      for (int q = 0; q < L.stage.n_problems; ++q) {
+        Problem& p = L.stage.p[q];
+        p.tmapA = p.tmapB = nullptr;
+        if (p.kind != PK_GEMM || !p.use_tc) continue;
+        const int groups = p.tile_count / std::max(1, p.tiles_per_group);
+        const int n_inner = std::max(1, p.groups_inner), n_outer = std::max(1, groups / n_inner);
+        const size_t ia = host.size();
+        if (!encode_operand_maps(p, true, n_outer, n_inner, host)) { ok_all = false; continue; }
+        const size_t ib = host.size();
+        if (!encode_operand_maps(p, false, n_outer, n_inner, host) || (int)host.size() > kMaxTensorMaps) {
+          host.resize(ia);
+          ok_all = false;
+          continue;
+        }
+        p.tmapA = dev_maps + ia;
+        p.tmapB = dev_maps + ib;
+      }
+    }
+  return ok_all;
+}
+
+
 int g_sm_count = 148;
 // tensor-core policy of the plan being built: 0 = fp32 FFMA tiles only, 1 = TF32 tcgen05 tiles where eligible
 thread_local int g_tc_mode = 0;
@@ -136,9 +230,13 @@ void finalize_problem(Problem& p, GroupShape gs) {
       p.b_vec = aligned16(p.B) && ok4(p.ldb) && ok4(p.b_go) && ok4(p.b_gi) && ok4(p.b_rc ? p.K : p.N);
       p.c_vec = aligned16(p.C) && ok4(p.ldc) && ok4(p.c_go) && ok4(p.c_gi) && ok4(p.c_split) && ok4(p.c_dup_stride);
       p.aux_vec = p.aux0 && aligned16(p.aux0) && ok4(p.ldaux) && ok4(p.aux0_go) && ok4(p.aux0_gi);
-      // tcgen05 path: both operands must be 16-byte copyable (tc.cuh stages them with cp.async.cg 16) and the
-      // reduction long enough to be worth a 128-row tile; no fused row-sum there (PK_COLSUM does the bias gradient)
-      p.use_tc = g_tc_mode && p.a_vec && p.b_vec && p.K >= 64 && !(p.aux1 && p.epi == EPI_STORE);
+      // TF32 mode: contractions whose operands the TMA unit can address (16-byte aligned rows) and whose reduction
+      // is long enough to fill a 128-row tensor-core tile; no fused row-sum there (PK_COLSUM does the bias gradient)
+      auto tma_ok = [&](const float* base, long long ld, long long go_, long long gi_) {
+        return aligned16(base) && ok4(ld) && ok4(go_) && ok4(gi_) && ld > 0;
+      };
+      p.use_tc = g_tc_mode && p.K >= 64 && !(p.aux1 && p.epi == EPI_STORE) && tma_ok(p.A, p.lda, p.a_go, p.a_gi) &&
+                 tma_ok(p.B, p.ldb, p.b_go, p.b_gi) && encode_tiled_fn() != nullptr && !getenv("TD3_NO_TMA");
       if (p.use_tc) {
         p.tiles_m = (p.M + 127) / 128;
         int nt = p.N <= 16 ? 16 : 32;
@@ -304,6 +402,7 @@ struct td3_agent {
   // persistent-kernel programs (device copies live in the workspace region "program")
   StageRec* prog_dev = nullptr;
   long long* prof_dev = nullptr;
+  CUtensorMap* tmaps_dev = nullptr;
   int n_prog_critic = 0, n_prog_policy = 0;
   bool prog_dirty = true;
   int persist_grid = 0;
@@ -790,6 +889,7 @@ int plan_agent(td3_agent* a, long long batch) {
   float* da = ws.take((long long)nA * B * A, "d_action");
   float* eye = ws.take((long long)A * A, "eye");
   a->prof_dev = reinterpret_cast<long long*>(ws.take(2LL * 2 * 128 * 3, "prof"));
+  a->tmaps_dev = reinterpret_cast<CUtensorMap*>(ws.take((long long)kMaxTensorMaps * (long long)(sizeof(CUtensorMap) / 4), "tensor_maps"));
   a->prog_dev = reinterpret_cast<StageRec*>(ws.take(2LL * kMaxProgStages * (long long)(sizeof(StageRec) / 4), "program"));
 
   // ---- passes ----
@@ -862,7 +962,7 @@ int plan_agent(td3_agent* a, long long batch) {
     lp.q_gi = (long long)B * qw; lp.q_go = lp.q_gi * nq; lp.y_go = (long long)B * qw; lp.r_go = B;
     lp.discount = c.discount;
     lp.inv_norm = 1.f / (float)((a->global_batch > 0 ? a->global_batch : batch) * qw);
-    lp.counters = a->state_u64;
+    lp.tick = AdamTick{a->state_u64, 0, 0, c.lr_critic, c.beta1, c.beta2};
     a->seq_critic_fb.push_back(L);
     Dx0Spec none;
     auto s_b = build_backward(c, c.q, Wc, Gc, g_crit, B, cc, a->dq, qw, (long long)B * qw * nq, (long long)B * qw, true,
@@ -878,7 +978,7 @@ int plan_agent(td3_agent* a, long long batch) {
     e.beta1 = c.beta1; e.beta2 = c.beta2; e.eps = c.adam_eps; e.tau = c.tau;
     EwRange& r = e.r[0];
     r.p = a->critic.params; r.g = a->critic.grad; r.m = a->critic.exp_avg; r.v = a->critic.exp_avg_sq; r.tgt = nullptr;
-    r.n = qn * nq * nA; r.blk_begin = 0; r.t_ptr = a->state_u64 + 1; r.lr = c.lr_critic; r.do_adam = 1; r.do_polyak = 0;
+    r.n = qn * nq * nA; r.blk_begin = 0; r.sc_ptr = reinterpret_cast<const float*>(a->state_u64 + 10); r.do_adam = 1; r.do_polyak = 0;
     L.grid_x = (int)((r.n + kEwPerBlock - 1) / kEwPerBlock);
     a->seq_critic_apply.push_back(L);
   }
@@ -922,8 +1022,8 @@ int plan_agent(td3_agent* a, long long batch) {
     }
     {
       Launch L;
-      L.kind = Launch::COUNTER;
-      L.counter = a->state_u64 + 2;
+      L.kind = Launch::TICK;
+      L.tick = AdamTick{a->state_u64, 1, 0, c.lr_actor, c.beta1, c.beta2};
       a->seq_actor_fb.push_back(L);
     }
     Dx0Spec none;
@@ -943,10 +1043,18 @@ int plan_agent(td3_agent* a, long long batch) {
     const long long b0 = (r0.n + kEwPerBlock - 1) / kEwPerBlock;
     EwRange& r1 = e.r[1];
     r1.p = a->actor.params; r1.g = a->actor.grad; r1.m = a->actor.exp_avg; r1.v = a->actor.exp_avg_sq;
-    r1.tgt = a->actor.target; r1.n = an * nA; r1.blk_begin = b0; r1.t_ptr = a->state_u64 + 2; r1.lr = c.lr_actor;
+    r1.tgt = a->actor.target; r1.n = an * nA; r1.blk_begin = b0; r1.sc_ptr = reinterpret_cast<const float*>(a->state_u64 + 11);
     r1.do_adam = 1; r1.do_polyak = 1;
     L.grid_x = (int)(b0 + (r1.n + kEwPerBlock - 1) / kEwPerBlock);
     a->seq_actor_apply.push_back(L);
+  }
+  // TMA descriptors of every tensor-core operand (pointers are fixed from here on: torch owns the buffers)
+  if (g_tc_mode) {
+    std::vector<CUtensorMap> host;
+    if (!attach_tensor_maps({&a->seq_target, &a->seq_critic_fb, &a->seq_actor_fb}, a->tmaps_dev, host))
+      return fail(TD3_ERR_CUDA, "cuTensorMapEncodeTiled failed for a tensor-core operand (or more than %d maps needed)", kMaxTensorMaps);
+    if (!host.empty())
+      cudaMemcpy(a->tmaps_dev, host.data(), host.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice);
   }
   // constant buffers: dq_pi = -1/(B*qw) (d(-mean)/dQ1), identity for the slice problem
   {
@@ -1029,17 +1137,17 @@ int plan_sample(td3_agent* a, const td3_replay_view* rb, int rng_mode) {
 // ------------------------------------------------------------------------------------
 // persistent-kernel programs: the launch sequences re-expressed as stage records
 // ------------------------------------------------------------------------------------
-int append_records(std::vector<StageRec>& prog, const std::vector<Launch>& seq, unsigned long long** pending_counter) {
+int append_records(std::vector<StageRec>& prog, const std::vector<Launch>& seq, AdamTick* pending_tick) {
   for (const Launch& L : seq) {
-    if (L.kind == Launch::COUNTER) {          // folded into the next record: CTA 0 bumps it on entry
-      *pending_counter = L.counter;
+    if (L.kind == Launch::TICK) {             // folded into the next record: CTA 0 performs it on entry
+      *pending_tick = L.tick;
       continue;
     }
     StageRec r;
     memset(&r, 0, sizeof(r));
     r.barrier_after = 1;
-    r.inc_counter = *pending_counter;
-    *pending_counter = nullptr;
+    r.tick = *pending_tick;
+    *pending_tick = AdamTick{};
     switch (L.kind) {
       case Launch::STAGE:
         r.kind = SK_STAGE; r.u.st = L.stage; r.main_tiles = L.stage.total_tiles;
@@ -1063,7 +1171,7 @@ int append_records(std::vector<StageRec>& prog, const std::vector<Launch>& seq, 
 int build_programs(td3_agent* a, cudaStream_t s) {
   if (!a->prog_dirty) return TD3_OK;
   std::vector<StageRec> pc, pp;
-  unsigned long long* pend = nullptr;
+  AdamTick pend{};
   for (auto* seq : {&a->seq_sample, &a->seq_target, &a->seq_critic_fb, &a->seq_critic_apply}) append_records(pc, *seq, &pend);
   for (auto* seq : {&a->seq_sample, &a->seq_target, &a->seq_critic_fb}) append_records(pp, *seq, &pend);
   // The critic's Adam step does not feed the actor forward (only Q1's forward, three stages later, reads the
@@ -1101,7 +1209,9 @@ int build_programs(td3_agent* a, cudaStream_t s) {
   int dev = 0, sms = 0, per_sm = 0;
   CUDA_TRY(cudaGetDevice(&dev));
   CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, persistent_update_kernel, kStageThreads, kDynSmemBytes));
+  const bool tc = a->cfg.precision == TD3_PRECISION_TF32;
+  if (tc) CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, persistent_update_kernel<true>, kStageThreads, kDynSmemBytes));
+  else CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, persistent_update_kernel<false>, kStageThreads, kDynSmemBytes));
   if (per_sm < 1) return fail(TD3_ERR_CUDA, "persistent kernel does not fit on an SM");
   if (const char* e = getenv("TD3_PERSIST_CTAS_PER_SM")) per_sm = std::max(1, std::min(per_sm, atoi(e)));
   a->persist_grid = std::min(sms * per_sm, max_tiles);
@@ -1135,8 +1245,9 @@ int launch_persistent(td3_agent* a, long long total_it, int iterations, cudaStre
   static const bool want_prof = getenv("TD3_PERSIST_PROF") != nullptr;
   args.prof = want_prof ? a->prof_dev : nullptr;
   void* kargs[] = {&args};
-  cudaError_t e = cudaLaunchCooperativeKernel((void*)persistent_update_kernel, dim3(a->persist_grid), dim3(kStageThreads),
-                                              kargs, (size_t)kDynSmemBytes, s);
+  const void* fn = a->cfg.precision == TD3_PRECISION_TF32 ? (const void*)persistent_update_kernel<true>
+                                                           : (const void*)persistent_update_kernel<false>;
+  cudaError_t e = cudaLaunchCooperativeKernel(fn, dim3(a->persist_grid), dim3(kStageThreads), kargs, (size_t)kDynSmemBytes, s);
   if (e != cudaSuccess) {
     a->bar_reset = true;
     return fail(TD3_ERR_CUDA, "cudaLaunchCooperativeKernel: %s", cudaGetErrorString(e));
@@ -1236,7 +1347,7 @@ int td3_debug_set(int idx, int val) {
 #ifdef TD3_TILE_PROF
 int td3_debug_tile_prof(long long* out) {
   CUDA_TRY(cudaDeviceSynchronize());
-  CUDA_TRY(cudaMemcpyFromSymbol(out, td3::g_tp, sizeof(long long) * 128 * 8));
+  CUDA_TRY(cudaMemcpyFromSymbol(out, td3::g_tp, sizeof(long long) * 128 * 16));
   return TD3_OK;
 }
 #endif
@@ -1331,7 +1442,10 @@ int adam_polyak_step(float* params, const float* grad, float* exp_avg, float* ex
   e.beta1 = beta1; e.beta2 = beta2; e.eps = eps; e.tau = tau;
   EwRange& r = e.r[0];
   r.p = params; r.g = grad; r.m = exp_avg; r.v = exp_avg_sq; r.tgt = target; r.n = n; r.blk_begin = 0;
-  r.t_ptr = nullptr; r.t_val = t; r.lr = lr; r.do_adam = grad != nullptr; r.do_polyak = target != nullptr;
+  r.sc_ptr = nullptr;
+  r.step_size = (float)(lr / (1.0 - pow(beta1, (double)t)));      // torch/optim/adam.py: step_size, bias_correction2_sqrt
+  r.bc2_sqrt = (float)sqrt(1.0 - pow(beta2, (double)t));
+  r.do_adam = grad != nullptr; r.do_polyak = target != nullptr;
   L.grid_x = (int)((n + kEwPerBlock - 1) / kEwPerBlock);
   return run_launch(L, (cudaStream_t)stream);
 }
@@ -1345,11 +1459,18 @@ int td3_gemm(int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, int32
   g_tc_mode = use_tc ? 1 : 0;
   cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, 0);
   finalize_problem(p, GroupShape{1, 1});
-  if (use_tc && !p.use_tc)
-    return fail(TD3_ERR_UNSUPPORTED, "td3_gemm: operands are not eligible for the tcgen05 tile (16-byte aligned rows, K >= 64, "
-                                     "reduction extent a multiple of 4)");
   std::vector<Launch> seq;
   emit_stage(seq, {p});
+  if (use_tc) {
+    static CUtensorMap* scratch = nullptr;      // two maps; calls on one stream are ordered, concurrent streams must not share it
+    if (!scratch) CUDA_TRY(cudaMalloc(&scratch, 8 * sizeof(CUtensorMap)));
+    std::vector<CUtensorMap> host;
+    if (!p.use_tc)
+      return fail(TD3_ERR_UNSUPPORTED, "td3_gemm: operands are not eligible for the tcgen05 tile (TMA needs 16-byte aligned rows; K >= 64)");
+    if (!attach_tensor_maps({&seq}, scratch, host)) return fail(TD3_ERR_CUDA, "cuTensorMapEncodeTiled failed");
+    if (!host.empty())
+      CUDA_TRY(cudaMemcpyAsync(scratch, host.data(), host.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  }
   return run_seq(seq, (cudaStream_t)stream);
 }
 

@@ -23,7 +23,7 @@ __host__ __device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t
 
 __host__ __device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint64_t seed) {
   uint32_t k[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
-#pragma unroll
+#pragma unroll 1
   for (int r = 0; r < 10; ++r) philox_round(c, k);
 }
 
@@ -50,9 +50,11 @@ __device__ __forceinline__ float philox_normal(uint64_t seed, uint32_t stream, u
   const uint32_t a = pair ? c[2] : c[0], b = pair ? c[3] : c[1];
   const float u1 = ((float)(a >> 8) + 0.5f) * (1.0f / 16777216.0f);
   const float u2 = ((float)(b >> 8) + 0.5f) * (1.0f / 16777216.0f);
-  const float rad = sqrtf(-2.0f * logf(u1));
+  // fast intrinsics: the draws only need to be N(0,1) to ~1e-6, and the accurate logf/sincospif paths are several
+  // KB of code that every CTA of the update kernel would have to fetch once per update
+  const float rad = sqrtf(-2.0f * __logf(u1));
   float s, co;
-  sincospif(2.0f * u2, &s, &co);
+  __sincosf(6.28318530717958648f * u2, &s, &co);
   return (elem & 1u) ? rad * s : rad * co;
 }
 
@@ -153,6 +155,33 @@ __global__ void philox_indices_kernel(long long* idx, long long batch, long long
 //   loss     = sum_g mean((q_g - y)^2)
 // One CTA per agent (deterministic block reduction).  Also advances the device step counters.
 // ------------------------------------------------------------------------------------
+// ------------------------------------------------------------------------------------
+// Adam step bookkeeping, kept on the device so that graph replays / the persistent kernel need no host
+// involvement.  State block (u64 index): [1 + w] step count t, [4 + 2w], [5 + 2w] beta1^t, beta2^t as doubles,
+// [10 + w] = {float step_size = lr / (1 - beta1^t), float sqrt(1 - beta2^t)}  (w = 0 critic, 1 actor).
+// torch computes the same scalars in Python doubles (torch/optim/adam.py, _single_tensor_adam); the running
+// products differ from pow() by < t * 2^-53 relative, far below the fp32 rounding of the two scalars.
+// One thread calls this once per optimiser step.
+// ------------------------------------------------------------------------------------
+struct AdamTick {
+  unsigned long long* state;       // base of the u64 state block, or nullptr
+  int which, pad;
+  double lr, beta1, beta2;
+};
+
+__device__ __forceinline__ void adam_tick(const AdamTick& T) {
+  unsigned long long* st = T.state;
+  const unsigned long long t0 = st[1 + T.which];
+  double* pw = reinterpret_cast<double*>(st + 4 + 2 * T.which);
+  const double p1 = (t0 == 0 ? 1.0 : pw[0]) * T.beta1, p2 = (t0 == 0 ? 1.0 : pw[1]) * T.beta2;
+  pw[0] = p1;
+  pw[1] = p2;
+  float* sc = reinterpret_cast<float*>(st + 10 + T.which);
+  sc[0] = (float)(T.lr / (1.0 - p1));
+  sc[1] = (float)sqrt(1.0 - p2);
+  st[1 + T.which] = t0 + 1;
+}
+
 struct LossParams {
   const float* q; const float* tq; const float* r; const float* nd;
   float* y; float* dq; float* loss;
@@ -160,7 +189,7 @@ struct LossParams {
   long long q_gi, q_go;            // strides between twins / agents in q, tq, dq
   long long y_go, r_go;
   float discount, inv_norm;        // inv_norm = 1 / (global_batch * width)
-  unsigned long long* counters;    // [0] sample step, [1] critic Adam t  (both += 1 here)
+  AdamTick tick;                   // critic optimiser step (and [0] sample step += 1) done here by one thread
 };
 
 __device__ __forceinline__ void loss_body(const LossParams& L, int agent, float* red) {
@@ -192,9 +221,9 @@ __device__ __forceinline__ void loss_body(const LossParams& L, int agent, float*
     float tot = 0.f;
     for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += red[w];
     L.loss[agent] = tot * L.inv_norm;
-    if (agent == 0 && L.counters) {
-      atomicAdd(L.counters + 0, 1ull);
-      atomicAdd(L.counters + 1, 1ull);
+    if (agent == 0 && L.tick.state) {
+      L.tick.state[0] += 1;          // sampling step (Philox counter); single writer, read after the next barrier
+      adam_tick(L.tick);
     }
   }
 }
@@ -204,8 +233,8 @@ __global__ void __launch_bounds__(256) loss_kernel(const __grid_constant__ LossP
   loss_body(L, blockIdx.x, red);
 }
 
-__global__ void counter_add_kernel(unsigned long long* c, unsigned long long inc) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) atomicAdd(c, inc);
+__global__ void adam_tick_kernel(const __grid_constant__ AdamTick T) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) adam_tick(T);
 }
 
 // ------------------------------------------------------------------------------------
@@ -221,9 +250,8 @@ __global__ void counter_add_kernel(unsigned long long* c, unsigned long long inc
 struct EwRange {
   float* p; const float* g; float* m; float* v; float* tgt;
   long long n, blk_begin;
-  const unsigned long long* t_ptr;   // device-resident Adam step (already incremented), or
-  long long t_val;                   // host-supplied step when t_ptr == nullptr
-  double lr;
+  const float* sc_ptr;               // device-resident {step_size, sqrt(1 - beta2^t)} written by adam_tick, or
+  float step_size, bc2_sqrt;         // host-supplied scalars when sc_ptr == nullptr
   int do_adam, do_polyak;
 };
 
@@ -236,77 +264,75 @@ struct EwParams {
 constexpr int kEwThreads = 256;
 constexpr int kEwPerBlock = kEwThreads * 8;   // 2 float4 per thread
 
-// smem2: two floats of shared scratch.  bx = block index within the launch / stage.
-__device__ __forceinline__ void adam_polyak_body(const EwParams& E, long long bx, float* smem2) {
+__device__ __forceinline__ void ew_load4(const float* p, long long e, long long n, float (&v)[4]) {
+  if (e + 4 <= n) {
+    const float4 t = __ldcg(reinterpret_cast<const float4*>(p + e));
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  } else {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = e + k < n ? __ldcg(p + e + k) : 0.f;
+  }
+}
+__device__ __forceinline__ void ew_store4(float* p, long long e, long long n, const float (&v)[4]) {
+  if (e + 4 <= n) {
+    *reinterpret_cast<float4*>(p + e) = make_float4(v[0], v[1], v[2], v[3]);
+  } else {
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (e + k < n) p[e + k] = v[k];
+  }
+}
+
+// One element of torch's single-tensor Adam; out of line so the IEEE div/sqrt sequences exist once.
+__device__ __noinline__ float adam_element(float p, float g, float& m, float& v, float w1, float b2, float w2, float bc2s,
+                                          float eps, float neg_step) {
+  m = fmaf(w1, __fsub_rn(g, m), m);
+  v = __fadd_rn(__fmul_rn(v, b2), __fmul_rn(__fmul_rn(w2, g), g));
+  const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(v), bc2s), eps);
+  return __fadd_rn(p, __fdiv_rn(__fmul_rn(neg_step, m), denom));
+}
+
+// bx = block index within the launch / stage.  Rolled on purpose (code size: see stage.cuh).
+__device__ __forceinline__ void adam_polyak_body(const EwParams& E, long long bx) {
   int ri = 0;
   for (int q = 1; q < 3; ++q)
     if (q < E.n_ranges && bx >= E.r[q].blk_begin) ri = q;
   const EwRange& R = E.r[ri];
-  __syncthreads();
-  if (R.do_adam && threadIdx.x == 0) {
-    const double t = (double)(R.t_ptr ? (long long)__ldcg(R.t_ptr) : R.t_val);
-    const double bc1 = 1.0 - pow(E.beta1, t);
-    const double bc2 = 1.0 - pow(E.beta2, t);
-    smem2[0] = (float)(R.lr / bc1);
-    smem2[1] = (float)sqrt(bc2);
-  }
-  __syncthreads();
-  const float s_step_size = smem2[0], s_bc2_sqrt = smem2[1];
+  const float s_step_size = R.do_adam ? (R.sc_ptr ? __ldcg(R.sc_ptr) : R.step_size) : 0.f;
+  const float s_bc2_sqrt = R.do_adam ? (R.sc_ptr ? __ldcg(R.sc_ptr + 1) : R.bc2_sqrt) : 1.f;
   const float w1 = (float)(1.0 - E.beta1), b2 = (float)E.beta2, w2 = (float)(1.0 - E.beta2);
   const float eps = (float)E.eps, tau = (float)E.tau, omt = (float)(1.0 - E.tau);
-  const float neg_step = R.do_adam ? -s_step_size : 0.f;
-  const float bc2s = R.do_adam ? s_bc2_sqrt : 1.f;
+  const float neg_step = -s_step_size;
   const long long base = (bx - R.blk_begin) * kEwPerBlock;
-#pragma unroll
+#pragma unroll 1
   for (int u = 0; u < 2; ++u) {
     const long long e = base + ((long long)u * kEwThreads + threadIdx.x) * 4;
     if (e >= R.n) continue;
-    if (e + 4 <= R.n) {
-      float4 p = __ldcg(reinterpret_cast<const float4*>(R.p + e));
-      float pv[4] = {p.x, p.y, p.z, p.w};
-      if (R.do_adam) {
-        const float4 g4 = __ldcg(reinterpret_cast<const float4*>(R.g + e));
-        float4 m4 = __ldcg(reinterpret_cast<const float4*>(R.m + e));
-        float4 v4 = __ldcg(reinterpret_cast<const float4*>(R.v + e));
-        float gv[4] = {g4.x, g4.y, g4.z, g4.w}, mv[4] = {m4.x, m4.y, m4.z, m4.w}, vv[4] = {v4.x, v4.y, v4.z, v4.w};
+    float pv[4];
+    ew_load4(R.p, e, R.n, pv);
+    if (R.do_adam) {
+      float gv[4], mv[4], vv[4];
+      ew_load4(R.g, e, R.n, gv);
+      ew_load4(R.m, e, R.n, mv);
+      ew_load4(R.v, e, R.n, vv);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          mv[k] = fmaf(w1, __fsub_rn(gv[k], mv[k]), mv[k]);
-          vv[k] = __fadd_rn(__fmul_rn(vv[k], b2), __fmul_rn(__fmul_rn(w2, gv[k]), gv[k]));
-          const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(vv[k]), bc2s), eps);
-          pv[k] = __fadd_rn(pv[k], __fdiv_rn(__fmul_rn(neg_step, mv[k]), denom));
-        }
-        *reinterpret_cast<float4*>(R.m + e) = make_float4(mv[0], mv[1], mv[2], mv[3]);
-        *reinterpret_cast<float4*>(R.v + e) = make_float4(vv[0], vv[1], vv[2], vv[3]);
-        *reinterpret_cast<float4*>(R.p + e) = make_float4(pv[0], pv[1], pv[2], pv[3]);
-      }
-      if (R.do_polyak) {
-        const float4 t4 = __ldcg(reinterpret_cast<const float4*>(R.tgt + e));
-        float tv[4] = {t4.x, t4.y, t4.z, t4.w};
+      for (int k = 0; k < 4; ++k) pv[k] = adam_element(pv[k], gv[k], mv[k], vv[k], w1, b2, w2, s_bc2_sqrt, eps, neg_step);
+      ew_store4(R.m, e, R.n, mv);
+      ew_store4(R.v, e, R.n, vv);
+      ew_store4(R.p, e, R.n, pv);
+    }
+    if (R.do_polyak) {
+      float tv[4];
+      ew_load4(R.tgt, e, R.n, tv);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) tv[k] = __fadd_rn(__fmul_rn(tau, pv[k]), __fmul_rn(omt, tv[k]));
-        *reinterpret_cast<float4*>(R.tgt + e) = make_float4(tv[0], tv[1], tv[2], tv[3]);
-      }
-    } else {
-      for (long long k = e; k < R.n; ++k) {
-        float pvk = __ldcg(R.p + k);
-        if (R.do_adam) {
-          const float g = __ldcg(R.g + k), m0 = __ldcg(R.m + k);
-          const float m = fmaf(w1, __fsub_rn(g, m0), m0);
-          const float v = __fadd_rn(__fmul_rn(__ldcg(R.v + k), b2), __fmul_rn(__fmul_rn(w2, g), g));
-          const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(v), bc2s), eps);
-          pvk = __fadd_rn(pvk, __fdiv_rn(__fmul_rn(neg_step, m), denom));
-          R.m[k] = m; R.v[k] = v; R.p[k] = pvk;
-        }
-        if (R.do_polyak) R.tgt[k] = __fadd_rn(__fmul_rn(tau, pvk), __fmul_rn(omt, __ldcg(R.tgt + k)));
-      }
+      for (int k = 0; k < 4; ++k) tv[k] = __fadd_rn(__fmul_rn(tau, pv[k]), __fmul_rn(omt, tv[k]));
+      ew_store4(R.tgt, e, R.n, tv);
     }
   }
 }
 
 __global__ void __launch_bounds__(kEwThreads) adam_polyak_kernel(const __grid_constant__ EwParams E) {
-  __shared__ float smem2[2];
-  adam_polyak_body(E, blockIdx.x, smem2);
+  adam_polyak_body(E, blockIdx.x);
 }
 
 }  // namespace td3

@@ -14,7 +14,7 @@ namespace td3 {
 
 // dynamic shared memory of both kernels: 1 KB alignment slack + the tensor-core operand ring.  The FFMA tile's
 // cp.async ring, epilogue tile and bias strip (kSmemBytes) alias the start of the same region.
-constexpr int kDynSmemBytes = 1024 + kTcRingBytes;
+constexpr int kDynSmemBytes = 1024 + kTcRingBytes + 512;   // + bias strip of the TC epilogue
 static_assert(kSmemBytes <= kTcRingBytes, "FFMA tile buffers must fit inside the TC ring");
 
 __device__ __forceinline__ unsigned char* aligned_smem(unsigned char* raw) {
@@ -22,7 +22,9 @@ __device__ __forceinline__ unsigned char* aligned_smem(unsigned char* raw) {
   return raw + ((1024u - (a & 1023u)) & 1023u);
 }
 
-// one tile of a stage: look up the problem the tile index falls into and run it
+// one tile of a stage: look up the problem the tile index falls into and run it.  kTc selects which GEMM tile is
+// compiled in: the tensor-core kernels carry no FFMA GEMM code and vice versa (instruction footprint).
+template <bool kTc>
 __device__ __forceinline__ void run_stage_tile(const StageParams& S, int tile_global, unsigned char* ring, TcState* tc) {
   int pi = 0;
 #pragma unroll
@@ -33,8 +35,10 @@ __device__ __forceinline__ void run_stage_tile(const StageParams& S, int tile_gl
   float* smem = reinterpret_cast<float*>(ring);
   switch (P.kind) {
     case PK_GEMM:
-      if (P.use_tc) gemm_tile_tc(P, tile, ring, tc);
-      else gemm_tile(P, tile, smem);
+      if constexpr (kTc) {
+        if (P.use_tc) { gemm_tile_tc(P, tile, ring, tc); break; }
+      }
+      gemm_tile(P, tile, smem);
       break;
     case PK_LN_FWD: ln_fwd_tile(P, tile); break;
     case PK_LN_BWD_ROWS: ln_bwd_rows_tile(P, tile); break;
@@ -49,13 +53,18 @@ __device__ __forceinline__ void run_stage_tile(const StageParams& S, int tile_gl
 }
 
 // stage-per-launch form (phase-by-phase API, CUDA-graph mode, B=small inference)
+template <bool kTc>
 __global__ void __launch_bounds__(kStageThreads, 1) stage_kernel(const __grid_constant__ StageParams S) {
   extern __shared__ unsigned char smem_raw[];
   __shared__ TcState tc;
   unsigned char* ring = aligned_smem(smem_raw);
-  if (S.any_tc) tc_setup(&tc);
-  run_stage_tile(S, blockIdx.x, ring, &tc);
-  if (S.any_tc) tc_teardown(&tc);
+  if constexpr (kTc) {
+    if (S.any_tc) tc_setup(&tc);
+  }
+  run_stage_tile<kTc>(S, blockIdx.x, ring, &tc);
+  if constexpr (kTc) {
+    if (S.any_tc) tc_teardown(&tc);
+  }
 }
 
 enum StageKind : int { SK_STAGE = 0, SK_GATHER = 1, SK_LOSS = 2, SK_EW_ONLY = 3 };
@@ -66,8 +75,7 @@ struct alignas(16) StageRec {
   int ew_tiles;                     // Adam/Polyak blocks appended after the main tiles (independent of them)
   int barrier_after;                // 0: the next stage does not depend on this one
   int gather_grid_x, pad0, pad1, pad2;
-  unsigned long long* inc_counter;  // CTA 0 adds 1 when it enters the stage (actor Adam step), or nullptr
-  unsigned long long pad3;
+  AdamTick tick;                    // tick.state != nullptr: CTA 0 performs the actor optimiser tick on entering the stage
   union Main {
     StageParams st;
     GatherParams g;
@@ -110,13 +118,14 @@ __device__ __forceinline__ void fetch_rec(StageRec* dst, const StageRec* src) {
   for (int i = threadIdx.x; i < kWords; i += blockDim.x) d4[i] = __ldcg(s4 + i);
 }
 
+template <bool kTc>
 __global__ void __launch_bounds__(kStageThreads, 1) persistent_update_kernel(const __grid_constant__ PersistArgs a) {
   extern __shared__ unsigned char smem_raw[];
   __shared__ StageRec rec[2];
   __shared__ TcState tc;
   __shared__ float red[8];
   unsigned char* ring = aligned_smem(smem_raw);
-  tc_setup(&tc);
+  if constexpr (kTc) tc_setup(&tc);
   int slot = 0;
   unsigned int bar_target = a.barrier_base;
   {
@@ -134,15 +143,16 @@ __global__ void __launch_bounds__(kStageThreads, 1) persistent_update_kernel(con
       long long* pr = prof ? a.prof + ((blockIdx.x == 0 ? 0 : 128) + s) * 3 : nullptr;
       if (prof) pr[0] = clock64();
 #ifdef TD3_TILE_PROF
-      if (threadIdx.x == 0 && blockIdx.x == 0) g_tp_stage = prof ? s : -1;
+      if (threadIdx.x == 0) tc.prof_stage = (a.prof && it == a.iterations - 1) ? s : -1;
+      __syncthreads();
 #endif
-      if (blockIdx.x == 0 && threadIdx.x == 0 && R.inc_counter) atomicAdd(R.inc_counter, 1ull);
+      if (blockIdx.x == 0 && threadIdx.x == 0 && R.tick.state) adam_tick(R.tick);
       const int total = R.main_tiles + R.ew_tiles;
       for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
         if (tile >= R.main_tiles) {
-          adam_polyak_body(R.ew, tile - R.main_tiles, red);
+          adam_polyak_body(R.ew, tile - R.main_tiles);
         } else if (R.kind == SK_STAGE) {
-          run_stage_tile(R.u.st, tile, ring, &tc);
+          run_stage_tile<kTc>(R.u.st, tile, ring, &tc);
         } else if (R.kind == SK_GATHER) {
           gather_body(R.u.g, tile % R.gather_grid_x, tile / R.gather_grid_x);
         } else if (R.kind == SK_LOSS) {
@@ -168,7 +178,7 @@ __global__ void __launch_bounds__(kStageThreads, 1) persistent_update_kernel(con
       if (prof) pr[2] = clock64();
     }
   }
-  tc_teardown(&tc);
+  if constexpr (kTc) tc_teardown(&tc);
 }
 
 }  // namespace td3

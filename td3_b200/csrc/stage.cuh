@@ -51,6 +51,7 @@ struct Problem {
   int tc_nt, c_vec, aux_vec;      // TC tile width; 16-byte stores to C / loads from aux0 are legal
   long long c_split, c_dup_stride;
   const float* A; const float* B; float* C; const float* bias;
+  const void* tmapA; const void* tmapB;   // device arrays of CUtensorMap (one per group) when the operand is TMA-loadable
   float* aux0; float* aux1; float* aux2; float* aux3;
   // per-group pointer strides (floats): *_go outer group (agent), *_gi inner group (twin)
   long long a_go, a_gi, b_go, b_gi, c_go, c_gi, bias_go, bias_gi;
@@ -100,7 +101,7 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // rc: rows index the output dim, cols the reduction; oc: the opposite.  The shared image keeps the
 // global orientation (rows kLd floats apart).
 #ifdef TD3_TILE_PROF
-__device__ long long g_tp[128 * 8];
+__device__ long long g_tp[128 * 16];
 __device__ int g_tp_stage = -1;
 #define TP(k) do { if (threadIdx.x == 0 && blockIdx.x == 0 && g_tp_stage >= 0) g_tp[g_tp_stage * 8 + (k)] = clock64(); } while (0)
 #else
@@ -133,26 +134,40 @@ __device__ __forceinline__ void issue_chunk(float* dst, const Operand& op, int k
   }
 }
 
-// Kept out of line on purpose: the update kernel runs ~20 different stages back to back, so its
-// instruction footprint (not its FLOPs) decides how long a tile takes; one copy of the epilogue.
-__device__ __noinline__ float2 apply_epilogue(int epi, float v, float bias, float aux, float f0, float f1) {
-  switch (epi) {                       // .x = output value, .y = value to store into aux0 (EPI_BIAS_TANH only)
-    case EPI_BIAS: return make_float2(v + bias, 0.f);
-    case EPI_BIAS_RELU: return make_float2(fmaxf(v + bias, 0.f), 0.f);
-    case EPI_BIAS_TANH: {
-      const float y = tanhf(v + bias);
-      return make_float2(f0 * y, y);
-    }
-    case EPI_BIAS_TANH_NOISE: {
-      float a = f0 * tanhf(v + bias) + aux;
-      if (f1 > 0.f) a = fminf(fmaxf(a, -f1), f1);
-      return make_float2(a, 0.f);
-    }
-    case EPI_RELU_MASK: return make_float2(aux > 0.f ? v : 0.f, 0.f);
-    case EPI_TANH_GRAD: return make_float2(v * f0 * (1.f - aux * aux), 0.f);
-    default: return make_float2(v, 0.f);
+// The update kernel runs ~20 different stages back to back and every tile walks its prologue and epilogue
+// exactly once, so the instruction footprint (unique 128-byte lines fetched, not instructions executed)
+// decides how long the once-per-tile code takes: epilogues are ROLLED loops with one copy of this switch.
+template <int EPI>
+__device__ __forceinline__ float epi_apply(float v, float bias, float aux, float f0, float f1, float& aux_out) {
+  if (EPI == EPI_BIAS) return v + bias;
+  if (EPI == EPI_BIAS_RELU) return fmaxf(v + bias, 0.f);
+  if (EPI == EPI_BIAS_TANH) {
+    const float y = tanhf(v + bias);
+    aux_out = y;                       // stored into aux0 by the caller
+    return f0 * y;
   }
+  if (EPI == EPI_BIAS_TANH_NOISE) {
+    float a = f0 * tanhf(v + bias) + aux;
+    if (f1 > 0.f) a = fminf(fmaxf(a, -f1), f1);
+    return a;
+  }
+  if (EPI == EPI_RELU_MASK) return aux > 0.f ? v : 0.f;
+  if (EPI == EPI_TANH_GRAD) return v * f0 * (1.f - aux * aux);
+  return v;
 }
+
+// The epilogue kind is dispatched ONCE per tile (a switch per element cost ~400 cycles each on B200: an indirect
+// branch over the two tanhf bodies); the per-kind code below is straight-line.
+#define TD3_DISPATCH_EPI(epi, CALL)                                        \
+  switch (epi) {                                                           \
+    case EPI_BIAS: { constexpr int E = EPI_BIAS; CALL; } break;            \
+    case EPI_BIAS_RELU: { constexpr int E = EPI_BIAS_RELU; CALL; } break;  \
+    case EPI_BIAS_TANH: { constexpr int E = EPI_BIAS_TANH; CALL; } break;  \
+    case EPI_BIAS_TANH_NOISE: { constexpr int E = EPI_BIAS_TANH_NOISE; CALL; } break; \
+    case EPI_RELU_MASK: { constexpr int E = EPI_RELU_MASK; CALL; } break;  \
+    case EPI_TANH_GRAD: { constexpr int E = EPI_TANH_GRAD; CALL; } break;  \
+    default: { constexpr int E = EPI_STORE; CALL; } break;                 \
+  }
 
 // 8 reduction steps (this thread's k-group share of a 32-wide chunk) of the 4x4 micro-tile
 template <bool ARC, bool BRC>
@@ -197,6 +212,29 @@ __device__ __forceinline__ void fma_block(const float* __restrict__ As, const fl
     if (want_rowsum) {
 #pragma unroll
       for (int ci = 0; ci < 4; ++ci) asum[ci] += (a[ci][0] + a[ci][1]) + (a[ci][2] + a[ci][3]);
+    }
+  }
+}
+
+template <int EPI>
+__device__ __forceinline__ void ffma_epilogue(const Problem& P, float* __restrict__ C, float* aux0, const float* red,
+                                              const float* aux_s, const float* bias_s, bool aux_read, int i0, int j0, int il,
+                                              int ci, int t64, int tj, int brc) {
+  const bool has_bias = P.bias != nullptr;
+  const int i = i0 + il;
+#pragma unroll
+  for (int cj = 0; cj < 4; ++cj) {
+    const int e = ci * 4 + cj;
+    float v = (red[(0 * 16 + e) * 64 + t64] + red[(1 * 16 + e) * 64 + t64]) +
+              (red[(2 * 16 + e) * 64 + t64] + red[(3 * 16 + e) * 64 + t64]);
+    const int jl = brc ? tj + 8 * cj : tj * 4 + cj;
+    const int j = j0 + jl;
+    if (i < P.M && j < P.N) {
+      float aux_out = 0.f;
+      v = epi_apply<EPI>(v, has_bias ? bias_s[jl] : 0.f, aux_read ? aux_s[il * kLd + jl] : 0.f, P.f0, P.f1, aux_out);
+      if (EPI == EPI_BIAS_TANH) aux0[(size_t)i * P.ldaux + j] = aux_out;
+#pragma unroll 1
+      for (int d = 0; d < P.c_dups; ++d) C[d * P.c_dup_stride + (size_t)i * P.ldc + j] = v;
     }
   }
 }
@@ -313,27 +351,9 @@ __device__ __forceinline__ void gemm_tile(const Problem& P, int tile, float* sme
 
   {
     float* __restrict__ C = P.C + go * P.c_go + gi * P.c_gi + (long long)ks * P.c_split;
-    const bool has_bias = P.bias != nullptr;
     const int ci = kg;
     const int il = arc ? ti + 8 * ci : ti * 4 + ci;      // row / column of this thread's outputs inside the tile
-    const int i = i0 + il;
-#pragma unroll
-    for (int cj = 0; cj < 4; ++cj) {
-      const int e = ci * 4 + cj;
-      float v = (red[(0 * 16 + e) * 64 + t64] + red[(1 * 16 + e) * 64 + t64]) +
-                (red[(2 * 16 + e) * 64 + t64] + red[(3 * 16 + e) * 64 + t64]);
-      const int jl = brc ? tj + 8 * cj : tj * 4 + cj;
-      const int j = j0 + jl;
-      if (i < P.M && j < P.N) {
-        if (epi != EPI_STORE) {
-          const float2 ev = apply_epilogue(epi, v, has_bias ? bias_s[jl] : 0.f, aux_read ? aux_s[il * kLd + jl] : 0.f, P.f0, P.f1);
-          v = ev.x;
-          if (epi == EPI_BIAS_TANH) aux0[(size_t)i * P.ldaux + j] = ev.y;
-        }
-#pragma unroll 1
-        for (int d = 0; d < P.c_dups; ++d) C[d * P.c_dup_stride + (size_t)i * P.ldc + j] = v;
-      }
-    }
+    TD3_DISPATCH_EPI(epi, (ffma_epilogue<E>(P, C, aux0, red, aux_s, bias_s, aux_read, i0, j0, il, ci, t64, tj, brc)));
   }
   if (want_rowsum && tid < 32) {
     const int rti = tid >> 2, rc = tid & 3;

@@ -262,8 +262,8 @@ class PackedAdam:
     exp_avg_sq}`` in ``parameters()`` order, one param group.
     """
 
-    def __init__(self, family: PackedFamily, lr: float, step_ref, betas=(0.9, 0.999), eps=1e-8):
-        self.family, self._step_ref = family, step_ref       # step_ref: () -> 0-dim int64 device tensor view
+    def __init__(self, family: PackedFamily, lr: float, step_ref, set_step, betas=(0.9, 0.999), eps=1e-8):
+        self.family, self._step_ref, self._set_step = family, step_ref, set_step   # step_ref: () -> 0-dim int64 device view
         self.defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=0, amsgrad=False, maximize=False, foreach=None,
                              capturable=False, differentiable=False, fused=None, decoupled_weight_decay=False)
         self.param_groups = [dict(self.defaults, params=list(family.online_module.parameters()))]
@@ -301,7 +301,7 @@ class PackedAdam:
                 steps.add(0)
         if len(steps) > 1:
             raise ValueError("per-parameter Adam step counts differ; the packed optimiser keeps one step per network")
-        self._step_ref().fill_(steps.pop() if steps else 0)
+        self._set_step(steps.pop() if steps else 0)
         g = sd["param_groups"][0]
         if abs(g["lr"] - self.defaults["lr"]) > 0 or tuple(g["betas"]) != tuple(self.defaults["betas"]):
             raise ValueError("loading an optimizer with different lr/betas is not supported (hyper-parameters are fixed "

@@ -24,13 +24,13 @@ def philox_index(seed, stream, step, elem, size):
 
 
 def make_featured(S=17, A=6, rows=512, norm=None, actor_widths=(500, 400, 300), q_widths=(500, 400, 200), lr=1e-3,
-                  seed=0, **hyper):
+                  seed=0, precision=None, **hyper):
     from td3_b200.TD3_featured import TD3
     from td3_b200.my_replay_buffer import ReplayBuffer_featured
     obs, act = O.Space(S), O.Space(A)
     torch.manual_seed(seed)
     ora = O.TD3Featured(obs, act, norm=norm, lr=lr, actor_widths=actor_widths, q_widths=q_widths, **hyper)
-    ours = TD3(obs, act, norm=norm, lr=lr, actor_widths=actor_widths, q_widths=q_widths, seed=1, **hyper)
+    ours = TD3(obs, act, norm=norm, lr=lr, actor_widths=actor_widths, q_widths=q_widths, seed=1, precision=precision, **hyper)
     copy_weights(ora, ours)
     data = O.synthetic_transitions_featured(rows, S, A, seed=0)
     orb = O.ReplayFeatured(obs, act, rows)
@@ -40,13 +40,13 @@ def make_featured(S=17, A=6, rows=512, norm=None, actor_widths=(500, 400, 300), 
     return ora, orb, ours, rb
 
 
-def make_particles(F=8, N=64, D=6, A=3, rows=64, norm=None, CDQ=True, lr=1e-3, seed=0, **hyper):
+def make_particles(F=8, N=64, D=6, A=3, rows=64, norm=None, CDQ=True, lr=1e-3, seed=0, precision=None, **hyper):
     from td3_b200.TD3_particles import TD3
     from td3_b200.my_replay_buffer import ReplayBuffer_particles
     obs, act = (O.Space(F), O.Space(N, D)), O.Space(A)
     torch.manual_seed(seed)
     ora = O.TD3Particles(obs, act, norm=norm, CDQ=CDQ, lr=lr, **hyper)
-    ours = TD3(obs, act, norm=norm, CDQ=CDQ, lr=lr, seed=1, **hyper)
+    ours = TD3(obs, act, norm=norm, CDQ=CDQ, lr=lr, seed=1, precision=precision, **hyper)
     copy_weights(ora, ours)
     data = O.synthetic_transitions_particles(rows, F, N, D, A, seed=0)
     orb = O.ReplayParticles(obs, act, rows)

@@ -8,7 +8,7 @@ Stated tolerances (strict-fp32 FFMA path; differences are summation order only):
     ~lr per step whatever the gradient's magnitude, so elements whose gradient is at summation-order noise level
     take different +-lr steps; through LayerNorm's 1/sigma that difference grows ~2x per update (measured
     7.7e-5 at update 4, 2.5e-4 at update 6) while staying far below the effect of any logic error (>1e-2).
-  parameters after N updates  per-tensor relative L2 <= 2e-4, max |d| <= 0.2 * lr * N
+  parameters after N updates  per-tensor relative L2 <= 2e-4 (norm="layer": 2e-3), max |d| <= 0.2 * lr * N
     (Adam divides by sqrt(v): an element whose gradient is at rounding-noise level can move by a
      fraction of lr in a different direction; such elements are rare and bounded by lr per step)
 """
@@ -26,7 +26,7 @@ from oracle import make_golden as MG
 pytestmark = pytest.mark.gpu
 
 
-def _run(ora, orb, ours, rb, B, steps, A, rows, lr, seed=7, check_every=1, use_graph=True, tol=2e-5, tol_fn=None):
+def _run(ora, orb, ours, rb, B, steps, A, rows, lr, seed=7, check_every=1, use_graph=True, tol=2e-5, tol_fn=None, tol_params=2e-4):
     rs = np.random.RandomState(seed)
     worst = None
     for t in range(steps):
@@ -50,7 +50,7 @@ def _run(ora, orb, ours, rb, B, steps, A, rows, lr, seed=7, check_every=1, use_g
         if ora.trace["actor_loss"] is not None:
             al = float(ours.last_actor_loss[0].item())
             assert abs(al - ora.trace["actor_loss"]) <= tol * max(1.0, abs(ora.trace["actor_loss"])), (t, al)
-        worst = compare_nets(ours, ora, tol_rel=2e-4, max_abs=0.2 * lr * (t + 1), label=f"step {t}")
+        worst = compare_nets(ours, ora, tol_rel=tol_params, max_abs=0.2 * lr * (t + 1), label=f"step {t}")
     assert ours.total_it == ora.total_it == steps
     return worst
 
@@ -61,7 +61,8 @@ def test_trajectory_matches_oracle(norm, widths):
     aw, qw = ((500, 400, 300), (500, 400, 200)) if widths == "fork" else ((400, 300), (400, 300))
     ora, orb, ours, rb = make_featured(norm=norm, actor_widths=aw, q_widths=qw, lr=1e-3)
     worst = _run(ora, orb, ours, rb, B=64, steps=10, A=6, rows=512, lr=1e-3,
-                 tol_fn=(lambda t: 5e-5 if t < 2 else 2e-3) if norm == "layer" else None)
+                 tol_fn=(lambda t: 5e-5 if t < 2 else 2e-3) if norm == "layer" else None,
+                 tol_params=2e-3 if norm == "layer" else 2e-4)
     print(f"featured norm={norm} widths={widths}: worst param rel err {worst}")
 
 
@@ -161,3 +162,30 @@ def test_host_rng_mode_reproduces_seeded_reference_run():
         ours.train(rb, 64)
     got = float(ours.last_critic_loss[0].item())
     assert abs(got - want) <= 5e-5 * max(1.0, abs(want)), (got, want)
+
+
+@pytest.mark.parametrize("norm", [None, "layer"])
+@pytest.mark.parametrize("mode", ["persistent", "graph"])
+def test_tf32_tensor_core_path_tracks_the_fp32_oracle(norm, mode):
+    """precision="tf32": the K >= 64 layer GEMMs run on tcgen05 (operands truncated to 10 mantissa bits, fp32
+    accumulation in TMEM).  Stated tolerance against the fp32 CPU oracle over 10 updates at lr = 1e-3:
+    Q-values / Bellman target |d| <= 2e-2 * max(1, |Q|), critic loss rel 3e-2, parameters per-tensor relative L2 <= 5e-2."""
+    ora, orb, ours, rb = make_featured(norm=norm, actor_widths=(400, 300), q_widths=(400, 300), rows=2048, lr=1e-3,
+                                       precision="tf32")
+    ours.exec_mode = mode
+    rs = np.random.RandomState(7)
+    worst_q = worst_l = 0.0
+    for t in range(10):
+        idx = rs.randint(0, 2048, size=256)
+        nz = rs.standard_normal((256, 6)).astype(np.float32)
+        ora.train(orb, 256, indices=idx, noise=nz)
+        ours.train(rb, 256, indices=idx, noise=nz)
+        dbg = ours.debug_tensors()
+        want, got = ora.trace["critic_loss"], float(ours.last_critic_loss[0].item())
+        worst_l = max(worst_l, abs(got - want) / max(1.0, abs(want)))
+        for g_, w_ in ((dbg["q"][0, 0], ora.trace["q1"]), (dbg["q"][0, 1], ora.trace["q2"]), (dbg["target_q"][0], ora.trace["target_q"])):
+            g_, w_ = g_.cpu().numpy(), w_.numpy()
+            worst_q = max(worst_q, float((np.abs(g_ - w_) / np.maximum(1.0, np.abs(w_))).max()))
+    worst_p = compare_nets(ours, ora, tol_rel=5e-2, max_abs=1.0, label="tf32")
+    print(f"tf32 norm={norm} mode={mode}: worst |dQ| {worst_q:.2e}, loss rel {worst_l:.2e}, params {worst_p}")
+    assert worst_q <= 2e-2 and worst_l <= 3e-2

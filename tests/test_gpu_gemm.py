@@ -40,11 +40,8 @@ def test_tcgen05_tile_exact_on_tf32_representable_operands(M, N, K, a_rc, b_rc):
     lib = _lib.require_cuda()
     gen = torch.Generator().manual_seed(M * 7 + N * 3 + K)
     A, B, want = _operands(M, N, K, a_rc, b_rc, gen, exact_tf32=True)
-    eligible = A.stride(0) % 4 == 0 and B.stride(0) % 4 == 0      # rows must be 16-byte copyable (cp.async.cg 16)
-    if not eligible:
-        with pytest.raises(RuntimeError, match="not eligible"):
-            _gemm(lib, _lib, A, a_rc, B, b_rc, M, N, K)
-        return
+    if A.stride(0) % 4 or B.stride(0) % 4:
+        pytest.skip("rows not 16-byte aligned: covered by test_operands_tma_cannot_address_are_refused")
     got = _gemm(lib, _lib, A, a_rc, B, b_rc, M, N, K).cpu().double()
     assert torch.isfinite(got).all()
     err = (got - want).abs().max().item()
@@ -77,11 +74,20 @@ def test_fp32_tile_matches_torch(M, N, K, a_rc, b_rc):
     assert (got - want).abs().max().item() <= 1e-5 * np.sqrt(K) * 4
 
 
-def test_ineligible_operands_are_refused_not_silently_rerouted():
+@pytest.mark.parametrize("a_rc,b_rc", [(1, 1), (1, 0), (0, 0), (0, 1)])
+@pytest.mark.parametrize("M,N,K", [(256, 400, 23), (400, 23, 256), (64, 6, 300), (37, 53, 17)])
+def test_operands_tma_cannot_address_are_refused_not_silently_rerouted(M, N, K, a_rc, b_rc):
+    """First-layer shapes: nn.Linear(23, 400).weight has 92-byte rows, which the TMA unit cannot address (16-byte
+    aligned rows needed).  td3_gemm(use_tc=1) says so instead of quietly running the fp32 tile; inside the update those
+    problems are planned on the fp32 FFMA tile (engine.cu finalize_problem)."""
     from td3_b200 import _lib
     lib = _lib.require_cuda()
-    A = torch.randn(64, 23, device="cuda")      # rows 92 bytes apart: not 16-byte copyable
-    B = torch.randn(32, 23, device="cuda")
-    Cm = torch.empty(64, 32, device="cuda")
-    rc = lib.td3_gemm(64, 32, 23, A.data_ptr(), 23, 1, B.data_ptr(), 23, 1, Cm.data_ptr(), 32, None, 0, 1, _lib.stream_ptr())
-    assert rc == -4
+    gen = torch.Generator().manual_seed(M + 2 * N + 3 * K)
+    A, B, want = _operands(M, N, K, a_rc, b_rc, gen, exact_tf32=True)
+    eligible = A.stride(0) % 4 == 0 and B.stride(0) % 4 == 0 and K >= 64
+    if eligible:
+        got = _gemm(lib, _lib, A, a_rc, B, b_rc, M, N, K).cpu().double()
+        assert (got - want).abs().max().item() <= 1e-5 * np.sqrt(K) * 4
+    else:
+        with pytest.raises(RuntimeError, match="not eligible"):
+            _gemm(lib, _lib, A, a_rc, B, b_rc, M, N, K)

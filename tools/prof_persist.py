@@ -19,11 +19,14 @@ for iters in (2, 1):   # last iteration = policy step (total_it even) then criti
     print("iteration cycles", tot, "=", tot / 1.965e3, "us")
     if os.environ.get("TD3_LIB_NAME"):
         import ctypes as C
-        buf = (C.c_longlong * (128 * 8))()
+        buf = (C.c_longlong * (128 * 16))()
         agent._lib.td3_debug_tile_prof(buf)
-        tp = np.array(buf).reshape(128, 8)
+        tp = np.array(buf).reshape(128, 2, 8)
         for s2 in range(s):
-            if tp[s2, 0]:
-                d = np.diff(tp[s2, :7])
-                print(f"  tile stamps stage {s2:2d}: setup {d[0]} first-data {d[1]} loop {d[2]} drain {d[3]} epi {d[4]} sync {d[5]}")
+            p0, p1 = tp[s2, 0], tp[s2, 1]
+            if p0[0]:
+                t0 = p0[0]
+                print(f"  TC tile stage {s2:2d} (cycles from tile start) producer: setup {p0[1]-t0} last-TMA-issued {p0[2]-t0} | "
+                      f"mma: first-data {p1[1]-t0} last-MMA-issued {p1[2]-t0} | all: epilogue-start {p0[3]-t0} accum-done {p0[4]-t0} "
+                      f"epilogue-end {p0[5]-t0} tile-end {p0[6]-t0}")
     agent._region("prof").zero_()
