@@ -8,8 +8,9 @@ twin-critic forward/backward + Adam, and on every policy_freq-th step the actor 
 (TD3_featured.py:123-171).  Default workload = BASELINE configs[1] ("cfg2"): S=17, A=6, 400-300 MLPs,
 batch 256, 1M-row device-resident replay buffer, one agent per GPU.
 
-  value  updates/s with everything resident in HBM (K updates queued as CUDA-graph replays, CUDA-event
-         timed, max over ranks).
+  value  updates/s with everything resident in HBM (the K updates run in one cooperative launch of the
+         persistent update kernel -- or as CUDA-graph replays with --exec-mode graph -- CUDA-event timed,
+         max over ranks).
   e2e    the same metric through the public Python API the reference's main.py loop uses, per step:
          replay_buffer.add(one host transition -> pinned -> H2D), policy.train(replay_buffer, 256),
          and a synchronous D2H read of the critic loss.
@@ -215,8 +216,13 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--precision", default=os.environ.get("TD3_PRECISION", "tf32"), choices=["tf32", "fp32"],
+                    help="tf32: layer GEMMs on tcgen05 tensor cores (default); fp32: strict-fp32 FFMA tiles")
+    ap.add_argument("--exec-mode", default=os.environ.get("TD3_EXEC_MODE", "persistent"), choices=["persistent", "graph", "launches"])
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
+    os.environ["TD3_PRECISION"], os.environ["TD3_EXEC_MODE"] = args.precision, args.exec_mode
+    dtype = "tf32" if args.precision == "tf32" else "f32"
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -226,6 +232,8 @@ def main():
         f"TD3_{w['kind']} S={w['S']} A={w['A']} actor {w['aw']} critic {w['qw']} norm={w['norm']}" if w["kind"] == "featured"
         else f"TD3_particles F={w['F']} N={w['N']} D={w['D']} A={w['A']} norm={w['norm']}"),
         "batch": w["B"], "replay_rows": w["rows"], "policy_freq": HYPER["policy_freq"], "agents_per_gpu": 1,
+        "precision": args.precision + (" (tcgen05 kind::tf32 GEMMs, fp32 accumulate and storage)" if args.precision == "tf32" else " (FFMA)"),
+        "exec_mode": args.exec_mode,
         "algorithmic_gflop_per_update": round(gflop, 4), "algorithmic_mb_per_update": round(mbytes, 3),
         "l2": "inputs larger than L2: the replay buffer (192 MB at 1M rows) is sampled uniformly at random every step; "
               "the parameters are re-used across steps by the algorithm itself"}
@@ -326,7 +334,7 @@ def main():
 
     line = {"metric": "TD3 gradient updates/sec (batch 256)", "value": value, "unit": "updates/s", "n_gpus": world,
             "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": config, "clocks": clocks,
+            "dtype": dtype, "data": "synthetic", "config": config, "clocks": clocks,
             "e2e": {"value": e2e, "unit": "updates/s", "h2d_bytes_per_step": int(rb.row_floats * 4), "d2h_bytes_per_step": 4,
                     "steps": Ke, "clocks": clocks_e2e,
                     "what": "rb.add(host row) + policy.train(rb, 256) + synchronous D2H of the critic loss, per step"},
@@ -341,9 +349,18 @@ def main():
             achieved, peak, unit = mbytes * 1e6 / (t_update_us * 1e-6) / 1e9, peaks["hbm"], "GB/s"
         else:
             achieved, peak, unit = gflop * 1e9 / (t_update_us * 1e-6) / 1e12, tf32_peak, "TFLOP/s"
+        traffic = None
+        try:       # dram__bytes_read+write per update from the committed ncu --set full capture of this workload, if any
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+                traffic = json.load(f).get(f"{args.workload}:{args.precision}:{args.exec_mode}")
+        except Exception:
+            pass
+        kernel = {"persistent": "td3::persistent_update_kernel (one cooperative launch = all K updates; per-update figures)",
+                  "graph": "td3::stage_kernel x ~19 graph nodes per update (per-update figures)",
+                  "launches": "td3::stage_kernel launches (per-update figures)"}[args.exec_mode]
         line["roofline"] = {
-            "bound": bound, "achieved": achieved, "peak": peak, "unit": unit, "frac": achieved / peak, "traffic": None,
-            "kernel": "td3::stage_kernel (every GEMM/LayerNorm stage of one update; averaged over the policy_freq cycle)",
+            "bound": bound, "achieved": achieved, "peak": peak, "unit": unit, "frac": achieved / peak, "traffic": traffic,
+            "kernel": kernel,
             "per": "update", "us_per_update": t_update_us, "hbm_floor_us": hbm_floor_us, "tensor_floor_us": tensor_floor_us,
             "peak_source": peaks["source"],
             "note": "single-agent MLP updates are bound by the ~20-stage dependency chain (launch/sync latency), not by "
