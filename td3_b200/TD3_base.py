@@ -171,6 +171,20 @@ class TD3_base(object):
                                              int(use_graph), s))
             self.total_it += 1
 
+    # ------------------------------------------------------------------ population members (n_agents > 1)
+    @property
+    def n_agents(self) -> int:
+        return self._cfg.n_agents
+
+    def agent_state_dict(self, net: str, agent: int):
+        """Reference-keyed views of one population member's ``net`` in {"actor","critic","actor_target","critic_target"}."""
+        fam = self._actor_family if net.startswith("actor") else self._critic_family
+        return fam.agent_state_dict(int(agent), target=net.endswith("_target"))
+
+    def load_agent_state_dict(self, net: str, agent: int, state_dict):
+        fam = self._actor_family if net.startswith("actor") else self._critic_family
+        fam.load_agent(int(agent), state_dict, which="target" if net.endswith("_target") else "online")
+
     # ------------------------------------------------------------------ diagnostics (device tensors, no sync)
     @property
     def last_critic_loss(self) -> torch.Tensor:

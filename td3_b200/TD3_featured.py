@@ -8,6 +8,10 @@ Same constructor keywords and methods; extra keyword-only options:
                             "host":   np.random.randint + torch.randn on the host, i.e. the reference's
                                       own random streams (seed-for-seed comparable with a CPU reference run)
   seed                      Philox key for rng="device" (default: drawn from torch's global generator)
+  n_agents                  N > 1: a population of N independent agents (own weights, optimiser state, replay
+                            buffer and Philox stream each) stepped in lock-step by the same launches; the module
+                            shells (``policy.actor`` ...) and the reference-style methods address agent 0, the
+                            ``agent=`` keyword and ``agent_state_dict`` the others (independent seeds)
   precision                 "tf32" (default; env TD3_PRECISION): the layer GEMMs with K >= 64 run on the tcgen05 tensor
                             cores in TF32 with fp32 accumulation; "fp32": every contraction in strict fp32 (parity mode)
 """
@@ -30,9 +34,12 @@ Actor, Critic = MlpActor, MlpCritic
 class TD3(TD3_base):
     def __init__(self, obs_space, action_space, max_action=1, lr=1e-4, norm=None, CDQ=True, *,
                  actor_widths=(500, 400, 300), q_widths=(500, 400, 200), rng="device", seed=None, precision=None,
-                 **kwargs):
+                 n_agents=1, **kwargs):
         _lib.require_cuda()
         S, A = obs_space.shape[0], action_space.shape[0]
+        n_agents = int(n_agents)
+        if n_agents < 1:
+            raise ValueError("n_agents must be >= 1")
         # Build on the CPU with torch's default initialisers in the reference's construction order
         # (actor, then critic q1, q2; TD3_featured.py:101-106) so that torch.manual_seed(s) gives the
         # same initial weights as the reference; targets start as copies (deepcopy at :102,107).
@@ -42,8 +49,11 @@ class TD3(TD3_base):
         critic_t = _clone_shell(critic)
         super(TD3, self).__init__(max_action=max_action, **kwargs)      # :110 (CDQ accepted and ignored, :100)
         dev = torch.device("cuda", torch.cuda.current_device())
-        fam_a = PackedFamily(actor, actor_t, [""], dev)
-        fam_c = PackedFamily(critic, critic_t, ["q1", "q2"], dev)
+        fam_a = PackedFamily(actor, actor_t, [""], dev, n_agents)
+        fam_c = PackedFamily(critic, critic_t, ["q1", "q2"], dev, n_agents)
+        for i in range(1, n_agents):      # further members of the population: fresh default initialisations, in order
+            fam_a.load_agent(i, MlpActor(S, A, max_action, norm, actor_widths).state_dict())
+            fam_c.load_agent(i, MlpCritic(S, A, norm, q_widths).state_dict())
         self.actor, self.actor_target, self.critic, self.critic_target = actor, actor_t, critic, critic_t
         for m, w in ((actor, 0), (actor_t, 1), (critic, 0), (critic_t, 1)):
             m._attach(self, w)
@@ -51,7 +61,7 @@ class TD3(TD3_base):
         cfg.variant, cfg.norm = _lib.VARIANT_FEATURED, (_lib.NORM_LAYER if norm == "layer" else _lib.NORM_NONE)
         cfg.n_q, cfg.state_dim, cfg.action_dim = 2, S, A
         cfg.n_particles = cfg.particle_dim = 0
-        cfg.clamp_target_action, cfg.n_agents = 1, 1
+        cfg.clamp_target_action, cfg.n_agents = 1, n_agents
         cfg.max_action, cfg.discount, cfg.tau = float(self.max_action), float(self.discount), float(self.tau)
         cfg.policy_noise, cfg.noise_clip = float(self.policy_noise), float(self.noise_clip)
         cfg.lr_actor = cfg.lr_critic = float(lr)
@@ -64,31 +74,31 @@ class TD3(TD3_base):
         self._engine_init(cfg, fam_a, fam_c, lr, rng)
 
     # ------------------------------------------------------------------ B=1 API (TD3_featured.py:113-121)
-    def select_action(self, state):
+    def select_action(self, state, agent=0):
         state = torch.as_tensor(np.asarray(state, dtype=np.float32).reshape(1, -1), device=self._device)
-        return self._actor_forward(0, state).cpu().numpy().flatten()
+        return self._actor_forward(0, state, agent=agent).cpu().numpy().flatten()
 
-    def eval_q(self, state, action):
+    def eval_q(self, state, action, agent=0):
         state = torch.as_tensor(np.asarray(state, dtype=np.float32).reshape(1, -1), device=self._device)
         action = torch.as_tensor(np.asarray(action, dtype=np.float32).reshape(1, -1), device=self._device)
-        return [q.cpu().numpy().flatten() for q in self._critic_forward(0, state, action)]
+        return [q.cpu().numpy().flatten() for q in self._critic_forward(0, state, action, agent=agent)]
 
-    def _actor_forward(self, which, state, particles=None):
+    def _actor_forward(self, which, state, particles=None, agent=0):
         state = state.to(self._device, torch.float32).contiguous()
         B = state.shape[0]
         self._ensure_plan(max(B, self._planned_batch))
         out = torch.empty(B, self._cfg.action_dim, device=self._device)
-        _lib.check(self._lib.td3_actor_forward(self._handle, which, 0, state.data_ptr(), None, B, out.data_ptr(),
+        _lib.check(self._lib.td3_actor_forward(self._handle, which, int(agent), state.data_ptr(), None, B, out.data_ptr(),
                                                _lib.stream_ptr()))
         return out
 
-    def _critic_forward(self, which, state, action, particles=None):
+    def _critic_forward(self, which, state, action, particles=None, agent=0):
         state = state.to(self._device, torch.float32).contiguous()
         action = action.to(self._device, torch.float32).contiguous()
         B = state.shape[0]
         self._ensure_plan(max(B, self._planned_batch))
         out = torch.empty(self._cfg.n_q, B, 1, device=self._device)
-        _lib.check(self._lib.td3_critic_forward(self._handle, which, 0, state.data_ptr(), None, action.data_ptr(), B,
+        _lib.check(self._lib.td3_critic_forward(self._handle, which, int(agent), state.data_ptr(), None, action.data_ptr(), B,
                                                 out.data_ptr(), _lib.stream_ptr()))
         return [out[i] for i in range(self._cfg.n_q)]
 

@@ -303,6 +303,20 @@ int emit_stage(std::vector<Launch>& seq, const ProblemList& probs) {
   return TD3_OK;
 }
 
+// fold the problems of stage launch `src` into `dst` (both STAGE launches of mutually independent work)
+bool merge_stage(Launch& dst, const Launch& src) {
+  if (dst.kind != Launch::STAGE || src.kind != Launch::STAGE) return false;
+  if (dst.stage.n_problems + src.stage.n_problems > kMaxProblemsPerStage) return false;
+  for (int q = 0; q < src.stage.n_problems; ++q) {
+    Problem p = src.stage.p[q];
+    p.tile_begin = dst.stage.total_tiles;
+    dst.stage.total_tiles += p.tile_count;
+    dst.stage.p[dst.stage.n_problems++] = p;
+  }
+  dst.stage.any_tc |= src.stage.any_tc;
+  return true;
+}
+
 // merge several per-pass stage sequences so that stage s of every pass shares one launch
 std::vector<ProblemList> zip_stages(const std::vector<std::vector<ProblemList>>& passes) {
   size_t depth = 0;
@@ -386,6 +400,10 @@ struct td3_agent {
   PassBuf pb_at, pb_ct, pb_c, pb_a, pb_q1;
 
   std::vector<Launch> seq_sample, seq_target, seq_critic_fb, seq_critic_apply, seq_actor_fb, seq_actor_apply;
+  // fused middle of a policy update (critic backward with the actor forward riding along, critic Adam, rest of the
+  // actor step): what the CUDA graph and the persistent program run instead of critic_fb + critic_apply + actor_fb
+  std::vector<Launch> seq_policy_mid;
+  int n_actor_fwd = 0;                       // leading launches of seq_actor_fb that are the actor's forward pass
   const float* plan_rows = nullptr;
   long long plan_row_stride = 0, plan_rb_agent_stride = 0;
   int plan_rng_mode = -1;
@@ -990,6 +1008,7 @@ int plan_agent(td3_agent* a, long long batch) {
     o.f0 = enc ? 1.f : c.max_action;
     auto s_a = build_forward(c, c.actor, Wa, g_actor, B, pa, o);
     for (auto& st : s_a) emit_stage(a->seq_actor_fb, st);
+    a->n_actor_fwd = (int)a->seq_actor_fb.size();
     OutSpec oq;
     oq.out = a->q_pi; oq.ld = qw; oq.go = (long long)B * qw; oq.epi = EPI_BIAS;
     auto s_q = build_forward(c, c.q, Wq1, g_q1, B, q1, oq);
@@ -1055,6 +1074,20 @@ int plan_agent(td3_agent* a, long long batch) {
       return fail(TD3_ERR_CUDA, "cuTensorMapEncodeTiled failed for a tensor-core operand (or more than %d maps needed)", kMaxTensorMaps);
     if (!host.empty())
       cudaMemcpy(a->tmaps_dev, host.data(), host.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice);
+  }
+  // The actor's forward pass (TD3_featured.py:159, actor(state)) reads nothing the critic update writes, so in the
+  // fused policy update its layers ride along with the critic's backward stages instead of owning barriers.
+  {
+    a->seq_policy_mid.clear();
+    size_t ai = 0;
+    for (const Launch& L : a->seq_critic_fb) {
+      Launch m = L;
+      if (L.kind == Launch::STAGE && (int)ai < a->n_actor_fwd && merge_stage(m, a->seq_actor_fb[ai])) ++ai;
+      a->seq_policy_mid.push_back(m);
+    }
+    for (; (int)ai < a->n_actor_fwd; ++ai) a->seq_policy_mid.push_back(a->seq_actor_fb[ai]);
+    for (const Launch& L : a->seq_critic_apply) a->seq_policy_mid.push_back(L);
+    for (size_t i = a->n_actor_fwd; i < a->seq_actor_fb.size(); ++i) a->seq_policy_mid.push_back(a->seq_actor_fb[i]);
   }
   // constant buffers: dq_pi = -1/(B*qw) (d(-mean)/dQ1), identity for the slice problem
   {
@@ -1173,23 +1206,7 @@ int build_programs(td3_agent* a, cudaStream_t s) {
   std::vector<StageRec> pc, pp;
   AdamTick pend{};
   for (auto* seq : {&a->seq_sample, &a->seq_target, &a->seq_critic_fb, &a->seq_critic_apply}) append_records(pc, *seq, &pend);
-  for (auto* seq : {&a->seq_sample, &a->seq_target, &a->seq_critic_fb}) append_records(pp, *seq, &pend);
-  // The critic's Adam step does not feed the actor forward (only Q1's forward, three stages later, reads the
-  // stepped critic: TD3_featured.py:153,159): it rides along with the first actor stage instead of owning a barrier.
-  const size_t first_actor = pp.size();
-  append_records(pp, a->seq_actor_fb, &pend);
-  bool merged = false;
-  if (pp.size() > first_actor && pp[first_actor].kind == SK_STAGE && a->seq_critic_apply.size() == 1 &&
-      a->seq_critic_apply[0].kind == Launch::EW) {
-    pp[first_actor].ew = a->seq_critic_apply[0].ew;
-    pp[first_actor].ew_tiles = a->seq_critic_apply[0].grid_x;
-    merged = true;
-  }
-  if (!merged) {
-    std::vector<StageRec> tmp;
-    append_records(tmp, a->seq_critic_apply, &pend);
-    pp.insert(pp.begin() + first_actor, tmp.begin(), tmp.end());
-  }
+  for (auto* seq : {&a->seq_sample, &a->seq_target, &a->seq_policy_mid}) append_records(pp, *seq, &pend);
   append_records(pp, a->seq_actor_apply, &pend);
   if (pc.empty() || pp.empty() || (int)pc.size() > kMaxProgStages || (int)pp.size() > kMaxProgStages)
     return fail(TD3_ERR_STATE, "persistent program has %zu / %zu stages (max %d)", pc.size(), pp.size(), kMaxProgStages);
@@ -1303,10 +1320,13 @@ int capture(td3_agent* a, bool with_actor, cudaGraphExec_t* out, long long* n_no
   CUDA_TRY(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
   int rc = run_seq(a->seq_sample, s);
   if (rc == TD3_OK) rc = run_seq(a->seq_target, s);
-  if (rc == TD3_OK) rc = run_seq(a->seq_critic_fb, s);
-  if (rc == TD3_OK) rc = run_seq(a->seq_critic_apply, s);
-  if (rc == TD3_OK && with_actor) rc = run_seq(a->seq_actor_fb, s);
-  if (rc == TD3_OK && with_actor) rc = run_seq(a->seq_actor_apply, s);
+  if (with_actor) {
+    if (rc == TD3_OK) rc = run_seq(a->seq_policy_mid, s);
+    if (rc == TD3_OK) rc = run_seq(a->seq_actor_apply, s);
+  } else {
+    if (rc == TD3_OK) rc = run_seq(a->seq_critic_fb, s);
+    if (rc == TD3_OK) rc = run_seq(a->seq_critic_apply, s);
+  }
   cudaError_t e = cudaStreamEndCapture(s, &graph);
   *n_nodes = g_launches.load() - launches_before;            // captured, not executed: move to per-replay accounting
   g_launches.fetch_sub(*n_nodes, std::memory_order_relaxed);

@@ -28,14 +28,18 @@ _STAGE_SLOTS = 256
 
 class _DeviceReplay(object):
     # subclasses define: fields (name -> (offset, shape)), store_np order
-    def _init_storage(self, max_size, load_folder):
+    def _init_storage(self, max_size, load_folder, n_agents=1):
         self._lib = _lib.require_cuda()
         self.max_size = int(max_size)
+        self.n_agents = int(n_agents)
         self.store_pkl = ["ptr", "size"]
         self.device = torch.device("cuda", torch.cuda.current_device())
         self.row_floats = sum(int(np.prod(shape)) for _, shape in self._fields.values())
         self.row_stride = (self.row_floats + 7) // 8 * 8          # rows start on 32-byte sector boundaries
-        self._rows = torch.zeros(self.max_size, self.row_stride, dtype=torch.float32, device=self.device)
+        # population (n_agents > 1): one ring per member, a constant stride apart; self._rows is member 0's ring
+        self._all_rows = torch.zeros(self.n_agents, self.max_size, self.row_stride, dtype=torch.float32, device=self.device)
+        self._rows = self._all_rows[0]
+        self._ptrs, self._sizes = [0] * self.n_agents, [0] * self.n_agents
         self._stage = torch.zeros(_STAGE_SLOTS, self.row_floats, dtype=torch.float32).pin_memory()
         self._stage_np = self._stage.numpy()
         self._slot = 0
@@ -51,7 +55,8 @@ class _DeviceReplay(object):
         v = _lib.ReplayView()
         v.rows = C.c_void_p(self._rows.data_ptr())
         v.row_stride, v.row_floats = self.row_stride, self.row_floats
-        v.max_size, v.size, v.agent_stride = self.max_size, self.size, 0
+        v.max_size, v.agent_stride = self.max_size, (self.max_size * self.row_stride if self.n_agents > 1 else 0)
+        v.size = self.size if self.n_agents == 1 else min(self.size, *self._sizes[1:])   # lock-step: common valid prefix
         return v
 
     # ------------------------------------------------------------------ add (my_replay_buffer.py:46-56,109-117)
@@ -70,9 +75,12 @@ class _DeviceReplay(object):
         self.ptr = (self.ptr + 1) % self.max_size
         self.size = min(self.size + 1, self.max_size)
 
-    def add_batch(self, **columns):
+    def add_batch(self, agent=0, **columns):
         """Bulk ``add`` of n transitions given as arrays keyed by field name (``done`` instead of
-        ``not_done``); equivalent to n calls of ``add`` in order, including ring wrap-around."""
+        ``not_done``); equivalent to n calls of ``add`` in order, including ring wrap-around.
+        ``agent`` selects the population member whose ring receives them."""
+        if agent:
+            return self._add_batch_member(int(agent), columns)
         n = len(next(iter(columns.values())))
         chunk = max(1, min(n, (64 << 20) // (4 * self.row_floats)))
         for lo in range(0, n, chunk):
@@ -96,6 +104,21 @@ class _DeviceReplay(object):
                 self.size = min(self.size + m, self.max_size)
                 done += m
             torch.cuda.current_stream().synchronize()       # pinned chunk is released after this
+
+    def _add_batch_member(self, agent, columns):
+        """add_batch for population member ``agent`` >= 1 (member 0 keeps the reference attributes ptr/size)."""
+        n = len(next(iter(columns.values())))
+        host = np.empty((n, self.row_floats), dtype=np.float32)
+        for name, (off, shape) in self._fields.items():
+            w = int(np.prod(shape))
+            src = (1.0 - np.asarray(columns["done"], dtype=np.float64).reshape(n, w)) if name == "not_done" \
+                else np.asarray(columns[name]).reshape(n, w)
+            host[:, off:off + w] = src
+        rows = self._all_rows[agent]
+        idx = (self._ptrs[agent] + np.arange(n)) % self.max_size
+        rows[torch.as_tensor(idx, device=self.device), :self.row_floats] = torch.from_numpy(host).to(self.device)
+        self._ptrs[agent] = int((self._ptrs[agent] + n) % self.max_size)
+        self._sizes[agent] = min(self._sizes[agent] + n, self.max_size)
 
     # ------------------------------------------------------------------ sample (:58-69,119-128)
     def sample(self, batch_size, indices=None):
@@ -178,11 +201,11 @@ def _layout(spec):
 class ReplayBuffer_featured(_DeviceReplay):
     """Row = [state | action | next_state | reward | not_done]  (my_replay_buffer.py:72-128)."""
 
-    def __init__(self, obs_space, action_space, max_size=int(1e6), load_folder=None):
+    def __init__(self, obs_space, action_space, max_size=int(1e6), load_folder=None, n_agents=1):
         S, A = obs_space.shape[0], action_space.shape[0]
         self.store_np = ["state", "action", "next_state", "reward", "not_done"]
         self._fields = _layout([("state", (S,)), ("action", (A,)), ("next_state", (S,)), ("reward", (1,)), ("not_done", (1,))])
-        self._init_storage(max_size, load_folder)
+        self._init_storage(max_size, load_folder, n_agents)
 
     def add(self, state, action, next_state, reward, done):
         slot = self._next_slot()

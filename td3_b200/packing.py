@@ -242,6 +242,19 @@ class PackedFamily:
             out[name] = flat[base + off: base + off + p.numel()].view(shape)
         return out
 
+    def load_agent(self, agent: int, state_dict, which: str = "both"):
+        """Write a reference-keyed state_dict into population member ``agent``'s slot of the online and/or target
+        buffer (a fresh member starts with target == online, like the reference's deepcopy)."""
+        with torch.no_grad():
+            for flat in ([self.params, self.target] if which == "both" else [self.params] if which == "online" else [self.target]):
+                views = self.flat_views(flat, agent)
+                for name, v in views.items():
+                    v.copy_(state_dict[name])
+
+    def agent_state_dict(self, agent: int, target: bool = False) -> "OrderedDict[str, torch.Tensor]":
+        """Views (not copies) of member ``agent``'s tensors under the reference's state_dict keys."""
+        return self.flat_views(self.target if target else self.params, agent)
+
     def param_set(self) -> _lib.ParamSet:
         ps = _lib.ParamSet()
         for k in ("params", "target", "grad", "exp_avg", "exp_avg_sq"):

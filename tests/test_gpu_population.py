@@ -1,0 +1,83 @@
+"""Populations (n_agents > 1): N independent agents stepped in lock-step by the same launches -- the unit that is
+sharded over GPUs with no communication (BASELINE config 5: 64 agents, 8 per GPU).
+Bar: every member's losses and parameters are BIT-IDENTICAL to a standalone agent given the same weights, data,
+indices and noise (both precisions, persistent kernel and graph), and the on-device Philox streams of member i equal
+those of a standalone agent keyed seed + i * 0x9E3779B97F4A7C15."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import td3_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+S, A, B, ROWS, N = 17, 6, 128, 1024, 3
+KW = dict(actor_widths=(400, 300), q_widths=(400, 300), lr=1e-3)
+NETS = ("actor", "critic", "actor_target", "critic_target")
+
+
+def _build(precision, mode, seed=5):
+    from td3_b200.TD3_featured import TD3
+    from td3_b200.my_replay_buffer import ReplayBuffer_featured
+    obs, act = O.Space(S), O.Space(A)
+    torch.manual_seed(3)
+    pop = TD3(obs, act, n_agents=N, precision=precision, seed=seed, **KW)
+    pop.exec_mode = mode
+    rbp = ReplayBuffer_featured(obs, act, max_size=ROWS, n_agents=N)
+    singles = []
+    for i in range(N):
+        a = TD3(obs, act, precision=precision, seed=(seed + i * 0x9E3779B97F4A7C15) % (1 << 64), **KW)
+        a.exec_mode = mode
+        for k in NETS:
+            getattr(a, k).load_state_dict({n: v.clone() for n, v in pop.agent_state_dict(k, i).items()})
+        data = O.synthetic_transitions_featured(ROWS, S, A, seed=10 + i)
+        rb = ReplayBuffer_featured(obs, act, max_size=ROWS)
+        rb.add_batch(**data)
+        rbp.add_batch(agent=i, **data)
+        singles.append((a, rb))
+    return pop, rbp, singles
+
+
+def _assert_same(pop, singles):
+    for i, (a, _) in enumerate(singles):
+        assert float(pop.last_critic_loss[i].item()) == float(a.last_critic_loss[0].item()), i
+        for k in NETS:
+            for (n, v), w in zip(pop.agent_state_dict(k, i).items(), getattr(a, k).state_dict().values()):
+                assert torch.equal(v, w), (i, k, n)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "tf32"])
+@pytest.mark.parametrize("mode", ["persistent", "graph"])
+def test_members_match_standalone_agents_bit_exactly(precision, mode):
+    pop, rbp, singles = _build(precision, mode)
+    assert not torch.equal(pop.agent_state_dict("actor", 0)["linears.0.weight"], pop.agent_state_dict("actor", 1)["linears.0.weight"])
+    rs = np.random.RandomState(1)
+    for t in range(4):
+        idx = rs.randint(0, ROWS, size=(N, B))
+        nz = rs.standard_normal((N, B, A)).astype(np.float32)
+        pop.train(rbp, B, indices=idx, noise=nz)
+        for i, (a, rb) in enumerate(singles):
+            a.train(rb, B, indices=idx[i], noise=nz[i])
+    _assert_same(pop, singles)
+    assert pop.total_it == 4
+
+
+def test_member_philox_streams_equal_standalone_streams():
+    pop, rbp, singles = _build("tf32", "persistent")
+    pop.train(rbp, B, iterations=6)
+    for a, rb in singles:
+        a.train(rb, B, iterations=6)
+    torch.cuda.synchronize()
+    _assert_same(pop, singles)
+    idx = pop.debug_tensors()["indices"].cpu().numpy()
+    assert not np.array_equal(idx[0], idx[1])            # members draw different batches
+
+
+def test_member_inference_addresses_its_own_weights():
+    pop, rbp, singles = _build("fp32", "persistent")
+    s = np.random.RandomState(0).standard_normal(S).astype(np.float32)
+    for i, (a, _) in enumerate(singles):
+        np.testing.assert_array_equal(pop.select_action(s, agent=i), a.select_action(s))
+        u = pop.select_action(s, agent=i)
+        for q_pop, q_one in zip(pop.eval_q(s, u, agent=i), a.eval_q(s, u)):
+            np.testing.assert_array_equal(q_pop, q_one)

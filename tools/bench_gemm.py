@@ -10,6 +10,7 @@ from td3_b200 import _lib
 ap = argparse.ArgumentParser()
 ap.add_argument("--reps", type=int, default=20)
 ap.add_argument("--only-tc", action="store_true")
+ap.add_argument("--shapes", default="", help="comma-separated indices into SHAPES (default: all)")
 args = ap.parse_args()
 lib = _lib.require_cuda()
 try:
@@ -27,7 +28,8 @@ SHAPES = [  # (M, N, K, a_rc, b_rc, what)
     (262144, 256, 128, 1, 0, "particle encoder layer-2 dX"),
 ]
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > L2 (126 MB): cold operands between repetitions
-for M, N, K, a_rc, b_rc, what in SHAPES:
+sel = [int(x) for x in args.shapes.split(",")] if args.shapes else range(len(SHAPES))
+for M, N, K, a_rc, b_rc, what in [SHAPES[i] for i in sel]:
     A = torch.randn((M, K) if a_rc else (K, M), device="cuda")
     B = torch.randn((N, K) if b_rc else (K, N), device="cuda")
     Cm = torch.empty(M, N, device="cuda")
