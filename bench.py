@@ -139,7 +139,7 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------- builders
-def build_ours(w, seed, rows=None):
+def build_ours(w, seed, rows=None, n_agents=1):
     import torch
     from oracle import td3_oracle as O              # synthetic-data generator only (inputs, not the measured path)
     rows = rows or w["rows"]
@@ -149,9 +149,10 @@ def build_ours(w, seed, rows=None):
         obs, act = O.Space(w["S"]), O.Space(w["A"])
         torch.manual_seed(seed)
         agent = TD3(obs, act, lr=1e-4, norm=w["norm"], actor_widths=w["aw"], q_widths=w["qw"], seed=seed + 1, max_action=1,
-                    **HYPER)
-        rb = ReplayBuffer_featured(obs, act, max_size=rows)
-        rb.add_batch(**O.synthetic_transitions_featured(rows, w["S"], w["A"], seed=0))
+                    n_agents=n_agents, **HYPER)
+        rb = ReplayBuffer_featured(obs, act, max_size=rows, n_agents=n_agents)
+        for i in range(n_agents):
+            rb.add_batch(agent=i, **O.synthetic_transitions_featured(rows, w["S"], w["A"], seed=i))
     else:
         from td3_b200.TD3_particles import TD3
         from td3_b200.my_replay_buffer import ReplayBuffer_particles
@@ -218,6 +219,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--precision", default=os.environ.get("TD3_PRECISION", "tf32"), choices=["tf32", "fp32"],
                     help="tf32: layer GEMMs on tcgen05 tensor cores (default); fp32: strict-fp32 FFMA tiles")
+    ap.add_argument("--population", type=int, default=8,
+                    help="also time a population of this many independent agents per GPU stepped in lock-step (0 = skip)")
     ap.add_argument("--exec-mode", default=os.environ.get("TD3_EXEC_MODE", "persistent"), choices=["persistent", "graph", "launches"])
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
@@ -323,11 +326,28 @@ def main():
         barrier()
     clocks_e2e = clk2.summary()
 
+    # ---------------- population: several independent agents per GPU in lock-step ----------------
+    pop_ms, n_pop = 0.0, (args.population if w["kind"] == "featured" else 0)
+    h2d_bytes = int(rb.row_floats * 4)
+    if n_pop > 1:
+        del agent, rb
+        torch.cuda.empty_cache()
+        pop, prb = build_ours(w, seed=1000 + 64 * rank, rows=min(w["rows"], 100_000), n_agents=n_pop)
+        Kp = max(3, K // 4)
+        pop.train(prb, B, iterations=max(3, W // 4))
+        barrier()
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record()
+        pop.train(prb, B, iterations=Kp)
+        p1.record()
+        barrier()
+        pop_ms = p0.elapsed_time(p1)
+
     # ---------------- reduce over ranks ----------------
     if world > 1:
-        t = torch.tensor([ms, e2e_s], device="cuda", dtype=torch.float64)
+        t = torch.tensor([ms, e2e_s, pop_ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, e2e_s = float(t[0]), float(t[1])
+        ms, e2e_s, pop_ms = float(t[0]), float(t[1]), float(t[2])
     value = world * K / (ms / 1000.0)
     e2e = world * Ke / e2e_s
     t_update_us = ms * 1000.0 / K
@@ -335,10 +355,16 @@ def main():
     line = {"metric": "TD3 gradient updates/sec (batch 256)", "value": value, "unit": "updates/s", "n_gpus": world,
             "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": dtype, "data": "synthetic", "config": config, "clocks": clocks,
-            "e2e": {"value": e2e, "unit": "updates/s", "h2d_bytes_per_step": int(rb.row_floats * 4), "d2h_bytes_per_step": 4,
+            "e2e": {"value": e2e, "unit": "updates/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                     "steps": Ke, "clocks": clocks_e2e,
                     "what": "rb.add(host row) + policy.train(rb, 256) + synchronous D2H of the critic loss, per step"},
             "gpu_launches": int(launches)}
+    if n_pop > 1 and pop_ms > 0:
+        line["population"] = {"agents_per_gpu": n_pop, "value": world * n_pop * Kp / (pop_ms / 1000.0), "unit": "updates/s",
+                              "ms_per_lockstep_update": pop_ms / Kp, "steps": Kp,
+                              "what": f"{n_pop} independent agents per GPU (own weights, optimiser state, 100k-row replay buffer and "
+                                      "Philox stream each) stepped by the same launches; value = agent-updates/s over all GPUs "
+                                      "(BASELINE config 5: independent seeds sharded with no communication)"}
 
     if rank == 0:
         hbm_floor_us = mbytes * 1e6 / (peaks["hbm"] * 1e9) * 1e6

