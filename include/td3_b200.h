@@ -195,8 +195,10 @@ int td3_critic_step(td3_agent* agent, int32_t apply, void* stream);  /* :145-153
 int td3_critic_apply(td3_agent* agent, void* stream);     /* Adam on the critic (:153) */
 int td3_actor_step(td3_agent* agent, int32_t apply, void* stream);   /* :159-164 */
 int td3_actor_apply(td3_agent* agent, void* stream);      /* actor Adam + Polyak of both targets (:164-171) */
-/* Loss normaliser for data-parallel critics: gradients are scaled by 1/(global_batch) instead of 1/batch. */
-int td3_agent_set_global_batch(td3_agent* agent, int64_t global_batch);
+/* Data-parallel shard of a larger batch: losses and gradients are normalised by 1/global_batch instead of
+ * 1/batch, and local row b draws element (b + batch_offset) of the global batch's Philox index / noise sequence, so the
+ * global batch does not depend on the number of ranks.  global_batch = 0 restores single-device behaviour. */
+int td3_agent_set_global_batch(td3_agent* agent, int64_t global_batch, int64_t batch_offset);
 
 /* B=small inference on caller buffers (device pointers):
  * actor(x)  -> select_action (TD3_featured.py:113-115, TD3_particles.py:153-157)

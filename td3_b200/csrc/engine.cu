@@ -385,7 +385,7 @@ struct td3_agent {
   bool params_bound = false;
   unsigned long long* state_u64 = nullptr;   // [0] sample step [1] critic Adam t [2] actor Adam t [3] rb size
   float* state_f32 = nullptr;                // critic_loss[n_agents], actor_loss[n_agents]
-  long long batch = 0, global_batch = 0;
+  long long batch = 0, global_batch = 0, batch_offset = 0;
   Bump ws;
   long long ws_floats = 0;
 
@@ -1125,6 +1125,7 @@ int plan_sample(td3_agent* a, const td3_replay_view* rb, int rng_mode) {
   G.idx_in = a->idx_in; G.idx_out = a->idx; G.step_ptr = a->state_u64; G.seed = c.seed;
   G.eps_out = a->eps; G.noise_in = a->noise_in; G.action_dim = A;
   G.policy_noise = c.policy_noise; G.noise_clip = c.noise_clip;
+  G.elem_offset = (int)a->batch_offset;
   int n = 0;
   auto seg = [&](int off, int len, float* dst, int ld, long long astride) {
     G.seg_off[n] = off; G.seg_len[n] = len; G.dst[n] = dst; G.dst_ld[n] = ld; G.dst_agent_stride[n] = astride; ++n;
@@ -1578,9 +1579,11 @@ int td3_agent_region(const td3_agent* a, const char* name, int64_t* offset, int6
   return TD3_OK;
 }
 
-int td3_agent_set_global_batch(td3_agent* a, int64_t global_batch) {
-  if (!a || global_batch < 0) return fail(TD3_ERR_INVALID, "td3_agent_set_global_batch: bad argument");
+int td3_agent_set_global_batch(td3_agent* a, int64_t global_batch, int64_t batch_offset) {
+  if (!a || global_batch < 0 || batch_offset < 0) return fail(TD3_ERR_INVALID, "td3_agent_set_global_batch: bad argument");
   a->global_batch = global_batch;
+  a->batch_offset = batch_offset;
+  a->plan_rows = nullptr;        // the sampling launch carries the offset: rebuild it
   if (a->batch > 0 && a->ws.base) return plan_agent(a, a->batch);
   return TD3_OK;
 }

@@ -83,6 +83,7 @@ struct GatherParams {
   float* eps_out;                 // [n_agents][batch][action_dim]  clipped noise
   const float* noise_in;          // N(0,1) draws (injected mode), same shape
   int action_dim, slices;         // slices = gridDim.y
+  int elem_offset, pad;           // data-parallel shard: local row b is element b + elem_offset of the global batch
   float policy_noise, noise_clip;
 };
 
@@ -97,7 +98,7 @@ __device__ __forceinline__ void gather_body(const GatherParams& G, int bx, int b
   long long idx;
   if (G.rng_mode == 0) {
     idx = philox_index(G.seed + (unsigned long long)agent * 0x9E3779B97F4A7C15ull, PHILOX_INDICES, step,
-                       (uint32_t)b, size);
+                       (uint32_t)(b + G.elem_offset), size);
   } else {
     idx = G.idx_in[job];
   }
@@ -108,7 +109,7 @@ __device__ __forceinline__ void gather_body(const GatherParams& G, int bx, int b
       const long long e = (long long)b * G.action_dim + a;
       float z = (G.rng_mode == 0)
                     ? philox_normal(G.seed + (unsigned long long)agent * 0x9E3779B97F4A7C15ull, PHILOX_NOISE, step,
-                                    (uint32_t)e)
+                                    (uint32_t)(e + (long long)G.elem_offset * G.action_dim))
                     : G.noise_in[(long long)agent * G.batch * G.action_dim + e];
       z = z * G.policy_noise;
       z = fminf(fmaxf(z, -G.noise_clip), G.noise_clip);
