@@ -8,6 +8,7 @@
 
 #include <cuda.h>   // CUtensorMap types only: the driver entry point is looked up at run time, nothing links libcuda
 
+#include <algorithm>
 #include <atomic>
 #include <cmath>
 #include <cstdarg>
@@ -74,29 +75,58 @@ int ensure_kernel_attrs() {
   return TD3_OK;
 }
 
+// every launch allows programmatic dependent launch of its successor (see misc.cuh: pdl_*)
+template <typename Kernel, typename Params>
+cudaError_t launch_pdl(Kernel k, dim3 grid, dim3 block, size_t smem, cudaStream_t s, const Params& p, int cluster = 1) {
+  static const bool use_pdl = getenv("TD3_PDL") != nullptr;   // measured: no gain on B200 graphs (124.1 vs 121.9 us/update), off by default
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (use_pdl) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  if (cluster > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = (unsigned)cluster;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+    cfg.gridDim.x = (grid.x + cluster - 1) / cluster * cluster;
+  }
+  cfg.attrs = attr; cfg.numAttrs = na;
+  return cudaLaunchKernelEx(&cfg, k, p);
+}
+
 int run_launch(const Launch& L, cudaStream_t s) {
+  cudaError_t e = cudaSuccess;
   switch (L.kind) {
     case Launch::STAGE: {
       if (L.stage.total_tiles <= 0) return TD3_OK;
       int rc = ensure_kernel_attrs();
       if (rc != TD3_OK) return rc;
-      if (L.stage.any_tc) stage_kernel<true><<<L.stage.total_tiles, kStageThreads, kDynSmemBytes, s>>>(L.stage);
-      else stage_kernel<false><<<L.stage.total_tiles, kStageThreads, kDynSmemBytes, s>>>(L.stage);
+      // fp32-only stages need the FFMA tile's buffers only: a small footprint lets the successor's CTAs co-reside
+      if (L.stage.any_tc)
+        e = launch_pdl(stage_kernel<true>, dim3(L.stage.total_tiles), dim3(kStageThreads), kDynSmemBytes, s, L.stage, L.stage.cluster);
+      else e = launch_pdl(stage_kernel<false>, dim3(L.stage.total_tiles), dim3(kStageThreads), kSmemBytes + 1024, s, L.stage);
       break;
     }
     case Launch::GATHER:
-      gather_kernel<<<dim3(L.grid_x, L.grid_y), 256, 0, s>>>(L.gather);
+      e = launch_pdl(gather_kernel, dim3(L.grid_x, L.grid_y), dim3(256), 0, s, L.gather);
       break;
     case Launch::LOSS:
-      loss_kernel<<<L.grid_x, 256, 0, s>>>(L.loss);
+      e = launch_pdl(loss_kernel, dim3(L.grid_x), dim3(256), 0, s, L.loss);
       break;
     case Launch::EW:
-      adam_polyak_kernel<<<L.grid_x, kEwThreads, 0, s>>>(L.ew);
+      e = launch_pdl(adam_polyak_kernel, dim3(L.grid_x), dim3(kEwThreads), 0, s, L.ew);
       break;
     case Launch::TICK:
-      adam_tick_kernel<<<1, 32, 0, s>>>(L.tick);
+      e = launch_pdl(adam_tick_kernel, dim3(1), dim3(32), 0, s, L.tick);
       break;
   }
+  if (e != cudaSuccess) return fail(TD3_ERR_CUDA, "kernel launch: %s", cudaGetErrorString(e));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   CUDA_TRY(cudaGetLastError());
   return TD3_OK;
@@ -167,7 +197,7 @@ bool encode_operand_maps(const Problem& p, bool is_a, int n_outer, int n_inner, 
       CUtensorMapSwizzle sw;
       if (rc) {        // memory [O rows][K cols]: K-major atoms, box = 32 reduction steps x (128 | NT) rows
         gdim[0] = (cuuint64_t)p.K; gdim[1] = (cuuint64_t)O;
-        box[0] = 32; box[1] = is_a ? 128 : (cuuint32_t)p.tc_nt;
+        box[0] = 32; box[1] = is_a ? (cuuint32_t)(128 / std::max(1, p.tc_cluster)) : (cuuint32_t)p.tc_nt;
         sw = CU_TENSOR_MAP_SWIZZLE_128B;
       } else {         // memory [K rows][O cols]: MN-major atoms with 32-byte swizzle base, box = 32 MN x 32 reduction rows
         gdim[0] = (cuuint64_t)O; gdim[1] = (cuuint64_t)p.K;
@@ -281,6 +311,67 @@ void finalize_problem(Problem& p, GroupShape gs) {
   p.tile_count = p.tiles_per_group * groups;
 }
 
+// thread-local planning switches: tensor-core policy is declared further down next to finalize_problem
+thread_local int g_cluster_mode = 0;     // 1: stage launches may use thread-block clusters (A-panel multicast)
+
+
+// Final tile layout of a stage launch: tensor-core problems first, one cluster size for the launch, every TC
+// problem's N-tile count padded to a multiple of it (padding tiles fetch their share of the A panel and store nothing).
+void layout_stage(Launch& L) {
+  StageParams& S = L.stage;
+  const int n = S.n_problems;
+  std::stable_partition(S.p, S.p + n, [](const Problem& p) { return p.kind == PK_GEMM && p.use_tc; });
+  int groups[kMaxProblemsPerStage];
+  long long other_tiles = 0;
+  bool any_tc = false;
+  for (int q = 0; q < n; ++q) {
+    Problem& p = S.p[q];
+    groups[q] = p.tile_count / std::max(1, p.tiles_per_group);
+    if (p.kind == PK_GEMM && p.use_tc) any_tc = true;
+    else other_tiles += p.tile_count;
+  }
+  int c = 1;
+  if (g_cluster_mode && any_tc) {
+    auto total_for = [&](int cand) {
+      long long total = other_tiles;
+      for (int q = 0; q < n; ++q) {
+        const Problem& p = S.p[q];
+        if (!(p.kind == PK_GEMM && p.use_tc)) continue;
+        const long long tn = ((p.N + p.tc_nt - 1) / p.tc_nt + cand - 1) / cand * cand;
+        total += (long long)groups[q] * p.tiles_m * tn * p.ksplit;
+      }
+      return total;
+    };
+    const long long base = total_for(1);
+    // single wave: padding tiles are free (idle SMs) and help fetch the A panel; several waves: only if padding is <= 10 %
+    for (int cand : {8, 4, 2}) {
+      const long long t = total_for(cand);
+      if (t <= g_sm_count || (base > g_sm_count && t * 10 <= base * 11)) { c = cand; break; }
+    }
+  }
+  int tiles = 0;
+  for (int q = 0; q < n; ++q) {
+    Problem& p = S.p[q];
+    if (p.kind == PK_GEMM && p.use_tc) {
+      p.tc_cluster = c;
+      if (g_cluster_mode) {          // stage-per-launch form (one tile per CTA): ring sized for this tile's width
+        p.tc_slot_bytes = 16384 + (p.tc_nt * 128 + 1023) / 1024 * 1024;
+        p.tc_slots = std::min(kTcMaxSlots, kTcRingBytes / p.tc_slot_bytes);
+      } else {
+        p.tc_slots = p.tc_slot_bytes = 0;
+      }
+      p.tiles_n = ((p.N + p.tc_nt - 1) / p.tc_nt + c - 1) / c * c;
+      p.tiles_per_group = p.tiles_m * p.tiles_n * p.ksplit;
+      p.tile_count = p.tiles_per_group * groups[q];
+    }
+    p.tile_begin = tiles;
+    tiles += p.tile_count;
+  }
+  S.total_tiles = tiles;
+  S.any_tc = any_tc ? 1 : 0;
+  S.cluster = c;
+}
+
 int emit_stage(std::vector<Launch>& seq, const ProblemList& probs) {
   // split into chunks of kMaxProblemsPerStage (they stay independent, so extra launches are still correct)
   size_t i = 0;
@@ -298,7 +389,10 @@ int emit_stage(std::vector<Launch>& seq, const ProblemList& probs) {
     }
     L.stage.n_problems = n;
     L.stage.total_tiles = tiles;
-    if (n > 0) seq.push_back(L);
+    if (n > 0) {
+      layout_stage(L);
+      seq.push_back(L);
+    }
   }
   return TD3_OK;
 }
@@ -314,6 +408,7 @@ bool merge_stage(Launch& dst, const Launch& src) {
     dst.stage.p[dst.stage.n_problems++] = p;
   }
   dst.stage.any_tc |= src.stage.any_tc;
+  layout_stage(dst);
   return true;
 }
 
@@ -424,6 +519,7 @@ struct td3_agent {
   int n_prog_critic = 0, n_prog_policy = 0;
   bool prog_dirty = true;
   int persist_grid = 0;
+  int cluster_mode = 1;                      // stage launches use clusters (graph / launches modes); the persistent kernel does not
   unsigned int bar_count = 0;               // value of the device barrier counter once all queued launches finish
   bool bar_reset = true;                    // zero the counter before the next launch (fresh state block)         // capture happens here: the caller's stream may be the legacy stream
 };
@@ -861,6 +957,9 @@ int plan_agent(td3_agent* a, long long batch) {
   ws.used = 0;
   ws.regions.clear();
   g_tc_mode = c.precision == TD3_PRECISION_TF32 ? 1 : 0;
+  // A-panel multicast over thread-block clusters is implemented and tested but measured no faster on B200 (the K loop
+  // is bound by the MMA's shared-memory A read, not by the operand stream: DESIGN.md section 5): opt-in.
+  g_cluster_mode = (a->cluster_mode && getenv("TD3_CLUSTER")) ? 1 : 0;
   cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, 0);
   if (g_sm_count <= 0) g_sm_count = 148;
   const int A = c.action_dim, S = c.state_dim, E = enc ? c.actor.enc_out : 0;
@@ -1067,14 +1166,6 @@ int plan_agent(td3_agent* a, long long batch) {
     L.grid_x = (int)(b0 + (r1.n + kEwPerBlock - 1) / kEwPerBlock);
     a->seq_actor_apply.push_back(L);
   }
-  // TMA descriptors of every tensor-core operand (pointers are fixed from here on: torch owns the buffers)
-  if (g_tc_mode) {
-    std::vector<CUtensorMap> host;
-    if (!attach_tensor_maps({&a->seq_target, &a->seq_critic_fb, &a->seq_actor_fb}, a->tmaps_dev, host))
-      return fail(TD3_ERR_CUDA, "cuTensorMapEncodeTiled failed for a tensor-core operand (or more than %d maps needed)", kMaxTensorMaps);
-    if (!host.empty())
-      cudaMemcpy(a->tmaps_dev, host.data(), host.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice);
-  }
   // The actor's forward pass (TD3_featured.py:159, actor(state)) reads nothing the critic update writes, so in the
   // fused policy update its layers ride along with the critic's backward stages instead of owning barriers.
   {
@@ -1088,6 +1179,15 @@ int plan_agent(td3_agent* a, long long batch) {
     for (; (int)ai < a->n_actor_fwd; ++ai) a->seq_policy_mid.push_back(a->seq_actor_fb[ai]);
     for (const Launch& L : a->seq_critic_apply) a->seq_policy_mid.push_back(L);
     for (size_t i = a->n_actor_fwd; i < a->seq_actor_fb.size(); ++i) a->seq_policy_mid.push_back(a->seq_actor_fb[i]);
+  }
+  // TMA descriptors of every tensor-core operand (pointers are fixed from here on: torch owns the buffers).  The fused
+  // policy sequence gets its own: merging stages can change a launch's cluster size and with it the A-panel box.
+  if (g_tc_mode) {
+    std::vector<CUtensorMap> host;
+    if (!attach_tensor_maps({&a->seq_target, &a->seq_critic_fb, &a->seq_actor_fb, &a->seq_policy_mid}, a->tmaps_dev, host))
+      return fail(TD3_ERR_CUDA, "cuTensorMapEncodeTiled failed for a tensor-core operand (or more than %d maps needed)", kMaxTensorMaps);
+    if (!host.empty())
+      cudaMemcpy(a->tmaps_dev, host.data(), host.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice);
   }
   // constant buffers: dq_pi = -1/(B*qw) (d(-mean)/dQ1), identity for the slice problem
   {
@@ -1478,6 +1578,7 @@ int td3_gemm(int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, int32
                         bias ? (relu ? EPI_BIAS_RELU : EPI_BIAS) : EPI_STORE);
   p.bias = bias;
   g_tc_mode = use_tc ? 1 : 0;
+  g_cluster_mode = getenv("TD3_CLUSTER") ? 1 : 0;
   cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, 0);
   finalize_problem(p, GroupShape{1, 1});
   std::vector<Launch> seq;
@@ -1635,6 +1736,15 @@ int td3_train_n(td3_agent* a, const td3_replay_view* rb, int64_t total_it, int32
   if (rng_mode == TD3_RNG_INJECTED && iterations != 1)
     return fail(TD3_ERR_INVALID, "injected indices/noise cover exactly one update: iterations must be 1");
   cudaStream_t s = (cudaStream_t)stream;
+  {   // the persistent kernel walks un-clustered tile layouts, the stage launches clustered ones: re-plan on a switch
+    const int want = use_graph == 2 ? 0 : 1;
+    if (want != a->cluster_mode) {
+      a->cluster_mode = want;
+      CUDA_TRY(cudaStreamSynchronize(s));
+      rc = plan_agent(a, a->batch);
+      if (rc != TD3_OK) return rc;
+    }
+  }
   rc = plan_sample(a, rb, rng_mode);
   if (rc == TD3_OK) rc = sync_rb_size(a, rb, s);
   if (rc != TD3_OK) return rc;

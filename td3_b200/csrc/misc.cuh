@@ -6,6 +6,12 @@
 
 namespace td3 {
 
+// Programmatic dependent launch: every kernel of the stage-per-launch / graph path lets its successor start early
+// (launch latency, TMEM allocation, barrier initialisation overlap this kernel's tail) and itself waits for its
+// predecessor's results only where it first touches global memory.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
+
 // ------------------------------------------------------------------------------------
 // Philox4x32-10 (Salmon et al., SC'11).  Counter-based: every draw is a pure function of
 // (seed, stream, step, element), so a captured CUDA graph replays correctly from a
@@ -140,6 +146,8 @@ __device__ __forceinline__ void gather_body(const GatherParams& G, int bx, int b
 }
 
 __global__ void __launch_bounds__(256) gather_kernel(const __grid_constant__ GatherParams G) {
+  pdl_launch_dependents();
+  pdl_wait();
   gather_body(G, blockIdx.x, blockIdx.y);
 }
 
@@ -231,10 +239,14 @@ __device__ __forceinline__ void loss_body(const LossParams& L, int agent, float*
 
 __global__ void __launch_bounds__(256) loss_kernel(const __grid_constant__ LossParams L) {
   __shared__ float red[8];
+  pdl_launch_dependents();
+  pdl_wait();
   loss_body(L, blockIdx.x, red);
 }
 
 __global__ void adam_tick_kernel(const __grid_constant__ AdamTick T) {
+  pdl_launch_dependents();
+  pdl_wait();
   if (threadIdx.x == 0 && blockIdx.x == 0) adam_tick(T);
 }
 
@@ -333,6 +345,8 @@ __device__ __forceinline__ void adam_polyak_body(const EwParams& E, long long bx
 }
 
 __global__ void __launch_bounds__(kEwThreads) adam_polyak_kernel(const __grid_constant__ EwParams E) {
+  pdl_launch_dependents();
+  pdl_wait();
   adam_polyak_body(E, blockIdx.x);
 }
 

@@ -58,11 +58,20 @@ __global__ void __launch_bounds__(kStageThreads, 1) stage_kernel(const __grid_co
   extern __shared__ unsigned char smem_raw[];
   __shared__ TcState tc;
   unsigned char* ring = aligned_smem(smem_raw);
+  pdl_launch_dependents();
+  const int cluster = S.cluster;
   if constexpr (kTc) {
-    if (S.any_tc) tc_setup(&tc);
+    if (S.any_tc) tc_setup(&tc, cluster > 1 ? cluster : 1);   // TMEM allocation + mbarrier init overlap the previous stage's tail
+    if (cluster > 1) cluster_sync_all();     // every peer's barriers exist before anybody multicasts into its shared memory
   }
-  run_stage_tile<kTc>(S, blockIdx.x, ring, &tc);
+  pdl_wait();                                // the previous stage's outputs are complete and visible from here on
+#ifdef TD3_TILE_PROF
+  if (threadIdx.x == 0) tc.prof_stage = 0;   // stage-per-launch form: block 0's stamps land in slot 0
+  __syncthreads();
+#endif
+  if ((int)blockIdx.x < S.total_tiles) run_stage_tile<kTc>(S, blockIdx.x, ring, &tc);
   if constexpr (kTc) {
+    if (cluster > 1) cluster_sync_all();     // nobody leaves while a peer may still write its shared memory or barriers
     if (S.any_tc) tc_teardown(&tc);
   }
 }

@@ -49,6 +49,8 @@ struct Problem {
   int c_dups;                     // epilogue writes C to c_dups destinations c_dup_stride apart
   int use_tc;                     // 1: tcgen05 TF32 tile (128 x tc_nt) instead of the fp32 FFMA tile (32 x 32)
   int tc_nt, c_vec, aux_vec;      // TC tile width; 16-byte stores to C / loads from aux0 are legal
+  int tc_cluster, pad_p;          // > 1: this many consecutive N tiles (one cluster) multicast their common A panel
+  int tc_slots, tc_slot_bytes;    // operand ring geometry of the tile (0: the kernel's default)
   long long c_split, c_dup_stride;
   const float* A; const float* B; float* C; const float* bias;
   const void* tmapA; const void* tmapB;   // device arrays of CUtensorMap (one per group) when the operand is TMA-loadable
@@ -64,7 +66,7 @@ constexpr int kMaxProblemsPerStage = 6;
 struct StageParams {
   int n_problems;
   int total_tiles;
-  int any_tc, pad;                // some problem of the stage runs on the tensor cores (TMEM must be allocated)
+  int any_tc, cluster;            // some problem runs on the tensor cores (TMEM must be allocated); cluster size of the launch
   Problem p[kMaxProblemsPerStage];
 };
 

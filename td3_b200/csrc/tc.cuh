@@ -31,9 +31,10 @@
 
 namespace td3 {
 
-constexpr int kTcSlots = 6;
+constexpr int kTcSlots = 6;                         // default ring geometry (persistent kernel: tiles of every width share it)
 constexpr int kTcSlotBytes = 32768;                 // A: 128 x 32 fp32 (16 KB) + B: up to 128 x 32 fp32 (16 KB)
 constexpr int kTcRingBytes = kTcSlots * kTcSlotBytes;
+constexpr int kTcMaxSlots = 11;                     // stage-per-launch form: slots sized for the tile's NT (16 KB + NT * 128 B)
 constexpr int kTcCols = 128;                        // TMEM columns allocated per CTA (fp32 accumulator columns)
 
 #ifdef TD3_TILE_PROF
@@ -43,8 +44,8 @@ constexpr int kTcCols = 128;                        // TMEM columns allocated pe
 #endif
 
 struct TcState {                                    // lives in shared memory, one per CTA
-  unsigned long long full_bar[kTcSlots];            // "this slot's operand bytes have landed" (TMA complete_tx)
-  unsigned long long empty_bar[kTcSlots];           // "the MMAs that read this slot have completed" (tcgen05.commit)
+  unsigned long long full_bar[kTcMaxSlots];         // "this slot's operand bytes have landed" (TMA complete_tx)
+  unsigned long long empty_bar[kTcMaxSlots];        // "the MMAs that read this slot have completed" (tcgen05.commit)
   unsigned long long done_bar;                      // "the tile's accumulator is complete"
   unsigned int tmem_base;
   unsigned int tma_chunk_count;                     // chunks staged so far (full/empty barrier phases)
@@ -71,12 +72,59 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned int 
       : "memory");
 }
 
-// called by all threads of the CTA once, before the first TC tile
-__device__ __forceinline__ void tc_setup(TcState* st) {
+__device__ __forceinline__ unsigned int cluster_ctarank() {
+  unsigned int r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+
+__device__ __forceinline__ bool elect_one() {
+  unsigned int pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void mbar_wait_u32(unsigned int bar, unsigned int parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(bar), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_u32(unsigned int dst, const void* tmap, int c0, int c1, unsigned int bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n" ::"r"(dst),
+               "l"(tmap), "r"(c0), "r"(c1), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_mc_u32(unsigned int dst, const void* tmap, int c0, int c1, unsigned int bar,
+                                                   unsigned short mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%2, %3}], [%4], %5;\n" ::"r"(dst),
+      "l"(tmap), "r"(c0), "r"(c1), "r"(bar), "h"(mask)
+      : "memory");
+}
+
+// called by all threads of the CTA once, before the first TC tile.  cluster = CTAs that share (multicast) the A panel:
+// a slot is free again only when the MMAs of ALL of them have finished reading it.
+__device__ __forceinline__ void tc_setup(TcState* st, int cluster = 1) {
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kTcSlots; ++i) {
+    for (int i = 0; i < kTcMaxSlots; ++i) {
       mbar_init(&st->full_bar[i], 1);
-      mbar_init(&st->empty_bar[i], 1);
+      mbar_init(&st->empty_bar[i], (unsigned)cluster);
     }
     mbar_init(&st->done_bar, 1);
     st->tma_chunk_count = 0;
@@ -145,6 +193,32 @@ __device__ __forceinline__ void tma_load_2d(unsigned int dst, const void* tmap, 
                "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar))
                : "memory");
 }
+__device__ __forceinline__ void tma_load_2d_mc(unsigned int dst, const void* tmap, int c0, int c1, unsigned long long* bar,
+                                               unsigned short mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%2, %3}], [%4], %5;\n" ::"r"(dst),
+      "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar)), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_mc(unsigned long long* bar, unsigned short mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n" ::"r"(smem_u32(bar)),
+               "h"(mask)
+               : "memory");
+}
+// The A chunk (128 rows x 32 k) of a cluster of `c` CTAs that share the same M tile: CTA `rank` fetches 1/c of it and
+// multicasts it into the same slot of every CTA of the cluster (each CTA's full barrier sees all 16 KB arrive).
+__device__ __forceinline__ void tma_issue_a_multicast(unsigned int dst, const void* tmap, int rc, int i0, int k0, int c, int rank,
+                                                      unsigned long long* bar) {
+  const unsigned short mask = (unsigned short)((1u << c) - 1u);
+  if (rc) {
+    const int rows = 128 / c;
+    tma_load_2d_mc(dst + rank * rows * 128, tmap, k0, i0 + rank * rows, bar, mask);
+  } else {
+    for (int g = 0; g < 4; ++g)
+      if (g % c == rank) tma_load_2d_mc(dst + g * 4096, tmap, i0 + g * 32, k0, bar, mask);
+  }
+}
+
 // one operand chunk: rc -> one box [rows_mn x 32 k]; oc -> one box [32 k x 32 mn] per 32-wide MN group
 __device__ __forceinline__ void tma_issue_operand(unsigned int dst, const void* tmap, int rc, int rows_mn, int o0, int k0,
                                                   unsigned long long* bar) {
@@ -275,36 +349,103 @@ __device__ __forceinline__ void gemm_tile_tc(const Problem& P, int tile, unsigne
     const unsigned char* mapB = reinterpret_cast<const unsigned char*>(P.tmapB) + (size_t)g * 128;
     const unsigned int bytes = 16384u + (arc ? 0u : 0u) + (brc ? (unsigned)NT * 128u : (unsigned)((NT + 31) >> 5) * 4096u);
     TCP(1);
-    if (tid == 0) {
+    // ring geometry: the operand stream is latency-bound (one slot = one outstanding chunk), so narrow tiles use
+    // smaller slots and keep more chunks in flight
+    const unsigned int n_slots = P.tc_slots > 0 ? (unsigned)P.tc_slots : (unsigned)kTcSlots;
+    const unsigned int slot_bytes = P.tc_slots > 0 ? (unsigned)P.tc_slot_bytes : (unsigned)kTcSlotBytes;
+    const int csz = P.tc_cluster > 1 ? P.tc_cluster : 1;
+    const int crank = csz > 1 ? (int)cluster_ctarank() : 0;
+    // Producer (warp 0) and MMA issuer (warp 1).  The whole warp walks the loop with warp-uniform values (made
+    // provably uniform with a shuffle) and one elected lane issues the TMA / tcgen05 instructions: UTMALDG / UTCHMMA
+    // take their operands from UNIFORM registers, and with thread-divergent operands the compiler wraps every single
+    // one in an ELECT + 4x R2UR.BROADCAST + branch "waterfall" loop (measured: 640-707 cycles per 4-MMA chunk,
+    // independent of tile width, ring depth, operand orientation and cluster size).
+#define TD3_UNI(x) __shfl_sync(0xffffffffu, (x), 0)
+    if (warp == 0) {
+      const unsigned int ring_u = TD3_UNI(smem_u32(ring)), fb0 = TD3_UNI(smem_u32(&st->full_bar[0])),
+                         eb0 = TD3_UNI(smem_u32(&st->empty_bar[0]));
+      const unsigned int nsl = TD3_UNI(n_slots), sbytes = TD3_UNI(slot_bytes), ubytes = TD3_UNI(bytes);
+      const unsigned int tch = TD3_UNI(tchunk);
+      const int nch = TD3_UNI(n_chunks), ui0 = TD3_UNI(i0), uj0 = TD3_UNI(j0), unt = TD3_UNI(NT);
+      const int uarc = TD3_UNI(arc), ubrc = TD3_UNI(brc), ucsz = TD3_UNI(csz), ucrank = TD3_UNI(crank);
+      const unsigned long long ma = ((unsigned long long)TD3_UNI((unsigned int)((unsigned long long)mapA >> 32)) << 32) |
+                                    TD3_UNI((unsigned int)(unsigned long long)mapA);
+      const unsigned long long mb = ((unsigned long long)TD3_UNI((unsigned int)((unsigned long long)mapB >> 32)) << 32) |
+                                    TD3_UNI((unsigned int)(unsigned long long)mapB);
+      int k0 = TD3_UNI(k_begin);
+      unsigned int slot = tch % nsl, use = tch / nsl;
+      unsigned int sa = ring_u + slot * sbytes, fb = fb0 + slot * 8, eb = eb0 + slot * 8;
+      const unsigned short mask = (unsigned short)((1u << ucsz) - 1u);
+      const int a_rows = 128 / ucsz;
 #pragma unroll 1
-      for (int c = 0; c < n_chunks; ++c) {
-        const unsigned int gc = tchunk + c, slot = gc % kTcSlots, use = gc / kTcSlots;
-        if (use > 0) mbar_wait(&st->empty_bar[slot], (use - 1) & 1);
-        mbar_expect_tx(&st->full_bar[slot], bytes);
-        const unsigned int sa = smem_u32(ring + slot * kTcSlotBytes);
-        tma_issue_operand(sa, mapA, arc, 128, i0, k_begin + c * 32, &st->full_bar[slot]);
-        tma_issue_operand(sa + 16384, mapB, brc, NT, j0, k_begin + c * 32, &st->full_bar[slot]);
+      for (int c = 0; c < nch; ++c) {
+        if (use > 0) mbar_wait_u32(eb, (use - 1) & 1);                     // every CTA of the cluster is done with the slot
+        if (elect_one()) {
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(fb), "r"(ubytes) : "memory");
+          if (ucsz > 1) {
+            if (uarc) {
+              tma_load_2d_mc_u32(sa + ucrank * a_rows * 128, (const void*)ma, k0, ui0 + ucrank * a_rows, fb, mask);
+            } else {
+              for (int g4 = ucrank; g4 < 4; g4 += ucsz) tma_load_2d_mc_u32(sa + g4 * 4096, (const void*)ma, ui0 + g4 * 32, k0, fb, mask);
+            }
+          } else if (uarc) {
+            tma_load_2d_u32(sa, (const void*)ma, k0, ui0, fb);
+          } else {
+#pragma unroll
+            for (int g4 = 0; g4 < 4; ++g4) tma_load_2d_u32(sa + g4 * 4096, (const void*)ma, ui0 + g4 * 32, k0, fb);
+          }
+          if (ubrc) {
+            tma_load_2d_u32(sa + 16384, (const void*)mb, k0, uj0, fb);
+          } else {
+            for (int g4 = 0; g4 * 32 < unt; ++g4) tma_load_2d_u32(sa + 16384 + g4 * 4096, (const void*)mb, uj0 + g4 * 32, k0, fb);
+          }
+        }
+        __syncwarp();
+        k0 += 32; sa += sbytes; fb += 8; eb += 8;
+        if (++slot == nsl) { slot = 0; ++use; sa = ring_u; fb = fb0; eb = eb0; }
       }
       TCP(2);
-    } else if (tid == 32) {
+    } else if (warp == 1) {
+      const unsigned int ring_u = TD3_UNI(smem_u32(ring)), fb0 = TD3_UNI(smem_u32(&st->full_bar[0])),
+                         eb0 = TD3_UNI(smem_u32(&st->empty_bar[0])), done_u = TD3_UNI(smem_u32(&st->done_bar));
+      const unsigned int nsl = TD3_UNI(n_slots), sbytes = TD3_UNI(slot_bytes), tch = TD3_UNI(tchunk);
+      const unsigned int utmem = TD3_UNI(tmem), uidesc = TD3_UNI(idesc);
+      const int nch = TD3_UNI(n_chunks), ucsz = TD3_UNI(csz);
+      // descriptor words: hi = SBO | version | layout type (constant per operand); lo = start address | LBO
+      const unsigned int a_hi = TD3_UNI((a_sbo >> 4) | (1u << 14) | (a_lt << 29)), b_hi = TD3_UNI((b_sbo >> 4) | (1u << 14) | (b_lt << 29));
+      const unsigned int a_lo0 = TD3_UNI((a_lbo >> 4) << 16), b_lo0 = TD3_UNI((b_lbo >> 4) << 16);
+      const unsigned int a_ks = TD3_UNI(a_kstep >> 4), b_ks = TD3_UNI(b_kstep >> 4);
+      unsigned int slot = tch % nsl, use = tch / nsl;
+      unsigned int sa = ring_u + slot * sbytes, fb = fb0 + slot * 8, eb = eb0 + slot * 8;
+      const unsigned short mask = (unsigned short)((1u << ucsz) - 1u);
 #pragma unroll 1
-      for (int c = 0; c < n_chunks; ++c) {
-        const unsigned int gc = tchunk + c, slot = gc % kTcSlots, use = gc / kTcSlots;
-        mbar_wait(&st->full_bar[slot], use & 1);
+      for (int c = 0; c < nch; ++c) {
+        mbar_wait_u32(fb, use & 1);
         if (c == 0) TCP(1);
         asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-        const unsigned int sa = smem_u32(ring + slot * kTcSlotBytes), sb = sa + 16384;
+        if (elect_one()) {
+          const unsigned int a_lo = a_lo0 | (sa >> 4), b_lo = b_lo0 | ((sa + 16384) >> 4);
+          tc_mma(utmem, ((unsigned long long)a_hi << 32) | a_lo, ((unsigned long long)b_hi << 32) | b_lo, uidesc, c > 0 ? 1u : 0u);
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {
-          const unsigned long long da = tc_desc(sa + kk * a_kstep, a_lbo, a_sbo, a_lt);
-          const unsigned long long db = tc_desc(sb + kk * b_kstep, b_lbo, b_sbo, b_lt);
-          tc_mma(tmem, da, db, idesc, (c > 0 || kk > 0) ? 1u : 0u);
+          for (int kk = 1; kk < 4; ++kk)
+            tc_mma(utmem, ((unsigned long long)a_hi << 32) | (a_lo + kk * a_ks), ((unsigned long long)b_hi << 32) | (b_lo + kk * b_ks),
+                   uidesc, 1u);
+          if (ucsz > 1)
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n" ::"r"(eb),
+                         "h"(mask)
+                         : "memory");
+          else
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(eb) : "memory");
+          if (c == nch - 1)
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(done_u) : "memory");
         }
-        tc_commit(&st->empty_bar[slot]);
-        if (c == n_chunks - 1) tc_commit(&st->done_bar);
+        __syncwarp();
+        sa += sbytes; fb += 8; eb += 8;
+        if (++slot == nsl) { slot = 0; ++use; sa = ring_u; fb = fb0; eb = eb0; }
       }
       TCP(2);
     }
+#undef TD3_UNI
     __syncwarp();
   }
 
