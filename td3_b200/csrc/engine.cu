@@ -354,12 +354,7 @@ void layout_stage(Launch& L) {
     Problem& p = S.p[q];
     if (p.kind == PK_GEMM && p.use_tc) {
       p.tc_cluster = c;
-      if (g_cluster_mode) {          // stage-per-launch form (one tile per CTA): ring sized for this tile's width
-        p.tc_slot_bytes = 16384 + (p.tc_nt * 128 + 1023) / 1024 * 1024;
-        p.tc_slots = std::min(kTcMaxSlots, kTcRingBytes / p.tc_slot_bytes);
-      } else {
-        p.tc_slots = p.tc_slot_bytes = 0;
-      }
+      p.tc_slots = p.tc_slot_bytes = 0;
       p.tiles_n = ((p.N + p.tc_nt - 1) / p.tc_nt + c - 1) / c * c;
       p.tiles_per_group = p.tiles_m * p.tiles_n * p.ksplit;
       p.tile_count = p.tiles_per_group * groups[q];

@@ -31,10 +31,12 @@
 
 namespace td3 {
 
-constexpr int kTcSlots = 6;                         // default ring geometry (persistent kernel: tiles of every width share it)
-constexpr int kTcSlotBytes = 32768;                 // A: 128 x 32 fp32 (16 KB) + B: up to 128 x 32 fp32 (16 KB)
+constexpr int kTcSub = 32768;                       // one 32-step chunk: A 128 x 32 fp32 (16 KB) + B up to 128 x 32 fp32 (16 KB)
+constexpr int kTcGroup = 2;                         // chunks per pipeline stage: one barrier round trip per 8 MMAs
+constexpr int kTcSlots = 3;                         // pipeline stages in flight
+constexpr int kTcSlotBytes = kTcGroup * kTcSub;
 constexpr int kTcRingBytes = kTcSlots * kTcSlotBytes;
-constexpr int kTcMaxSlots = 11;                     // stage-per-launch form: slots sized for the tile's NT (16 KB + NT * 128 B)
+constexpr int kTcMaxSlots = kTcSlots;
 constexpr int kTcCols = 128;                        // TMEM columns allocated per CTA (fp32 accumulator columns)
 
 #ifdef TD3_TILE_PROF
@@ -247,47 +249,89 @@ __device__ __forceinline__ float4 tc_load_aux(const Problem& P, const float* aux
   return v;
 }
 
-// Epilogue of one warp: its 32 accumulator rows (TMEM lanes) x `half` columns starting at local column jw, four columns
-// per rolled iteration: tcgen05.ld -> bias / activation -> 16-byte store.
+// One group of W (16 or 8) accumulator columns of this thread's row: operands of the epilogue loaded up front (they are in
+// flight while the tile's last MMAs finish: the caller waits for the accumulator between the two halves), one
+// tcgen05.ld for all W columns, straight-line per-kind math, 16-byte stores.
+template <int W>
+__device__ __forceinline__ void tc_load_aux_group(const Problem& P, const float* aux0, bool aux_read, bool x_vec, bool row_ok, int i,
+                                                  int j, float (&ax)[W]) {
+#pragma unroll
+  for (int q = 0; q < W / 4; ++q) {
+    const float4 v = tc_load_aux(P, aux0, aux_read, x_vec, row_ok, i, j + 4 * q);
+    ax[4 * q] = v.x; ax[4 * q + 1] = v.y; ax[4 * q + 2] = v.z; ax[4 * q + 3] = v.w;
+  }
+}
+
+template <int EPI, int W>
+__device__ __forceinline__ void tc_epilogue_group(const Problem& P, float* __restrict__ C, float* aux0, const float* bias_s,
+                                                  bool has_bias, bool c_vec, bool row_ok, bool have_acc, int i, int j, int jl,
+                                                  unsigned int taddr, const float (&ax)[W]) {
+  unsigned int r[W];
+  if (W == 16) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8 % W]), "=r"(r[9 % W]),
+          "=r"(r[10 % W]), "=r"(r[11 % W]), "=r"(r[12 % W]), "=r"(r[13 % W]), "=r"(r[14 % W]), "=r"(r[15 % W])
+        : "r"(taddr)
+        : "memory");
+  } else {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+  }
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+  if (!row_ok) return;
+#pragma unroll
+  for (int q = 0; q < W / 4; ++q) {
+    const int jq = j + 4 * q;
+    if (jq >= P.N) break;
+    float o[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float aux_out = 0.f;
+      const float v = have_acc ? __uint_as_float(r[4 * q + e]) : 0.f;
+      o[e] = epi_apply<EPI>(v, has_bias ? bias_s[jl + 4 * q + e] : 0.f, ax[4 * q + e], P.f0, P.f1, aux_out);
+      if (EPI == EPI_BIAS_TANH && jq + e < P.N) aux0[(size_t)i * P.ldaux + jq + e] = aux_out;
+    }
+#pragma unroll 1
+    for (int d = 0; d < P.c_dups; ++d) {
+      float* cp = C + d * P.c_dup_stride + (size_t)i * P.ldc + jq;
+      if (c_vec && jq + 3 < P.N) {
+        *reinterpret_cast<float4*>(cp) = make_float4(o[0], o[1], o[2], o[3]);
+      } else {
+        cp[0] = o[0];
+        if (jq + 1 < P.N) cp[1] = o[1];
+        if (jq + 2 < P.N) cp[2] = o[2];
+        if (jq + 3 < P.N) cp[3] = o[3];
+      }
+    }
+  }
+}
+
+// Epilogue of one warp: its 32 accumulator rows (TMEM lanes) x `half` columns starting at local column jw.
 template <int EPI>
 __device__ __forceinline__ void tc_epilogue_cols(const Problem& P, float* __restrict__ C, float* aux0, const float* bias_s,
                                                  bool has_bias, bool aux_read, bool x_vec, bool c_vec, bool row_ok, bool have_acc,
-                                                 int i, int j0, int jw, int half, unsigned int tmem_lane) {
-  float4 av = tc_load_aux(P, aux0, aux_read, x_vec, row_ok, i, j0 + jw);
+                                                 int i, int j0, int jw, int half, unsigned int tmem_lane, unsigned int done_bar,
+                                                 unsigned int done_parity) {
+  if (half >= 16) {
+    float ax[16];
+    tc_load_aux_group<16>(P, aux0, aux_read, x_vec, row_ok, i, j0 + jw, ax);
+    if (have_acc) mbar_wait_u32(done_bar, done_parity);
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
 #pragma unroll 1
-  for (int jc = 0; jc < half; jc += 4) {
-    const int jl = jw + jc, j = j0 + jl;
-    const float4 a_cur = av;
-    if (jc + 4 < half) av = tc_load_aux(P, aux0, aux_read, x_vec, row_ok, i, j + 4);   // next iteration's operand
-    unsigned int r0, r1, r2, r3;
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];\n"
-                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
-                 : "r"(tmem_lane + (unsigned)jl)
-                 : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
-    if (row_ok && j < P.N) {
-      float o[4] = {__uint_as_float(r0), __uint_as_float(r1), __uint_as_float(r2), __uint_as_float(r3)};
-      const float ax[4] = {a_cur.x, a_cur.y, a_cur.z, a_cur.w};
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        float aux_out = 0.f;
-        const float v = have_acc ? o[e] : 0.f;
-        o[e] = epi_apply<EPI>(v, has_bias ? bias_s[jl + e] : 0.f, ax[e], P.f0, P.f1, aux_out);
-        if (EPI == EPI_BIAS_TANH && j + e < P.N) aux0[(size_t)i * P.ldaux + j + e] = aux_out;
-      }
-#pragma unroll 1
-      for (int d = 0; d < P.c_dups; ++d) {
-        float* cp = C + d * P.c_dup_stride + (size_t)i * P.ldc + j;
-        if (c_vec && j + 3 < P.N) {
-          *reinterpret_cast<float4*>(cp) = make_float4(o[0], o[1], o[2], o[3]);
-        } else {
-          cp[0] = o[0];
-          if (j + 1 < P.N) cp[1] = o[1];
-          if (j + 2 < P.N) cp[2] = o[2];
-          if (j + 3 < P.N) cp[3] = o[3];
-        }
-      }
+    for (int jc = 0; jc < half; jc += 16) {
+      if (jc > 0) tc_load_aux_group<16>(P, aux0, aux_read, x_vec, row_ok, i, j0 + jw + jc, ax);
+      tc_epilogue_group<EPI, 16>(P, C, aux0, bias_s, has_bias, c_vec, row_ok, have_acc, i, j0 + jw + jc, jw + jc,
+                                 tmem_lane + (unsigned)(jw + jc), ax);
     }
+  } else {   // NT = 16: eight columns per warp half
+    float ax[8];
+    tc_load_aux_group<8>(P, aux0, aux_read, x_vec, row_ok, i, j0 + jw, ax);
+    if (have_acc) mbar_wait_u32(done_bar, done_parity);
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    tc_epilogue_group<EPI, 8>(P, C, aux0, bias_s, has_bias, c_vec, row_ok, have_acc, i, j0 + jw, jw, tmem_lane + (unsigned)jw, ax);
   }
 }
 
@@ -349,10 +393,10 @@ __device__ __forceinline__ void gemm_tile_tc(const Problem& P, int tile, unsigne
     const unsigned char* mapB = reinterpret_cast<const unsigned char*>(P.tmapB) + (size_t)g * 128;
     const unsigned int bytes = 16384u + (arc ? 0u : 0u) + (brc ? (unsigned)NT * 128u : (unsigned)((NT + 31) >> 5) * 4096u);
     TCP(1);
-    // ring geometry: the operand stream is latency-bound (one slot = one outstanding chunk), so narrow tiles use
-    // smaller slots and keep more chunks in flight
-    const unsigned int n_slots = P.tc_slots > 0 ? (unsigned)P.tc_slots : (unsigned)kTcSlots;
-    const unsigned int slot_bytes = P.tc_slots > 0 ? (unsigned)P.tc_slot_bytes : (unsigned)kTcSlotBytes;
+    const unsigned int n_slots = kTcSlots, slot_bytes = kTcSlotBytes;
+    const int n_stages = (n_chunks + kTcGroup - 1) / kTcGroup;
+    if (tid == 0) asm volatile("prefetch.tensormap [%0];\n" ::"l"(mapA) : "memory");
+    if (tid == 32) asm volatile("prefetch.tensormap [%0];\n" ::"l"(mapB) : "memory");
     const int csz = P.tc_cluster > 1 ? P.tc_cluster : 1;
     const int crank = csz > 1 ? (int)cluster_ctarank() : 0;
     // Producer (warp 0) and MMA issuer (warp 1).  The whole warp walks the loop with warp-uniform values (made
@@ -372,16 +416,22 @@ __device__ __forceinline__ void gemm_tile_tc(const Problem& P, int tile, unsigne
                                     TD3_UNI((unsigned int)(unsigned long long)mapA);
       const unsigned long long mb = ((unsigned long long)TD3_UNI((unsigned int)((unsigned long long)mapB >> 32)) << 32) |
                                     TD3_UNI((unsigned int)(unsigned long long)mapB);
-      int k0 = TD3_UNI(k_begin);
+      int kc = TD3_UNI(k_begin);
       unsigned int slot = tch % nsl, use = tch / nsl;
-      unsigned int sa = ring_u + slot * sbytes, fb = fb0 + slot * 8, eb = eb0 + slot * 8;
+      unsigned int sa0 = ring_u + slot * sbytes, fb = fb0 + slot * 8, eb = eb0 + slot * 8;
       const unsigned short mask = (unsigned short)((1u << ucsz) - 1u);
       const int a_rows = 128 / ucsz;
+      const int nst = TD3_UNI(n_stages);
 #pragma unroll 1
-      for (int c = 0; c < nch; ++c) {
+      for (int c = 0; c < nst; ++c) {
         if (use > 0) mbar_wait_u32(eb, (use - 1) & 1);                     // every CTA of the cluster is done with the slot
+        const int nsub = min(kTcGroup, nch - c * kTcGroup);
         if (elect_one()) {
-          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(fb), "r"(ubytes) : "memory");
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(fb), "r"(ubytes * nsub) : "memory");
+#pragma unroll 1
+          for (int u = 0; u < nsub; ++u) {
+          const unsigned int sa = sa0 + u * kTcSub;
+          const int k0 = kc + u * 32;
           if (ucsz > 1) {
             if (uarc) {
               tma_load_2d_mc_u32(sa + ucrank * a_rows * 128, (const void*)ma, k0, ui0 + ucrank * a_rows, fb, mask);
@@ -399,10 +449,11 @@ __device__ __forceinline__ void gemm_tile_tc(const Problem& P, int tile, unsigne
           } else {
             for (int g4 = 0; g4 * 32 < unt; ++g4) tma_load_2d_u32(sa + 16384 + g4 * 4096, (const void*)mb, uj0 + g4 * 32, k0, fb);
           }
+          }
         }
         __syncwarp();
-        k0 += 32; sa += sbytes; fb += 8; eb += 8;
-        if (++slot == nsl) { slot = 0; ++use; sa = ring_u; fb = fb0; eb = eb0; }
+        kc += kTcGroup * 32; sa0 += sbytes; fb += 8; eb += 8;
+        if (++slot == nsl) { slot = 0; ++use; sa0 = ring_u; fb = fb0; eb = eb0; }
       }
       TCP(2);
     } else if (warp == 1) {
@@ -418,11 +469,13 @@ __device__ __forceinline__ void gemm_tile_tc(const Problem& P, int tile, unsigne
       unsigned int slot = tch % nsl, use = tch / nsl;
       unsigned int sa = ring_u + slot * sbytes, fb = fb0 + slot * 8, eb = eb0 + slot * 8;
       const unsigned short mask = (unsigned short)((1u << ucsz) - 1u);
+      const int nst = TD3_UNI(n_stages);
 #pragma unroll 1
-      for (int c = 0; c < nch; ++c) {
+      for (int c = 0; c < nst; ++c) {
         mbar_wait_u32(fb, use & 1);
         if (c == 0) TCP(1);
         asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+        const int nsub = min(kTcGroup, nch - c * kTcGroup);
         if (elect_one()) {
           const unsigned int a_lo = a_lo0 | (sa >> 4), b_lo = b_lo0 | ((sa + 16384) >> 4);
           tc_mma(utmem, ((unsigned long long)a_hi << 32) | a_lo, ((unsigned long long)b_hi << 32) | b_lo, uidesc, c > 0 ? 1u : 0u);
@@ -430,13 +483,20 @@ __device__ __forceinline__ void gemm_tile_tc(const Problem& P, int tile, unsigne
           for (int kk = 1; kk < 4; ++kk)
             tc_mma(utmem, ((unsigned long long)a_hi << 32) | (a_lo + kk * a_ks), ((unsigned long long)b_hi << 32) | (b_lo + kk * b_ks),
                    uidesc, 1u);
+          if (nsub > 1) {
+            const unsigned int a2 = a_lo + (kTcSub >> 4), b2 = b_lo + (kTcSub >> 4);
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+              tc_mma(utmem, ((unsigned long long)a_hi << 32) | (a2 + kk * a_ks), ((unsigned long long)b_hi << 32) | (b2 + kk * b_ks),
+                     uidesc, 1u);
+          }
           if (ucsz > 1)
             asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n" ::"r"(eb),
                          "h"(mask)
                          : "memory");
           else
             asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(eb) : "memory");
-          if (c == nch - 1)
+          if (c == nst - 1)
             asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(done_u) : "memory");
         }
         __syncwarp();
@@ -462,11 +522,9 @@ __device__ __forceinline__ void gemm_tile_tc(const Problem& P, int tile, unsigne
   const int half = NT >> 1, jw = (warp >> 2) * half;
   __syncthreads();                                         // bias strip visible (the MMA pipeline is busy meanwhile)
   TCP(3);
-  if (n_chunks > 0) mbar_wait(&st->done_bar, tile_no & 1);
-  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-  TCP(4);
   TD3_DISPATCH_EPI(epi, (tc_epilogue_cols<E>(P, C, aux0, bias_s, has_bias, aux_read, x_vec, c_vec, row_ok, n_chunks > 0, i, j0, jw,
-                                             half, tmem + (((unsigned)(warp & 3) * 32u) << 16))));
+                                             half, tmem + (((unsigned)(warp & 3) * 32u) << 16), smem_u32(&st->done_bar), tile_no & 1)));
+  TCP(4);
   TCP(5);
   // every warp is past its TMEM reads before the next tile's first MMA overwrites the accumulator
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
@@ -479,7 +537,7 @@ __device__ __forceinline__ void gemm_tile_tc(const Problem& P, int tile, unsigne
   }
 #endif
   if (tid == 0) {
-    st->tma_chunk_count += (unsigned)max(n_chunks, 0);
+    st->tma_chunk_count += (unsigned)max((n_chunks + kTcGroup - 1) / kTcGroup, 0);
     if (n_chunks > 0) st->tile_count = tile_no + 1;
   }
   __syncthreads();
