@@ -55,7 +55,9 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 // launch list
 // ------------------------------------------------------------------------------------
 struct Launch {
-  enum Kind { STAGE, GATHER, LOSS, EW, TICK } kind = STAGE;
+  enum Kind { STAGE, GATHER, LOSS, EW, TICK, HEAD } kind = STAGE;
+  HeadParams head{};
+  int smem_bytes = 0;
   StageParams stage{};
   GatherParams gather{};
   LossParams loss{};
@@ -67,6 +69,7 @@ struct Launch {
 int ensure_kernel_attrs() {
   static bool done = false;
   if (done) return TD3_OK;
+  CUDA_TRY(cudaFuncSetAttribute(head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
   CUDA_TRY(cudaFuncSetAttribute(stage_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynSmemBytes));
   CUDA_TRY(cudaFuncSetAttribute(stage_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynSmemBytes));
   CUDA_TRY(cudaFuncSetAttribute(persistent_update_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynSmemBytes));
@@ -125,6 +128,12 @@ int run_launch(const Launch& L, cudaStream_t s) {
     case Launch::TICK:
       e = launch_pdl(adam_tick_kernel, dim3(1), dim3(32), 0, s, L.tick);
       break;
+    case Launch::HEAD: {
+      int rc = ensure_kernel_attrs();
+      if (rc != TD3_OK) return rc;
+      e = launch_pdl(head_kernel, dim3(L.grid_x), dim3(kHeadThreads), (size_t)L.smem_bytes, s, L.head);
+      break;
+    }
   }
   if (e != cudaSuccess) return fail(TD3_ERR_CUDA, "kernel launch: %s", cudaGetErrorString(e));
   g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -536,7 +545,8 @@ void set_groups(Problem& p, long long a_go, long long a_gi, long long b_go, long
 
 std::vector<ProblemList> build_forward(const td3_agent_config& cfg, const td3_net_layout& net, ParamRef W, GroupShape gs,
                                        int B, const PassBuf& pb, const OutSpec& out, int pool_dups = 1,
-                                       long long pool_dup_stride = 0) {
+                                       long long pool_dup_stride = 0, bool skip_last = false) {
+  // skip_last: the output layer is computed by the fused head kernel (misc.cuh: head_body)
   std::vector<ProblemList> st;
   const bool ln = cfg.norm == TD3_NORM_LAYER;
   const bool enc = cfg.variant == TD3_VARIANT_PARTICLES;
@@ -585,6 +595,7 @@ std::vector<ProblemList> build_forward(const td3_agent_config& cfg, const td3_ne
   for (int l = 0; l < L; ++l) {
     const int K = net.dims[l], N = net.dims[l + 1];
     const bool last = l == L - 1;
+    if (last && skip_last) break;
     Problem g = make_gemm(B, N, K, in, ld_in, true, W.base + net.w_off[l], K, true, last ? out.out : pb.r[l],
                           last ? out.ld : N, last ? out.epi : EPI_BIAS_RELU);
     set_groups(g, in_go, in_gi, W.go, W.gi, last ? out.go : pb.h_go[l], last ? out.gi : pb.h_gi[l]);
@@ -650,7 +661,9 @@ int choose_ksplit(int tiles, int groups, int K) {
 std::vector<ProblemList> build_backward(const td3_agent_config& cfg, const td3_net_layout& net, ParamRef W, GradRef G,
                                         GroupShape gs, int B, const PassBuf& pb, const float* dout, int ld_dout,
                                         long long dout_go, long long dout_gi, bool want_dw, const Dx0Spec& dx0,
-                                        const BwdScratch& sc) {
+                                        const BwdScratch& sc, bool head_done = false) {
+  // head_done: the output layer's dW/db and the gradient w.r.t. its input were produced by the fused head kernel
+  // (into sc.dz[0], or sc.dn with LayerNorm): the walk starts below it
   std::vector<ProblemList> st;
   const bool ln = cfg.norm == TD3_NORM_LAYER;
   const bool enc = cfg.variant == TD3_VARIANT_PARTICLES;
@@ -672,7 +685,8 @@ std::vector<ProblemList> build_backward(const td3_agent_config& cfg, const td3_n
     } else {
       in = ln ? pb.n[l - 1] : pb.r[l - 1]; ld_in = K; in_go = pb.h_go[l - 1]; in_gi = pb.h_gi[l - 1];
     }
-    if (want_dw) {   // dW_l[n,k] = sum_b dz[b,n] in[b,k] ; db_l[n] = sum_b dz[b,n]
+    const bool skip = head_done && l == L - 1 && l > 0;
+    if (want_dw && !skip) {   // dW_l[n,k] = sum_b dz[b,n] in[b,k] ; db_l[n] = sum_b dz[b,n]
       Problem p = make_gemm(N, K, B, dz, ld_dz, false, in, ld_in, false, G.base + net.w_off[l], K, EPI_STORE);
       set_groups(p, dz_go, dz_gi, in_go, in_gi, G.go, G.gi);
       finalize_problem(p, gs);
@@ -692,13 +706,15 @@ std::vector<ProblemList> build_backward(const td3_agent_config& cfg, const td3_n
     if (l > 0) {     // d(in_l) = dz . W_l
       const bool mask_now = !ln;
       float* dst = mask_now ? sc.dz[pp] : sc.dn;
-      Problem p = make_gemm(B, K, N, dz, ld_dz, true, W.base + net.w_off[l], K, false, dst, K,
-                            mask_now ? EPI_RELU_MASK : EPI_STORE);
-      set_groups(p, dz_go, dz_gi, W.go, W.gi, sc.go, sc.gi);
-      if (mask_now) { p.aux0 = pb.r[l - 1]; p.ldaux = K; p.aux0_go = pb.h_go[l - 1]; p.aux0_gi = pb.h_gi[l - 1]; }
-      finalize_problem(p, gs);
-      stage.push_back(p);
-      st.push_back(stage);
+      if (!skip) {
+        Problem p = make_gemm(B, K, N, dz, ld_dz, true, W.base + net.w_off[l], K, false, dst, K,
+                              mask_now ? EPI_RELU_MASK : EPI_STORE);
+        set_groups(p, dz_go, dz_gi, W.go, W.gi, sc.go, sc.gi);
+        if (mask_now) { p.aux0 = pb.r[l - 1]; p.ldaux = K; p.aux0_go = pb.h_go[l - 1]; p.aux0_gi = pb.h_gi[l - 1]; }
+        finalize_problem(p, gs);
+        stage.push_back(p);
+      }
+      if (!stage.empty()) st.push_back(stage);
       if (ln) {      // through LayerNorm then ReLU
         ProblemList s2;
         Problem rr = blank_problem(PK_LN_BWD_ROWS);
@@ -1000,6 +1016,14 @@ int plan_agent(td3_agent* a, long long batch) {
   a->tanh_y = ws.take((long long)nA * B * A, "tanh_y");
   float* da = ws.take((long long)nA * B * A, "d_action");
   float* eye = ws.take((long long)A * A, "eye");
+  // fused critic heads (misc.cuh: head_body): small output width, hidden width within the kernel's register tile
+  const int Lq = c.q.n_linear, wq_last = Lq >= 2 ? c.q.dims[Lq - 1] : 0;
+  const bool fuse_heads = Lq >= 2 && qw <= kHeadMaxQw && wq_last <= kHeadMaxW && !getenv("TD3_NO_HEAD_FUSION");
+  const int head_ctas = (B + kHeadRows - 1) / kHeadRows;
+  const long long head_per_g = (long long)qw * wq_last + qw;
+  const long long head_part_go = (long long)head_ctas * nq * head_per_g + head_ctas;
+  float* head_part = ws.take(fuse_heads ? nA * head_part_go * 2 : 1, "head_partials");
+  unsigned int* head_counter = reinterpret_cast<unsigned int*>(ws.take(2LL * nA, "head_counters"));
   a->prof_dev = reinterpret_cast<long long*>(ws.take(2LL * 2 * 128 * 3, "prof"));
   a->tmaps_dev = reinterpret_cast<CUtensorMap*>(ws.take((long long)kMaxTensorMaps * (long long)(sizeof(CUtensorMap) / 4), "tensor_maps"));
   a->prog_dev = reinterpret_cast<StageRec*>(ws.take(2LL * kMaxProgStages * (long long)(sizeof(StageRec) / 4), "program"));
@@ -1055,11 +1079,11 @@ int plan_agent(td3_agent* a, long long batch) {
     auto s_at = build_forward(c, c.actor, Wat, g_actor, B, at, o);
     OutSpec oq;
     oq.out = a->tq; oq.ld = qw; oq.gi = (long long)B * qw; oq.go = oq.gi * nq; oq.epi = EPI_BIAS;
-    auto s_ct = build_forward(c, c.q, Wct, g_crit, B, ct, oq);
+    auto s_ct = build_forward(c, c.q, Wct, g_crit, B, ct, oq, 1, 0, fuse_heads);
     // the online critic forward is independent of the target path: run it alongside the target actor
     OutSpec oc;
     oc.out = a->q; oc.ld = qw; oc.gi = (long long)B * qw; oc.go = oc.gi * nq; oc.epi = EPI_BIAS;
-    auto s_cc = build_forward(c, c.q, Wc, g_crit, B, cc, oc);
+    auto s_cc = build_forward(c, c.q, Wc, g_crit, B, cc, oc, 1, 0, fuse_heads);
     for (auto& st : zip_stages({s_at, s_cc})) emit_stage(a->seq_target, st);
     for (auto& st : s_ct) emit_stage(a->seq_target, st);
   }
@@ -1075,10 +1099,34 @@ int plan_agent(td3_agent* a, long long batch) {
     lp.discount = c.discount;
     lp.inv_norm = 1.f / (float)((a->global_batch > 0 ? a->global_batch : batch) * qw);
     lp.tick = AdamTick{a->state_u64, 0, 0, c.lr_critic, c.beta1, c.beta2};
+    if (fuse_heads) {       // both heads + loss + head backward in one launch
+      const float inv_norm = lp.inv_norm;
+      const AdamTick tick = lp.tick;
+      L = Launch{};
+      L.kind = Launch::HEAD;
+      HeadParams& H = L.head;
+      memset(&H, 0, sizeof(H));
+      const int l2 = Lq - 2;
+      H.h = ln ? cc.n[l2] : cc.r[l2]; H.h_go = cc.h_go[l2]; H.h_gi = cc.h_gi[l2];
+      H.ht = ln ? ct.n[l2] : ct.r[l2]; H.ht_go = ct.h_go[l2]; H.ht_gi = ct.h_gi[l2];
+      H.W = a->critic.params + c.q.w_off[Lq - 1]; H.b = a->critic.params + c.q.b_off[Lq - 1]; H.w_go = qn * nq; H.w_gi = qn;
+      H.Wt = a->critic.target + c.q.w_off[Lq - 1]; H.bt = a->critic.target + c.q.b_off[Lq - 1]; H.wt_go = qn * nq; H.wt_gi = qn;
+      H.r = a->r; H.nd = a->nd; H.r_go = B;
+      H.q = a->q; H.tq = a->tq; H.dq = a->dq; H.q_gi = (long long)B * qw; H.q_go = H.q_gi * nq;
+      H.y = a->y; H.y_go = (long long)B * qw;
+      H.dz = ln ? sc_c.dn : sc_c.dz[0]; H.dz_go = sc_c.go; H.dz_gi = sc_c.gi;
+      H.gW = a->critic.grad + c.q.w_off[Lq - 1]; H.gb = a->critic.grad + c.q.b_off[Lq - 1]; H.g_go = qn * nq; H.g_gi = qn;
+      H.part = head_part; H.part_go = head_part_go; H.counter = head_counter; H.loss = a->state_f32;
+      H.batch = B; H.w = wq_last; H.qw = qw; H.n_q = nq; H.ldh = wq_last; H.lddz = wq_last; H.n_cta = head_ctas;
+      H.mode = 0; H.relu_mask = ln ? 0 : 1;
+      H.discount = c.discount; H.inv_norm = inv_norm; H.tick = tick;
+      L.grid_x = nA * head_ctas;
+      L.smem_bytes = (int)((2LL * nq * qw * wq_last + 4 * kHeadMaxQw + (long long)kHeadRows * nq * head_per_g + kHeadRows + 16) * sizeof(float));
+    }
     a->seq_critic_fb.push_back(L);
     Dx0Spec none;
     auto s_b = build_backward(c, c.q, Wc, Gc, g_crit, B, cc, a->dq, qw, (long long)B * qw * nq, (long long)B * qw, true,
-                              none, sc_c);
+                              none, sc_c, fuse_heads);
     for (auto& st : s_b) emit_stage(a->seq_critic_fb, st);
   }
   // ---- critic Adam (:153) ----
@@ -1105,8 +1153,27 @@ int plan_agent(td3_agent* a, long long batch) {
     a->n_actor_fwd = (int)a->seq_actor_fb.size();
     OutSpec oq;
     oq.out = a->q_pi; oq.ld = qw; oq.go = (long long)B * qw; oq.epi = EPI_BIAS;
-    auto s_q = build_forward(c, c.q, Wq1, g_q1, B, q1, oq);
+    auto s_q = build_forward(c, c.q, Wq1, g_q1, B, q1, oq, 1, 0, fuse_heads);
     for (auto& st : s_q) emit_stage(a->seq_actor_fb, st);
+    if (fuse_heads) {       // Q1 head + (-mean) + head backward + actor optimiser tick
+      Launch L;
+      L.kind = Launch::HEAD;
+      HeadParams& H = L.head;
+      memset(&H, 0, sizeof(H));
+      const int l2 = Lq - 2;
+      H.h = ln ? q1.n[l2] : q1.r[l2]; H.h_go = q1.h_go[l2]; H.h_gi = q1.h_gi[l2];
+      H.W = a->critic.params + c.q.w_off[Lq - 1]; H.b = a->critic.params + c.q.b_off[Lq - 1]; H.w_go = qn * nq; H.w_gi = 0;
+      H.q = a->q_pi; H.q_go = (long long)B * qw; H.q_gi = 0;
+      H.dz = ln ? sc_q1.dn : sc_q1.dz[0]; H.dz_go = sc_q1.go; H.dz_gi = sc_q1.gi;
+      H.part = head_part + nA * head_part_go; H.part_go = head_part_go; H.counter = head_counter + nA; H.loss = a->state_f32 + nA;
+      H.batch = B; H.w = wq_last; H.qw = qw; H.n_q = 1; H.ldh = wq_last; H.lddz = wq_last; H.n_cta = head_ctas;
+      H.mode = 1; H.relu_mask = ln ? 0 : 1;
+      H.inv_norm = 1.f / (float)((a->global_batch > 0 ? a->global_batch : batch) * qw);
+      H.tick = AdamTick{a->state_u64, 1, 0, c.lr_actor, c.beta1, c.beta2};
+      L.grid_x = nA * head_ctas;
+      L.smem_bytes = (int)((1LL * qw * wq_last + 4 * kHeadMaxQw + kHeadRows + 16) * sizeof(float));
+      a->seq_actor_fb.push_back(L);
+    }
     // actor_loss = -mean(Q1) (read-back only) + bump the actor Adam step counter
     {
       Problem nm = blank_problem(PK_NEG_MEAN);
@@ -1121,8 +1188,8 @@ int plan_agent(td3_agent* a, long long batch) {
       dx.epi = lnin ? EPI_STORE : EPI_TANH_GRAD;
       dx.aux0 = a->tanh_y; dx.ldaux = A; dx.aux0_go = (long long)B * A; dx.f0 = enc ? 1.f : c.max_action;
       auto s_qb = build_backward(c, c.q, Wq1, GradRef{}, g_q1, B, q1, a->dq_pi, qw, (long long)B * qw, 0, false, dx,
-                                 sc_q1);
-      if (!s_qb.empty()) s_qb[0].push_back(nm);
+                                 sc_q1, fuse_heads);
+      if (!fuse_heads && !s_qb.empty()) s_qb[0].push_back(nm);
       for (auto& st : s_qb) emit_stage(a->seq_actor_fb, st);
       if (lnin) {
         // d(action) = slice of the full input gradient, then through tanh: identity-GEMM slice
@@ -1133,7 +1200,7 @@ int plan_agent(td3_agent* a, long long batch) {
         emit_stage(a->seq_actor_fb, {sl});
       }
     }
-    {
+    if (!fuse_heads) {
       Launch L;
       L.kind = Launch::TICK;
       L.tick = AdamTick{a->state_u64, 1, 0, c.lr_actor, c.beta1, c.beta2};
@@ -1289,6 +1356,9 @@ int append_records(std::vector<StageRec>& prog, const std::vector<Launch>& seq, 
         break;
       case Launch::EW:
         r.kind = SK_EW_ONLY; r.ew = L.ew; r.ew_tiles = L.grid_x;
+        break;
+      case Launch::HEAD:
+        r.kind = SK_HEAD; r.u.h = L.head; r.main_tiles = L.grid_x;
         break;
       default: break;
     }

@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(kStageThreads, 1) stage_kernel(const __grid_co
   }
 }
 
-enum StageKind : int { SK_STAGE = 0, SK_GATHER = 1, SK_LOSS = 2, SK_EW_ONLY = 3 };
+enum StageKind : int { SK_STAGE = 0, SK_GATHER = 1, SK_LOSS = 2, SK_EW_ONLY = 3, SK_HEAD = 4 };
 
 struct alignas(16) StageRec {
   int kind;
@@ -89,6 +89,7 @@ struct alignas(16) StageRec {
     StageParams st;
     GatherParams g;
     LossParams l;
+    HeadParams h;
   } u;
   EwParams ew;
 };
@@ -167,6 +168,9 @@ __global__ void __launch_bounds__(kStageThreads, 1) persistent_update_kernel(con
         } else if (R.kind == SK_LOSS) {
           __syncthreads();
           loss_body(R.u.l, tile, red);
+        } else if (R.kind == SK_HEAD) {
+          __syncthreads();
+          head_body(R.u.h, tile, reinterpret_cast<float*>(ring));
         }
       }
       // descriptor of the next stage (static data) while the others are still working
