@@ -8,9 +8,9 @@ twin-critic forward/backward + Adam, and on every policy_freq-th step the actor 
 (TD3_featured.py:123-171).  Default workload = BASELINE configs[1] ("cfg2"): S=17, A=6, 400-300 MLPs,
 batch 256, 1M-row device-resident replay buffer, one agent per GPU.
 
-  value  updates/s with everything resident in HBM (the K updates run in one cooperative launch of the
-         persistent update kernel -- or as CUDA-graph replays with --exec-mode graph -- CUDA-event timed,
-         max over ranks).
+  value  updates/s with everything resident in HBM (the K updates are K CUDA-graph replays of the update's
+         stage kernels -- or one cooperative launch of the persistent update kernel with --exec-mode
+         persistent -- CUDA-event timed, max over ranks).
   e2e    the same metric through the public Python API the reference's main.py loop uses, per step:
          replay_buffer.add(one host transition -> pinned -> H2D), policy.train(replay_buffer, 256),
          and a synchronous D2H read of the critic loss.
@@ -221,7 +221,7 @@ def main():
                     help="tf32: layer GEMMs on tcgen05 tensor cores (default); fp32: strict-fp32 FFMA tiles")
     ap.add_argument("--population", type=int, default=8,
                     help="also time a population of this many independent agents per GPU stepped in lock-step (0 = skip)")
-    ap.add_argument("--exec-mode", default=os.environ.get("TD3_EXEC_MODE", "persistent"), choices=["persistent", "graph", "launches"])
+    ap.add_argument("--exec-mode", default=os.environ.get("TD3_EXEC_MODE", "graph"), choices=["persistent", "graph", "launches"])
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
     os.environ["TD3_PRECISION"], os.environ["TD3_EXEC_MODE"] = args.precision, args.exec_mode

@@ -527,7 +527,7 @@ struct EwParams {
 };
 
 constexpr int kEwThreads = 256;
-constexpr int kEwPerBlock = kEwThreads * 8;   // 2 float4 per thread
+constexpr int kEwPerBlock = kEwThreads * 4;   // one float4 per thread
 
 __device__ __forceinline__ void ew_load4(const float* p, long long e, long long n, float (&v)[4]) {
   if (e + 4 <= n) {
@@ -549,7 +549,7 @@ __device__ __forceinline__ void ew_store4(float* p, long long e, long long n, co
 }
 
 // One element of torch's single-tensor Adam; out of line so the IEEE div/sqrt sequences exist once.
-__device__ __noinline__ float adam_element(float p, float g, float& m, float& v, float w1, float b2, float w2, float bc2s,
+__device__ __forceinline__ float adam_element(float p, float g, float& m, float& v, float w1, float b2, float w2, float bc2s,
                                           float eps, float neg_step) {
   m = fmaf(w1, __fsub_rn(g, m), m);
   v = __fadd_rn(__fmul_rn(v, b2), __fmul_rn(__fmul_rn(w2, g), g));
@@ -557,42 +557,39 @@ __device__ __noinline__ float adam_element(float p, float g, float& m, float& v,
   return __fadd_rn(p, __fdiv_rn(__fmul_rn(neg_step, m), denom));
 }
 
-// bx = block index within the launch / stage.  Rolled on purpose (code size: see stage.cuh).
+// bx = block index within the launch / stage.  Each thread owns one float4 of every buffer: all of its loads are
+// issued before anything is consumed (the kernel is a link of the update's dependency chain: one L2 round trip).
 __device__ __forceinline__ void adam_polyak_body(const EwParams& E, long long bx) {
   int ri = 0;
   for (int q = 1; q < 3; ++q)
     if (q < E.n_ranges && bx >= E.r[q].blk_begin) ri = q;
   const EwRange& R = E.r[ri];
+  const long long e = (bx - R.blk_begin) * kEwPerBlock + (long long)threadIdx.x * 4;
+  if (e >= R.n) return;
+  float pv[4], gv[4], mv[4], vv[4], tv[4];
+  ew_load4(R.p, e, R.n, pv);
+  if (R.do_adam) {
+    ew_load4(R.g, e, R.n, gv);
+    ew_load4(R.m, e, R.n, mv);
+    ew_load4(R.v, e, R.n, vv);
+  }
+  if (R.do_polyak) ew_load4(R.tgt, e, R.n, tv);
   const float s_step_size = R.do_adam ? (R.sc_ptr ? __ldcg(R.sc_ptr) : R.step_size) : 0.f;
   const float s_bc2_sqrt = R.do_adam ? (R.sc_ptr ? __ldcg(R.sc_ptr + 1) : R.bc2_sqrt) : 1.f;
   const float w1 = (float)(1.0 - E.beta1), b2 = (float)E.beta2, w2 = (float)(1.0 - E.beta2);
   const float eps = (float)E.eps, tau = (float)E.tau, omt = (float)(1.0 - E.tau);
   const float neg_step = -s_step_size;
-  const long long base = (bx - R.blk_begin) * kEwPerBlock;
-#pragma unroll 1
-  for (int u = 0; u < 2; ++u) {
-    const long long e = base + ((long long)u * kEwThreads + threadIdx.x) * 4;
-    if (e >= R.n) continue;
-    float pv[4];
-    ew_load4(R.p, e, R.n, pv);
-    if (R.do_adam) {
-      float gv[4], mv[4], vv[4];
-      ew_load4(R.g, e, R.n, gv);
-      ew_load4(R.m, e, R.n, mv);
-      ew_load4(R.v, e, R.n, vv);
+  if (R.do_adam) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) pv[k] = adam_element(pv[k], gv[k], mv[k], vv[k], w1, b2, w2, s_bc2_sqrt, eps, neg_step);
-      ew_store4(R.m, e, R.n, mv);
-      ew_store4(R.v, e, R.n, vv);
-      ew_store4(R.p, e, R.n, pv);
-    }
-    if (R.do_polyak) {
-      float tv[4];
-      ew_load4(R.tgt, e, R.n, tv);
+    for (int k = 0; k < 4; ++k) pv[k] = adam_element(pv[k], gv[k], mv[k], vv[k], w1, b2, w2, s_bc2_sqrt, eps, neg_step);
+    ew_store4(R.m, e, R.n, mv);
+    ew_store4(R.v, e, R.n, vv);
+    ew_store4(R.p, e, R.n, pv);
+  }
+  if (R.do_polyak) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) tv[k] = __fadd_rn(__fmul_rn(tau, pv[k]), __fmul_rn(omt, tv[k]));
-      ew_store4(R.tgt, e, R.n, tv);
-    }
+    for (int k = 0; k < 4; ++k) tv[k] = __fadd_rn(__fmul_rn(tau, pv[k]), __fmul_rn(omt, tv[k]));
+    ew_store4(R.tgt, e, R.n, tv);
   }
 }
 
