@@ -305,13 +305,15 @@ def main():
                      (rs.standard_normal(w["F"]), rs.standard_normal((w["N"], w["D"])).astype(np.float32)),
                      float(rs.standard_normal()), 0.0) for _ in range(8)]
     loss_host = torch.zeros(1).pin_memory()
+    loss_dev = agent.last_critic_loss                                # device view of the step's result
+    stream = torch.cuda.current_stream()
     Ke = min(K, 2000)
 
     def e2e_step(i):
         rb.add(*new_rows[i % len(new_rows)])                       # host transition -> pinned slot -> H2D
         agent.train(rb, B)                                          # the call main.py:269 makes
-        loss_host.copy_(agent.last_critic_loss, non_blocking=True)  # D2H of the step's result
-        torch.cuda.current_stream().synchronize()
+        loss_host.copy_(loss_dev, non_blocking=True)                # D2H of the step's result
+        stream.synchronize()
         return float(loss_host[0])
 
     for i in range(min(W, 50)):

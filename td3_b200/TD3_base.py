@@ -154,8 +154,9 @@ class TD3_base(object):
         s = _lib.stream_ptr()
         injected = indices is not None or noise is not None or self.rng == "host"
         if not injected:
-            _lib.check(self._lib.td3_train_n(self._handle, C.byref(view), self.total_it, iterations, _lib.RNG_PHILOX,
-                                             int(use_graph), s))
+            rc = self._lib.td3_train_n(self._handle, C.byref(view), self.total_it, iterations, _lib.RNG_PHILOX, use_graph, s)
+            if rc:
+                _lib.check(rc)
             self.total_it += iterations
             return
         if (indices is not None or noise is not None) and iterations != 1:

@@ -145,5 +145,9 @@ def require_cuda():
 
 
 def stream_ptr():
+    """The current CUDA stream of the current device as a void* (raw handle: no torch Stream object is built)."""
     import torch
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    try:
+        return C.c_void_p(torch._C._cuda_getCurrentRawStream(torch.cuda.current_device()))
+    except AttributeError:                                   # older / newer torch without the private accessor
+        return C.c_void_p(torch.cuda.current_stream().cuda_stream)

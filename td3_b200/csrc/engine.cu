@@ -304,11 +304,17 @@ void finalize_problem(Problem& p, GroupShape gs) {
       p.tiles_per_group = (p.N + 31) / 32;
       break;
     case PK_POOL_FWD:
-      p.tiles_n = (p.N + 31) / 32;
-      p.tiles_per_group = p.M * p.tiles_n;
+      p.tiles_n = 1;
+      p.tiles_per_group = p.M;          // one CTA per sample, all channels (<= 256)
+      break;
+    case PK_SMALLK_FWD:
+      p.tiles_per_group = (p.M + 127) / 128;
+      break;
+    case PK_SMALLK_DW:
+      p.tiles_per_group = p.ksplit;
       break;
     case PK_POOL_BWD:
-      p.tiles_per_group = (int)(((long long)p.M * p.K + 7) / 8);
+      p.tiles_per_group = (int)(((long long)p.M * p.K + 63) / 64);
       break;
     case PK_REDUCE_SPLITS:
       p.tiles_per_group = (p.M + 1023) / 1024;
@@ -558,6 +564,7 @@ std::vector<ProblemList> build_forward(const td3_agent_config& cfg, const td3_ne
                            cfg.particle_dim, true, pb.h1, net.enc_hidden, EPI_BIAS_RELU);
     set_groups(e1, pb.P_go, 0, W.go, W.gi, pb.h1_go, pb.h1_gi);
     e1.bias = W.base + net.c1b_off; e1.bias_go = W.go; e1.bias_gi = W.gi;
+    if (cfg.particle_dim <= 8) e1.kind = PK_SMALLK_FWD;   // D-long reduction: dedicated HBM-write-bound tile
     finalize_problem(e1, gs);
     st.push_back({e1});
     // conv2 (1x1) == linear enc_hidden -> enc_out (:30,56)
@@ -809,7 +816,9 @@ std::vector<ProblemList> build_backward(const td3_agent_config& cfg, const td3_n
       st.push_back({pbk});
       // conv2: dW2 = dH2^T H1 (split-K over B*N), dH1 = (dH2 W2) * (H1 > 0)
       const int tiles2 = ((O + 31) / 32) * ((H + 31) / 32);
-      const int ks2 = choose_ksplit(tiles2, groups, rows);
+      // tensor-core dW2: many short slices (64 chunks each) so that the long reduction balances against the dX tiles of
+      // the same stage under the static tile -> CTA assignment
+      const int ks2 = g_tc_mode ? std::max(1, std::min(128, rows / 2048)) : choose_ksplit(tiles2, groups, rows);
       Problem dw2 = make_gemm(O, H, rows, sc.dh2, O, false, pb.h1, H, false, ks2 > 1 ? sc.part : G.base + net.c2w_off, H,
                               EPI_STORE);
       dw2.ksplit = ks2; dw2.c_split = (long long)O * H;
@@ -851,7 +860,8 @@ std::vector<ProblemList> build_backward(const td3_agent_config& cfg, const td3_n
       }
       // conv1: dW1 = dH1^T P (split-K), second half of the partial buffer
       const int tiles1 = ((H + 31) / 32) * ((D + 31) / 32);
-      const int ks1 = choose_ksplit(tiles1, groups, rows);
+      // the small-K tile reads dH1 once, coalesced: give every SM a couple of row slices
+      const int ks1 = (D <= 8 && H <= kStageThreads) ? std::max(1, std::min(128, rows / 512)) : choose_ksplit(tiles1, groups, rows);
       float* part1 = sc.part + (long long)ks2 * (O * H + O);
       Problem dw1 = make_gemm(H, D, rows, sc.dh1, H, false, pb.P, D, false, ks1 > 1 ? part1 : G.base + net.c1w_off, D,
                               EPI_STORE);
@@ -859,6 +869,7 @@ std::vector<ProblemList> build_backward(const td3_agent_config& cfg, const td3_n
       set_groups(dw1, sc.dh1_go, sc.dh1_gi, pb.P_go, 0, ks1 > 1 ? sc.part_go : G.go, ks1 > 1 ? sc.part_gi : G.gi);
       dw1.aux1 = ks1 > 1 ? part1 + (long long)ks1 * H * D : G.base + net.c1b_off;
       dw1.aux1_go = ks1 > 1 ? sc.part_go : G.go; dw1.aux1_gi = ks1 > 1 ? sc.part_gi : G.gi;
+      if (D <= 8 && H <= kStageThreads) dw1.kind = PK_SMALLK_DW;
       finalize_problem(dw1, gs);
       s3.push_back(dw1);
       st.push_back(s3);
@@ -1560,6 +1571,10 @@ int rb_add_rows(float* rows, int64_t row_stride, int64_t row_floats, int64_t max
     return fail(TD3_ERR_INVALID, "rb_add_rows: bad arguments (ptr=%lld n=%lld max=%lld)", (long long)ptr, (long long)n_rows, (long long)max_size);
   cudaStream_t s = (cudaStream_t)stream;
   const int64_t first = std::min<int64_t>(n_rows, max_size - ptr);
+  if (n_rows == 1) {   // ReplayBuffer_*.add: one contiguous row
+    CUDA_TRY(cudaMemcpyAsync(rows + ptr * row_stride, host_rows, row_floats * sizeof(float), cudaMemcpyHostToDevice, s));
+    return TD3_OK;
+  }
   // host rows are packed row_floats apart; device rows row_stride apart
   if (first > 0)
     CUDA_TRY(cudaMemcpy2DAsync(rows + ptr * row_stride, row_stride * sizeof(float), host_rows, row_floats * sizeof(float),

@@ -48,6 +48,8 @@ __device__ __forceinline__ void run_stage_tile(const StageParams& S, int tile_gl
     case PK_REDUCE_SPLITS: reduce_splits_tile(P, tile); break;
     case PK_NEG_MEAN: neg_mean_tile(P, tile, smem); break;
     case PK_COLSUM: colsum_tile(P, tile, smem); break;
+    case PK_SMALLK_FWD: smallk_fwd_tile(P, tile, smem); break;
+    case PK_SMALLK_DW: smallk_dw_tile(P, tile, smem); break;
     default: break;
   }
 }

@@ -23,7 +23,9 @@ enum ProblemKind : int {
   PK_POOL_BWD = 5,      // dH2 = dpool/N * (pool>0) * (h2>0)
   PK_REDUCE_SPLITS = 6, // C = sum_s partial[s]   (split-K second phase)
   PK_NEG_MEAN = 7,      // scalar = -mean(A)      (actor loss read-back)
-  PK_COLSUM = 8         // C[j] = sum_i A[i,j]    (bias gradient next to a tensor-core dW)
+  PK_COLSUM = 8,        // C[j] = sum_i A[i,j]    (bias gradient next to a tensor-core dW)
+  PK_SMALLK_FWD = 9,    // C[i,j] = relu(bias[j] + sum_{d<K} A[i,d] B[j,d]), K <= 8   (particle encoder layer 1: HBM-write bound)
+  PK_SMALLK_DW = 10     // C[j,d] = sum_i A[i,j] B[i,d], aux1[j] = sum_i A[i,j], N <= 8, reduction split over CTAs
 };
 
 enum Epilogue : int {
@@ -498,27 +500,46 @@ __device__ __forceinline__ void ln_bwd_cols_tile(const Problem& P, int tile, flo
 //   (sample, 32-channel strip); 8 row-lanes walk the particles.
 // ------------------------------------------------------------------------------------
 __device__ __forceinline__ void pool_fwd_tile(const Problem& P, int tile, float* smem) {
+  // one CTA per sample; a thread owns 4 consecutive channels (one 16-byte load per particle row), 1024 / N row-lanes walk
+  // the particles with 8 loads in flight each: the stage is bound by reading h2 once from HBM
   const int g = tile / P.tiles_per_group;
-  int t = tile - g * P.tiles_per_group;
+  const int b = tile - g * P.tiles_per_group;
   long long go, gi;
   group_ptrs(P, g, go, gi);
-  const int b = t / P.tiles_n, strip = t - b * P.tiles_n;
-  const int rl = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int c = strip * 32 + lane;
-  const float* h = P.A + go * P.a_go + gi * P.a_gi + (size_t)b * P.K * P.lda;
-  float s = 0.f;
-  if (c < P.N)
-    #pragma unroll 4
-    for (int n = rl; n < P.K; n += 8) s += h[(size_t)n * P.lda + c];
-  smem[rl * 32 + lane] = s;
-  __syncthreads();
-  if (rl == 0 && c < P.N) {
-    float tot = 0.f;
+  const int N4 = P.N >> 2;                                 // channel quads (N <= 1024, N % 4 == 0)
+  const int lanes = max(1, kStageThreads / N4);
+  const int c4 = threadIdx.x % N4, rl = threadIdx.x / N4;
+  const float* h = P.A + go * P.a_go + gi * P.a_gi + (size_t)b * P.K * P.lda + c4 * 4;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (rl < lanes) {
+    int n = rl;
+    for (; n + 7 * lanes < P.K; n += 8 * lanes) {
+      float4 v[8];
 #pragma unroll
-    for (int r = 0; r < 8; ++r) tot += smem[r * 32 + lane];
-    const float v = fmaxf(tot / (float)P.K, 0.f);
+      for (int u = 0; u < 8; ++u) v[u] = *reinterpret_cast<const float4*>(h + (size_t)(n + u * lanes) * P.lda);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { s.x += v[u].x; s.y += v[u].y; s.z += v[u].z; s.w += v[u].w; }
+    }
+    for (; n < P.K; n += lanes) {
+      const float4 v = *reinterpret_cast<const float4*>(h + (size_t)n * P.lda);
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+  }
+  reinterpret_cast<float4*>(smem)[threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.x < N4) {
+    float4 tot = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int r = 0; r < lanes; ++r) {
+      const float4 v = reinterpret_cast<float4*>(smem)[r * N4 + c4];
+      tot.x += v.x; tot.y += v.y; tot.z += v.z; tot.w += v.w;
+    }
+    const float inv = 1.f / (float)P.K;
+    const float4 o = make_float4(fmaxf(tot.x * inv, 0.f), fmaxf(tot.y * inv, 0.f), fmaxf(tot.z * inv, 0.f), fmaxf(tot.w * inv, 0.f));
     float* C = P.C + go * P.c_go + gi * P.c_gi;
-    for (int d = 0; d < P.c_dups; ++d) C[d * P.c_dup_stride + (size_t)b * P.ldc + c] = v;
+    for (int d = 0; d < P.c_dups; ++d) {
+      float* cp = C + d * P.c_dup_stride + (size_t)b * P.ldc + c4 * 4;
+      cp[0] = o.x; cp[1] = o.y; cp[2] = o.z; cp[3] = o.w;
+    }
   }
   __syncthreads();
 }
@@ -527,23 +548,38 @@ __device__ __forceinline__ void pool_fwd_tile(const Problem& P, int tile, float*
 //   A = d(pool out) [M, lda], aux0 = pool out [M, ldaux], aux1 = h2 [M*K, N] (ld = ldb), C = dH2 [M*K, ldc]
 //   tile = 8 particle rows x all channels
 __device__ __forceinline__ void pool_bwd_tile(const Problem& P, int tile) {
+  // tile = 64 particle rows of one sample; a thread owns 4 channels (16-byte accesses) and walks the rows
   const int g = tile / P.tiles_per_group;
   const int t = tile - g * P.tiles_per_group;
   long long go, gi;
   group_ptrs(P, g, go, gi);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long row = (long long)t * 8 + warp;
-  if (row >= (long long)P.M * P.K) return;
-  const int b = (int)(row / P.K);
-  const float* dp = P.A + go * P.a_go + gi * P.a_gi + (size_t)b * P.lda;
-  const float* pool = P.aux0 + go * P.aux0_go + gi * P.aux0_gi + (size_t)b * P.ldaux;
-  const float* h2 = P.aux1 + go * P.aux1_go + gi * P.aux1_gi + (size_t)row * P.ldb;
-  float* out = P.C + go * P.c_go + gi * P.c_gi + (size_t)row * P.ldc;
+  const int N4 = P.N >> 2;
+  const int lanes = max(1, kStageThreads / N4);
+  const int c4 = threadIdx.x % N4, rl = threadIdx.x / N4;
+  const long long row0 = (long long)t * 64;
+  if (rl >= lanes) return;
+  const float* dpb = P.A + go * P.a_go + gi * P.a_gi + c4 * 4;
+  const float* poolb = P.aux0 + go * P.aux0_go + gi * P.aux0_gi + c4 * 4;
   const float inv = 1.f / (float)P.K;
-  #pragma unroll 2
-  for (int c = lane; c < P.N; c += 32) {
-    const float gate = (pool[c] > 0.f && h2[c] > 0.f) ? 1.f : 0.f;
-    out[c] = dp[c] * inv * gate;
+  int b_cur = -1;
+  float gsc[4] = {0.f, 0.f, 0.f, 0.f};
+  const float* h2 = P.aux1 + go * P.aux1_go + gi * P.aux1_gi + c4 * 4;
+  float* out = P.C + go * P.c_go + gi * P.c_gi + c4 * 4;
+#pragma unroll 8
+  for (int r = rl; r < 64; r += lanes) {
+    const long long row = row0 + r;
+    if (row >= (long long)P.M * P.K) break;
+    const int b = (int)(row / P.K);                         // a tile may straddle samples when 64 does not divide N
+    if (b != b_cur) {
+      b_cur = b;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) gsc[e] = poolb[(size_t)b * P.ldaux + e] > 0.f ? dpb[(size_t)b * P.lda + e] * inv : 0.f;
+    }
+    const float4 hv = *reinterpret_cast<const float4*>(h2 + (size_t)row * P.ldb);
+    float4 o;
+    o.x = hv.x > 0.f ? gsc[0] : 0.f; o.y = hv.y > 0.f ? gsc[1] : 0.f;
+    o.z = hv.z > 0.f ? gsc[2] : 0.f; o.w = hv.w > 0.f ? gsc[3] : 0.f;
+    *reinterpret_cast<float4*>(out + (size_t)row * P.ldc) = o;
   }
 }
 
@@ -565,6 +601,89 @@ __device__ __forceinline__ void reduce_splits_tile(const Problem& P, int tile) {
       out[e] = s;
     }
   }
+}
+
+// Particle-encoder layer 1 (TD3_particles.py:29,54: Conv2d(1,256,(1,D)) == a D -> 256 linear layer per particle).  The
+// reduction is D <= 8 long: a GEMM tile would spend its time on overhead, and the layer is bound by writing its
+// [B*N, 256] output.  Tile = 128 particles; thread = output channel (weights in registers), particles from shared memory.
+__device__ __forceinline__ void smallk_fwd_tile(const Problem& P, int tile, float* smem) {
+  const int g = tile / P.tiles_per_group;
+  const int t = tile - g * P.tiles_per_group;
+  long long go, gi;
+  group_ptrs(P, g, go, gi);
+  const float* A = P.A + go * P.a_go + gi * P.a_gi;
+  const float* W = P.B + go * P.b_go + gi * P.b_gi;
+  const float* bias = P.bias + go * P.bias_go + gi * P.bias_gi;
+  float* C = P.C + go * P.c_go + gi * P.c_gi;
+  const int K = P.K, r0 = t * 128, nr = min(128, P.M - r0);
+  for (int e = threadIdx.x; e < nr * K; e += kStageThreads) {
+    const int r = e / K, d = e - r * K;
+    smem[r * 8 + d] = A[(size_t)(r0 + r) * P.lda + d];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < P.N; c += kStageThreads) {
+    float w[8];
+#pragma unroll
+    for (int d = 0; d < 8; ++d) w[d] = d < K ? W[(size_t)c * P.ldb + d] : 0.f;
+    const float b = bias[c];
+#pragma unroll 8
+    for (int r = 0; r < nr; ++r) {
+      float v = b;
+#pragma unroll
+      for (int d = 0; d < 8; ++d)
+        if (d < K) v = fmaf(smem[r * 8 + d], w[d], v);
+      C[(size_t)(r0 + r) * P.ldc + c] = fmaxf(v, 0.f);
+    }
+  }
+  __syncthreads();
+}
+
+// Weight gradient of the same layer: dW1[c, d] = sum_r dH1[r, c] P[r, d], db1[c] = sum_r dH1[r, c], reduction over the
+// B*N particles split over `ksplit` CTAs (partials at C + ks*c_split and aux1 + ks*M, reduced by PK_REDUCE_SPLITS).
+//   A = dH1 [K rows, lda] (M = channels), B = P [K rows, ldb] (N = D <= 8 columns)
+__device__ __forceinline__ void smallk_dw_tile(const Problem& P, int tile, float* smem) {
+  const int g = tile / P.tiles_per_group;
+  const int ks = tile - g * P.tiles_per_group;
+  long long go, gi;
+  group_ptrs(P, g, go, gi);
+  const float* A = P.A + go * P.a_go + gi * P.a_gi;
+  const float* Bm = P.B + go * P.b_go + gi * P.b_gi;
+  float* C = P.C + go * P.c_go + gi * P.c_gi + (long long)ks * P.c_split;
+  float* db = P.aux1 + go * P.aux1_go + gi * P.aux1_gi + (long long)ks * P.M;
+  const int D = P.N;
+  const int per = (P.K + P.ksplit - 1) / P.ksplit;
+  const int r_begin = ks * per, r_end = min(P.K, r_begin + per);
+  float acc[8], accb = 0.f;
+#pragma unroll
+  for (int d = 0; d < 8; ++d) acc[d] = 0.f;
+  const int c = threadIdx.x;            // channel (M <= 256)
+#pragma unroll 1
+  for (int rb = r_begin; rb < r_end; rb += 128) {
+    const int nr = min(128, r_end - rb);
+    __syncthreads();
+    for (int e = threadIdx.x; e < nr * D; e += kStageThreads) {
+      const int r = e / D, d = e - r * D;
+      smem[r * 8 + d] = Bm[(size_t)(rb + r) * P.ldb + d];
+    }
+    __syncthreads();
+    if (c < P.M) {
+#pragma unroll 16
+      for (int r = 0; r < nr; ++r) {
+        const float a = A[(size_t)(rb + r) * P.lda + c];
+        accb += a;
+#pragma unroll
+        for (int d = 0; d < 8; ++d)
+          if (d < D) acc[d] = fmaf(a, smem[r * 8 + d], acc[d]);
+      }
+    }
+  }
+  if (c < P.M) {
+#pragma unroll
+    for (int d = 0; d < 8; ++d)
+      if (d < D) C[(size_t)c * P.ldc + d] = acc[d];
+    db[c] = accb;
+  }
+  __syncthreads();
 }
 
 // C[ks*c_split + j] = sum over this slice's rows i of A[i, j]  (A [K rows, lda], N columns; tile = 32-column strip)

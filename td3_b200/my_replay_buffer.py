@@ -42,6 +42,7 @@ class _DeviceReplay(object):
         self._ptrs, self._sizes = [0] * self.n_agents, [0] * self.n_agents
         self._stage = torch.zeros(_STAGE_SLOTS, self.row_floats, dtype=torch.float32).pin_memory()
         self._stage_np = self._stage.numpy()
+        self._rows_ptr, self._stage_ptr = self._rows.data_ptr(), self._stage.data_ptr()
         self._slot = 0
         self.ptr = 0
         self.size = 0
@@ -52,10 +53,13 @@ class _DeviceReplay(object):
 
     # ------------------------------------------------------------------ C-ABI view
     def _view(self) -> _lib.ReplayView:
-        v = _lib.ReplayView()
-        v.rows = C.c_void_p(self._rows.data_ptr())
-        v.row_stride, v.row_floats = self.row_stride, self.row_floats
-        v.max_size, v.agent_stride = self.max_size, (self.max_size * self.row_stride if self.n_agents > 1 else 0)
+        v = self.__dict__.get("_cached_view")
+        if v is None:                                        # the storage never moves: only `size` changes between calls
+            v = _lib.ReplayView()
+            v.rows = C.c_void_p(self._rows.data_ptr())
+            v.row_stride, v.row_floats = self.row_stride, self.row_floats
+            v.max_size, v.agent_stride = self.max_size, (self.max_size * self.row_stride if self.n_agents > 1 else 0)
+            self.__dict__["_cached_view"] = v
         v.size = self.size if self.n_agents == 1 else min(self.size, *self._sizes[1:])   # lock-step: common valid prefix
         return v
 
@@ -69,9 +73,10 @@ class _DeviceReplay(object):
         return s
 
     def _commit_row(self, slot):
-        _lib.check(self._lib.rb_add_rows(C.c_void_p(self._rows.data_ptr()), self.row_stride, self.row_floats,
-                                         self.max_size, self.ptr, C.c_void_p(self._stage[slot].data_ptr()), 1,
-                                         _lib.stream_ptr()))
+        rc = self._lib.rb_add_rows(self._rows_ptr, self.row_stride, self.row_floats, self.max_size, self.ptr,
+                                   self._stage_ptr + slot * self.row_floats * 4, 1, _lib.stream_ptr())
+        if rc:
+            _lib.check(rc)
         self.ptr = (self.ptr + 1) % self.max_size
         self.size = min(self.size + 1, self.max_size)
 
