@@ -33,7 +33,12 @@ typedef enum td3_status {
   TD3_ERR_UNSUPPORTED = -4
 } td3_status;
 
-typedef enum td3_norm { TD3_NORM_NONE = 0, TD3_NORM_LAYER = 1 } td3_norm;
+typedef enum td3_norm {
+  TD3_NORM_NONE = 0,
+  TD3_NORM_LAYER = 1,             /* post-ReLU nn.LayerNorm on every hidden layer (TD3_featured.py:44-46, TD3_particles.py:60-67) */
+  TD3_NORM_WEIGHT = 2             /* torch.nn.utils.weight_norm on every `linears` module (TD3_particles.py:48-50): parameters are
+                                     weight_g [out,1] and weight_v [out,in], the layer uses W = g * v / ||v||_row */
+} td3_norm;
 typedef enum td3_variant { TD3_VARIANT_FEATURED = 0, TD3_VARIANT_PARTICLES = 1 } td3_variant;
 typedef enum td3_precision {
   TD3_PRECISION_FP32 = 0,         /* every contraction on strict-fp32 FFMA tiles (matches the CPU reference to ~1e-6) */
@@ -54,7 +59,8 @@ typedef enum td3_rng_mode {
 typedef struct td3_net_layout {
   int32_t n_linear;                        /* len(self.linears) */
   int32_t dims[TD3_MAX_LINEAR + 1];        /* dims[0] = trunk input width, dims[n_linear] = output width */
-  int64_t w_off[TD3_MAX_LINEAR];           /* linears.i.weight  [dims[i+1], dims[i]] row-major */
+  int64_t w_off[TD3_MAX_LINEAR];           /* linears.i.weight  [dims[i+1], dims[i]] row-major (weight norm: linears.i.weight_v) */
+  int64_t wg_off[TD3_MAX_LINEAR];          /* linears.i.weight_g [dims[i+1]]   (norm == weight only) */
   int64_t b_off[TD3_MAX_LINEAR];           /* linears.i.bias    [dims[i+1]] */
   int64_t ln_g_off[TD3_MAX_LINEAR];        /* lnorms.i.weight   [dims[i+1]]   (norm == layer) */
   int64_t ln_b_off[TD3_MAX_LINEAR];        /* lnorms.i.bias */

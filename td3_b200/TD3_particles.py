@@ -50,7 +50,8 @@ class TD3(TD3_base):
             m._attach(self, w)
         self.CDQ = CDQ
         cfg = _lib.AgentConfig()
-        cfg.variant, cfg.norm = _lib.VARIANT_PARTICLES, (_lib.NORM_LAYER if norm == "layer" else _lib.NORM_NONE)
+        cfg.variant = _lib.VARIANT_PARTICLES
+        cfg.norm = {None: _lib.NORM_NONE, "layer": _lib.NORM_LAYER, "weight_normalization": _lib.NORM_WEIGHT}[norm]
         cfg.n_q, cfg.state_dim, cfg.action_dim = (2 if CDQ else 1), F, A
         cfg.n_particles, cfg.particle_dim = N, D
         cfg.clamp_target_action, cfg.n_agents = 0, 1

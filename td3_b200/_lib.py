@@ -17,7 +17,7 @@ TD3_MAX_LINEAR = 8
 TD3_MAX_SEGMENTS = 16
 RNG_PHILOX, RNG_INJECTED = 0, 1
 VARIANT_FEATURED, VARIANT_PARTICLES = 0, 1
-NORM_NONE, NORM_LAYER = 0, 1
+NORM_NONE, NORM_LAYER, NORM_WEIGHT = 0, 1, 2
 PRECISION_FP32, PRECISION_TF32 = 0, 1
 PRECISIONS = {"fp32": PRECISION_FP32, "tf32": PRECISION_TF32}
 
@@ -27,6 +27,7 @@ class NetLayout(C.Structure):
         ("n_linear", C.c_int32),
         ("dims", C.c_int32 * (TD3_MAX_LINEAR + 1)),
         ("w_off", C.c_int64 * TD3_MAX_LINEAR),
+        ("wg_off", C.c_int64 * TD3_MAX_LINEAR),
         ("b_off", C.c_int64 * TD3_MAX_LINEAR),
         ("ln_g_off", C.c_int64 * TD3_MAX_LINEAR),
         ("ln_b_off", C.c_int64 * TD3_MAX_LINEAR),

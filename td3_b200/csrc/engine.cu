@@ -55,8 +55,9 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 // launch list
 // ------------------------------------------------------------------------------------
 struct Launch {
-  enum Kind { STAGE, GATHER, LOSS, EW, TICK, HEAD } kind = STAGE;
+  enum Kind { STAGE, GATHER, LOSS, EW, TICK, HEAD, WN } kind = STAGE;
   HeadParams head{};
+  WnParams wn{};
   int smem_bytes = 0;
   StageParams stage{};
   GatherParams gather{};
@@ -134,6 +135,9 @@ int run_launch(const Launch& L, cudaStream_t s) {
       e = launch_pdl(head_kernel, dim3(L.grid_x), dim3(kHeadThreads), (size_t)L.smem_bytes, s, L.head);
       break;
     }
+    case Launch::WN:
+      e = launch_pdl(wn_kernel, dim3(L.grid_x), dim3(256), 0, s, L.wn);
+      break;
   }
   if (e != cudaSuccess) return fail(TD3_ERR_CUDA, "kernel launch: %s", cudaGetErrorString(e));
   g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -503,6 +507,8 @@ struct td3_agent {
   long long *idx = nullptr, *idx_in = nullptr;
   float *q = nullptr, *tq = nullptr, *y = nullptr, *dq = nullptr, *q_pi = nullptr, *dq_pi = nullptr, *tanh_y = nullptr;
   PassBuf pb_at, pb_ct, pb_c, pb_a, pb_q1;
+  // weight normalisation: effective parameters (W = g v / ||v|| in every weight_v slot) the contractions read
+  float *eff_a = nullptr, *eff_at = nullptr, *eff_c = nullptr, *eff_ct = nullptr;
 
   std::vector<Launch> seq_sample, seq_target, seq_critic_fb, seq_critic_apply, seq_actor_fb, seq_actor_apply;
   // fused middle of a policy update (critic backward with the actor forward riding along, critic Adam, rest of the
@@ -969,11 +975,68 @@ Problem make_slice(int B, int ncols, const float* in, int ld_in, const float* ey
   return p;
 }
 
+// ---- weight normalisation (misc.cuh: wn_body) ----
+// Row blocks (and, for the effective-parameter pass, pass-through chunks) of one network of a family.
+bool make_wn_layout(const td3_net_layout& net, bool with_copies, WnLayout& Y) {
+  memset(&Y, 0, sizeof(Y));
+  const int L = net.n_linear;
+  if (L > kWnMaxLayers) return false;
+  Y.n_layers = L;
+  int units = 0;
+  std::vector<std::pair<long long, long long>> vs;
+  for (int l = 0; l < L; ++l) {
+    Y.w_off[l] = net.w_off[l]; Y.g_off[l] = net.wg_off[l];
+    Y.out[l] = net.dims[l + 1]; Y.in[l] = net.dims[l];
+    Y.unit_begin[l] = units;
+    units += (Y.out[l] + 7) / 8;
+    vs.push_back({net.w_off[l], net.w_off[l] + (long long)Y.out[l] * Y.in[l]});
+  }
+  if (with_copies) {     // everything that is not a weight_v slot is copied through unchanged
+    std::sort(vs.begin(), vs.end());
+    long long at = 0;
+    vs.push_back({net.n_floats, net.n_floats});
+    for (auto& iv : vs) {
+      if (iv.first > at) {
+        if (Y.n_copies >= kWnMaxCopies) return false;
+        Y.c_off[Y.n_copies] = at; Y.c_len[Y.n_copies] = (int)(iv.first - at); Y.c_unit_begin[Y.n_copies] = units;
+        units += (Y.c_len[Y.n_copies] + kWnCopyChunk - 1) / kWnCopyChunk;
+        ++Y.n_copies;
+      }
+      at = std::max(at, iv.second);
+    }
+  }
+  Y.units = units;
+  return true;
+}
+
+struct WnJobSpec { const float* src; float* dst; long long net_stride; int n_nets; int family; };   // family: 0 actor, 1 critic
+
+bool make_wn_launch(const td3_agent_config& c, int mode, std::initializer_list<WnJobSpec> jobs, Launch& L) {
+  L = Launch{};
+  L.kind = Launch::WN;
+  WnParams& P = L.wn;
+  memset(&P, 0, sizeof(P));
+  P.mode = mode; P.rows_per_tile = 8;
+  if (!make_wn_layout(c.actor, mode == 0, P.lay[0]) || !make_wn_layout(c.q, mode == 0, P.lay[1])) return false;
+  int tiles = 0;
+  for (const WnJobSpec& j : jobs) {
+    if (P.n_jobs >= kWnMaxJobs) return false;
+    WnJob& J = P.job[P.n_jobs++];
+    J.src = j.src; J.dst = j.dst; J.net_stride = j.net_stride; J.n_nets = j.n_nets; J.layout = j.family;
+    J.tile_begin = tiles;
+    tiles += j.n_nets * P.lay[j.family].units;
+  }
+  P.total_tiles = tiles;
+  L.grid_x = tiles;
+  return tiles > 0;
+}
+
 int plan_agent(td3_agent* a, long long batch) {
   const td3_agent_config& c = a->cfg;
   const int B = (int)batch, nA = c.n_agents, nq = c.n_q;
   const bool enc = c.variant == TD3_VARIANT_PARTICLES;
   const bool ln = c.norm == TD3_NORM_LAYER;
+  const bool wn = c.norm == TD3_NORM_WEIGHT;
   const GroupShape g_actor{nA, 1}, g_crit{nA, nq}, g_q1{nA, 1};
   Bump& ws = a->ws;
   ws.used = 0;
@@ -1035,6 +1098,13 @@ int plan_agent(td3_agent* a, long long batch) {
   const long long head_part_go = (long long)head_ctas * nq * head_per_g + head_ctas;
   float* head_part = ws.take(fuse_heads ? nA * head_part_go * 2 : 1, "head_partials");
   unsigned int* head_counter = reinterpret_cast<unsigned int*>(ws.take(2LL * nA, "head_counters"));
+  a->eff_a = a->eff_at = a->eff_c = a->eff_ct = nullptr;
+  if (wn) {
+    a->eff_a = ws.take((long long)nA * c.actor.n_floats, "effective_actor");
+    a->eff_at = ws.take((long long)nA * c.actor.n_floats, "effective_actor_target");
+    a->eff_c = ws.take((long long)nA * nq * c.q.n_floats, "effective_critic");
+    a->eff_ct = ws.take((long long)nA * nq * c.q.n_floats, "effective_critic_target");
+  }
   a->prof_dev = reinterpret_cast<long long*>(ws.take(2LL * 2 * 128 * 3, "prof"));
   a->tmaps_dev = reinterpret_cast<CUtensorMap*>(ws.take((long long)kMaxTensorMaps * (long long)(sizeof(CUtensorMap) / 4), "tensor_maps"));
   a->prog_dev = reinterpret_cast<StageRec*>(ws.take(2LL * kMaxProgStages * (long long)(sizeof(StageRec) / 4), "program"));
@@ -1071,13 +1141,26 @@ int plan_agent(td3_agent* a, long long batch) {
 
   // ---- parameter references ----
   const long long qn = c.q.n_floats, an = c.actor.n_floats;
-  ParamRef Wa{a->actor.params, an, 0}, Wat{a->actor.target, an, 0};
-  ParamRef Wc{a->critic.params, qn * nq, qn}, Wct{a->critic.target, qn * nq, qn};
-  ParamRef Wq1{a->critic.params, qn * nq, 0};
+  // what the contractions read: the packed parameters, or their weight-normalised copies
+  const float* pa_w = wn ? a->eff_a : a->actor.params;
+  const float* pat_w = wn ? a->eff_at : a->actor.target;
+  const float* pc_w = wn ? a->eff_c : a->critic.params;
+  const float* pct_w = wn ? a->eff_ct : a->critic.target;
+  ParamRef Wa{pa_w, an, 0}, Wat{pat_w, an, 0};
+  ParamRef Wc{pc_w, qn * nq, qn}, Wct{pct_w, qn * nq, qn};
+  ParamRef Wq1{pc_w, qn * nq, 0};
   GradRef Ga{a->actor.grad, an, 0}, Gc{a->critic.grad, qn * nq, qn};
 
   a->seq_sample.clear(); a->seq_target.clear(); a->seq_critic_fb.clear(); a->seq_critic_apply.clear();
   a->seq_actor_fb.clear(); a->seq_actor_apply.clear();
+
+  if (wn) {   // refresh all four effective buffers (the caller may have loaded or edited parameters since the last update)
+    Launch L;
+    if (!make_wn_launch(c, 0, {{a->actor.params, a->eff_a, an, nA, 0}, {a->actor.target, a->eff_at, an, nA, 0},
+                               {a->critic.params, a->eff_c, qn, nA * nq, 1}, {a->critic.target, a->eff_ct, qn, nA * nq, 1}}, L))
+      return fail(TD3_ERR_INVALID, "weight normalisation: unsupported layout");
+    a->seq_target.push_back(L);
+  }
 
   // ---- target step (TD3_featured.py:129-142) ----
   {
@@ -1120,8 +1203,8 @@ int plan_agent(td3_agent* a, long long batch) {
       const int l2 = Lq - 2;
       H.h = ln ? cc.n[l2] : cc.r[l2]; H.h_go = cc.h_go[l2]; H.h_gi = cc.h_gi[l2];
       H.ht = ln ? ct.n[l2] : ct.r[l2]; H.ht_go = ct.h_go[l2]; H.ht_gi = ct.h_gi[l2];
-      H.W = a->critic.params + c.q.w_off[Lq - 1]; H.b = a->critic.params + c.q.b_off[Lq - 1]; H.w_go = qn * nq; H.w_gi = qn;
-      H.Wt = a->critic.target + c.q.w_off[Lq - 1]; H.bt = a->critic.target + c.q.b_off[Lq - 1]; H.wt_go = qn * nq; H.wt_gi = qn;
+      H.W = pc_w + c.q.w_off[Lq - 1]; H.b = pc_w + c.q.b_off[Lq - 1]; H.w_go = qn * nq; H.w_gi = qn;
+      H.Wt = pct_w + c.q.w_off[Lq - 1]; H.bt = pct_w + c.q.b_off[Lq - 1]; H.wt_go = qn * nq; H.wt_gi = qn;
       H.r = a->r; H.nd = a->nd; H.r_go = B;
       H.q = a->q; H.tq = a->tq; H.dq = a->dq; H.q_gi = (long long)B * qw; H.q_go = H.q_gi * nq;
       H.y = a->y; H.y_go = (long long)B * qw;
@@ -1139,6 +1222,12 @@ int plan_agent(td3_agent* a, long long batch) {
     auto s_b = build_backward(c, c.q, Wc, Gc, g_crit, B, cc, a->dq, qw, (long long)B * qw * nq, (long long)B * qw, true,
                               none, sc_c, fuse_heads);
     for (auto& st : s_b) emit_stage(a->seq_critic_fb, st);
+    if (wn) {     // dL/dW -> (dL/dg, dL/dv) in place
+      Launch Lw;
+      if (!make_wn_launch(c, 1, {{a->critic.params, a->critic.grad, qn, nA * nq, 1}}, Lw))
+        return fail(TD3_ERR_INVALID, "weight normalisation: unsupported layout");
+      a->seq_critic_fb.push_back(Lw);
+    }
   }
   // ---- critic Adam (:153) ----
   {
@@ -1162,6 +1251,12 @@ int plan_agent(td3_agent* a, long long batch) {
     auto s_a = build_forward(c, c.actor, Wa, g_actor, B, pa, o);
     for (auto& st : s_a) emit_stage(a->seq_actor_fb, st);
     a->n_actor_fwd = (int)a->seq_actor_fb.size();
+    if (wn) {     // Q1 below reads the critic the Adam step just changed
+      Launch Lw;
+      if (!make_wn_launch(c, 0, {{a->critic.params, a->eff_c, qn, nA * nq, 1}}, Lw))
+        return fail(TD3_ERR_INVALID, "weight normalisation: unsupported layout");
+      a->seq_actor_fb.push_back(Lw);
+    }
     OutSpec oq;
     oq.out = a->q_pi; oq.ld = qw; oq.go = (long long)B * qw; oq.epi = EPI_BIAS;
     auto s_q = build_forward(c, c.q, Wq1, g_q1, B, q1, oq, 1, 0, fuse_heads);
@@ -1173,7 +1268,7 @@ int plan_agent(td3_agent* a, long long batch) {
       memset(&H, 0, sizeof(H));
       const int l2 = Lq - 2;
       H.h = ln ? q1.n[l2] : q1.r[l2]; H.h_go = q1.h_go[l2]; H.h_gi = q1.h_gi[l2];
-      H.W = a->critic.params + c.q.w_off[Lq - 1]; H.b = a->critic.params + c.q.b_off[Lq - 1]; H.w_go = qn * nq; H.w_gi = 0;
+      H.W = pc_w + c.q.w_off[Lq - 1]; H.b = pc_w + c.q.b_off[Lq - 1]; H.w_go = qn * nq; H.w_gi = 0;
       H.q = a->q_pi; H.q_go = (long long)B * qw; H.q_gi = 0;
       H.dz = ln ? sc_q1.dn : sc_q1.dz[0]; H.dz_go = sc_q1.go; H.dz_gi = sc_q1.gi;
       H.part = head_part + nA * head_part_go; H.part_go = head_part_go; H.counter = head_counter + nA; H.loss = a->state_f32 + nA;
@@ -1220,6 +1315,12 @@ int plan_agent(td3_agent* a, long long batch) {
     Dx0Spec none;
     auto s_ab = build_backward(c, c.actor, Wa, Ga, g_actor, B, pa, da, A, (long long)B * A, 0, true, none, sc_a);
     for (auto& st : s_ab) emit_stage(a->seq_actor_fb, st);
+    if (wn) {
+      Launch Lw;
+      if (!make_wn_launch(c, 1, {{a->actor.params, a->actor.grad, an, nA, 0}}, Lw))
+        return fail(TD3_ERR_INVALID, "weight normalisation: unsupported layout");
+      a->seq_actor_fb.push_back(Lw);
+    }
   }
   // ---- actor Adam + Polyak of both targets (:164-171) ----
   {
@@ -1370,6 +1471,9 @@ int append_records(std::vector<StageRec>& prog, const std::vector<Launch>& seq, 
         break;
       case Launch::HEAD:
         r.kind = SK_HEAD; r.u.h = L.head; r.main_tiles = L.grid_x;
+        break;
+      case Launch::WN:
+        r.kind = SK_WN; r.u.w = L.wn; r.main_tiles = L.grid_x;
         break;
       default: break;
     }
@@ -1891,11 +1995,20 @@ int td3_actor_forward(td3_agent* a, int32_t which, int32_t agent_index, const fl
   if (enc)
     CUDA_TRY(cudaMemcpyAsync(const_cast<float*>(pb.P), particles, sizeof(float) * batch * c.n_particles * c.particle_dim,
                              cudaMemcpyDeviceToDevice, s));
-  ParamRef W{(which ? a->actor.target : a->actor.params) + (long long)agent_index * c.actor.n_floats, 0, 0};
+  const long long w_at = (long long)agent_index * c.actor.n_floats;
+  const float* w_raw = (which ? a->actor.target : a->actor.params) + w_at;
+  std::vector<Launch> seq;
+  if (c.norm == TD3_NORM_WEIGHT) {
+    float* eff = (which ? a->eff_at : a->eff_a) + w_at;
+    Launch Lw;
+    if (!make_wn_launch(c, 0, {{w_raw, eff, c.actor.n_floats, 1, 0}}, Lw)) return fail(TD3_ERR_INVALID, "weight normalisation: unsupported layout");
+    seq.push_back(Lw);
+    w_raw = eff;
+  }
+  ParamRef W{w_raw, 0, 0};
   OutSpec o;
   o.out = action_out; o.ld = A; o.epi = EPI_BIAS_TANH; o.aux0 = a->tanh_y; o.ldaux = A;
   o.f0 = enc ? 1.f : c.max_action;
-  std::vector<Launch> seq;
   for (auto& st : build_forward(c, c.actor, W, GroupShape{1, 1}, (int)batch, pb, o)) emit_stage(seq, st);
   return run_seq(seq, s);
 }
@@ -1922,10 +2035,19 @@ int td3_critic_forward(td3_agent* a, int32_t which, int32_t agent_index, const f
   if (enc)
     CUDA_TRY(cudaMemcpyAsync(const_cast<float*>(pb.P), particles, sizeof(float) * batch * c.n_particles * c.particle_dim,
                              cudaMemcpyDeviceToDevice, s));
-  ParamRef W{(which ? a->critic.target : a->critic.params) + (long long)agent_index * c.q.n_floats * nq, 0, c.q.n_floats};
+  const long long w_at = (long long)agent_index * c.q.n_floats * nq;
+  const float* w_raw = (which ? a->critic.target : a->critic.params) + w_at;
+  std::vector<Launch> seq;
+  if (c.norm == TD3_NORM_WEIGHT) {
+    float* eff = (which ? a->eff_ct : a->eff_c) + w_at;
+    Launch Lw;
+    if (!make_wn_launch(c, 0, {{w_raw, eff, c.q.n_floats, nq, 1}}, Lw)) return fail(TD3_ERR_INVALID, "weight normalisation: unsupported layout");
+    seq.push_back(Lw);
+    w_raw = eff;
+  }
+  ParamRef W{w_raw, 0, c.q.n_floats};
   OutSpec o;
   o.out = q_out; o.ld = qw; o.gi = batch * qw; o.epi = EPI_BIAS;
-  std::vector<Launch> seq;
   for (auto& st : build_forward(c, c.q, W, GroupShape{1, nq}, (int)batch, pb, o)) emit_stage(seq, st);
   return run_seq(seq, s);
 }

@@ -496,6 +496,98 @@ __global__ void __launch_bounds__(kHeadThreads) head_kernel(const __grid_constan
   head_body(H, blockIdx.x, head_smem);
 }
 
+// ------------------------------------------------------------------------------------
+// Weight normalisation (TD3_particles.py:48-50, torch.nn.utils.weight_norm on every `linears` module):
+// the packed buffers hold (bias, weight_g [out], weight_v [out, in]) per layer and the layer computes with
+//   W[n, :] = v[n, :] * (g[n] / ||v[n, :]||)                      (aten::_weight_norm, dim = 0).
+// mode 0 materialises an "effective" copy of a family's packed buffer in which every weight_v slot holds W (all
+//        other tensors are copied through), which is what every contraction then reads;
+// mode 1 turns dL/dW, which the backward contractions leave in the gradient buffer's weight_v slot, into
+//        dL/dg[n] = (dW[n]·v[n]) / ||v[n]||  and  dL/dv[n] = (g/||v||) * (dW[n] - (dL/dg[n] / ||v[n]||) v[n])  in place.
+// One warp per output row; the row blocks of all layers, networks and jobs are flattened into one tile index.
+// ------------------------------------------------------------------------------------
+constexpr int kWnMaxLayers = 8, kWnMaxCopies = 12, kWnMaxJobs = 4, kWnCopyChunk = 2048;
+
+struct WnLayout {
+  int n_layers, n_copies, units, pad;                  // units = row blocks + copy chunks of one network
+  long long w_off[kWnMaxLayers], g_off[kWnMaxLayers];
+  int out[kWnMaxLayers], in[kWnMaxLayers], unit_begin[kWnMaxLayers];
+  long long c_off[kWnMaxCopies];
+  int c_len[kWnMaxCopies], c_unit_begin[kWnMaxCopies];
+};
+
+struct WnJob {
+  const float* src;       // packed parameters (weight_g / weight_v)
+  float* dst;             // mode 0: effective parameters; mode 1: gradient buffer (converted in place)
+  long long net_stride;   // floats between consecutive networks of the buffer
+  int n_nets, layout, tile_begin, pad;
+};
+
+struct WnParams {
+  int mode, n_jobs, rows_per_tile, total_tiles;
+  WnJob job[kWnMaxJobs];
+  WnLayout lay[2];
+};
+
+__device__ __forceinline__ void wn_body(const WnParams& P, int tile) {
+  int j = 0;
+#pragma unroll
+  for (int i = 1; i < kWnMaxJobs; ++i)
+    if (i < P.n_jobs && tile >= P.job[i].tile_begin) j = i;
+  const WnJob& J = P.job[j];
+  const WnLayout& Y = P.lay[J.layout];
+  const int local = tile - J.tile_begin;
+  const int net = local / Y.units, unit = local - net * Y.units;
+  const float* src = J.src + (long long)net * J.net_stride;
+  float* dst = J.dst + (long long)net * J.net_stride;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (Y.n_copies > 0 && unit >= Y.c_unit_begin[0]) {       // pass-through tensors (biases, encoder): mode 0 only
+    int cseg = 0;
+    for (int i = 1; i < Y.n_copies; ++i)
+      if (unit >= Y.c_unit_begin[i]) cseg = i;
+    const int beg = (unit - Y.c_unit_begin[cseg]) * kWnCopyChunk;
+    const int end = min(beg + kWnCopyChunk, Y.c_len[cseg]);
+    const long long off = Y.c_off[cseg];
+    for (int i = beg + (int)threadIdx.x; i < end; i += blockDim.x) dst[off + i] = src[off + i];
+    return;
+  }
+  int l = 0;
+  for (int i = 1; i < Y.n_layers; ++i)
+    if (unit >= Y.unit_begin[i]) l = i;
+  const int row = (unit - Y.unit_begin[l]) * P.rows_per_tile + warp;
+  if (warp >= P.rows_per_tile || row >= Y.out[l]) return;
+  const int K = Y.in[l];
+  const float* v = src + Y.w_off[l] + (long long)row * K;
+  float* o = dst + Y.w_off[l] + (long long)row * K;
+  const float g = src[Y.g_off[l] + row];
+  float ss = 0.f, dot = 0.f;
+  if (P.mode == 0) {
+    for (int k = lane; k < K; k += 32) { const float x = v[k]; ss = fmaf(x, x, ss); }
+  } else {
+    for (int k = lane; k < K; k += 32) { const float x = v[k]; ss = fmaf(x, x, ss); dot = fmaf(o[k], x, dot); }
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    ss += __shfl_xor_sync(0xffffffffu, ss, d);
+    dot += __shfl_xor_sync(0xffffffffu, dot, d);
+  }
+  const float nrm = sqrtf(ss);
+  if (P.mode == 0) {
+    const float sc = g / nrm;
+    for (int k = lane; k < K; k += 32) o[k] = v[k] * sc;
+  } else {
+    const float dg = dot / nrm, sc = g / nrm, back = dg / nrm;
+    for (int k = lane; k < K; k += 32) o[k] = sc * (o[k] - back * v[k]);
+    if (lane == 0) dst[Y.g_off[l] + row] = dg;
+  }
+}
+
+__global__ void __launch_bounds__(256) wn_kernel(const __grid_constant__ WnParams P) {
+  pdl_launch_dependents();
+  pdl_wait();
+  wn_body(P, blockIdx.x);
+}
+
 __global__ void adam_tick_kernel(const __grid_constant__ AdamTick T) {
   pdl_launch_dependents();
   pdl_wait();

@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(kStageThreads, 1) stage_kernel(const __grid_co
   }
 }
 
-enum StageKind : int { SK_STAGE = 0, SK_GATHER = 1, SK_LOSS = 2, SK_EW_ONLY = 3, SK_HEAD = 4 };
+enum StageKind : int { SK_STAGE = 0, SK_GATHER = 1, SK_LOSS = 2, SK_EW_ONLY = 3, SK_HEAD = 4, SK_WN = 5 };
 
 struct alignas(16) StageRec {
   int kind;
@@ -92,6 +92,7 @@ struct alignas(16) StageRec {
     GatherParams g;
     LossParams l;
     HeadParams h;
+    WnParams w;
   } u;
   EwParams ew;
 };
@@ -173,6 +174,8 @@ __global__ void __launch_bounds__(kStageThreads, 1) persistent_update_kernel(con
         } else if (R.kind == SK_HEAD) {
           __syncthreads();
           head_body(R.u.h, tile, reinterpret_cast<float*>(ring));
+        } else if (R.kind == SK_WN) {
+          wn_body(R.u.w, tile);
         }
       }
       // descriptor of the next stage (static data) while the others are still working

@@ -41,12 +41,22 @@ class _Net(nn.Module):
         object.__setattr__(self, "_owner", owner)
         object.__setattr__(self, "_which", which)
 
-    def _check_norm(self, norm):
+    def _check_norm(self, norm, allow_weight_norm=False):
+        if norm == "weight_normalization" and allow_weight_norm:
+            return
         if norm not in (None, "layer"):
-            # TD3_featured + weight_normalization cannot even be constructed in the reference under
-            # torch 2.x (deepcopy of weight-normed modules raises); the particles variant
-            # is not implemented here yet.
-            raise NotImplementedError(f"norm={norm!r} is not supported by td3_b200 (supported: None, 'layer')")
+            # TD3_featured + weight_normalization cannot even be constructed in the reference under torch 2.x
+            # (deepcopy of weight-normed modules raises): there is nothing to be a drop-in for.
+            raise NotImplementedError(f"norm={norm!r} is not supported here (TD3_featured: None, 'layer'; "
+                                      "TD3_particles: None, 'layer', 'weight_normalization')")
+
+    def _apply_weight_norm(self):
+        """TD3_particles.py:48-50: weight_norm on the `linears` only (the encoder convolutions stay plain)."""
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            for i in range(len(self.linears)):
+                self.linears[i] = nn.utils.weight_norm(self.linears[i])
 
 
 class MlpActor(_Net):
@@ -105,7 +115,7 @@ class SetActor(_Net):
 
     def __init__(self, feat_dim, n_particles, particle_dim, action_dim, norm, widths):
         super().__init__()
-        self._check_norm(norm)
+        self._check_norm(norm, allow_weight_norm=True)
         self.num_features = ENC_OUT
         _encoder(self, n_particles, particle_dim)
         in_dim = ENC_OUT + feat_dim
@@ -114,6 +124,8 @@ class SetActor(_Net):
         if norm == "layer":
             self.lnorm1 = nn.LayerNorm(in_dim)
             self.lnorms = nn.ModuleList(nn.LayerNorm(w) for w in widths)
+        if norm == "weight_normalization":
+            self._apply_weight_norm()
         self.architecture = tuple(widths)
 
     def forward(self, state_features, state_particles):
@@ -125,7 +137,7 @@ class SetQ(_Net):
 
     def __init__(self, feat_dim, n_particles, particle_dim, action_dim, norm, widths):
         super().__init__()
-        self._check_norm(norm)
+        self._check_norm(norm, allow_weight_norm=True)
         self.num_features = ENC_OUT
         _encoder(self, n_particles, particle_dim)
         in_dim = ENC_OUT + feat_dim + action_dim
@@ -134,6 +146,8 @@ class SetQ(_Net):
         if norm == "layer":
             self.lnorm1 = nn.LayerNorm(in_dim)
             self.lnorms = nn.ModuleList(nn.LayerNorm(w) for w in widths)
+        if norm == "weight_normalization":
+            self._apply_weight_norm()
         self.architecture = tuple(widths)
 
 
@@ -180,9 +194,14 @@ def net_layout(single_net: nn.Module, prefix_table=None) -> _lib.NetLayout:
     if lay.n_linear > _lib.TD3_MAX_LINEAR:
         raise ValueError(f"at most {_lib.TD3_MAX_LINEAR} linear layers are supported")
     lay.dims[0] = linears[0].in_features
+    wn = getattr(single_net, "norm", None) == "weight_normalization"
     for i, lin in enumerate(linears):
         lay.dims[i + 1] = lin.out_features
-        lay.w_off[i] = table[f"linears.{i}.weight"][0]
+        if wn:       # parameters are (bias, weight_g, weight_v); the engine materialises W = g * v / ||v|| per row
+            lay.w_off[i] = table[f"linears.{i}.weight_v"][0]
+            lay.wg_off[i] = table[f"linears.{i}.weight_g"][0]
+        else:
+            lay.w_off[i] = table[f"linears.{i}.weight"][0]
         lay.b_off[i] = table[f"linears.{i}.bias"][0]
         if getattr(single_net, "norm", None) == "layer" and i < len(linears) - 1:
             lay.ln_g_off[i] = table[f"lnorms.{i}.weight"][0]

@@ -44,6 +44,42 @@ def test_trajectory_matches_oracle(norm, CDQ):
     _run(ora, orb, ours, rb, B=8, steps=4, A=3, rows=64, lr=1e-3)
 
 
+@pytest.mark.parametrize("CDQ", [True, False])
+@pytest.mark.parametrize("exec_mode", ["graph", "persistent", "launches"])
+def test_weight_normalization_trajectory(CDQ, exec_mode):
+    """norm="weight_normalization" (TD3_particles.py:48-50): parameters are (bias, weight_g, weight_v); the gradient
+    reaches g and v through W = g v / ||v||, Adam and Polyak run on g and v themselves."""
+    if exec_mode != "graph" and not CDQ:
+        pytest.skip("one CDQ setting per alternative executor is enough")
+    ora, orb, ours, rb = make_particles(norm="weight_normalization", CDQ=CDQ)
+    ours.exec_mode = exec_mode
+    assert [n for n, _ in ours.critic.named_parameters()][:5] == [n for n, _ in ora.critic.named_parameters()][:5]
+    assert any(n.endswith("weight_g") for n, _ in ours.actor.named_parameters())
+    _run(ora, orb, ours, rb, B=8, steps=4, A=3, rows=64, lr=1e-3)
+    # B = 1 surface reads the current (g, v), not a stale effective weight
+    rs = np.random.RandomState(3)
+    st = (rs.standard_normal(8), rs.standard_normal((64, 6)))
+    np.testing.assert_allclose(ours.select_action(st), ora.select_action(st), rtol=1e-4, atol=1e-5)
+    ac = np.linspace(-0.5, 0.5, 3)
+    np.testing.assert_allclose(np.stack(ours.eval_q(st, ac)), np.stack(ora.eval_q(st, ac)), rtol=1e-4, atol=1e-4)
+
+
+def test_weight_normalization_ragged_policy_freq_1_tf32():
+    ora, orb, ours, rb = make_particles(F=5, N=37, D=3, A=2, rows=50, policy_freq=1, norm="weight_normalization",
+                                        precision="tf32")
+    rs = np.random.RandomState(7)
+    for t in range(3):
+        idx = rs.randint(0, 50, size=19)
+        nz = rs.standard_normal((19, 2)).astype(np.float32)
+        ora.train(orb, 19, indices=idx, noise=nz)
+        ours.train(rb, 19, indices=idx, noise=nz)
+        want = ora.trace["critic_loss"]
+        assert abs(float(ours.last_critic_loss[0].item()) - want) <= 3e-2 * max(1.0, abs(want))
+    # an Adam step moves an element by at most ~lr whatever the gradient's size, so a TF32-rounded gradient near zero can
+    # flip an element's direction: bound the absolute difference by the distance two opposite trajectories can reach
+    compare_nets(ours, ora, tol_rel=5e-2, max_abs=2 * 1e-3 * 3, label="tf32 weight norm")
+
+
 def test_ragged_shapes_and_policy_freq_1():
     # N not a multiple of 8/32, D = 3, F = 5, A = 2, batch not a multiple of the tile
     ora, orb, ours, rb = make_particles(F=5, N=37, D=3, A=2, rows=50, policy_freq=1)
