@@ -70,6 +70,8 @@ CASES = {
     "particles_none": dict(kind="particles", F=8, N=64, D=6, A=3, norm=None, policy_freq=2, B=8, steps=4, rows=64, CDQ=True),
     "particles_layer": dict(kind="particles", F=8, N=64, D=6, A=3, norm="layer", policy_freq=2, B=8, steps=4, rows=64, CDQ=True),
     "particles_nocdq": dict(kind="particles", F=5, N=32, D=4, A=2, norm=None, policy_freq=1, B=8, steps=3, rows=64, CDQ=False),
+    "particles_wn": dict(kind="particles", F=8, N=64, D=6, A=3, norm="weight_normalization", policy_freq=2, B=8, steps=4,
+                         rows=64, CDQ=True),
 }
 
 
@@ -208,12 +210,16 @@ def sample_case(RB):
 
 
 def main():
+    only = sys.argv[1:]                     # optional: names of the cases to (re)generate
     RF, RP, RB = import_reference()
     gold = os.path.join(ROOT, "tests", "golden")
     os.makedirs(gold, exist_ok=True)
-    np.savez_compressed(os.path.join(gold, "replay_sample.npz"), **sample_case(RB))
-    print("replay_sample: oracle == reference (bit-exact); fixture written")
+    if not only:
+        np.savez_compressed(os.path.join(gold, "replay_sample.npz"), **sample_case(RB))
+        print("replay_sample: oracle == reference (bit-exact); fixture written")
     for name, case in CASES.items():
+        if only and name not in only:
+            continue
         res = run_case(name, case, RF, RP, RB)
         np.savez_compressed(os.path.join(gold, f"{name}.npz"), **res)
         print(f"{name}: oracle == reference bit-exact over {case['steps']} steps; "

@@ -21,6 +21,7 @@
 #include "misc.cuh"
 #include "stage.cuh"
 #include "tc.cuh"
+#include "front.cuh"
 #include "persist.cuh"
 
 using namespace td3;
@@ -55,9 +56,10 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 // launch list
 // ------------------------------------------------------------------------------------
 struct Launch {
-  enum Kind { STAGE, GATHER, LOSS, EW, TICK, HEAD, WN } kind = STAGE;
+  enum Kind { STAGE, GATHER, LOSS, EW, TICK, HEAD, WN, FRONT } kind = STAGE;
   HeadParams head{};
   WnParams wn{};
+  FrontParams front{};
   int smem_bytes = 0;
   StageParams stage{};
   GatherParams gather{};
@@ -71,6 +73,7 @@ int ensure_kernel_attrs() {
   static bool done = false;
   if (done) return TD3_OK;
   CUDA_TRY(cudaFuncSetAttribute(head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+  CUDA_TRY(cudaFuncSetAttribute(front_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFrontSmemBytes));
   CUDA_TRY(cudaFuncSetAttribute(stage_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynSmemBytes));
   CUDA_TRY(cudaFuncSetAttribute(stage_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynSmemBytes));
   CUDA_TRY(cudaFuncSetAttribute(persistent_update_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynSmemBytes));
@@ -138,6 +141,12 @@ int run_launch(const Launch& L, cudaStream_t s) {
     case Launch::WN:
       e = launch_pdl(wn_kernel, dim3(L.grid_x), dim3(256), 0, s, L.wn);
       break;
+    case Launch::FRONT: {
+      int rc = ensure_kernel_attrs();
+      if (rc != TD3_OK) return rc;
+      e = launch_pdl(front_kernel, dim3(L.grid_x), dim3(256), (size_t)kFrontSmemBytes, s, L.front);
+      break;
+    }
   }
   if (e != cudaSuccess) return fail(TD3_ERR_CUDA, "kernel launch: %s", cudaGetErrorString(e));
   g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -509,6 +518,9 @@ struct td3_agent {
   PassBuf pb_at, pb_ct, pb_c, pb_a, pb_q1;
   // weight normalisation: effective parameters (W = g v / ||v|| in every weight_v slot) the contractions read
   float *eff_a = nullptr, *eff_at = nullptr, *eff_c = nullptr, *eff_ct = nullptr;
+  // row-local front kernels (front.cuh): template of the sampling launch (gather + first layers), filled by plan_sample
+  bool front_on = false;
+  FrontParams front_sample{};
 
   std::vector<Launch> seq_sample, seq_target, seq_critic_fb, seq_critic_apply, seq_actor_fb, seq_actor_apply;
   // fused middle of a policy update (critic backward with the actor forward riding along, critic Adam, rest of the
@@ -557,8 +569,9 @@ void set_groups(Problem& p, long long a_go, long long a_gi, long long b_go, long
 
 std::vector<ProblemList> build_forward(const td3_agent_config& cfg, const td3_net_layout& net, ParamRef W, GroupShape gs,
                                        int B, const PassBuf& pb, const OutSpec& out, int pool_dups = 1,
-                                       long long pool_dup_stride = 0, bool skip_last = false) {
-  // skip_last: the output layer is computed by the fused head kernel (misc.cuh: head_body)
+                                       long long pool_dup_stride = 0, bool skip_last = false, bool skip_first = false) {
+  // skip_last: the output layer is computed by the fused head kernel (misc.cuh: head_body) or a front kernel
+  // skip_first: the first layer's relu(x W^T + b) is computed by a front kernel (front.cuh)
   std::vector<ProblemList> st;
   const bool ln = cfg.norm == TD3_NORM_LAYER;
   const bool enc = cfg.variant == TD3_VARIANT_PARTICLES;
@@ -619,7 +632,7 @@ std::vector<ProblemList> build_forward(const td3_agent_config& cfg, const td3_ne
       g.c_dups = out.dups; g.c_dup_stride = out.dup_stride;
     }
     finalize_problem(g, gs);
-    st.push_back({g});
+    if (!(l == 0 && skip_first)) st.push_back({g});
     if (last) break;
     in = pb.r[l]; ld_in = N; in_go = pb.h_go[l]; in_gi = pb.h_gi[l];
     if (ln) {   // post-ReLU LayerNorm (TD3_featured.py:44-46)
@@ -674,7 +687,9 @@ int choose_ksplit(int tiles, int groups, int K) {
 std::vector<ProblemList> build_backward(const td3_agent_config& cfg, const td3_net_layout& net, ParamRef W, GradRef G,
                                         GroupShape gs, int B, const PassBuf& pb, const float* dout, int ld_dout,
                                         long long dout_go, long long dout_gi, bool want_dw, const Dx0Spec& dx0,
-                                        const BwdScratch& sc, bool head_done = false) {
+                                        const BwdScratch& sc, bool head_done = false, bool din_top_done = false) {
+  // din_top_done: the gradient w.r.t. the output layer's input is already in sc.dz[0] (front.cuh); the output layer's
+  // dW/db still have to be computed and ride along with the next layer's stage
   // head_done: the output layer's dW/db and the gradient w.r.t. its input were produced by the fused head kernel
   // (into sc.dz[0], or sc.dn with LayerNorm): the walk starts below it
   std::vector<ProblemList> st;
@@ -686,9 +701,11 @@ std::vector<ProblemList> build_backward(const td3_agent_config& cfg, const td3_n
   int ld_dz = ld_dout;
   long long dz_go = dout_go, dz_gi = dout_gi;
   int pp = 0;
+  ProblemList carry;
   for (int l = L - 1; l >= 0; --l) {
     const int K = net.dims[l], N = net.dims[l + 1];
-    ProblemList stage;
+    ProblemList stage = carry;
+    carry.clear();
     // input activation of layer l
     const float* in; int ld_in; long long in_go, in_gi;
     if (l == 0) {
@@ -719,6 +736,12 @@ std::vector<ProblemList> build_backward(const td3_agent_config& cfg, const td3_n
     if (l > 0) {     // d(in_l) = dz . W_l
       const bool mask_now = !ln;
       float* dst = mask_now ? sc.dz[pp] : sc.dn;
+      if (din_top_done && l == L - 1 && mask_now) {
+        carry = stage;
+        dz = sc.dz[pp]; ld_dz = K; dz_go = sc.go; dz_gi = sc.gi;
+        pp ^= 1;
+        continue;
+      }
       if (!skip) {
         Problem p = make_gemm(B, K, N, dz, ld_dz, true, W.base + net.w_off[l], K, false, dst, K,
                               mask_now ? EPI_RELU_MASK : EPI_STORE);
@@ -975,6 +998,33 @@ Problem make_slice(int B, int ncols, const float* in, int ld_in, const float* ey
   return p;
 }
 
+// ---- row-local front kernels (front.cuh) ----
+// first layer of `net` as a front job: out = relu(x[:, :K] W_0^T + b_0) into the pass's r[0]
+FrontNet front_first_layer(const td3_net_layout& net, ParamRef W, int n_inner, const PassBuf& pb) {
+  FrontNet n;
+  memset(&n, 0, sizeof(n));
+  n.W = W.base + net.w_off[0]; n.bias = W.base + net.b_off[0]; n.w_go = W.go; n.w_gi = W.gi;
+  n.ws_c = net.dims[0]; n.ws_k = 1;
+  n.out = pb.r[0]; n.out_go = pb.h_go[0]; n.out_gi = pb.h_gi[0]; n.ldo = net.dims[1];
+  n.K = net.dims[0]; n.N = net.dims[1]; n.n_inner = n_inner; n.act_col = -1;
+  return n;
+}
+
+// job table + grid of a front launch
+void front_finish(Launch& L, int B, int nA) {
+  FrontParams& F = L.front;
+  F.batch = B; F.n_agents = nA; F.row_blocks = (B + kFrontRows - 1) / kFrontRows;
+  int jobs = 0;
+  for (int i = 0; i < F.n_nets; ++i) {
+    F.net[i].job_begin = jobs;
+    F.net[i].col_blocks = (F.net[i].N + kFrontCols - 1) / kFrontCols;
+    jobs += F.net[i].n_inner * F.net[i].col_blocks;
+  }
+  F.jobs = jobs;
+  L.kind = Launch::FRONT;
+  L.grid_x = nA * F.row_blocks * jobs;
+}
+
 // ---- weight normalisation (misc.cuh: wn_body) ----
 // Row blocks (and, for the effective-parameter pass, pass-through chunks) of one network of a family.
 bool make_wn_layout(const td3_net_layout& net, bool with_copies, WnLayout& Y) {
@@ -1154,6 +1204,27 @@ int plan_agent(td3_agent* a, long long batch) {
   a->seq_sample.clear(); a->seq_target.clear(); a->seq_critic_fb.clear(); a->seq_critic_apply.clear();
   a->seq_actor_fb.clear(); a->seq_actor_apply.clear();
 
+  // Row-local links of the chain (sampling + first layers, actor output layer + the critic's first layer, and their
+  // mirror in the actor's backward pass) run as front kernels when the shapes fit (front.cuh).
+  const int La = c.actor.n_linear;
+  const bool front = !enc && A <= kFrontMaxA && S + A <= kFrontMaxK && La >= 2 && Lq >= 2 &&
+                     c.actor.dims[La - 1] <= kFrontMaxKh && c.q.dims[1] <= kFrontMaxKh && !getenv("TD3_NO_FRONT");
+  a->front_on = front;
+  if (front) {
+    // sampling launch: gather + target-actor L1 on s' + online-critic L1 on [s, a]; plan_sample adds the replay view
+    Launch L;
+    FrontParams& F = L.front;
+    memset(&F, 0, sizeof(F));
+    F.gather = 1; F.A = A;
+    F.n_nets = 2;
+    F.net[0] = front_first_layer(c.q, Wc, nq, cc);      // x_off 0 first: job 0 stages (and scatters) the whole row
+    F.net[0].x_off = 0;
+    F.net[1] = front_first_layer(c.actor, Wat, 1, at);
+    F.net[1].x_off = S + A;
+    front_finish(L, B, nA);
+    a->front_sample = F;
+  }
+
   if (wn) {   // refresh all four effective buffers (the caller may have loaded or edited parameters since the last update)
     Launch L;
     if (!make_wn_launch(c, 0, {{a->actor.params, a->eff_a, an, nA, 0}, {a->actor.target, a->eff_at, an, nA, 0},
@@ -1170,15 +1241,34 @@ int plan_agent(td3_agent* a, long long batch) {
     o.f0 = enc ? 1.f : c.max_action;
     o.f1 = c.clamp_target_action ? c.max_action : 0.f;
     o.dups = xq_inner; o.dup_stride = a->xq_gi;
-    auto s_at = build_forward(c, c.actor, Wat, g_actor, B, at, o);
+    auto s_at = build_forward(c, c.actor, Wat, g_actor, B, at, o, 1, 0, front, front);
     OutSpec oq;
     oq.out = a->tq; oq.ld = qw; oq.gi = (long long)B * qw; oq.go = oq.gi * nq; oq.epi = EPI_BIAS;
-    auto s_ct = build_forward(c, c.q, Wct, g_crit, B, ct, oq, 1, 0, fuse_heads);
+    auto s_ct = build_forward(c, c.q, Wct, g_crit, B, ct, oq, 1, 0, fuse_heads, front);
     // the online critic forward is independent of the target path: run it alongside the target actor
     OutSpec oc;
     oc.out = a->q; oc.ld = qw; oc.gi = (long long)B * qw; oc.go = oc.gi * nq; oc.epi = EPI_BIAS;
-    auto s_cc = build_forward(c, c.q, Wc, g_crit, B, cc, oc, 1, 0, fuse_heads);
+    auto s_cc = build_forward(c, c.q, Wc, g_crit, B, cc, oc, 1, 0, fuse_heads, front);
     for (auto& st : zip_stages({s_at, s_cc})) emit_stage(a->seq_target, st);
+    if (front) {
+      // next_action = clamp(max_action * tanh(h W_L^T + b_L) + eps) (TD3_featured.py:131-138), then both target
+      // critics' first layer on [s', next_action]
+      Launch L;
+      FrontParams& F = L.front;
+      memset(&F, 0, sizeof(F));
+      F.head = 1; F.A = A;
+      F.h = ln ? at.n[La - 2] : at.r[La - 2]; F.h_go = at.h_go[La - 2]; F.ldh = c.actor.dims[La - 1]; F.Kh = c.actor.dims[La - 1];
+      F.Wh = pat_w + c.actor.w_off[La - 1]; F.bh = pat_w + c.actor.b_off[La - 1]; F.wh_go = an;
+      F.hs_j = c.actor.dims[La - 1]; F.hs_k = 1;
+      F.head_epi = EPI_BIAS_TANH_NOISE; F.aux_in = a->eps; F.aux_go = (long long)B * A;
+      F.a_out = a->xq2 + S; F.a_go = a->xq_go; F.a_ld = ld_q;
+      F.f0 = o.f0; F.f1 = o.f1;
+      F.n_nets = 1;
+      F.net[0] = front_first_layer(c.q, Wct, nq, ct);
+      F.net[0].x = a->xq2; F.net[0].x_go = a->xq_go; F.net[0].ldx = ld_q; F.net[0].x_off = 0; F.net[0].act_col = S;
+      front_finish(L, B, nA);
+      a->seq_target.push_back(L);
+    }
     for (auto& st : s_ct) emit_stage(a->seq_target, st);
   }
   // ---- critic loss + backward (:145-152) ----
@@ -1248,7 +1338,7 @@ int plan_agent(td3_agent* a, long long batch) {
     o.out = a->xpi + E + S; o.ld = ld_q; o.go = a->xpi_go; o.gi = 0;
     o.epi = EPI_BIAS_TANH; o.aux0 = a->tanh_y; o.ldaux = A; o.aux0_go = (long long)B * A;
     o.f0 = enc ? 1.f : c.max_action;
-    auto s_a = build_forward(c, c.actor, Wa, g_actor, B, pa, o);
+    auto s_a = build_forward(c, c.actor, Wa, g_actor, B, pa, o, 1, 0, front);
     for (auto& st : s_a) emit_stage(a->seq_actor_fb, st);
     a->n_actor_fwd = (int)a->seq_actor_fb.size();
     if (wn) {     // Q1 below reads the critic the Adam step just changed
@@ -1259,7 +1349,25 @@ int plan_agent(td3_agent* a, long long batch) {
     }
     OutSpec oq;
     oq.out = a->q_pi; oq.ld = qw; oq.go = (long long)B * qw; oq.epi = EPI_BIAS;
-    auto s_q = build_forward(c, c.q, Wq1, g_q1, B, q1, oq, 1, 0, fuse_heads);
+    if (front) {
+      // action = max_action * tanh(h W_L^T + b_L) (:159), then Q1's first layer on [s, action] with the stepped critic
+      Launch L;
+      FrontParams& F = L.front;
+      memset(&F, 0, sizeof(F));
+      F.head = 1; F.A = A;
+      F.h = ln ? pa.n[La - 2] : pa.r[La - 2]; F.h_go = pa.h_go[La - 2]; F.ldh = c.actor.dims[La - 1]; F.Kh = c.actor.dims[La - 1];
+      F.Wh = pa_w + c.actor.w_off[La - 1]; F.bh = pa_w + c.actor.b_off[La - 1]; F.wh_go = an;
+      F.hs_j = c.actor.dims[La - 1]; F.hs_k = 1;
+      F.head_epi = EPI_BIAS_TANH; F.aux_out = a->tanh_y; F.aux_go = (long long)B * A;
+      F.a_out = a->xpi + S; F.a_go = a->xpi_go; F.a_ld = ld_q;
+      F.f0 = o.f0;
+      F.n_nets = 1;
+      F.net[0] = front_first_layer(c.q, Wq1, 1, q1);
+      F.net[0].x = a->xpi; F.net[0].x_go = a->xpi_go; F.net[0].ldx = ld_q; F.net[0].x_off = 0; F.net[0].act_col = S;
+      front_finish(L, B, nA);
+      a->seq_actor_fb.push_back(L);
+    }
+    auto s_q = build_forward(c, c.q, Wq1, g_q1, B, q1, oq, 1, 0, fuse_heads, front);
     for (auto& st : s_q) emit_stage(a->seq_actor_fb, st);
     if (fuse_heads) {       // Q1 head + (-mean) + head backward + actor optimiser tick
       Launch L;
@@ -1287,8 +1395,10 @@ int plan_agent(td3_agent* a, long long batch) {
       nm.C = a->state_f32 + nA; nm.c_go = 1; nm.f0 = -1.f;
       finalize_problem(nm, g_q1);
       // first backward stage of Q1 shares the launch with the read-back
+      // without LayerNorm the action gradient and the actor's top-layer input gradient are one front kernel
+      const bool front_bwd = front && !ln;
       Dx0Spec dx;
-      dx.mode = 1; dx.col0 = E + S; dx.ncols = A;
+      dx.mode = front_bwd ? 0 : 1; dx.col0 = E + S; dx.ncols = A;
       const bool lnin = enc && ln;
       dx.out = da; dx.ld = A; dx.go = (long long)B * A;
       dx.epi = lnin ? EPI_STORE : EPI_TANH_GRAD;
@@ -1296,7 +1406,30 @@ int plan_agent(td3_agent* a, long long batch) {
       auto s_qb = build_backward(c, c.q, Wq1, GradRef{}, g_q1, B, q1, a->dq_pi, qw, (long long)B * qw, 0, false, dx,
                                  sc_q1, fuse_heads);
       if (!fuse_heads && !s_qb.empty()) s_qb[0].push_back(nm);
+      else if (!fuse_heads) emit_stage(a->seq_actor_fb, {nm});
       for (auto& st : s_qb) emit_stage(a->seq_actor_fb, st);
+      if (front_bwd) {
+        // d(action) = (dz1 . W_0[:, S:S+A]) * max_action * (1 - tanh^2)  (through Q1's first layer and the actor's tanh),
+        // then the actor's top layer: dz = (d(action) . W_L) * (hidden > 0)
+        Launch L;
+        FrontParams& F = L.front;
+        memset(&F, 0, sizeof(F));
+        F.head = 1; F.A = A;
+        F.h = sc_q1.dz[(Lq - 2) & 1]; F.h_go = sc_q1.go; F.ldh = c.q.dims[1]; F.Kh = c.q.dims[1];
+        F.Wh = pc_w + c.q.w_off[0] + S; F.bh = nullptr; F.wh_go = qn * nq; F.hs_j = 1; F.hs_k = c.q.dims[0];
+        F.head_epi = EPI_TANH_GRAD; F.aux_in = a->tanh_y; F.aux_go = (long long)B * A;
+        F.a_out = da; F.a_go = (long long)B * A; F.a_ld = A;
+        F.f0 = dx.f0;
+        F.n_nets = 1;
+        FrontNet& n = F.net[0];
+        n.W = pa_w + c.actor.w_off[La - 1]; n.bias = nullptr; n.w_go = an; n.w_gi = 0;
+        n.ws_c = 1; n.ws_k = c.actor.dims[La - 1];
+        n.out = sc_a.dz[0]; n.out_go = sc_a.go; n.out_gi = sc_a.gi; n.ldo = c.actor.dims[La - 1];
+        n.mask = pa.r[La - 2]; n.mask_go = pa.h_go[La - 2]; n.mask_gi = pa.h_gi[La - 2];
+        n.K = A; n.N = c.actor.dims[La - 1]; n.n_inner = 1; n.act_col = 0;
+        front_finish(L, B, nA);
+        a->seq_actor_fb.push_back(L);
+      }
       if (lnin) {
         // d(action) = slice of the full input gradient, then through tanh: identity-GEMM slice
         Problem sl = make_slice(B, A, sc_q1.dx0_full + E + S, ld_q, eye, da, A, EPI_TANH_GRAD);
@@ -1313,7 +1446,8 @@ int plan_agent(td3_agent* a, long long batch) {
       a->seq_actor_fb.push_back(L);
     }
     Dx0Spec none;
-    auto s_ab = build_backward(c, c.actor, Wa, Ga, g_actor, B, pa, da, A, (long long)B * A, 0, true, none, sc_a);
+    auto s_ab = build_backward(c, c.actor, Wa, Ga, g_actor, B, pa, da, A, (long long)B * A, 0, true, none, sc_a, false,
+                               front && !ln);
     for (auto& st : s_ab) emit_stage(a->seq_actor_fb, st);
     if (wn) {
       Launch Lw;
@@ -1434,6 +1568,15 @@ int plan_sample(td3_agent* a, const td3_replay_view* rb, int rng_mode) {
   L.grid_x = (int)((jobs + 7) / 8);
   L.grid_y = rb->row_floats > 2048 ? (int)std::min<long long>(32, (rb->row_floats + 2047) / 2048) : 1;
   G.slices = L.grid_y;
+  if (a->front_on) {       // sampling + the first layers that read nothing but the sampled rows, in one launch
+    G.slices = 1;
+    G.row_floats = 2 * S + A + 2;
+    const GatherParams gp = G;
+    L = Launch{};
+    L.front = a->front_sample;
+    L.front.g = gp;
+    front_finish(L, B, nA);
+  }
   a->seq_sample.clear();
   a->seq_sample.push_back(L);
   a->plan_rows = rb->rows; a->plan_row_stride = rb->row_stride; a->plan_rng_mode = rng_mode;
@@ -1474,6 +1617,9 @@ int append_records(std::vector<StageRec>& prog, const std::vector<Launch>& seq, 
         break;
       case Launch::WN:
         r.kind = SK_WN; r.u.w = L.wn; r.main_tiles = L.grid_x;
+        break;
+      case Launch::FRONT:
+        r.kind = SK_FRONT; r.u.f = L.front; r.main_tiles = L.grid_x;
         break;
       default: break;
     }

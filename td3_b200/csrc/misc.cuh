@@ -89,28 +89,26 @@ struct GatherParams {
   float* eps_out;                 // [n_agents][batch][action_dim]  clipped noise
   const float* noise_in;          // N(0,1) draws (injected mode), same shape
   int action_dim, slices;         // slices = gridDim.y
-  int elem_offset, pad;           // data-parallel shard: local row b is element b + elem_offset of the global batch
+  int elem_offset, row_floats;    // data-parallel shard: local row b is element b + elem_offset of the global batch
   float policy_noise, noise_clip;
 };
 
-__device__ __forceinline__ void gather_body(const GatherParams& G, int bx, int by) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int warps_per_block = blockDim.x >> 5;
-  const long long job = (long long)bx * warps_per_block + warp;   // (agent, b)
-  if (job >= (long long)G.n_agents * G.batch) return;
-  const int agent = (int)(job / G.batch), b = (int)(job - (long long)agent * G.batch);
+// replay index of element b of agent's batch (Philox draw, or the injected one)
+__device__ __forceinline__ long long gather_index(const GatherParams& G, int agent, int b) {
+  if (G.rng_mode != 0) return G.idx_in[(long long)agent * G.batch + b];
   const unsigned long long step = __ldcg(G.step_ptr);
   const long long size = G.size_ptr ? (long long)__ldcg(G.size_ptr) : G.size;
-  long long idx;
-  if (G.rng_mode == 0) {
-    idx = philox_index(G.seed + (unsigned long long)agent * 0x9E3779B97F4A7C15ull, PHILOX_INDICES, step,
-                       (uint32_t)(b + G.elem_offset), size);
-  } else {
-    idx = G.idx_in[job];
-  }
-  const int slice = by;
+  return philox_index(G.seed + (unsigned long long)agent * 0x9E3779B97F4A7C15ull, PHILOX_INDICES, step,
+                      (uint32_t)(b + G.elem_offset), size);
+}
+
+// one warp scatters (its slice of) transition `idx` to every destination segment; slice 0 also records the index and
+// draws the row's clipped smoothing noise
+__device__ __forceinline__ void gather_row(const GatherParams& G, int agent, int b, long long idx, int slice, int lane) {
+  const long long job = (long long)agent * G.batch + b;
   if (slice == 0) {
     if (lane == 0) G.idx_out[job] = idx;
+    const unsigned long long step = __ldcg(G.step_ptr);
     for (int a = lane; a < G.action_dim; a += 32) {
       const long long e = (long long)b * G.action_dim + a;
       float z = (G.rng_mode == 0)
@@ -143,6 +141,36 @@ __device__ __forceinline__ void gather_body(const GatherParams& G, int bx, int b
       for (int i = lo + lane; i < hi; i += 32) d[i] = __ldg(sp + i);
     }
   }
+}
+
+// the same scatter from a copy of the transition in shared memory (front.cuh), plus the row's smoothing noise
+__device__ __forceinline__ void gather_scatter(const GatherParams& G, int agent, int b, const float* row, int lane) {
+  const unsigned long long step = __ldcg(G.step_ptr);
+  for (int a = lane; a < G.action_dim; a += 32) {
+    const long long e = (long long)b * G.action_dim + a;
+    float z = (G.rng_mode == 0)
+                  ? philox_normal(G.seed + (unsigned long long)agent * 0x9E3779B97F4A7C15ull, PHILOX_NOISE, step,
+                                  (uint32_t)(e + (long long)G.elem_offset * G.action_dim))
+                  : G.noise_in[(long long)agent * G.batch * G.action_dim + e];
+    z = z * G.policy_noise;
+    z = fminf(fmaxf(z, -G.noise_clip), G.noise_clip);
+    G.eps_out[(long long)agent * G.batch * G.action_dim + e] = z;
+  }
+#pragma unroll 1
+  for (int s = 0; s < G.n_seg; ++s) {
+    float* d = G.dst[s] + (long long)agent * G.dst_agent_stride[s] + (long long)b * G.dst_ld[s];
+    const float* sp = row + G.seg_off[s];
+    for (int i = lane; i < G.seg_len[s]; i += 32) d[i] = sp[i];
+  }
+}
+
+__device__ __forceinline__ void gather_body(const GatherParams& G, int bx, int by) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  const long long job = (long long)bx * warps_per_block + warp;   // (agent, b)
+  if (job >= (long long)G.n_agents * G.batch) return;
+  const int agent = (int)(job / G.batch), b = (int)(job - (long long)agent * G.batch);
+  gather_row(G, agent, b, gather_index(G, agent, b), by, lane);
 }
 
 __global__ void __launch_bounds__(256) gather_kernel(const __grid_constant__ GatherParams G) {

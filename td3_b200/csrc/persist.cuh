@@ -9,6 +9,7 @@
 #include "misc.cuh"
 #include "stage.cuh"
 #include "tc.cuh"
+#include "front.cuh"
 
 namespace td3 {
 
@@ -78,7 +79,7 @@ __global__ void __launch_bounds__(kStageThreads, 1) stage_kernel(const __grid_co
   }
 }
 
-enum StageKind : int { SK_STAGE = 0, SK_GATHER = 1, SK_LOSS = 2, SK_EW_ONLY = 3, SK_HEAD = 4, SK_WN = 5 };
+enum StageKind : int { SK_STAGE = 0, SK_GATHER = 1, SK_LOSS = 2, SK_EW_ONLY = 3, SK_HEAD = 4, SK_WN = 5, SK_FRONT = 6 };
 
 struct alignas(16) StageRec {
   int kind;
@@ -93,6 +94,7 @@ struct alignas(16) StageRec {
     LossParams l;
     HeadParams h;
     WnParams w;
+    FrontParams f;
   } u;
   EwParams ew;
 };
@@ -176,6 +178,8 @@ __global__ void __launch_bounds__(kStageThreads, 1) persistent_update_kernel(con
           head_body(R.u.h, tile, reinterpret_cast<float*>(ring));
         } else if (R.kind == SK_WN) {
           wn_body(R.u.w, tile);
+        } else if (R.kind == SK_FRONT) {
+          front_body(R.u.f, tile, reinterpret_cast<float*>(ring));
         }
       }
       // descriptor of the next stage (static data) while the others are still working

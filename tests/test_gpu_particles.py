@@ -92,7 +92,7 @@ def test_split_k_path_large_particle_count():
     _run(ora, orb, ours, rb, B=16, steps=2, A=3, rows=32, lr=1e-3)
 
 
-@pytest.mark.parametrize("name", ["particles_none", "particles_layer", "particles_nocdq"])
+@pytest.mark.parametrize("name", ["particles_none", "particles_layer", "particles_nocdq", "particles_wn"])
 def test_matches_reference_golden_fixture(name):
     z = np.load(os.path.join(GOLDEN, name + ".npz"))
     case = ast.literal_eval(str(z["case"]))

@@ -77,7 +77,7 @@ def test_sample_empty_buffer_raises():
 
 
 @pytest.mark.skipif(not has_reference(), reason="/root/reference only exists in the build container")
-@pytest.mark.parametrize("name", ["featured_layer", "particles_nocdq"])
+@pytest.mark.parametrize("name", ["featured_layer", "particles_nocdq", "particles_wn"])
 def test_oracle_matches_live_reference(name):
     RF, RP, RB = MG.import_reference()
     res = MG.run_case(name, MG.CASES[name], RF, RP, RB)               # asserts bit-equality internally
