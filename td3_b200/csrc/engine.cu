@@ -22,6 +22,7 @@
 #include "stage.cuh"
 #include "tc.cuh"
 #include "front.cuh"
+#include "apply.cuh"
 #include "persist.cuh"
 
 using namespace td3;
@@ -65,6 +66,7 @@ struct Launch {
   GatherParams gather{};
   LossParams loss{};
   EwParams ew{};
+  DwParams dw{};        // EW launches: first-layer gradient tiles that step their own parameters (apply.cuh)
   AdamTick tick{};
   int grid_x = 1, grid_y = 1;
 };
@@ -127,7 +129,18 @@ int run_launch(const Launch& L, cudaStream_t s) {
       e = launch_pdl(loss_kernel, dim3(L.grid_x), dim3(256), 0, s, L.loss);
       break;
     case Launch::EW:
-      e = launch_pdl(adam_polyak_kernel, dim3(L.grid_x), dim3(kEwThreads), 0, s, L.ew);
+      if (L.dw.n_tiles > 0) {
+        static const bool use_pdl = getenv("TD3_PDL") != nullptr;
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(L.dw.n_tiles + L.grid_x); cfg.blockDim = dim3(kDwThreads); cfg.dynamicSmemBytes = 0; cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr; cfg.numAttrs = use_pdl ? 1 : 0;
+        e = cudaLaunchKernelEx(&cfg, apply_kernel, L.ew, L.dw);
+      } else {
+        e = launch_pdl(adam_polyak_kernel, dim3(L.grid_x), dim3(kEwThreads), 0, s, L.ew);
+      }
       break;
     case Launch::TICK:
       e = launch_pdl(adam_tick_kernel, dim3(1), dim3(32), 0, s, L.tick);
@@ -526,6 +539,11 @@ struct td3_agent {
   // fused middle of a policy update (critic backward with the actor forward riding along, critic Adam, rest of the
   // actor step): what the CUDA graph and the persistent program run instead of critic_fb + critic_apply + actor_fb
   std::vector<Launch> seq_policy_mid;
+  // what train_n runs after seq_sample (CUDA graph and plain-launch modes): either the sequences above back to back, or
+  // -- plain MLPs -- the tail-fused form: first-layer gradient + Adam (+ Polyak) in ONE launch (apply.cuh) and the
+  // actor's forward layers riding along with the target pass
+  std::vector<Launch> seq_run_critic, seq_run_policy;
+  bool tail_fused = false;
   int n_actor_fwd = 0;                       // leading launches of seq_actor_fb that are the actor's forward pass
   const float* plan_rows = nullptr;
   long long plan_row_stride = 0, plan_rb_agent_stride = 0;
@@ -668,6 +686,8 @@ struct BwdScratch {
   long long part_cap = 0;
 };
 
+struct Dz0Info { const float* dz = nullptr; int ld = 0; long long go = 0, gi = 0; };
+
 struct Dx0Spec {
   int mode = 0;
   int col0 = 0, ncols = 0;
@@ -687,7 +707,10 @@ int choose_ksplit(int tiles, int groups, int K) {
 std::vector<ProblemList> build_backward(const td3_agent_config& cfg, const td3_net_layout& net, ParamRef W, GradRef G,
                                         GroupShape gs, int B, const PassBuf& pb, const float* dout, int ld_dout,
                                         long long dout_go, long long dout_gi, bool want_dw, const Dx0Spec& dx0,
-                                        const BwdScratch& sc, bool head_done = false, bool din_top_done = false) {
+                                        const BwdScratch& sc, bool head_done = false, bool din_top_done = false,
+                                        Dz0Info* dz0 = nullptr) {
+  // dz0 != nullptr: the first layer's dW/db are NOT emitted; *dz0 says where the gradient w.r.t. its pre-activation
+  // ends up, for the fused gradient + optimiser tiles of the apply launch (apply.cuh)
   // din_top_done: the gradient w.r.t. the output layer's input is already in sc.dz[0] (front.cuh); the output layer's
   // dW/db still have to be computed and ride along with the next layer's stage
   // head_done: the output layer's dW/db and the gradient w.r.t. its input were produced by the fused head kernel
@@ -716,7 +739,8 @@ std::vector<ProblemList> build_backward(const td3_agent_config& cfg, const td3_n
       in = ln ? pb.n[l - 1] : pb.r[l - 1]; ld_in = K; in_go = pb.h_go[l - 1]; in_gi = pb.h_gi[l - 1];
     }
     const bool skip = head_done && l == L - 1 && l > 0;
-    if (want_dw && !skip) {   // dW_l[n,k] = sum_b dz[b,n] in[b,k] ; db_l[n] = sum_b dz[b,n]
+    if (l == 0 && dz0) { dz0->dz = dz; dz0->ld = ld_dz; dz0->go = dz_go; dz0->gi = dz_gi; }
+    if (want_dw && !skip && !(l == 0 && dz0)) {   // dW_l[n,k] = sum_b dz[b,n] in[b,k] ; db_l[n] = sum_b dz[b,n]
       Problem p = make_gemm(N, K, B, dz, ld_dz, false, in, ld_in, false, G.base + net.w_off[l], K, EPI_STORE);
       set_groups(p, dz_go, dz_gi, in_go, in_gi, G.go, G.gi);
       finalize_problem(p, gs);
@@ -1210,6 +1234,19 @@ int plan_agent(td3_agent* a, long long batch) {
   const bool front = !enc && A <= kFrontMaxA && S + A <= kFrontMaxK && La >= 2 && Lq >= 2 &&
                      c.actor.dims[La - 1] <= kFrontMaxKh && c.q.dims[1] <= kFrontMaxKh && !getenv("TD3_NO_FRONT");
   a->front_on = front;
+  // tail fusion (apply.cuh): plain MLPs whose first layer sits at the head of each network's packed block
+  auto l0_fusable = [](const td3_net_layout& n) {
+    return n.n_linear >= 2 && n.dims[0] <= kDwMaxK && (n.dims[1] & 3) == 0 && n.w_off[0] == 0 && (n.w_off[1] & 3) == 0 &&
+           n.b_off[0] >= (long long)n.dims[0] * n.dims[1] && n.w_off[1] >= n.b_off[0] + n.dims[1] && (n.n_floats & 3) == 0;
+  };
+  const bool fuse_tail = front && !ln && !wn && a->cluster_mode && l0_fusable(c.q) && l0_fusable(c.actor) && (ld_q & 3) == 0 &&
+                         Lq >= 2 && qw <= kHeadMaxQw && c.q.dims[Lq - 1] <= kHeadMaxW && !getenv("TD3_NO_HEAD_FUSION") &&
+                         !getenv("TD3_NO_TAIL_FUSION");
+  a->tail_fused = fuse_tail;
+  std::vector<Launch> v_cb, v_abf, v_tp;     // fused-mode pieces: critic head + backward, actor backward, target pass + actor forward
+  std::vector<ProblemList> s_abf;
+  Dz0Info dz0_c, dz0_a;
+  size_t n_actor_pre_bwd = 0;
   if (front) {
     // sampling launch: gather + target-actor L1 on s' + online-critic L1 on [s, a]; plan_sample adds the replay view
     Launch L;
@@ -1312,6 +1349,12 @@ int plan_agent(td3_agent* a, long long batch) {
     auto s_b = build_backward(c, c.q, Wc, Gc, g_crit, B, cc, a->dq, qw, (long long)B * qw * nq, (long long)B * qw, true,
                               none, sc_c, fuse_heads);
     for (auto& st : s_b) emit_stage(a->seq_critic_fb, st);
+    if (fuse_tail) {
+      v_cb.push_back(L);
+      auto s_bf = build_backward(c, c.q, Wc, Gc, g_crit, B, cc, a->dq, qw, (long long)B * qw * nq, (long long)B * qw, true,
+                                 none, sc_c, fuse_heads, false, &dz0_c);
+      for (auto& st : s_bf) emit_stage(v_cb, st);
+    }
     if (wn) {     // dL/dW -> (dL/dg, dL/dv) in place
       Launch Lw;
       if (!make_wn_launch(c, 1, {{a->critic.params, a->critic.grad, qn, nA * nq, 1}}, Lw))
@@ -1448,7 +1491,13 @@ int plan_agent(td3_agent* a, long long batch) {
     Dx0Spec none;
     auto s_ab = build_backward(c, c.actor, Wa, Ga, g_actor, B, pa, da, A, (long long)B * A, 0, true, none, sc_a, false,
                                front && !ln);
+    n_actor_pre_bwd = a->seq_actor_fb.size();
     for (auto& st : s_ab) emit_stage(a->seq_actor_fb, st);
+    if (fuse_tail) {
+      s_abf = build_backward(c, c.actor, Wa, Ga, g_actor, B, pa, da, A, (long long)B * A, 0, true, none, sc_a, false,
+                             front && !ln, &dz0_a);
+      for (auto& st : s_abf) emit_stage(v_abf, st);
+    }
     if (wn) {
       Launch Lw;
       if (!make_wn_launch(c, 1, {{a->actor.params, a->actor.grad, an, nA, 0}}, Lw))
@@ -1488,14 +1537,70 @@ int plan_agent(td3_agent* a, long long batch) {
     for (const Launch& L : a->seq_critic_apply) a->seq_policy_mid.push_back(L);
     for (size_t i = a->n_actor_fwd; i < a->seq_actor_fb.size(); ++i) a->seq_policy_mid.push_back(a->seq_actor_fb[i]);
   }
-  // TMA descriptors of every tensor-core operand (pointers are fixed from here on: torch owns the buffers).  The fused
-  // policy sequence gets its own: merging stages can change a launch's cluster size and with it the A-panel box.
+  if (fuse_tail) {
+    // the actor's forward layers (they read the sampled states and the actor only) ride along with the target pass
+    a->seq_policy_mid.clear();
+    size_t ai = 0;
+    for (const Launch& L : a->seq_target) {
+      Launch m = L;
+      if (L.kind == Launch::STAGE && (int)ai < a->n_actor_fwd && merge_stage(m, a->seq_actor_fb[ai])) ++ai;
+      v_tp.push_back(m);
+    }
+    for (; (int)ai < a->n_actor_fwd; ++ai) v_tp.push_back(a->seq_actor_fb[ai]);
+  }
+  // TMA descriptors of every tensor-core operand (pointers are fixed from here on: torch owns the buffers).  Merged
+  // sequences get their own: merging stages can change a launch's cluster size and with it the A-panel box.
   if (g_tc_mode) {
     std::vector<CUtensorMap> host;
-    if (!attach_tensor_maps({&a->seq_target, &a->seq_critic_fb, &a->seq_actor_fb, &a->seq_policy_mid}, a->tmaps_dev, host))
+    if (!attach_tensor_maps({&a->seq_target, &a->seq_critic_fb, &a->seq_actor_fb, &a->seq_policy_mid, &v_cb, &v_abf, &v_tp},
+                            a->tmaps_dev, host))
       return fail(TD3_ERR_CUDA, "cuTensorMapEncodeTiled failed for a tensor-core operand (or more than %d maps needed)", kMaxTensorMaps);
     if (!host.empty())
       cudaMemcpy(a->tmaps_dev, host.data(), host.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice);
+  }
+  // ---- what train_n runs after the sampling launch ----
+  a->seq_run_critic.clear(); a->seq_run_policy.clear();
+  auto append = [](std::vector<Launch>& dst, const std::vector<Launch>& src, size_t from = 0, size_t to = (size_t)-1) {
+    for (size_t i = from; i < std::min(to, src.size()); ++i) dst.push_back(src[i]);
+  };
+  if (fuse_tail) {
+    auto fill_dw = [&](DwParams& D, const td3_net_layout& n, const Dz0Info& z, const PassBuf& pb, const td3_param_set& ps,
+                       int n_inner, long long net_floats, const float* sc_ptr, bool polyak) {
+      memset(&D, 0, sizeof(D));
+      D.batch = B; D.n_agents = nA; D.n_inner = n_inner; D.N = n.dims[1]; D.K = n.dims[0];
+      D.col_blocks = (D.N + kDwCols - 1) / kDwCols;
+      D.n_tiles = nA * n_inner * D.col_blocks;
+      D.dz = z.dz; D.ld_dz = z.ld; D.dz_go = z.go; D.dz_gi = z.gi;
+      D.x = pb.x0; D.ldx = pb.ld0; D.x_go = pb.x0_go; D.x_gi = pb.x0_gi;
+      D.p = ps.params; D.g = ps.grad; D.m = ps.exp_avg; D.v = ps.exp_avg_sq; D.tgt = polyak ? ps.target : nullptr;
+      D.do_polyak = polyak ? 1 : 0;
+      D.p_go = net_floats * n_inner; D.p_gi = net_floats; D.w_off = n.w_off[0]; D.b_off = n.b_off[0];
+      D.sc_ptr = sc_ptr;
+    };
+    Launch apply_c = a->seq_critic_apply[0];
+    apply_c.ew.r[0].skip_period = qn; apply_c.ew.r[0].skip_len = c.q.w_off[1];
+    fill_dw(apply_c.dw, c.q, dz0_c, cc, a->critic, nq, qn, reinterpret_cast<const float*>(a->state_u64 + 10), false);
+    Launch apply_a = a->seq_actor_apply[0];
+    apply_a.ew.r[1].skip_period = an; apply_a.ew.r[1].skip_len = c.actor.w_off[1];
+    fill_dw(apply_a.dw, c.actor, dz0_a, pa, a->actor, 1, an, reinterpret_cast<const float*>(a->state_u64 + 11), true);
+    if (!dz0_c.dz || !dz0_a.dz || (dz0_c.ld & 3) || (dz0_a.ld & 3))
+      return fail(TD3_ERR_STATE, "tail fusion: first-layer gradient not located");
+    append(a->seq_run_critic, a->seq_target);
+    append(a->seq_run_critic, v_cb);
+    a->seq_run_critic.push_back(apply_c);
+    append(a->seq_run_policy, v_tp);
+    append(a->seq_run_policy, v_cb);
+    a->seq_run_policy.push_back(apply_c);
+    append(a->seq_run_policy, a->seq_actor_fb, (size_t)a->n_actor_fwd, n_actor_pre_bwd);
+    append(a->seq_run_policy, v_abf);
+    a->seq_run_policy.push_back(apply_a);
+  } else {
+    append(a->seq_run_critic, a->seq_target);
+    append(a->seq_run_critic, a->seq_critic_fb);
+    append(a->seq_run_critic, a->seq_critic_apply);
+    append(a->seq_run_policy, a->seq_target);
+    append(a->seq_run_policy, a->seq_policy_mid);
+    append(a->seq_run_policy, a->seq_actor_apply);
   }
   // constant buffers: dq_pi = -1/(B*qw) (d(-mean)/dQ1), identity for the slice problem
   {
@@ -1746,14 +1851,7 @@ int capture(td3_agent* a, bool with_actor, cudaGraphExec_t* out, long long* n_no
   cudaStream_t s = a->cap_stream;
   CUDA_TRY(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
   int rc = run_seq(a->seq_sample, s);
-  if (rc == TD3_OK) rc = run_seq(a->seq_target, s);
-  if (with_actor) {
-    if (rc == TD3_OK) rc = run_seq(a->seq_policy_mid, s);
-    if (rc == TD3_OK) rc = run_seq(a->seq_actor_apply, s);
-  } else {
-    if (rc == TD3_OK) rc = run_seq(a->seq_critic_fb, s);
-    if (rc == TD3_OK) rc = run_seq(a->seq_critic_apply, s);
-  }
+  if (rc == TD3_OK) rc = run_seq(with_actor ? a->seq_run_policy : a->seq_run_critic, s);
   cudaError_t e = cudaStreamEndCapture(s, &graph);
   *n_nodes = g_launches.load() - launches_before;            // captured, not executed: move to per-replay accounting
   g_launches.fetch_sub(*n_nodes, std::memory_order_relaxed);
@@ -2105,11 +2203,7 @@ int td3_train_n(td3_agent* a, const td3_replay_view* rb, int64_t total_it, int32
       g_launches.fetch_add(policy_step ? a->graphs.nodes_with_actor : a->graphs.nodes_critic_only, std::memory_order_relaxed);
     } else {
       rc = run_seq(a->seq_sample, s);
-      if (rc == TD3_OK) rc = run_seq(a->seq_target, s);
-      if (rc == TD3_OK) rc = run_seq(a->seq_critic_fb, s);
-      if (rc == TD3_OK) rc = run_seq(a->seq_critic_apply, s);
-      if (rc == TD3_OK && policy_step) rc = run_seq(a->seq_actor_fb, s);
-      if (rc == TD3_OK && policy_step) rc = run_seq(a->seq_actor_apply, s);
+      if (rc == TD3_OK) rc = run_seq(policy_step ? a->seq_run_policy : a->seq_run_critic, s);
       if (rc != TD3_OK) return rc;
     }
   }

@@ -16,8 +16,8 @@
 // Weight element (j, k) of the head is Wh[j*hs_j + k*hs_k] and element (c, k) of a layer is W[c*ws_c + k*ws_k], so
 // both orientations are the same code.
 //
-// Work split: a tile is (agent, block of 16 rows, job); a job is a block of 128 output columns of one network.
-// Every tile stages its rows (and recomputes the head for them: 16 rows x A dot products, far cheaper than a
+// Work split: a tile is (agent, block of kFrontRows rows, job); a job is a block of 128 output columns of one network.
+// Every tile stages its rows (and recomputes the head for them: kFrontRows x A dot products, far cheaper than a
 // launch); tile job 0 of a row block also writes what later stages read from global memory (the gathered batch,
 // the action, tanh(y)).  Accumulation is fp32 FFMA in every precision mode.
 #pragma once
@@ -30,7 +30,7 @@
 
 namespace td3 {
 
-constexpr int kFrontRows = 16, kFrontCols = 128, kFrontMaxK = 32, kFrontMaxA = 8, kFrontMaxNets = 4;
+constexpr int kFrontRows = 8, kFrontCols = 128, kFrontMaxK = 32, kFrontMaxA = 8, kFrontMaxNets = 4;
 constexpr int kFrontMaxKh = 512;                    // head reduction length (hidden width)
 constexpr int kFrontXs = 72;                        // staged row: a transition prefix [s | a | s'] (<= 2*32 + 8 floats)
 constexpr int kFrontWs = kFrontMaxK + 1;            // odd stride: column-per-thread reads are conflict-free
@@ -156,6 +156,16 @@ __device__ __forceinline__ void front_body(const FrontParams& P, int tile, float
         for (int k = tid; k < Kh; k += nthr) cp_async4(hs + r * h_ld + k, h + (long long)r * P.ldh + k, true);
     }
   }
+  // columns [K, 32) of the staged rows are multiplied by zero weights in phase 3: they must be finite.  The sampling
+  // writer's rows hold the rest of the transition there; everything else is cleared.
+  {
+    const int filled = (P.gather && writer) ? (int)P.g.row_floats : K;
+#pragma unroll 1
+    for (int i = tid; i < nrows * kFrontMaxK; i += nthr) {
+      const int r = i / kFrontMaxK, k = i - r * kFrontMaxK;
+      if (k >= filled) xs[r * kFrontXs + k] = 0.f;
+    }
+  }
   cp_async_commit();
   cp_async_wait<0>();
   __syncthreads();
@@ -232,12 +242,12 @@ __device__ __forceinline__ void front_body(const FrontParams& P, int tile, float
         float v = bias;
 #pragma unroll
         for (int k4 = 0; k4 < kFrontMaxK / 4; ++k4)
-          if (4 * k4 < K) {                            // columns past K hold stale shared memory: never multiply them
+          if (4 * k4 < K) {                            // w[k >= K] == 0 and the staged columns there are finite
             const float4 x4 = xr[k4];
             v = fmaf(x4.x, w[4 * k4], v);
-            if (4 * k4 + 1 < K) v = fmaf(x4.y, w[4 * k4 + 1], v);
-            if (4 * k4 + 2 < K) v = fmaf(x4.z, w[4 * k4 + 2], v);
-            if (4 * k4 + 3 < K) v = fmaf(x4.w, w[4 * k4 + 3], v);
+            v = fmaf(x4.y, w[4 * k4 + 1], v);
+            v = fmaf(x4.z, w[4 * k4 + 2], v);
+            v = fmaf(x4.w, w[4 * k4 + 3], v);
           }
         out[o] = mask ? (m > 0.f ? v : 0.f) : fmaxf(v, 0.f);
       }

@@ -638,6 +638,8 @@ struct EwRange {
   const float* sc_ptr;               // device-resident {step_size, sqrt(1 - beta2^t)} written by adam_tick, or
   float step_size, bc2_sqrt;         // host-supplied scalars when sc_ptr == nullptr
   int do_adam, do_polyak;
+  long long skip_period, skip_len;   // > 0: elements with (index % skip_period) < skip_len belong to the fused
+                                     // first-layer tiles of the same launch (apply.cuh) and are left alone here
 };
 
 struct EwParams {
@@ -686,6 +688,7 @@ __device__ __forceinline__ void adam_polyak_body(const EwParams& E, long long bx
   const EwRange& R = E.r[ri];
   const long long e = (bx - R.blk_begin) * kEwPerBlock + (long long)threadIdx.x * 4;
   if (e >= R.n) return;
+  if (R.skip_period > 0 && (e % R.skip_period) < R.skip_len) return;    // both multiples of 4: a float4 never straddles
   float pv[4], gv[4], mv[4], vv[4], tv[4];
   ew_load4(R.p, e, R.n, pv);
   if (R.do_adam) {
