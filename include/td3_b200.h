@@ -220,6 +220,11 @@ int td3_critic_forward(td3_agent* agent, int32_t which, int32_t agent_index, con
 /* Number of kernel launches issued by this library since load (bench.py "gpu_launches"). */
 int64_t td3_launch_count(void);
 
+/* Diagnostics (tools/prefix_times.py): microseconds per replay of the first k launches of an update, k = 1..n,
+ * each prefix captured into its own CUDA graph and timed with CUDA events.  Mutates the agent. */
+int td3_debug_prefix_times(td3_agent* a, const td3_replay_view* rb, int32_t with_actor, int32_t reps, float* us_out,
+                           int32_t* kinds_out, int32_t cap, int32_t* n_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -86,6 +86,7 @@ SIGNATURES = {
     "td3_agent_region": (C.c_int, [_vp, C.c_char_p, _P(_i64), _P(_i64)]),
     "td3_agent_set_global_batch": (C.c_int, [_vp, _i64, _i64]),
     "td3_train_n": (C.c_int, [_vp, _P(ReplayView), _i64, _i32, _i32, _i32, _vp]),
+    "td3_debug_prefix_times": (C.c_int, [_vp, _P(ReplayView), _i32, _i32, _P(C.c_float), _P(_i32), _i32, _P(_i32)]),
     "td3_sample_batch": (C.c_int, [_vp, _P(ReplayView), _i32, _vp]),
     "td3_target_step": (C.c_int, [_vp, _vp]),
     "td3_critic_step": (C.c_int, [_vp, _i32, _vp]),

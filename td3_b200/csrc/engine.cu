@@ -362,6 +362,51 @@ void layout_stage(Launch& L) {
   StageParams& S = L.stage;
   const int n = S.n_problems;
   std::stable_partition(S.p, S.p + n, [](const Problem& p) { return p.kind == PK_GEMM && p.use_tc; });
+  // One wave: a tensor-core launch runs one CTA per SM, so tile number sm_count + 1 waits for a whole tile to finish.
+  // The K loop of a tile costs the same for every N width, so when a launch is a little over
+  // one wave, widen the N tiles of its most numerous tensor-core problems until it fits; leave it alone if it cannot.
+  if (!getenv("TD3_NO_WAVE_FIT")) {
+    auto count = [&](const int* nt) {
+      long long total = 0;
+      for (int q = 0; q < n; ++q) {
+        const Problem& p = S.p[q];
+        if (p.kind == PK_GEMM && p.use_tc) {
+          const int g = p.tile_count / std::max(1, p.tiles_per_group);
+          total += (long long)g * p.tiles_m * ((p.N + nt[q] - 1) / nt[q]) * p.ksplit;
+        } else {
+          total += p.tile_count;
+        }
+      }
+      return total;
+    };
+    int nt[kMaxProblemsPerStage];
+    bool any = false;
+    for (int q = 0; q < n; ++q) { nt[q] = S.p[q].tc_nt; any |= S.p[q].kind == PK_GEMM && S.p[q].use_tc; }
+    if (any && count(nt) > g_sm_count && count(nt) <= 2LL * g_sm_count) {
+      while (count(nt) > g_sm_count) {
+        int best = -1;
+        long long best_tiles = 0;
+        for (int q = 0; q < n; ++q) {
+          const Problem& p = S.p[q];
+          if (!(p.kind == PK_GEMM && p.use_tc) || nt[q] >= 128 || p.N <= nt[q]) continue;
+          const long long t = (long long)(p.tile_count / std::max(1, p.tiles_per_group)) * p.tiles_m * ((p.N + nt[q] - 1) / nt[q]) * p.ksplit;
+          if (t > best_tiles) { best_tiles = t; best = q; }
+        }
+        if (best < 0) break;
+        nt[best] *= 2;
+      }
+      if (count(nt) <= g_sm_count)
+        for (int q = 0; q < n; ++q) {
+          Problem& p = S.p[q];
+          if (!(p.kind == PK_GEMM && p.use_tc) || nt[q] == p.tc_nt) continue;
+          const int g = p.tile_count / std::max(1, p.tiles_per_group);
+          p.tc_nt = nt[q];
+          p.tiles_n = (p.N + p.tc_nt - 1) / p.tc_nt;
+          p.tiles_per_group = p.tiles_m * p.tiles_n * p.ksplit;
+          p.tile_count = p.tiles_per_group * g;
+        }
+    }
+  }
   int groups[kMaxProblemsPerStage];
   long long other_tiles = 0;
   bool any_tc = false;
@@ -1168,6 +1213,9 @@ int plan_agent(td3_agent* a, long long batch) {
   const int Lq = c.q.n_linear, wq_last = Lq >= 2 ? c.q.dims[Lq - 1] : 0;
   const bool fuse_heads = Lq >= 2 && qw <= kHeadMaxQw && wq_last <= kHeadMaxW && !getenv("TD3_NO_HEAD_FUSION");
   const int head_ctas = (B + kHeadRows - 1) / kHeadRows;
+  // the head's own dW/db: a GEMM problem of the first backward stage (from dq and the hidden activations) instead of a
+  // cross-CTA reduction inside the head kernel, wherever the backward walk can start below the head (no LayerNorm)
+  const bool head_dw_in_stage = fuse_heads && !ln && !getenv("TD3_HEAD_DW");
   const long long head_per_g = (long long)qw * wq_last + qw;
   const long long head_part_go = (long long)head_ctas * nq * head_per_g + head_ctas;
   float* head_part = ws.take(fuse_heads ? nA * head_part_go * 2 : 1, "head_partials");
@@ -1339,20 +1387,21 @@ int plan_agent(td3_agent* a, long long batch) {
       H.gW = a->critic.grad + c.q.w_off[Lq - 1]; H.gb = a->critic.grad + c.q.b_off[Lq - 1]; H.g_go = qn * nq; H.g_gi = qn;
       H.part = head_part; H.part_go = head_part_go; H.counter = head_counter; H.loss = a->state_f32;
       H.batch = B; H.w = wq_last; H.qw = qw; H.n_q = nq; H.ldh = wq_last; H.lddz = wq_last; H.n_cta = head_ctas;
-      H.mode = 0; H.relu_mask = ln ? 0 : 1;
+      H.mode = 0; H.relu_mask = ln ? 0 : 1; H.skip_dw = head_dw_in_stage ? 1 : 0;
       H.discount = c.discount; H.inv_norm = inv_norm; H.tick = tick;
       L.grid_x = nA * head_ctas;
-      L.smem_bytes = (int)((2LL * nq * qw * wq_last + 4 * kHeadMaxQw + (long long)kHeadRows * nq * head_per_g + kHeadRows + 16) * sizeof(float));
+      L.smem_bytes = (int)((2LL * nq * qw * wq_last + 4 * kHeadMaxQw + kHeadRows * 2 * (kHeadMaxQw + 1) +
+                            (head_dw_in_stage ? 0 : (long long)kHeadRows * nq * head_per_g) + 16) * sizeof(float));
     }
     a->seq_critic_fb.push_back(L);
     Dx0Spec none;
     auto s_b = build_backward(c, c.q, Wc, Gc, g_crit, B, cc, a->dq, qw, (long long)B * qw * nq, (long long)B * qw, true,
-                              none, sc_c, fuse_heads);
+                              none, sc_c, fuse_heads && !head_dw_in_stage, head_dw_in_stage);
     for (auto& st : s_b) emit_stage(a->seq_critic_fb, st);
     if (fuse_tail) {
       v_cb.push_back(L);
       auto s_bf = build_backward(c, c.q, Wc, Gc, g_crit, B, cc, a->dq, qw, (long long)B * qw * nq, (long long)B * qw, true,
-                                 none, sc_c, fuse_heads, false, &dz0_c);
+                                 none, sc_c, fuse_heads && !head_dw_in_stage, head_dw_in_stage, &dz0_c);
       for (auto& st : s_bf) emit_stage(v_cb, st);
     }
     if (wn) {     // dL/dW -> (dL/dg, dL/dv) in place
@@ -1428,7 +1477,7 @@ int plan_agent(td3_agent* a, long long batch) {
       H.inv_norm = 1.f / (float)((a->global_batch > 0 ? a->global_batch : batch) * qw);
       H.tick = AdamTick{a->state_u64, 1, 0, c.lr_actor, c.beta1, c.beta2};
       L.grid_x = nA * head_ctas;
-      L.smem_bytes = (int)((1LL * qw * wq_last + 4 * kHeadMaxQw + kHeadRows + 16) * sizeof(float));
+      L.smem_bytes = (int)((1LL * qw * wq_last + 4 * kHeadMaxQw + kHeadRows * 2 * (kHeadMaxQw + 1) + 16) * sizeof(float));
       a->seq_actor_fb.push_back(L);
     }
     // actor_loss = -mean(Q1) (read-back only) + bump the actor Adam step counter
@@ -1541,9 +1590,21 @@ int plan_agent(td3_agent* a, long long batch) {
     // the actor's forward layers (they read the sampled states and the actor only) ride along with the target pass
     a->seq_policy_mid.clear();
     size_t ai = 0;
+    // the actor's first layer (K = S <= 32) is a job of the front kernel between the two stages; its second layer
+    // then rides with the stage after it
+    bool l1_in_front = false;
     for (const Launch& L : a->seq_target) {
       Launch m = L;
-      if (L.kind == Launch::STAGE && (int)ai < a->n_actor_fwd && merge_stage(m, a->seq_actor_fb[ai])) ++ai;
+      if (L.kind == Launch::FRONT && ai == 0 && a->n_actor_fwd >= 1 && L.front.n_nets < kFrontMaxNets && !L.front.gather) {
+        FrontNet& n = m.front.net[m.front.n_nets++];
+        n = front_first_layer(c.actor, Wa, 1, pa);
+        n.x = a->xpi; n.x_go = a->xpi_go; n.ldx = ld_q; n.x_off = 0; n.act_col = -1;
+        front_finish(m, B, nA);
+        l1_in_front = true;
+        ++ai;
+      } else if (L.kind == Launch::STAGE && l1_in_front && (int)ai < a->n_actor_fwd && merge_stage(m, a->seq_actor_fb[ai])) {
+        ++ai;
+      }
       v_tp.push_back(m);
     }
     for (; (int)ai < a->n_actor_fwd; ++ai) v_tp.push_back(a->seq_actor_fb[ai]);
@@ -2207,6 +2268,56 @@ int td3_train_n(td3_agent* a, const td3_replay_view* rb, int64_t total_it, int32
       if (rc != TD3_OK) return rc;
     }
   }
+  return TD3_OK;
+}
+
+// ---- diagnostics: marginal cost of every launch of an update, measured in situ ----------
+// Captures the sampling launch plus the first k launches of the critic-only (with_actor = 0) or policy update into a
+// graph for k = 1..n and times `reps` back-to-back replays of each with CUDA events: us_out[k-1] = microseconds per
+// replay of the k-launch prefix, kinds_out[k-1] = Launch::Kind of launch k (0 stage, 1 gather, 3 Adam/apply, 5 head,
+// 7 front).  Differences of consecutive entries are what each launch adds to the chain with everything before it
+// warm/cold exactly as in the real update.  The prefixes mutate the agent (they are real work): tools only.
+int td3_debug_prefix_times(td3_agent* a, const td3_replay_view* rb, int32_t with_actor, int32_t reps, float* us_out,
+                           int32_t* kinds_out, int32_t cap, int32_t* n_out) {
+  int rc = check_ready(a);
+  if (rc == TD3_OK) rc = check_rb(a, rb);
+  if (rc == TD3_OK) rc = plan_sample(a, rb, TD3_RNG_PHILOX);
+  if (rc != TD3_OK) return rc;
+  if (!a->cap_stream) CUDA_TRY(cudaStreamCreateWithFlags(&a->cap_stream, cudaStreamNonBlocking));
+  cudaStream_t s = a->cap_stream;
+  rc = sync_rb_size(a, rb, s);
+  if (rc != TD3_OK) return rc;
+  std::vector<Launch> all = a->seq_sample;
+  for (const Launch& L : (with_actor ? a->seq_run_policy : a->seq_run_critic)) all.push_back(L);
+  const int n = (int)std::min<size_t>(all.size(), (size_t)cap);
+  const long long launches_before = g_launches.load();
+  cudaEvent_t e0, e1;
+  CUDA_TRY(cudaEventCreate(&e0));
+  CUDA_TRY(cudaEventCreate(&e1));
+  for (int k = 1; k <= n; ++k) {
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    CUDA_TRY(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+    for (int i = 0; i < k && rc == TD3_OK; ++i) rc = run_launch(all[i], s);
+    cudaError_t e = cudaStreamEndCapture(s, &graph);
+    if (rc != TD3_OK || e != cudaSuccess) return rc != TD3_OK ? rc : fail(TD3_ERR_CUDA, "prefix capture: %s", cudaGetErrorString(e));
+    CUDA_TRY(cudaGraphInstantiate(&exec, graph, 0));
+    for (int i = 0; i < 20; ++i) CUDA_TRY(cudaGraphLaunch(exec, s));
+    CUDA_TRY(cudaEventRecord(e0, s));
+    for (int i = 0; i < reps; ++i) CUDA_TRY(cudaGraphLaunch(exec, s));
+    CUDA_TRY(cudaEventRecord(e1, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    us_out[k - 1] = ms * 1000.f / (float)reps;
+    kinds_out[k - 1] = (int)all[k - 1].kind;
+    cudaGraphExecDestroy(exec);
+    cudaGraphDestroy(graph);
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  g_launches.store(launches_before);      // captured launches are not executed launches
+  *n_out = n;
   return TD3_OK;
 }
 

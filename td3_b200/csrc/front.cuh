@@ -109,6 +109,7 @@ __device__ __forceinline__ void front_body(const FrontParams& P, int tile, float
   const int nrows = min(kFrontRows, P.batch - r0);
   const int h_ld = (Kh + 3) & ~3;                     // rows of hs / whs (a flat copy when the source is dense)
   const int ws_ld = K;                                // weight block [nc][K], flat
+  const bool do_head = P.head && (writer || N.act_col >= 0);   // tiles of a network that does not consume the head skip it
 
   // ---- phase 1: every global read, as asynchronous copies ----
   if (P.gather) {
@@ -138,7 +139,7 @@ __device__ __forceinline__ void front_body(const FrontParams& P, int tile, float
     }
     if (N.bias && tid < nc) cp_async4(bs + tid, N.bias + (long long)agent * N.w_go + (long long)inner * N.w_gi + c0 + tid, true);
   }
-  if (P.head) {
+  if (do_head) {
     const float* Wh = P.Wh + (long long)agent * P.wh_go;
     if (P.hs_k == 1 && P.hs_j == h_ld) {
       front_copy(whs, Wh, A * Kh, tid, nthr);
@@ -177,7 +178,7 @@ __device__ __forceinline__ void front_body(const FrontParams& P, int tile, float
   }
 
   // ---- phase 2: head, A numbers per row; one warp per row, the reduction split over the lanes ----
-  if (P.head) {
+  if (do_head) {
 #pragma unroll 1
     for (int r = warp; r < nrows; r += (nthr >> 5)) {
       float acc[kFrontMaxA];

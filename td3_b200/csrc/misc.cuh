@@ -285,7 +285,7 @@ __global__ void __launch_bounds__(256) loss_kernel(const __grid_constant__ LossP
 // mode 1 (actor step, :159): q = Q1(s, pi(s)) head only, loss = -mean(q), dq = -1/norm, no weight gradients.
 // One warp per row, lanes over the hidden width (<= 512), qw <= 4.
 // ------------------------------------------------------------------------------------
-constexpr int kHeadMaxQw = 4, kHeadMaxW = 512, kHeadRows = 16, kHeadThreads = 512;
+constexpr int kHeadMaxQw = 4, kHeadMaxW = 512, kHeadRows = 8, kHeadThreads = 512;
 
 struct HeadParams {
   const float* h; const float* ht;            // last hidden activations of the online / target critics [B, ldh]
@@ -300,104 +300,75 @@ struct HeadParams {
   float* part; long long part_go;             // scratch [n_cta][n_q][qw * w + qw] + [n_cta] loss partials, per agent
   unsigned int* counter;                      // per-agent arrival counter (zero between launches)
   float* loss;                                // loss[agent]
-  int batch, w, qw, n_q, ldh, lddz, n_cta, mode, relu_mask, pad;
+  int batch, w, qw, n_q, ldh, lddz, n_cta, mode, relu_mask;
+  int skip_dw;                                // 1: dW/db of the head are a GEMM problem of the next stage (from dq and h)
   float discount, inv_norm;
   AdamTick tick;                              // critic optimiser tick + sampling step (mode 0), done by the finishing CTA
 };
 
-// One warp per batch row (every global load of the row is issued before anything is consumed: the kernel sits on a
-// dependency chain, so its latency -- not its throughput -- is what the update pays for), kHeadRows rows per CTA.
-template <int QW>
+// One warp per (batch row, twin): every global load of the pair is issued before anything is consumed -- the kernel
+// sits on a dependency chain, so the length of one warp's instruction stream, not throughput, is what the update
+// pays for.  kHeadRows rows per CTA; the twins of a row meet in shared memory for min(Q1', Q2').
+template <int QW, int WI>
 __device__ __forceinline__ void head_body_t(const HeadParams& H, int tile, float* smem) {
-  constexpr int WI = kHeadMaxW / 32, NQ = 2;
+  constexpr int NQ = 2;
   const int agent = tile / H.n_cta, cb = tile - agent * H.n_cta;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int w = H.w, qw = H.qw, nq = H.n_q, per_g = qw * w + qw;
   const bool critic = H.mode == 0;
+  const bool want_dw = critic && !H.skip_dw;
   float* Ws = smem;                                     // [n_q][qw][w] online head weights, then [n_q][qw] biases
   float* bs = Ws + nq * qw * w;
   float* Wts = bs + NQ * kHeadMaxQw;                    // target
   float* bts = Wts + (critic ? nq * qw * w : 0);
-  float* red = bts + NQ * kHeadMaxQw;                   // [kHeadRows warps][n_q][per_g] weight-gradient terms of each row
-  float* lred = red + (critic ? kHeadRows * nq * per_g : 0);   // [kHeadRows] loss terms
+  float* tqs = bts + NQ * kHeadMaxQw;                   // [kHeadRows][NQ][kHeadMaxQw] target-head outputs of the CTA's rows
+  float* lred = tqs + kHeadRows * NQ * kHeadMaxQw;      // [kHeadRows * NQ] loss terms
+  float* red = lred + kHeadRows * NQ;                   // [kHeadRows][n_q][per_g] weight-gradient terms of each row
   const int nwarps = blockDim.x >> 5;                   // 16 in head_kernel (one pass), 8 in the persistent kernel (two)
+  const int pairs = kHeadRows * nq;
   bool staged = false;
-  float loss_term = 0.f;
 #pragma unroll 1
-  for (int rl = warp; rl < kHeadRows; rl += nwarps) {
-  const int row = cb * kHeadRows + rl;
-  const bool row_ok = row < H.batch;
-  // ---- issue every global load of this row ----
-  float hv[NQ][WI], tv[NQ][WI];
-  float rv = 0.f, ndv = 0.f;
+  for (int base = 0; base < pairs; base += nwarps) {
+    const int pi = base + warp;
+    const bool active = pi < pairs;
+    const int rl = pi / nq, g = pi - rl * nq;
+    const int row = cb * kHeadRows + rl;
+    const bool row_ok = active && row < H.batch;
+    // ---- issue every global load of this (row, twin) ----
+    float hv[WI], tv[WI];
+    float rv = 0.f, ndv = 0.f;
+    {
+      const float* hrow = H.h + agent * H.h_go + g * H.h_gi + (size_t)row * H.ldh;
+      const float* trow = critic ? H.ht + agent * H.ht_go + g * H.ht_gi + (size_t)row * H.ldh : nullptr;
 #pragma unroll
-  for (int g = 0; g < NQ; ++g) {
-    const float* hrow = H.h + agent * H.h_go + g * H.h_gi + (size_t)row * H.ldh;
-    const float* trow = critic ? H.ht + agent * H.ht_go + g * H.ht_gi + (size_t)row * H.ldh : nullptr;
-#pragma unroll
-    for (int i = 0; i < WI; ++i) {
-      const int k = lane + 32 * i;
-      const bool ok = row_ok && g < nq && k < w;
-      hv[g][i] = ok ? hrow[k] : 0.f;
-      tv[g][i] = ok && critic ? trow[k] : 0.f;
-    }
-  }
-  if (row_ok && critic) {
-    rv = H.r[agent * H.r_go + row];
-    ndv = H.nd[agent * H.r_go + row];
-  }
-  if (!staged) {                                        // head parameters -> shared memory (first pass only)
-    for (int g = 0; g < nq; ++g) {
-      for (int e = threadIdx.x; e < qw * w; e += blockDim.x) {
-        Ws[g * qw * w + e] = H.W[agent * H.w_go + g * H.w_gi + e];
-        if (critic) Wts[g * qw * w + e] = H.Wt[agent * H.wt_go + g * H.wt_gi + e];
-      }
-      if ((int)threadIdx.x < qw) {
-        bs[g * kHeadMaxQw + threadIdx.x] = H.b[agent * H.w_go + g * H.w_gi + threadIdx.x];
-        if (critic) bts[g * kHeadMaxQw + threadIdx.x] = H.bt[agent * H.wt_go + g * H.wt_gi + threadIdx.x];
+      for (int i = 0; i < WI; ++i) {
+        const int k = lane + 32 * i;
+        const bool ok = row_ok && k < w;
+        hv[i] = ok ? hrow[k] : 0.f;
+        tv[i] = ok && critic ? trow[k] : 0.f;
       }
     }
-    __syncthreads();
-    staged = true;
-  }
-  float row_loss = 0.f;
-  if (row_ok) {
-    // ---- Bellman target (TD3_featured.py:140-142) ----
-    float yv[QW];
-    if (critic) {
-      float tmin[QW];
-#pragma unroll
-      for (int g = 0; g < NQ; ++g) {
-        if (g < nq) {
-#pragma unroll
-          for (int j = 0; j < QW; ++j) {
-            float d = 0.f;
-            if (j < qw) {
-#pragma unroll
-              for (int i = 0; i < WI; ++i) {
-                const int k = lane + 32 * i;
-                if (k < w) d = fmaf(tv[g][i], Wts[(g * qw + j) * w + k], d);
-              }
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
-            d += bts[g * kHeadMaxQw + j];
-            if (lane == 0 && j < qw) H.tq[agent * H.q_go + g * H.q_gi + (size_t)row * qw + j] = d;
-            tmin[j] = g == 0 ? d : fminf(tmin[j], d);
-          }
+    if (row_ok && critic) {
+      rv = H.r[agent * H.r_go + row];
+      ndv = H.nd[agent * H.r_go + row];
+    }
+    if (!staged) {                                        // head parameters -> shared memory (first pass only)
+      for (int gg = 0; gg < nq; ++gg) {
+        for (int e = threadIdx.x; e < qw * w; e += blockDim.x) {
+          Ws[gg * qw * w + e] = H.W[agent * H.w_go + gg * H.w_gi + e];
+          if (critic) Wts[gg * qw * w + e] = H.Wt[agent * H.wt_go + gg * H.wt_gi + e];
+        }
+        if ((int)threadIdx.x < qw) {
+          bs[gg * kHeadMaxQw + threadIdx.x] = H.b[agent * H.w_go + gg * H.w_gi + threadIdx.x];
+          if (critic) bts[gg * kHeadMaxQw + threadIdx.x] = H.bt[agent * H.wt_go + gg * H.wt_gi + threadIdx.x];
         }
       }
-#pragma unroll
-      for (int j = 0; j < QW; ++j) {
-        yv[j] = __fadd_rn(rv, __fmul_rn(__fmul_rn(ndv, H.discount), tmin[j]));
-        if (lane == 0 && j < qw) H.y[agent * H.y_go + (size_t)row * qw + j] = yv[j];
-      }
+      __syncthreads();
+      staged = true;
     }
-    // ---- online heads, gradient w.r.t. the hidden activations, this row's weight-gradient terms ----
-#pragma unroll
-    for (int g = 0; g < NQ; ++g) {
-      if (g < nq) {
-        float dqv[QW];
+    // ---- target head of this twin (TD3_featured.py:140); the twins of a row meet in shared memory ----
+    if (critic) {
+      if (row_ok) {
 #pragma unroll
         for (int j = 0; j < QW; ++j) {
           float d = 0.f;
@@ -405,73 +376,105 @@ __device__ __forceinline__ void head_body_t(const HeadParams& H, int tile, float
 #pragma unroll
             for (int i = 0; i < WI; ++i) {
               const int k = lane + 32 * i;
-              if (k < w) d = fmaf(hv[g][i], Ws[(g * qw + j) * w + k], d);
+              if (k < w) d = fmaf(tv[i], Wts[(g * qw + j) * w + k], d);
             }
           }
 #pragma unroll
           for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
-          d += bs[g * kHeadMaxQw + j];
-          dqv[j] = 0.f;
-          if (j < qw) {
-            const size_t qo = agent * H.q_go + g * H.q_gi + (size_t)row * qw + j;
-            if (lane == 0) H.q[qo] = d;
-            if (critic) {
-              const float diff = d - yv[j];
-              dqv[j] = 2.f * H.inv_norm * diff;
-              row_loss = fmaf(diff, diff, row_loss);
-            } else {
-              dqv[j] = -H.inv_norm;
-              row_loss += d;
-            }
-            if (lane == 0 && H.dq) H.dq[qo] = dqv[j];
+          d += bts[g * kHeadMaxQw + j];
+          if (lane == 0 && j < qw) {
+            H.tq[agent * H.q_go + g * H.q_gi + (size_t)row * qw + j] = d;
+            tqs[(rl * NQ + g) * kHeadMaxQw + j] = d;
           }
-        }
-        float* dzr = H.dz + agent * H.dz_go + g * H.dz_gi + (size_t)row * H.lddz;
-#pragma unroll
-        for (int i = 0; i < WI; ++i) {
-          const int k = lane + 32 * i;
-          if (k < w) {
-            float s = 0.f;
-#pragma unroll
-            for (int j = 0; j < QW; ++j)
-              if (j < qw) {
-                s = fmaf(dqv[j], Ws[(g * qw + j) * w + k], s);
-                if (critic) red[(rl * nq + g) * per_g + j * w + k] = dqv[j] * hv[g][i];
-              }
-            dzr[k] = (H.relu_mask && !(hv[g][i] > 0.f)) ? 0.f : s;
-          }
-        }
-        if (critic && lane < qw) {
-          float dj = dqv[0];
-#pragma unroll
-          for (int j = 1; j < QW; ++j)
-            if (lane == j) dj = dqv[j];
-          red[(rl * nq + g) * per_g + qw * w + lane] = dj;
         }
       }
+      __syncthreads();
     }
-  } else if (critic) {                         // rows past the batch contribute zeros
-    for (int e = lane; e < nq * per_g; e += 32) red[rl * nq * per_g + e] = 0.f;
-  }
-  if (lane == 0) lred[rl] = row_loss;
-  }   // pass over this warp's rows
-  (void)loss_term;
+    float pair_loss = 0.f;
+    if (row_ok) {
+      // ---- Bellman target (:141-142) ----
+      float yv[QW];
+      if (critic) {
+#pragma unroll
+        for (int j = 0; j < QW; ++j) {
+          float tmin = tqs[(rl * NQ) * kHeadMaxQw + j];
+          if (nq > 1) tmin = fminf(tmin, tqs[(rl * NQ + 1) * kHeadMaxQw + j]);
+          yv[j] = __fadd_rn(rv, __fmul_rn(__fmul_rn(ndv, H.discount), tmin));
+          if (g == 0 && lane == 0 && j < qw) H.y[agent * H.y_go + (size_t)row * qw + j] = yv[j];
+        }
+      }
+      // ---- online head, gradient w.r.t. the hidden activations, this row's weight-gradient terms ----
+      float dqv[QW];
+#pragma unroll
+      for (int j = 0; j < QW; ++j) {
+        float d = 0.f;
+        if (j < qw) {
+#pragma unroll
+          for (int i = 0; i < WI; ++i) {
+            const int k = lane + 32 * i;
+            if (k < w) d = fmaf(hv[i], Ws[(g * qw + j) * w + k], d);
+          }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+        d += bs[g * kHeadMaxQw + j];
+        dqv[j] = 0.f;
+        if (j < qw) {
+          const size_t qo = agent * H.q_go + g * H.q_gi + (size_t)row * qw + j;
+          if (lane == 0) H.q[qo] = d;
+          if (critic) {
+            const float diff = d - yv[j];
+            dqv[j] = 2.f * H.inv_norm * diff;
+            pair_loss = fmaf(diff, diff, pair_loss);
+          } else {
+            dqv[j] = -H.inv_norm;
+            pair_loss += d;
+          }
+          if (lane == 0 && H.dq) H.dq[qo] = dqv[j];
+        }
+      }
+      float* dzr = H.dz + agent * H.dz_go + g * H.dz_gi + (size_t)row * H.lddz;
+#pragma unroll
+      for (int i = 0; i < WI; ++i) {
+        const int k = lane + 32 * i;
+        if (k < w) {
+          float sacc = 0.f;
+#pragma unroll
+          for (int j = 0; j < QW; ++j)
+            if (j < qw) {
+              sacc = fmaf(dqv[j], Ws[(g * qw + j) * w + k], sacc);
+              if (want_dw) red[(rl * nq + g) * per_g + j * w + k] = dqv[j] * hv[i];
+            }
+          dzr[k] = (H.relu_mask && !(hv[i] > 0.f)) ? 0.f : sacc;
+        }
+      }
+      if (want_dw && lane < qw) {
+        float dj = dqv[0];
+#pragma unroll
+        for (int j = 1; j < QW; ++j)
+          if (lane == j) dj = dqv[j];
+        red[(rl * nq + g) * per_g + qw * w + lane] = dj;
+      }
+    } else if (want_dw && active) {                // rows past the batch contribute zeros
+      for (int e = lane; e < per_g; e += 32) red[(rl * nq + g) * per_g + e] = 0.f;
+    }
+    if (active && lane == 0) lred[pi] = pair_loss;
+  }   // pass over this warp's (row, twin) pairs
   __syncthreads();
   // ---- CTA partials (fixed order over the rows), then the last CTA to arrive sums the CTA partials in order ----
   float* pbase = H.part + agent * H.part_go;
-  if (critic)
+  if (want_dw)
     for (int e = threadIdx.x; e < nq * per_g; e += blockDim.x) {
-      float s = 0.f;
+      float sacc = 0.f;
 #pragma unroll
-      for (int wv = 0; wv < kHeadRows; ++wv) s += red[wv * nq * per_g + e];
-      pbase[(size_t)cb * nq * per_g + e] = s;
+      for (int wv = 0; wv < kHeadRows; ++wv) sacc += red[wv * nq * per_g + e];
+      pbase[(size_t)cb * nq * per_g + e] = sacc;
     }
   __shared__ int s_last;
   float* lpart = pbase + (size_t)H.n_cta * nq * per_g;
   if (threadIdx.x == 0) {
     float t = 0.f;
-#pragma unroll
-    for (int wv = 0; wv < kHeadRows; ++wv) t += lred[wv];
+    for (int wv = 0; wv < pairs; ++wv) t += lred[wv];
     lpart[cb] = t;
   }
   __syncthreads();
@@ -484,37 +487,49 @@ __device__ __forceinline__ void head_body_t(const HeadParams& H, int tile, float
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  if (critic) {
+  if (want_dw) {
     const long long cstride = (long long)nq * per_g;
     for (int e = threadIdx.x; e < nq * per_g; e += blockDim.x) {
-      float s = 0.f;
+      float sacc = 0.f;
 #pragma unroll 1
       for (int c0 = 0; c0 < H.n_cta; c0 += 8) {       // eight independent loads in flight, summed in CTA order
         float v[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) v[u] = c0 + u < H.n_cta ? __ldcg(pbase + (c0 + u) * cstride + e) : 0.f;
 #pragma unroll
-        for (int u = 0; u < 8; ++u) s += v[u];
+        for (int u = 0; u < 8; ++u) sacc += v[u];
       }
       const int g = e / per_g, o = e - g * per_g;
-      if (o < qw * w) H.gW[agent * H.g_go + g * H.g_gi + o] = s;
-      else H.gb[agent * H.g_go + g * H.g_gi + (o - qw * w)] = s;
+      if (o < qw * w) H.gW[agent * H.g_go + g * H.g_gi + o] = sacc;
+      else H.gb[agent * H.g_go + g * H.g_gi + (o - qw * w)] = sacc;
     }
   }
-  if (threadIdx.x == 0) {
+  if (threadIdx.x < 32) {
     float t = 0.f;
-    for (int c2 = 0; c2 < H.n_cta; ++c2) t += __ldcg(lpart + c2);
-    H.loss[agent] = critic ? t * H.inv_norm : -t * H.inv_norm;
-    if (agent == 0 && H.tick.state) {
-      if (critic) H.tick.state[0] += 1;          // sampling step (Philox counter)
-      adam_tick(H.tick);
+    for (int c2 = lane; c2 < ((H.n_cta + 31) & ~31); c2 += 32) {
+      float v = c2 < H.n_cta ? __ldcg(lpart + c2) : 0.f;
+      // fixed-order tree over the 32 lanes, then accumulate the groups of 32 CTAs in order
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      t += v;
+    }
+    if (lane == 0) {
+      H.loss[agent] = critic ? t * H.inv_norm : -t * H.inv_norm;
+      if (agent == 0 && H.tick.state) {
+        if (critic) H.tick.state[0] += 1;          // sampling step (Philox counter)
+        adam_tick(H.tick);
+      }
     }
   }
 }
 
 __device__ __forceinline__ void head_body(const HeadParams& H, int tile, float* smem) {
-  if (H.qw == 1) head_body_t<1>(H, tile, smem);
-  else head_body_t<kHeadMaxQw>(H, tile, smem);
+  if (H.qw == 1) {
+    if (H.w <= 320) head_body_t<1, 10>(H, tile, smem);
+    else head_body_t<1, kHeadMaxW / 32>(H, tile, smem);
+  } else {
+    head_body_t<kHeadMaxQw, kHeadMaxW / 32>(H, tile, smem);
+  }
 }
 
 __global__ void __launch_bounds__(kHeadThreads) head_kernel(const __grid_constant__ HeadParams H) {
