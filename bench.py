@@ -312,8 +312,14 @@ def main():
     def e2e_step(i):
         rb.add(*new_rows[i % len(new_rows)])                       # host transition -> pinned slot -> H2D
         agent.train(rb, B)                                          # the call main.py:269 makes
-        loss_host.copy_(loss_dev, non_blocking=True)                # D2H of the step's result
-        stream.synchronize()
+        return agent.wait_critic_loss()                             # D2H: the step's loss, stored to pinned host memory
+                                                                    # by the critic-head kernel; the host blocks until it lands
+
+    def e2e_step_drain(i):
+        rb.add(*new_rows[i % len(new_rows)])
+        agent.train(rb, B)
+        loss_host.copy_(loss_dev, non_blocking=True)                # D2H copy behind the whole update
+        stream.synchronize()                                        # ... and drain the stream before the next step
         return float(loss_host[0])
 
     for i in range(min(W, 50)):
@@ -321,12 +327,25 @@ def main():
     with ClockSampler(local_rank) as clk2:
         barrier()
         t0 = time.perf_counter()
+        last = 0.0
         for i in range(Ke):
-            e2e_step(i)
+            last = e2e_step(i)
         torch.cuda.synchronize()
         e2e_s = time.perf_counter() - t0
         barrier()
     clocks_e2e = clk2.summary()
+    # the step's loss must be the one the device holds once everything has drained
+    if abs(last - float(loss_dev[0])) > 1e-6 * max(1.0, abs(last)):
+        raise RuntimeError(f"host mirror of the critic loss {last} != device value {float(loss_dev[0])}")
+    Kd = min(Ke, 500)
+    for i in range(20):
+        e2e_step_drain(i)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(Kd):
+        e2e_step_drain(i)
+    torch.cuda.synchronize()
+    e2e_drain_s = time.perf_counter() - t0
 
     # ---------------- population: several independent agents per GPU in lock-step ----------------
     pop_ms, n_pop = 0.0, (args.population if w["kind"] == "featured" else 0)
@@ -347,9 +366,9 @@ def main():
 
     # ---------------- reduce over ranks ----------------
     if world > 1:
-        t = torch.tensor([ms, e2e_s, pop_ms], device="cuda", dtype=torch.float64)
+        t = torch.tensor([ms, e2e_s, pop_ms, e2e_drain_s], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, e2e_s, pop_ms = float(t[0]), float(t[1]), float(t[2])
+        ms, e2e_s, pop_ms, e2e_drain_s = float(t[0]), float(t[1]), float(t[2]), float(t[3])
     value = world * K / (ms / 1000.0)
     e2e = world * Ke / e2e_s
     t_update_us = ms * 1000.0 / K
@@ -357,9 +376,16 @@ def main():
     line = {"metric": "TD3 gradient updates/sec (batch 256)", "value": value, "unit": "updates/s", "n_gpus": world,
             "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": dtype, "data": "synthetic", "config": config, "clocks": clocks,
-            "e2e": {"value": e2e, "unit": "updates/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
+            "e2e": {"value": e2e, "unit": "updates/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 8,
                     "steps": Ke, "clocks": clocks_e2e,
-                    "what": "rb.add(host row) + policy.train(rb, 256) + synchronous D2H of the critic loss, per step"},
+                    "what": "per step: rb.add(host row -> pinned slot -> H2D copy) + policy.train(rb, 256) + "
+                            "policy.wait_critic_loss(): the host blocks until THIS step's critic loss -- an 8-byte "
+                            "{fp32 loss, update count} word the critic-head kernel stores to pinned host memory -- "
+                            "has landed, then enqueues the next step behind the optimiser kernels still running; the "
+                            "timed region ends with a full device synchronise",
+                    "drain_value": world * Kd / e2e_drain_s, "drain_steps": Kd,
+                    "drain_what": "same loop with a D2H copy of the loss behind the whole update and a stream "
+                                  "synchronise every step (the GPU idles while the host prepares the next step)"},
             "gpu_launches": int(launches)}
     if n_pop > 1 and pop_ms > 0:
         line["population"] = {"agents_per_gpu": n_pop, "value": world * n_pop * Kp / (pop_ms / 1000.0), "unit": "updates/s",

@@ -176,6 +176,16 @@ int td3_agent_bind_params(td3_agent* agent, const td3_param_set* actor, const td
  *   reads them back -- TD3_featured.py:148,159 -- they exist for tests and metrics).
  * n_bytes >= 128 + 8*n_agents.  The Adam steps are what torch.optim.Adam keeps in state["step"]. */
 int td3_agent_bind_state(td3_agent* agent, void* state_dev, int64_t n_bytes);
+/* Optional host mirror of the critic loss (the reference computes critic_loss at TD3_featured.py:148 and never reads
+ * it; a training loop that logs it would call .item(), i.e. drain the stream).  host_words = n_agents 8-byte words in
+ * page-locked host memory that the device can address (cudaHostAlloc / torch pin_memory under UVA), zero-initialised.
+ * The fused critic-head kernel of every update stores {low 32 bits: loss as fp32, high 32 bits: number of critic
+ * updates completed by this plan} to word[agent] as soon as the loss exists; a host thread that polls the sequence
+ * half gets the step's result without waiting for the optimiser kernels behind it.  Call before td3_agent_plan (it
+ * invalidates the plan).  td3_agent_host_status_live() says whether the planned update writes the words (it does
+ * whenever the critic head is fused: output width <= 4, last hidden width <= 512). */
+int td3_agent_bind_host_status(td3_agent* agent, void* host_words);
+int td3_agent_host_status_live(const td3_agent* agent);
 /* Workspace (activations, batch staging) for a given batch size, in floats. */
 int64_t td3_agent_workspace_floats(const td3_agent* agent, int64_t batch);
 /* Bind the workspace and build the launch plan for `batch`.  Drops captured graphs. */

@@ -7,6 +7,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import time
 from typing import Optional
 
 import numpy as np
@@ -77,6 +78,13 @@ class TD3_base(object):
         a_ps, c_ps = actor_family.param_set(), critic_family.param_set()
         _lib.check(self._lib.td3_agent_bind_params(handle, C.byref(a_ps), C.byref(c_ps)))
         _lib.check(self._lib.td3_agent_bind_state(handle, C.c_void_p(self._state.data_ptr()), self._state.numel() * 8))
+        # host mirror of the critic loss: 8-byte words {fp32 loss, update count} in pinned memory that the fused critic
+        # head writes over PCIe as soon as the loss exists (wait_critic_loss)
+        self._host_status = torch.zeros(n_agents, dtype=torch.int64).pin_memory()
+        self._host_words = self._host_status.numpy()
+        _lib.check(self._lib.td3_agent_bind_host_status(handle, C.c_void_p(self._host_status.data_ptr())))
+        self._seq_expected = 0
+        self._status_live = False
         self._workspace: Optional[torch.Tensor] = None
         self._planned_batch = 0
         self._global_batch = 0
@@ -122,6 +130,10 @@ class TD3_base(object):
         _lib.check(self._lib.td3_agent_plan(self._handle, batch, C.c_void_p(self._workspace.data_ptr()),
                                             self._workspace.numel(), _lib.stream_ptr()))
         self._planned_batch = batch
+        torch.cuda.synchronize()
+        self._host_status.zero_()                      # the plan starts its update count from zero
+        self._seq_expected = 0
+        self._status_live = bool(self._lib.td3_agent_host_status_live(self._handle))
 
     def _region(self, name: str) -> torch.Tensor:
         off, n = C.c_int64(), C.c_int64()
@@ -158,6 +170,7 @@ class TD3_base(object):
             if rc:
                 _lib.check(rc)
             self.total_it += iterations
+            self._seq_expected += iterations
             return
         if (indices is not None or noise is not None) and iterations != 1:
             raise ValueError("indices/noise injection covers exactly one update (iterations=1)")
@@ -171,6 +184,7 @@ class TD3_base(object):
             _lib.check(self._lib.td3_train_n(self._handle, C.byref(view), self.total_it, 1, _lib.RNG_INJECTED,
                                              int(use_graph), s))
             self.total_it += 1
+            self._seq_expected += 1
 
     # ------------------------------------------------------------------ population members (n_agents > 1)
     @property
@@ -194,6 +208,35 @@ class TD3_base(object):
     @property
     def last_actor_loss(self) -> torch.Tensor:
         return self._losses[self._cfg.n_agents: 2 * self._cfg.n_agents]
+
+    def wait_critic_loss(self, timeout: float = 10.0):
+        """Critic loss of the most recently enqueued update, as host numbers (float for one agent, float32 array for
+        a population).  Blocks only until that loss has landed in pinned host memory -- the fused critic-head kernel
+        stores it there together with the update count -- not until the optimiser kernels queued behind it have
+        drained: the next ``add``/``train`` can be enqueued while they run.  Falls back to a stream synchronise and a
+        D2H copy when the planned update has no fused head or other entry points advanced the device-side count."""
+        nA = self._cfg.n_agents
+        if self._status_live and self._seq_expected > 0:
+            words, exp = self._host_words, self._seq_expected & 0xFFFFFFFF
+            t_end = None
+            while True:
+                done = True
+                for i in range(nA):
+                    if ((int(words[i]) >> 32) & 0xFFFFFFFF) != exp:
+                        done = False
+                        break
+                if done:
+                    bits = np.array([int(words[i]) & 0xFFFFFFFF for i in range(nA)], dtype=np.uint32).view(np.float32)
+                    return float(bits[0]) if nA == 1 else bits
+                if t_end is None:
+                    t_end = time.perf_counter() + timeout
+                elif time.perf_counter() > t_end:
+                    break
+        torch.cuda.current_stream().synchronize()
+        if self._status_live:                            # re-base on what the device has counted
+            self._seq_expected = (int(self._host_words[0]) >> 32) & 0xFFFFFFFF
+        out = self.last_critic_loss.cpu().numpy()
+        return float(out[0]) if nA == 1 else out
 
     def debug_tensors(self):
         """Views of the last update's Q-values / Bellman target (tests)."""

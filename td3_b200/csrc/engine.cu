@@ -561,6 +561,9 @@ struct td3_agent {
   bool params_bound = false;
   unsigned long long* state_u64 = nullptr;   // [0] sample step [1] critic Adam t [2] actor Adam t [3] rb size
   float* state_f32 = nullptr;                // critic_loss[n_agents], actor_loss[n_agents]
+  unsigned long long* host_status = nullptr; // mapped pinned host words {loss bits, sequence}[n_agents], or nullptr
+  bool host_status_live = false;             // the planned update writes them (fused critic head)
+  unsigned int* head_seq = nullptr;          // per-agent count of critic updates completed under the current plan
   long long batch = 0, global_batch = 0, batch_offset = 0;
   Bump ws;
   long long ws_floats = 0;
@@ -1220,6 +1223,9 @@ int plan_agent(td3_agent* a, long long batch) {
   const long long head_part_go = (long long)head_ctas * nq * head_per_g + head_ctas;
   float* head_part = ws.take(fuse_heads ? nA * head_part_go * 2 : 1, "head_partials");
   unsigned int* head_counter = reinterpret_cast<unsigned int*>(ws.take(2LL * nA, "head_counters"));
+  unsigned int* head_seq = reinterpret_cast<unsigned int*>(ws.take(nA, "head_seq"));
+  a->host_status_live = fuse_heads && a->host_status != nullptr;
+  a->head_seq = head_seq;
   a->eff_a = a->eff_at = a->eff_c = a->eff_ct = nullptr;
   if (wn) {
     a->eff_a = ws.take((long long)nA * c.actor.n_floats, "effective_actor");
@@ -1389,6 +1395,7 @@ int plan_agent(td3_agent* a, long long batch) {
       H.batch = B; H.w = wq_last; H.qw = qw; H.n_q = nq; H.ldh = wq_last; H.lddz = wq_last; H.n_cta = head_ctas;
       H.mode = 0; H.relu_mask = ln ? 0 : 1; H.skip_dw = head_dw_in_stage ? 1 : 0;
       H.discount = c.discount; H.inv_norm = inv_norm; H.tick = tick;
+      H.host_status = a->host_status; H.seq = head_seq;
       L.grid_x = nA * head_ctas;
       L.smem_bytes = (int)((2LL * nq * qw * wq_last + 4 * kHeadMaxQw + kHeadRows * 2 * (kHeadMaxQw + 1) +
                             (head_dw_in_stage ? 0 : (long long)kHeadRows * nq * head_per_g) + 16) * sizeof(float));
@@ -2137,6 +2144,16 @@ int td3_agent_bind_state(td3_agent* a, void* state_dev, int64_t n_bytes) {
   return TD3_OK;
 }
 
+int td3_agent_bind_host_status(td3_agent* a, void* host_words) {
+  if (!a) return fail(TD3_ERR_INVALID, "td3_agent_bind_host_status: null agent");
+  a->host_status = reinterpret_cast<unsigned long long*>(host_words);
+  a->batch = 0;                 // the head launch carries the pointer: plan again
+  drop_graphs(a);
+  return TD3_OK;
+}
+
+int td3_agent_host_status_live(const td3_agent* a) { return a && a->host_status_live ? 1 : 0; }
+
 int64_t td3_agent_workspace_floats(const td3_agent* agent, int64_t batch) {
   if (!agent || batch <= 0) return -1;
   td3_agent tmp;
@@ -2157,6 +2174,7 @@ int td3_agent_plan(td3_agent* a, int64_t batch, float* workspace, int64_t worksp
   a->ws.base = workspace;
   rc = plan_agent(a, batch);
   if (rc != TD3_OK) a->batch = 0;
+  else if (a->head_seq) CUDA_TRY(cudaMemset(a->head_seq, 0, sizeof(unsigned int) * a->cfg.n_agents));
   return rc;
 }
 

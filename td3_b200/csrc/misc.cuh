@@ -304,6 +304,11 @@ struct HeadParams {
   int skip_dw;                                // 1: dW/db of the head are a GEMM problem of the next stage (from dq and h)
   float discount, inv_norm;
   AdamTick tick;                              // critic optimiser tick + sampling step (mode 0), done by the finishing CTA
+  // optional host mirror of the loss (mode 0): the finishing CTA of agent i bumps seq[i] and stores the 8-byte word
+  // {loss bits, seq} to host_status[i] in mapped pinned host memory, so a host thread can pick the step's result up
+  // as soon as it exists instead of draining the stream (td3_agent_bind_host_status)
+  unsigned long long* host_status;
+  unsigned int* seq;
 };
 
 // One warp per (batch row, twin): every global load of the pair is issued before anything is consumed -- the kernel
@@ -515,6 +520,13 @@ __device__ __forceinline__ void head_body_t(const HeadParams& H, int tile, float
     }
     if (lane == 0) {
       H.loss[agent] = critic ? t * H.inv_norm : -t * H.inv_norm;
+      if (critic && H.host_status) {
+        const unsigned int sq = H.seq[agent] + 1u;
+        H.seq[agent] = sq;
+        const unsigned long long word = ((unsigned long long)sq << 32) | (unsigned long long)__float_as_uint(t * H.inv_norm);
+        *reinterpret_cast<volatile unsigned long long*>(H.host_status + agent) = word;
+        __threadfence_system();
+      }
       if (agent == 0 && H.tick.state) {
         if (critic) H.tick.state[0] += 1;          // sampling step (Philox counter)
         adam_tick(H.tick);

@@ -102,3 +102,22 @@ def test_wrong_buffer_type_and_weight_norm_raise():
     empty = ReplayBuffer_featured(O.Space(17), O.Space(6), max_size=16)
     with pytest.raises(ValueError):
         ours.train(empty, 8)
+
+
+def test_wait_critic_loss_matches_device_value():
+    """The host mirror of the critic loss (8-byte word written by the fused head kernel to pinned memory) is the value
+    the device holds, for single updates, multi-iteration calls and after a re-plan."""
+    _, _, ours, rb = make_featured(rows=1024, actor_widths=(400, 300), q_widths=(400, 300))
+    for step in range(6):
+        ours.train(rb, 64)
+        got = ours.wait_critic_loss()
+        torch.cuda.synchronize()
+        assert got == float(ours.last_critic_loss[0])
+    ours.train(rb, 64, iterations=5)
+    got = ours.wait_critic_loss()
+    torch.cuda.synchronize()
+    assert got == float(ours.last_critic_loss[0])
+    ours.train(rb, 32)                       # new batch size: new plan, the update count restarts
+    got = ours.wait_critic_loss()
+    torch.cuda.synchronize()
+    assert got == float(ours.last_critic_loss[0])
