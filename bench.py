@@ -80,6 +80,22 @@ def algorithmic_per_update(w):
     return flops / 1e9, nbytes / 1e6
 
 
+def stage_gflop_per_cycle(w):
+    """GFLOP of the contractions the stage kernels run in one policy_freq cycle (policy_freq - 1 critic-only updates +
+    one policy update): everything of algorithmic_per_update except first layers and output heads (featured), which
+    live in the front / head / apply kernels."""
+    pf, B = HYPER["policy_freq"], w["B"]
+    if w["kind"] != "featured":
+        return algorithmic_per_update(w)[0] * pf
+
+    def hidden(dims):
+        return sum(dims[i] * dims[i + 1] for i in range(1, len(dims) - 2))
+    Ha, Hq = hidden([w["S"], *w["aw"], w["A"]]), hidden([w["S"] + w["A"], *w["qw"], 1])
+    critic = 2 * B * (Ha + 2 * Hq + 2 * Hq + 2 * (2 * Hq))          # target actor, target critics, critics fwd, critics bwd (dW + dX)
+    actor = 2 * B * (Ha + Hq + Hq + 2 * Ha)                         # actor fwd, Q1 fwd, Q1 bwd (dX only), actor bwd (dW + dX)
+    return (critic * pf + actor) / 1e9
+
+
 def measured_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -347,6 +363,29 @@ def main():
     torch.cuda.synchronize()
     e2e_drain_s = time.perf_counter() - t0
 
+    # ---------------- dominant kernel, measured in situ ----------------
+    # td3_debug_prefix_times replays the first k launches of an update as a CUDA graph for k = 1..n and times each
+    # with CUDA events on the replay stream: consecutive differences are what every launch adds to the chain.
+    stage_info = None
+    if rank == 0 and args.exec_mode == "graph":
+        import ctypes as C
+        from td3_b200 import _lib as L_
+        view = agent._rb_view(rb)
+        tot_us, stage_us, n_stage, n_all = 0.0, 0.0, 0, 0
+        for with_actor in (0, 1):                      # one policy_freq = 2 cycle: a critic-only and a policy update
+            us, kinds, n = (C.c_float * 128)(), (C.c_int32 * 128)(), C.c_int32()
+            L_.check(lib.td3_debug_prefix_times(agent._handle, C.byref(view), with_actor, 200, us, kinds, 128, C.byref(n)))
+            prev = 0.0
+            for k in range(n.value):
+                if kinds[k] == 0:
+                    stage_us += us[k] - prev
+                    n_stage += 1
+                prev = us[k]
+            tot_us += us[n.value - 1]
+            n_all += n.value
+        stage_info = dict(stage_us=stage_us, cycle_us=tot_us, n_stage=n_stage, n_all=n_all)
+        torch.cuda.synchronize()
+
     # ---------------- population: several independent agents per GPU in lock-step ----------------
     pop_ms, n_pop = 0.0, (args.population if w["kind"] == "featured" else 0)
     h2d_bytes = int(rb.row_floats * 4)
@@ -410,15 +449,33 @@ def main():
         except Exception:
             pass
         kernel = {"persistent": "td3::persistent_update_kernel (one cooperative launch = all K updates; per-update figures)",
-                  "graph": "td3::stage_kernel x ~19 graph nodes per update (per-update figures)",
+                  "graph": "whole update = 7 (critic-only) / 14 (policy) graph nodes (per-update figures)",
                   "launches": "td3::stage_kernel launches (per-update figures)"}[args.exec_mode]
-        line["roofline"] = {
-            "bound": bound, "achieved": achieved, "peak": peak, "unit": unit, "frac": achieved / peak, "traffic": traffic,
-            "kernel": kernel,
-            "per": "update", "us_per_update": t_update_us, "hbm_floor_us": hbm_floor_us, "tensor_floor_us": tensor_floor_us,
-            "peak_source": peaks["source"],
-            "note": "single-agent MLP updates are bound by the ~20-stage dependency chain (launch/sync latency), not by "
-                    "HBM or tensor throughput (SURVEY.md 8d); frac is reported against the binding floor anyway"}
+        whole = {"bound": bound, "achieved": achieved, "peak": peak, "unit": unit, "frac": achieved / peak,
+                 "us_per_update": t_update_us, "hbm_floor_us": hbm_floor_us, "tensor_floor_us": tensor_floor_us, "kernel": kernel}
+        note = ("single-agent MLP updates are bound by the dependency chain of 7-14 launches (cold code, first-operand "
+                "latency, a K loop one SM's tensor pipe walks at ~100 cycles per K=8 MMA), not by HBM or tensor throughput "
+                "(SURVEY.md 8d, DESIGN.md 5); fractions are reported against the floors anyway")
+        if stage_info and stage_info["n_stage"] > 0:
+            # dominant kernel: td3::stage_kernel<true>, the tcgen05 TF32 GEMM stages (hidden-layer contractions of all
+            # passes).  Algorithmic flops = every contraction of the cycle that is not a first layer (front / apply
+            # kernels) or an output head (head / front kernels).
+            sg = stage_gflop_per_cycle(w)
+            st_s = stage_info["stage_us"] * 1e-6
+            ach = sg * 1e9 / st_s / 1e12
+            line["roofline"] = {
+                "bound": "tensor", "achieved": ach, "peak": tf32_peak, "unit": "TFLOP/s", "frac": ach / tf32_peak,
+                "traffic": traffic,
+                "kernel": "td3::stage_kernel<true> (tcgen05 kind::tf32 GEMM stages)",
+                "launches_per_cycle": stage_info["n_stage"], "us_per_launch": stage_info["stage_us"] / stage_info["n_stage"],
+                "share_of_update_time": stage_info["stage_us"] / stage_info["cycle_us"],
+                "algorithmic_gflop_per_launch": sg / stage_info["n_stage"],
+                "how": "CUDA events around graph replays of the first k launches of a critic-only and a policy update, "
+                       "k = 1..n (td3_debug_prefix_times, on the replay stream); a launch's duration = prefix(k) - prefix(k-1)",
+                "peak_source": peaks["source"] + " (bf16 sustained / 2 for kind::tf32)", "whole_update": whole, "note": note}
+        else:
+            whole.update({"traffic": traffic, "per": "update", "peak_source": peaks["source"], "note": note})
+            line["roofline"] = whole
         if not args.no_cpu_baseline:
             steps_cpu, warm_cpu = cpu_sample_size(w)
             ups, th, dt = time_cpu(w, steps_cpu, warm_cpu, threads_list, min(w["rows"], 100_000))
