@@ -177,6 +177,7 @@ Problem blank_problem(int kind) {
   p.groups_inner = 1;
   p.c_dups = 1;
   p.ksplit = 1;
+  p.map_a = p.map_b = -1;
   return p;
 }
 
@@ -259,9 +260,11 @@ bool attach_tensor_maps(std::initializer_list<std::vector<Launch>*> seqs, CUtens
   for (auto* seq : seqs)
     for (Launch& L : *seq) {
       if (L.kind != Launch::STAGE) continue;
+      int n_param = 0;        // maps of this launch that also travel in its kernel parameters
       for (int q = 0; q < L.stage.n_problems; ++q) {
         Problem& p = L.stage.p[q];
         p.tmapA = p.tmapB = nullptr;
+        p.map_a = p.map_b = -1;
         if (p.kind != PK_GEMM || !p.use_tc) continue;
         const int groups = p.tile_count / std::max(1, p.tiles_per_group);
         const int n_inner = std::max(1, p.groups_inner), n_outer = std::max(1, groups / n_inner);
@@ -275,6 +278,16 @@ bool attach_tensor_maps(std::initializer_list<std::vector<Launch>*> seqs, CUtens
         }
         p.tmapA = dev_maps + ia;
         p.tmapB = dev_maps + ib;
+        const int na = (int)(ib - ia), nb = (int)(host.size() - ib);
+        if (n_param + na + nb <= kStageMaps && !getenv("TD3_NO_PARAM_MAPS")) {
+          static_assert(sizeof(CUtensorMap) == sizeof(TensorMapBlob), "tensor map blob size");
+          memcpy(&L.stage.maps[n_param], &host[ia], (size_t)na * sizeof(CUtensorMap));
+          p.map_a = n_param;
+          n_param += na;
+          memcpy(&L.stage.maps[n_param], &host[ib], (size_t)nb * sizeof(CUtensorMap));
+          p.map_b = n_param;
+          n_param += nb;
+        }
       }
     }
   return ok_all;
@@ -362,9 +375,9 @@ void layout_stage(Launch& L) {
   StageParams& S = L.stage;
   const int n = S.n_problems;
   std::stable_partition(S.p, S.p + n, [](const Problem& p) { return p.kind == PK_GEMM && p.use_tc; });
-  // One wave: a tensor-core launch runs one CTA per SM, so tile number sm_count + 1 waits for a whole tile to finish.
-  // The K loop of a tile costs the same for every N width, so when a launch is a little over
-  // one wave, widen the N tiles of its most numerous tensor-core problems until it fits; leave it alone if it cannot.
+  // Waves: a tensor-core launch runs one CTA per SM, so tile number sm_count + 1 waits for a whole tile to finish, and
+  // the K loop of a tile costs the same for every N width.  When a launch is over one wave, widen
+  // the N tiles of its most numerous tensor-core problems as long as that removes whole waves.
   if (!getenv("TD3_NO_WAVE_FIT")) {
     auto count = [&](const int* nt) {
       long long total = 0;
@@ -382,8 +395,13 @@ void layout_stage(Launch& L) {
     int nt[kMaxProblemsPerStage];
     bool any = false;
     for (int q = 0; q < n; ++q) { nt[q] = S.p[q].tc_nt; any |= S.p[q].kind == PK_GEMM && S.p[q].use_tc; }
-    if (any && count(nt) > g_sm_count && count(nt) <= 2LL * g_sm_count) {
-      while (count(nt) > g_sm_count) {
+    if (any && count(nt) > g_sm_count) {
+      // greedy walk towards wider tiles; keep the first configuration with the fewest waves
+      auto waves = [&](const int* v) { return (count(v) + g_sm_count - 1) / g_sm_count; };
+      int best_nt[kMaxProblemsPerStage];
+      std::copy(nt, nt + n, best_nt);
+      long long best_waves = waves(nt);
+      while (best_waves > 1) {
         int best = -1;
         long long best_tiles = 0;
         for (int q = 0; q < n; ++q) {
@@ -394,9 +412,13 @@ void layout_stage(Launch& L) {
         }
         if (best < 0) break;
         nt[best] *= 2;
+        if (waves(nt) < best_waves) {
+          best_waves = waves(nt);
+          std::copy(nt, nt + n, best_nt);
+        }
       }
-      if (count(nt) <= g_sm_count)
-        for (int q = 0; q < n; ++q) {
+      std::copy(best_nt, best_nt + n, nt);
+      for (int q = 0; q < n; ++q) {
           Problem& p = S.p[q];
           if (!(p.kind == PK_GEMM && p.use_tc) || nt[q] == p.tc_nt) continue;
           const int g = p.tile_count / std::max(1, p.tiles_per_group);
@@ -440,7 +462,6 @@ void layout_stage(Launch& L) {
     Problem& p = S.p[q];
     if (p.kind == PK_GEMM && p.use_tc) {
       p.tc_cluster = c;
-      p.tc_slots = p.tc_slot_bytes = 0;
       p.tiles_n = ((p.N + p.tc_nt - 1) / p.tc_nt + c - 1) / c * c;
       p.tiles_per_group = p.tiles_m * p.tiles_n * p.ksplit;
       p.tile_count = p.tiles_per_group * groups[q];
@@ -1224,7 +1245,7 @@ int plan_agent(td3_agent* a, long long batch) {
   float* head_part = ws.take(fuse_heads ? nA * head_part_go * 2 : 1, "head_partials");
   unsigned int* head_counter = reinterpret_cast<unsigned int*>(ws.take(2LL * nA, "head_counters"));
   unsigned int* head_seq = reinterpret_cast<unsigned int*>(ws.take(nA, "head_seq"));
-  a->host_status_live = fuse_heads && a->host_status != nullptr;
+  a->host_status_live = fuse_heads && a->host_status != nullptr && !getenv("TD3_NO_HOST_STATUS");
   a->head_seq = head_seq;
   a->eff_a = a->eff_at = a->eff_c = a->eff_ct = nullptr;
   if (wn) {
@@ -1395,7 +1416,7 @@ int plan_agent(td3_agent* a, long long batch) {
       H.batch = B; H.w = wq_last; H.qw = qw; H.n_q = nq; H.ldh = wq_last; H.lddz = wq_last; H.n_cta = head_ctas;
       H.mode = 0; H.relu_mask = ln ? 0 : 1; H.skip_dw = head_dw_in_stage ? 1 : 0;
       H.discount = c.discount; H.inv_norm = inv_norm; H.tick = tick;
-      H.host_status = a->host_status; H.seq = head_seq;
+      H.host_status = a->host_status_live ? a->host_status : nullptr; H.seq = head_seq;
       L.grid_x = nA * head_ctas;
       L.smem_bytes = (int)((2LL * nq * qw * wq_last + 4 * kHeadMaxQw + kHeadRows * 2 * (kHeadMaxQw + 1) +
                             (head_dw_in_stage ? 0 : (long long)kHeadRows * nq * head_per_g) + 16) * sizeof(float));

@@ -524,8 +524,9 @@ __device__ __forceinline__ void head_body_t(const HeadParams& H, int tile, float
         const unsigned int sq = H.seq[agent] + 1u;
         H.seq[agent] = sq;
         const unsigned long long word = ((unsigned long long)sq << 32) | (unsigned long long)__float_as_uint(t * H.inv_norm);
+        // plain posted store: no system-scope fence here (it would hold the chain for a PCIe round trip); the word
+        // is a single aligned 8-byte write, and the end of the kernel flushes it at the latest
         *reinterpret_cast<volatile unsigned long long*>(H.host_status + agent) = word;
-        __threadfence_system();
       }
       if (agent == 0 && H.tick.state) {
         if (critic) H.tick.state[0] += 1;          // sampling step (Philox counter)

@@ -52,7 +52,8 @@ struct Problem {
   int use_tc;                     // 1: tcgen05 TF32 tile (128 x tc_nt) instead of the fp32 FFMA tile (32 x 32)
   int tc_nt, c_vec, aux_vec;      // TC tile width; 16-byte stores to C / loads from aux0 are legal
   int tc_cluster, pad_p;          // > 1: this many consecutive N tiles (one cluster) multicast their common A panel
-  int tc_slots, tc_slot_bytes;    // operand ring geometry of the tile (0: the kernel's default)
+  int map_a, map_b;               // >= 0: first tensor map of operand A / B inside StageParams::maps (kernel-parameter space:
+                                  // the TMA unit reads the descriptor without a global-memory round trip); < 0: tmapA / tmapB
   long long c_split, c_dup_stride;
   const float* A; const float* B; float* C; const float* bias;
   const void* tmapA; const void* tmapB;   // device arrays of CUtensorMap (one per group) when the operand is TMA-loadable
@@ -64,12 +65,16 @@ struct Problem {
 };
 
 constexpr int kMaxProblemsPerStage = 6;
+constexpr int kStageMaps = 16;    // tensor maps carried in the kernel parameters of a stage launch
+
+struct alignas(64) TensorMapBlob { unsigned long long v[16]; };   // CUtensorMap (128 bytes, opaque)
 
 struct StageParams {
   int n_problems;
   int total_tiles;
   int any_tc, cluster;            // some problem runs on the tensor cores (TMEM must be allocated); cluster size of the launch
   Problem p[kMaxProblemsPerStage];
+  TensorMapBlob maps[kStageMaps];
 };
 
 constexpr int kStageThreads = 256;

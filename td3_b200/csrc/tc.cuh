@@ -38,6 +38,7 @@ constexpr int kTcSlotBytes = kTcGroup * kTcSub;
 constexpr int kTcRingBytes = kTcSlots * kTcSlotBytes;
 constexpr int kTcMaxSlots = kTcSlots;
 constexpr int kTcCols = 128;                        // TMEM columns allocated per CTA (fp32 accumulator columns)
+constexpr int kTcAllocWarp = 2;                     // allocates / frees TMEM (warp 0 produces, warp 1 issues MMAs)
 
 #ifdef TD3_TILE_PROF
 #define TCP(k) do { tp_[k] = clock64(); } while (0)
@@ -49,6 +50,7 @@ struct TcState {                                    // lives in shared memory, o
   unsigned long long full_bar[kTcMaxSlots];         // "this slot's operand bytes have landed" (TMA complete_tx)
   unsigned long long empty_bar[kTcMaxSlots];        // "the MMAs that read this slot have completed" (tcgen05.commit)
   unsigned long long done_bar;                      // "the tile's accumulator is complete"
+  unsigned long long tmem_bar;                      // "tmem_base is valid" (the allocation runs beside the first TMA loads)
   unsigned int tmem_base;
   unsigned int tma_chunk_count;                     // chunks staged so far (full/empty barrier phases)
   unsigned int tile_count;                          // TC tiles finished so far (done_bar phase)
@@ -129,27 +131,41 @@ __device__ __forceinline__ void tc_setup(TcState* st, int cluster = 1) {
       mbar_init(&st->empty_bar[i], (unsigned)cluster);
     }
     mbar_init(&st->done_bar, 1);
+    mbar_init(&st->tmem_bar, 1);
     st->tma_chunk_count = 0;
     st->prof_stage = -1;
     st->tile_count = 0;
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
-  if ((threadIdx.x >> 5) == 0) {
+  __syncthreads();                                  // barriers exist: the producer warp may start loading operands
+  // The TMEM allocation (~270 cycles, longer under contention) is only needed by the first MMA, a full L2 round trip
+  // later: warp kTcAllocWarp performs it and publishes the base address through tmem_bar instead of a CTA-wide sync.
+  if ((threadIdx.x >> 5) == kTcAllocWarp) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&st->tmem_base)),
                  "r"(kTcCols)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0)
+      asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(&st->tmem_bar)) : "memory");
   }
-  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
-  __syncthreads();
+}
+
+// every reader of tmem_base passes through here first (a completed phase: later calls return at once)
+__device__ __forceinline__ unsigned int tc_tmem_base(TcState* st) {
+  mbar_wait(&st->tmem_bar, 0);
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  return *reinterpret_cast<volatile unsigned int*>(&st->tmem_base);
 }
 
 __device__ __forceinline__ void tc_teardown(TcState* st) {
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
   __syncthreads();
-  if ((threadIdx.x >> 5) == 0)
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(st->tmem_base), "r"(kTcCols) : "memory");
+  if ((threadIdx.x >> 5) == kTcAllocWarp) {
+    const unsigned int base = tc_tmem_base(st);
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(base), "r"(kTcCols) : "memory");
+  }
 }
 
 // shared-memory matrix descriptor, 128-byte swizzle, version 1 (sm_100)
@@ -338,7 +354,8 @@ __device__ __forceinline__ void tc_epilogue_cols(const Problem& P, float* __rest
 // ------------------------------------------------------------------------------------
 // One 128 x NT tile.  `ring` is kTcRingBytes of 1024-byte-aligned shared memory.
 // ------------------------------------------------------------------------------------
-__device__ __forceinline__ void gemm_tile_tc(const Problem& P, int tile, unsigned char* ring, TcState* st) {
+__device__ __forceinline__ void gemm_tile_tc(const Problem& P, int tile, unsigned char* ring, TcState* st,
+                                             const TensorMapBlob* param_maps = nullptr) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int NT = P.tc_nt;
 #ifdef TD3_TILE_PROF
@@ -369,7 +386,6 @@ __device__ __forceinline__ void gemm_tile_tc(const Problem& P, int tile, unsigne
   }
   const int n_chunks = (k_end - k_begin + 31) / 32;
 
-  const unsigned int tmem = st->tmem_base;
   const unsigned int idesc = tc_idesc(NT, !arc, !brc);
   // per-operand descriptor geometry
   const unsigned int a_lbo = arc ? 16 : 4096, b_lbo = brc ? 16 : 4096;
@@ -389,8 +405,11 @@ __device__ __forceinline__ void gemm_tile_tc(const Problem& P, int tile, unsigne
   {
     // warp-specialised: one producer thread (TMA), one MMA-issuing thread; everybody else waits for the accumulator
     const unsigned int tchunk = st->tma_chunk_count;
-    const unsigned char* mapA = reinterpret_cast<const unsigned char*>(P.tmapA) + (size_t)g * 128;
-    const unsigned char* mapB = reinterpret_cast<const unsigned char*>(P.tmapB) + (size_t)g * 128;
+    const bool pm = param_maps != nullptr && P.map_a >= 0 && P.map_b >= 0;
+    const unsigned char* mapA = pm ? reinterpret_cast<const unsigned char*>(param_maps + P.map_a + g)
+                                   : reinterpret_cast<const unsigned char*>(P.tmapA) + (size_t)g * 128;
+    const unsigned char* mapB = pm ? reinterpret_cast<const unsigned char*>(param_maps + P.map_b + g)
+                                   : reinterpret_cast<const unsigned char*>(P.tmapB) + (size_t)g * 128;
     const unsigned int bytes = 16384u + (arc ? 0u : 0u) + (brc ? (unsigned)NT * 128u : (unsigned)((NT + 31) >> 5) * 4096u);
     TCP(1);
     const unsigned int n_slots = kTcSlots, slot_bytes = kTcSlotBytes;
@@ -457,6 +476,7 @@ __device__ __forceinline__ void gemm_tile_tc(const Problem& P, int tile, unsigne
       }
       TCP(2);
     } else if (warp == 1) {
+      const unsigned int tmem = tc_tmem_base(st);
       const unsigned int ring_u = TD3_UNI(smem_u32(ring)), fb0 = TD3_UNI(smem_u32(&st->full_bar[0])),
                          eb0 = TD3_UNI(smem_u32(&st->empty_bar[0])), done_u = TD3_UNI(smem_u32(&st->done_bar));
       const unsigned int nsl = TD3_UNI(n_slots), sbytes = TD3_UNI(slot_bytes), tch = TD3_UNI(tchunk);
@@ -521,6 +541,7 @@ __device__ __forceinline__ void gemm_tile_tc(const Problem& P, int tile, unsigne
   // warps 0-3 own the lower half of the tile's columns, warps 4-7 the upper half; 4 columns per (rolled) iteration
   const int half = NT >> 1, jw = (warp >> 2) * half;
   __syncthreads();                                         // bias strip visible (the MMA pipeline is busy meanwhile)
+  const unsigned int tmem = tc_tmem_base(st);
   TCP(3);
   TD3_DISPATCH_EPI(epi, (tc_epilogue_cols<E>(P, C, aux0, bias_s, has_bias, aux_read, x_vec, c_vec, row_ok, n_chunks > 0, i, j0, jw,
                                              half, tmem + (((unsigned)(warp & 3) * 32u) << 16), smem_u32(&st->done_bar), tile_no & 1)));
