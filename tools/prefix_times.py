@@ -2,7 +2,7 @@
 k launches, k = 1..n, each timed with CUDA events over back-to-back replays; consecutive differences are what each
 launch adds to the dependency chain (launch boundary + cold code/parameter fetch + work), with no profiler attached.
 
-    python tools/prefix_times.py [cfg2] [reps]
+    python tools/prefix_times.py [cfg2] [reps] [agents_per_gpu]
 """
 import ctypes as C
 import os, sys
@@ -18,7 +18,8 @@ def main():
     name = sys.argv[1] if len(sys.argv) > 1 else "cfg2"
     reps = int(sys.argv[2]) if len(sys.argv) > 2 else 300
     w = bench.WORKLOADS[name]
-    agent, rb = bench.build_ours(w, seed=100)
+    n_agents = int(sys.argv[3]) if len(sys.argv) > 3 else 1
+    agent, rb = bench.build_ours(w, seed=100, rows=min(w["rows"], 100_000) if n_agents > 1 else None, n_agents=n_agents)
     agent.train(rb, w["B"], iterations=20)
     torch.cuda.synchronize()
     view = agent._rb_view(rb)
