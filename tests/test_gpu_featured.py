@@ -197,3 +197,32 @@ def test_tf32_tensor_core_path_tracks_the_fp32_oracle(norm, mode):
     worst_p = compare_nets(ours, ora, tol_rel=5e-2, max_abs=1.0, label="tf32", abs_floor=1e-3 * 10)
     print(f"tf32 norm={norm} mode={mode}: worst |dQ| {worst_q:.2e}, loss rel {worst_l:.2e}, params {worst_p}")
     assert worst_q <= 2e-2 and worst_l <= 3e-2
+
+
+def test_tail_fused_update_matches_the_unfused_sequences(monkeypatch):
+    """The default execution of a plain-MLP update (first-layer dW + Adam inside the optimiser launch, actor forward
+    riding with the target pass, one-wave tile widths: engine.cu plan_agent / layout_stage) and the unfused stage
+    sequences are the same arithmetic up to summation order: strict-fp32 mode, identical seeds -> parameters agree to
+    fp32 round-off after a policy_freq cycle and stay within 1e-5 relative after 20 updates."""
+    def run(unfused):
+        if unfused:
+            monkeypatch.setenv("TD3_NO_TAIL_FUSION", "1")
+            monkeypatch.setenv("TD3_NO_WAVE_FIT", "1")
+        else:
+            monkeypatch.delenv("TD3_NO_TAIL_FUSION", raising=False)
+            monkeypatch.delenv("TD3_NO_WAVE_FIT", raising=False)
+        _, _, ours, rb = make_featured(rows=2048, actor_widths=(400, 300), q_widths=(400, 300), precision="fp32")
+        out = []
+        for n in (2, 18):
+            ours.train(rb, 256, iterations=n)
+            torch.cuda.synchronize()
+            out.append({k: {name: t.detach().clone() for name, t in getattr(ours, k).state_dict().items()}
+                        for k in ("actor", "critic", "actor_target", "critic_target")})
+        return out
+    fused, unfused = run(False), run(True)
+    for tol, a, b in ((2e-6, fused[0], unfused[0]), (1e-5, fused[1], unfused[1])):
+        for k in a:
+            for name in a[k]:
+                x, y = a[k][name].double(), b[k][name].double()
+                rel = float((x - y).norm() / y.norm().clamp_min(1e-30))
+                assert rel <= tol, f"{k}.{name}: fused vs unfused rel {rel:.3e} > {tol}"
