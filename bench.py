@@ -402,6 +402,27 @@ def main():
         p1.record()
         barrier()
         pop_ms = p0.elapsed_time(p1)
+        # HBM-bound kernel of the path: the optimiser launch over the population's packed critic buffers (Adam reads
+        # p, g, m, v and writes p, m, v = 28 B/param; 8 agents x 0.25 M params x 5 buffers do not fit the L2), timed in
+        # situ as the last launch of a critic-only update
+        pop_adam = None
+        if rank == 0 and args.exec_mode == "graph":
+            import ctypes as C
+            from td3_b200 import _lib as L_
+            us, kinds, n = (C.c_float * 128)(), (C.c_int32 * 128)(), C.c_int32()
+            pview = pop._rb_view(prb)
+            L_.check(lib.td3_debug_prefix_times(pop._handle, C.byref(pview), 0, 300, us, kinds, 128, C.byref(n)))
+            if n.value >= 2 and kinds[n.value - 1] == 3:
+                t_us = us[n.value - 1] - us[n.value - 2]
+                pc = sum(int(t.numel()) for t in pop.critic.parameters()) if n_pop == 1 else int(pop._critic_family.params.numel())
+                nbytes = 28.0 * pc
+                pop_adam = {"kernel": "td3::apply_kernel (first-layer dW tiles + Adam over the packed critic buffers of all agents)",
+                            "bound": "hbm", "us_per_launch": t_us, "algorithmic_mb_per_launch": nbytes / 1e6,
+                            "achieved": nbytes / (t_us * 1e-6) / 1e9, "peak": peaks["hbm"], "unit": "GB/s",
+                            "frac": nbytes / (t_us * 1e-6) / 1e9 / peaks["hbm"],
+                            "how": "td3_debug_prefix_times on the population agent: prefix(7 launches) - prefix(6 launches), "
+                                   "CUDA events, 300 graph replays each (a replay is quantised to ~2 us by the GPU front end)"}
+            torch.cuda.synchronize()
 
     # ---------------- reduce over ranks ----------------
     if world > 1:
@@ -427,7 +448,7 @@ def main():
                                   "synchronise every step (the GPU idles while the host prepares the next step)"},
             "gpu_launches": int(launches)}
     if n_pop > 1 and pop_ms > 0:
-        line["population"] = {"agents_per_gpu": n_pop, "value": world * n_pop * Kp / (pop_ms / 1000.0), "unit": "updates/s",
+        line["population"] = {"adam_kernel_roofline": pop_adam, "agents_per_gpu": n_pop, "value": world * n_pop * Kp / (pop_ms / 1000.0), "unit": "updates/s",
                               "ms_per_lockstep_update": pop_ms / Kp, "steps": Kp,
                               "what": f"{n_pop} independent agents per GPU (own weights, optimiser state, 100k-row replay buffer and "
                                       "Philox stream each) stepped by the same launches; value = agent-updates/s over all GPUs "
