@@ -35,7 +35,15 @@ struct DwParams {
   const float* sc_ptr;                          // device-resident {step_size, sqrt(1 - beta2^t)} (adam_tick)
 };
 
-// 256 threads = 2 batch halves x 16 channels x 8 groups of 4 input columns.
+// 256 threads = 4 batch slices x 8 channel pairs x 8 groups of 4 input columns: a thread accumulates a 2 x 4 block of
+// dW_0 (+ the two bias sums) over its slice, so one 8-byte and one 16-byte shared-memory load feed 8 FMAs.  The slices
+// meet in shared memory (summed in slice order), and the optimiser step then walks the tile's parameters -- 16 whole
+// rows of W_0, i.e. one contiguous run of 16 K floats, plus 16 biases -- with consecutive threads on consecutive
+// addresses; their p / m / v / target values were requested before the first operand was staged.
+constexpr int kDwSlices = 4, kDwPartLd = kDwMaxK + 4;      // partial tile [slice][16][36]: 32 dW columns + the bias sum + pad
+static_assert(kDwSlices * kDwCols * kDwPartLd <= kDwRows * kDwCols, "slice partials reuse the dz buffer");
+constexpr int kDwElems = 2;                                  // optimiser elements per thread: 16 * (32 + 1) <= 2 * 256 + 16
+
 __device__ __forceinline__ void dw_adam_body(const DwParams& D, const EwParams& E, int tile, float* smem) {
   float* dzs = smem;                              // [kDwRows][kDwCols]
   float* xs = smem + kDwRows * kDwCols;           // [kDwRows][kDwMaxK]
@@ -44,29 +52,29 @@ __device__ __forceinline__ void dw_adam_body(const DwParams& D, const EwParams& 
   const int agent = tile / per_agent;
   const int rem = tile - agent * per_agent;
   const int inner = rem / D.col_blocks, c0 = (rem - inner * D.col_blocks) * kDwCols;
-  const int half = tid >> 7, u = tid & 127, c = u >> 3, kq = u & 7;
+  const int slice = tid >> 6, u = tid & 63, cp = u >> 3, kq = u & 7;
   const int N = D.N, K = D.K;
-  const bool c_ok = c0 + c < N;
+  const int nch = min(kDwCols, N - c0);           // channels of this tile
   const long long net = (long long)agent * D.p_go + (long long)inner * D.p_gi;
-  const long long wi = net + D.w_off + (long long)(c0 + c) * K + 4 * kq;
-  const long long bi = net + D.b_off + c0 + c;
-  const bool owner = half == 0 && c_ok;
-  // ---- optimiser operands of this thread's parameters: issued first, consumed last ----
-  float pv[5], mv[5], vv[5], tv[5];
+  const int n_w = nch * K, n_all = n_w + nch;     // the tile's parameters: W_0 rows c0.. (contiguous), then biases
+  // ---- optimiser operands: element e of the tile for e = tid, tid + 256 (+ 512 only when K > 30) ----
+  float pv[kDwElems + 1], mv[kDwElems + 1], vv[kDwElems + 1], tv[kDwElems + 1];
+  long long pi[kDwElems + 1];
 #pragma unroll
-  for (int j = 0; j < 5; ++j) {
-    const bool ok = owner && (j < 4 ? 4 * kq + j < K : kq == 0);
-    const long long i = j < 4 ? wi + j : bi;
-    pv[j] = ok ? __ldcg(D.p + i) : 0.f;
-    mv[j] = ok ? __ldcg(D.m + i) : 0.f;
-    vv[j] = ok ? __ldcg(D.v + i) : 0.f;
-    tv[j] = ok && D.do_polyak ? __ldcg(D.tgt + i) : 0.f;
+  for (int j = 0; j <= kDwElems; ++j) {
+    const int e = tid + j * kDwThreads;
+    const bool ok = e < n_all;
+    pi[j] = e < n_w ? net + D.w_off + (long long)c0 * K + e : net + D.b_off + c0 + (e - n_w);
+    pv[j] = ok ? __ldcg(D.p + pi[j]) : 0.f;
+    mv[j] = ok ? __ldcg(D.m + pi[j]) : 0.f;
+    vv[j] = ok ? __ldcg(D.v + pi[j]) : 0.f;
+    tv[j] = ok && D.do_polyak ? __ldcg(D.tgt + pi[j]) : 0.f;
   }
   const float step_size = __ldcg(D.sc_ptr), bc2s = __ldcg(D.sc_ptr + 1);
   const float* dz = D.dz + (long long)agent * D.dz_go + (long long)inner * D.dz_gi + c0;
   const float* x = D.x + (long long)agent * D.x_go + (long long)inner * D.x_gi;
   const int kg = (K + 3) >> 2;                    // 16-byte granules per input row
-  float acc[4] = {0.f, 0.f, 0.f, 0.f}, accb = 0.f;
+  float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}}, accb[2] = {0.f, 0.f};
 #pragma unroll 1
   for (int b0 = 0; b0 < D.batch; b0 += kDwRows) {
     const int rows = min(kDwRows, D.batch - b0);
@@ -84,47 +92,49 @@ __device__ __forceinline__ void dw_adam_body(const DwParams& D, const EwParams& 
     cp_async_commit();
     cp_async_wait<0>();
     __syncthreads();
-    const int hr = (rows + 1) >> 1;
-    const int rb = half * hr, re = min(rows, rb + hr);
+    const int sr = (rows + kDwSlices - 1) / kDwSlices;
+    const int rb = slice * sr, re = min(rows, rb + sr);
     const float4* xs4 = reinterpret_cast<const float4*>(xs);
+    const float2* dz2 = reinterpret_cast<const float2*>(dzs);
 #pragma unroll 4
     for (int r = rb; r < re; ++r) {
-      const float d = dzs[r * kDwCols + c];
+      const float2 d = dz2[r * (kDwCols / 2) + cp];
       const float4 xv = xs4[r * (kDwMaxK / 4) + kq];
-      acc[0] = fmaf(d, xv.x, acc[0]);
-      acc[1] = fmaf(d, xv.y, acc[1]);
-      acc[2] = fmaf(d, xv.z, acc[2]);
-      acc[3] = fmaf(d, xv.w, acc[3]);
-      accb += d;
+      acc[0][0] = fmaf(d.x, xv.x, acc[0][0]); acc[0][1] = fmaf(d.x, xv.y, acc[0][1]);
+      acc[0][2] = fmaf(d.x, xv.z, acc[0][2]); acc[0][3] = fmaf(d.x, xv.w, acc[0][3]);
+      acc[1][0] = fmaf(d.y, xv.x, acc[1][0]); acc[1][1] = fmaf(d.y, xv.y, acc[1][1]);
+      acc[1][2] = fmaf(d.y, xv.z, acc[1][2]); acc[1][3] = fmaf(d.y, xv.w, acc[1][3]);
+      accb[0] += d.x; accb[1] += d.y;
     }
   }
-  // ---- the two batch halves: second half hands over through shared memory, first half adds (fixed order) ----
+  // ---- slice partials -> shared memory; summed in slice order by whoever owns the parameter ----
   __syncthreads();
-  float* hand = smem;                             // [128][5]
-  if (half == 1) {
+  float* part = smem;                             // [kDwSlices][kDwCols][kDwPartLd]
 #pragma unroll
-    for (int j = 0; j < 4; ++j) hand[u * 5 + j] = acc[j];
-    hand[u * 5 + 4] = accb;
+  for (int h = 0; h < 2; ++h) {
+    float* row = part + (slice * kDwCols + 2 * cp + h) * kDwPartLd;
+    *reinterpret_cast<float4*>(row + 4 * kq) = make_float4(acc[h][0], acc[h][1], acc[h][2], acc[h][3]);
+    if (kq == 0) row[kDwMaxK] = accb[h];
   }
   __syncthreads();
-  if (!owner) return;
-  float gv[5];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) gv[j] = acc[j] + hand[u * 5 + j];
-  gv[4] = accb + hand[u * 5 + 4];
   const float w1 = (float)(1.0 - E.beta1), b2 = (float)E.beta2, w2 = (float)(1.0 - E.beta2);
   const float eps = (float)E.eps, tau = (float)E.tau, omt = (float)(1.0 - E.tau);
 #pragma unroll
-  for (int j = 0; j < 5; ++j) {
-    const bool ok = j < 4 ? 4 * kq + j < K : kq == 0;
-    if (!ok) continue;
-    const long long i = j < 4 ? wi + j : bi;
-    const float pn = adam_element(pv[j], gv[j], mv[j], vv[j], w1, b2, w2, bc2s, eps, -step_size);
-    D.g[i] = gv[j];
-    D.m[i] = mv[j];
-    D.v[i] = vv[j];
-    D.p[i] = pn;
-    if (D.do_polyak) D.tgt[i] = __fadd_rn(__fmul_rn(tau, pn), __fmul_rn(omt, tv[j]));
+  for (int j = 0; j <= kDwElems; ++j) {
+    const int e = tid + j * kDwThreads;
+    if (e >= n_all) break;
+    int c, k;
+    if (e < n_w) { c = e / K; k = e - c * K; }
+    else { c = e - n_w; k = kDwMaxK; }
+    float g = part[c * kDwPartLd + k];
+#pragma unroll
+    for (int sl = 1; sl < kDwSlices; ++sl) g += part[(sl * kDwCols + c) * kDwPartLd + k];
+    const float pn = adam_element(pv[j], g, mv[j], vv[j], w1, b2, w2, bc2s, eps, -step_size);
+    D.g[pi[j]] = g;
+    D.m[pi[j]] = mv[j];
+    D.v[pi[j]] = vv[j];
+    D.p[pi[j]] = pn;
+    if (D.do_polyak) D.tgt[pi[j]] = __fadd_rn(__fmul_rn(tau, pn), __fmul_rn(omt, tv[j]));
   }
 }
 
