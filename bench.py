@@ -205,6 +205,7 @@ def time_cpu(w, steps, warmup, threads_list, rows):
     for th in threads_list:
         torch.set_num_threads(th)
         agent, rb = build_oracle(w, 0, rows)
+        agent.keep_trace = False                       # time the reference's work only (no parity bookkeeping)
         np.random.seed(7)
         torch.manual_seed(7)
         for _ in range(warmup):
@@ -217,6 +218,31 @@ def time_cpu(w, steps, warmup, threads_list, rows):
         if best is None or ups > best[0]:
             best = (ups, th, dt)
     return best
+
+
+def time_torch_gpu(w, steps, warmup, rows):
+    """The same oracle port run the way the reference runs on a GPU box (TD3_featured.py:10 picks cuda when present):
+    networks and optimiser state on the device, float64 host replay arrays, five (seven) pageable H2D copies per sample
+    (my_replay_buffer.py:122-128), eager PyTorch kernels, TF32 off (torch default).  An 'existing Blackwell path'
+    comparator beside the CPU arm; not the reference arm."""
+    import numpy as np
+    import torch
+    agent, rb = build_oracle(w, 0, rows)
+    agent.keep_trace = False
+    for name in ("actor", "actor_target", "critic", "critic_target"):
+        getattr(agent, name).cuda()
+    host_sample = rb.sample
+    rb.sample = lambda *a, **k: tuple(t.cuda() for t in host_sample(*a, **k))
+    np.random.seed(7)
+    torch.manual_seed(7)
+    for _ in range(warmup):
+        agent.train(rb, w["B"])
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        agent.train(rb, w["B"])
+    torch.cuda.synchronize()
+    return steps / (time.perf_counter() - t0)
 
 
 def cpu_sample_size(w):
@@ -498,6 +524,16 @@ def main():
             whole.update({"traffic": traffic, "per": "update", "peak_source": peaks["source"], "note": note})
             line["roofline"] = whole
         if not args.no_cpu_baseline:
+            try:
+                n_e = 300 if w["kind"] == "featured" else 20
+                line["torch_eager_gpu"] = {
+                    "value": time_torch_gpu(w, n_e, 30 if w["kind"] == "featured" else 2, min(w["rows"], 100_000)),
+                    "unit": "updates/s", "steps": n_e,
+                    "what": "oracle port of the reference with its networks on this GPU (eager PyTorch, fp32, host replay "
+                            "arrays + per-sample H2D copies as my_replay_buffer.py does): what the reference gets from a B200 "
+                            "unchanged"}
+            except Exception as exc:                          # a comparator, never a reason to lose the bench line
+                line["torch_eager_gpu"] = {"unavailable": repr(exc)[:200]}
             steps_cpu, warm_cpu = cpu_sample_size(w)
             ups, th, dt = time_cpu(w, steps_cpu, warm_cpu, threads_list, min(w["rows"], 100_000))
             line["cpu_baseline"] = {"value": ups, "unit": "updates/s", "cores": th, "kind": "port",

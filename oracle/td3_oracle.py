@@ -277,6 +277,9 @@ class _AgentBase:
         self.policy_noise, self.noise_clip, self.policy_freq = policy_noise, noise_clip, policy_freq
         self.total_it = 0
         self.trace = {}
+        # parity tests read self.trace after every update; timing runs switch it off so that the timed work is exactly
+        # the reference's (the trace adds clones and a float() per update that TD3_featured.py does not have)
+        self.keep_trace = True
 
     def _smoothing_noise(self, action, noise):
         eps = torch.randn_like(action) if noise is None else torch.as_tensor(noise, dtype=action.dtype)
@@ -328,14 +331,16 @@ class TD3Featured(_AgentBase):
         self.critic_optimizer.zero_grad()
         critic_loss.backward()
         self.critic_optimizer.step()                                                   # :151-153
-        self.trace = dict(critic_loss=float(critic_loss.detach()), q1=q1.detach().clone(), q2=q2.detach().clone(),
-                          target_q=target_q.clone(), next_action=next_action.clone(), actor_loss=None)
+        if self.keep_trace:
+            self.trace = dict(critic_loss=float(critic_loss.detach()), q1=q1.detach().clone(), q2=q2.detach().clone(),
+                              target_q=target_q.clone(), next_action=next_action.clone(), actor_loss=None)
         if self.total_it % self.policy_freq == 0:                                      # :156
             actor_loss = -self.critic.Q1(state, self.actor(state)).mean()              # :159
             self.actor_optimizer.zero_grad()
             actor_loss.backward()
             self.actor_optimizer.step()                                                # :162-164
-            self.trace["actor_loss"] = float(actor_loss.detach())
+            if self.keep_trace:
+                self.trace["actor_loss"] = float(actor_loss.detach())
             self._polyak()
 
 
@@ -387,9 +392,10 @@ class TD3Particles(_AgentBase):
         self.critic_optimizer.zero_grad()
         critic_loss.backward()
         self.critic_optimizer.step()                                                   # :201-203
-        self.trace = dict(critic_loss=float(critic_loss.detach()), q1=qs[0].detach().clone(),
-                          q2=qs[1].detach().clone() if self.CDQ else None,
-                          target_q=target_q.clone(), next_action=next_action.clone(), actor_loss=None)
+        if self.keep_trace:
+            self.trace = dict(critic_loss=float(critic_loss.detach()), q1=qs[0].detach().clone(),
+                              q2=qs[1].detach().clone() if self.CDQ else None,
+                              target_q=target_q.clone(), next_action=next_action.clone(), actor_loss=None)
         if self.total_it % self.policy_freq == 0:
             self._actor_learn(sf, sp)                                                  # :206-207
 
@@ -399,7 +405,8 @@ class TD3Particles(_AgentBase):
         self.actor_optimizer.zero_grad()
         actor_loss.backward()
         self.actor_optimizer.step()
-        self.trace["actor_loss"] = float(actor_loss.detach())
+        if self.keep_trace:
+            self.trace["actor_loss"] = float(actor_loss.detach())
         self._polyak()
 
 

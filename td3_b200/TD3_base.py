@@ -220,11 +220,15 @@ class TD3_base(object):
             words, exp = self._host_words, self._seq_expected & 0xFFFFFFFF
             t_end = None
             while True:
-                done = True
+                done, ahead = True, False
                 for i in range(nA):
-                    if ((int(words[i]) >> 32) & 0xFFFFFFFF) != exp:
+                    seq = (int(words[i]) >> 32) & 0xFFFFFFFF
+                    if seq != exp:
                         done = False
+                        ahead = 0 < ((seq - exp) & 0xFFFFFFFF) < 0x80000000   # other entry points ran updates too
                         break
+                if ahead:
+                    break
                 if done:
                     bits = np.array([int(words[i]) & 0xFFFFFFFF for i in range(nA)], dtype=np.uint32).view(np.float32)
                     return float(bits[0]) if nA == 1 else bits
