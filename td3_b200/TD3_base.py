@@ -209,7 +209,7 @@ class TD3_base(object):
     def last_actor_loss(self) -> torch.Tensor:
         return self._losses[self._cfg.n_agents: 2 * self._cfg.n_agents]
 
-    def wait_critic_loss(self, timeout: float = 10.0):
+    def wait_critic_loss(self, timeout: float = 2.0):
         """Critic loss of the most recently enqueued update, as host numbers (float for one agent, float32 array for
         a population).  Blocks only until that loss has landed in pinned host memory -- the fused critic-head kernel
         stores it there together with the update count -- not until the optimiser kernels queued behind it have
@@ -235,6 +235,7 @@ class TD3_base(object):
                 if t_end is None:
                     t_end = time.perf_counter() + timeout
                 elif time.perf_counter() > t_end:
+                    self._status_live = False            # the mirror is not arriving on this system: stop relying on it
                     break
         torch.cuda.current_stream().synchronize()
         if self._status_live:                            # re-base on what the device has counted
