@@ -81,3 +81,17 @@ def test_member_inference_addresses_its_own_weights():
         u = pop.select_action(s, agent=i)
         for q_pop, q_one in zip(pop.eval_q(s, u, agent=i), a.eval_q(s, u)):
             np.testing.assert_array_equal(q_pop, q_one)
+
+
+@pytest.mark.parametrize("mode", ["graph", "persistent", "launches"])
+def test_host_mirror_of_the_losses_covers_every_member(mode):
+    """wait_critic_loss() on a population returns every member's critic loss of the last enqueued update -- the
+    8-byte words the fused head kernel stores to pinned host memory -- and they equal the device values, in every
+    execution mode."""
+    pop, rbp, _ = _build("tf32", mode)
+    for it in (1, 1, 3):
+        pop.train(rbp, B, iterations=it)
+        got = pop.wait_critic_loss()
+        torch.cuda.synchronize()
+        want = pop.last_critic_loss.cpu().numpy()
+        assert got.shape == (N,) and np.array_equal(got, want), (mode, it, got, want)
