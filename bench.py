@@ -155,7 +155,7 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------- builders
-def build_ours(w, seed, rows=None, n_agents=1):
+def build_ours(w, seed, rows=None, n_agents=1, rng_seed=None):
     import torch
     from oracle import td3_oracle as O              # synthetic-data generator only (inputs, not the measured path)
     rows = rows or w["rows"]
@@ -164,8 +164,8 @@ def build_ours(w, seed, rows=None, n_agents=1):
         from td3_b200.my_replay_buffer import ReplayBuffer_featured
         obs, act = O.Space(w["S"]), O.Space(w["A"])
         torch.manual_seed(seed)
-        agent = TD3(obs, act, lr=1e-4, norm=w["norm"], actor_widths=w["aw"], q_widths=w["qw"], seed=seed + 1, max_action=1,
-                    n_agents=n_agents, **HYPER)
+        agent = TD3(obs, act, lr=1e-4, norm=w["norm"], actor_widths=w["aw"], q_widths=w["qw"],
+                    seed=seed + 1 if rng_seed is None else rng_seed, max_action=1, n_agents=n_agents, **HYPER)
         rb = ReplayBuffer_featured(obs, act, max_size=rows, n_agents=n_agents)
         for i in range(n_agents):
             rb.add_batch(agent=i, **O.synthetic_transitions_featured(rows, w["S"], w["A"], seed=i))
@@ -420,7 +420,12 @@ def main():
     if n_pop > 1:
         del agent, rb
         torch.cuda.empty_cache()
-        pop, prb = build_ours(w, seed=1000 + 64 * rank, rows=min(w["rows"], 100_000), n_agents=n_pop)
+        # global agent ids: rank r owns agents [r * n_pop, (r + 1) * n_pop) of one population keyed 1001, so that the
+        # members' random streams do not depend on how many GPUs the population is spread over (td3_b200/population.py)
+        from td3_b200.population import shard_range, shard_seed
+        first_agent, _ = shard_range(world * n_pop, world, rank)
+        pop, prb = build_ours(w, seed=1000 + 64 * rank, rows=min(w["rows"], 100_000), n_agents=n_pop,
+                              rng_seed=shard_seed(1001, first_agent))
         Kp = max(3, K // 4)
         pop.train(prb, B, iterations=max(3, W // 4))
         barrier()

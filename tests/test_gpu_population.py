@@ -95,3 +95,42 @@ def test_host_mirror_of_the_losses_covers_every_member(mode):
         torch.cuda.synchronize()
         want = pop.last_critic_loss.cpu().numpy()
         assert got.shape == (N,) and np.array_equal(got, want), (mode, it, got, want)
+
+
+def test_sharded_population_equals_the_unsharded_one():
+    """A population of 4 on one GPU and the same 4 global agents as two shards of 2 (keyed by population.shard_seed)
+    give bit-identical members: what makes `64 agents over 8 GPUs` independent of the number of GPUs."""
+    from td3_b200.TD3_featured import TD3
+    from td3_b200.my_replay_buffer import ReplayBuffer_featured
+    from td3_b200.population import shard_range, shard_seed
+    obs, act = O.Space(S), O.Space(A)
+    seed, total = 77, 4
+
+    def run(first, count, init):
+        torch.manual_seed(3)
+        pop = TD3(obs, act, n_agents=count, precision="tf32", seed=shard_seed(seed, first), **KW)
+        rb = ReplayBuffer_featured(obs, act, max_size=ROWS, n_agents=count)
+        for i in range(count):
+            for k in NETS:
+                pop.load_agent_state_dict(k, i, init[first + i][k])
+            rb.add_batch(agent=i, **O.synthetic_transitions_featured(ROWS, S, A, seed=20 + first + i))
+        pop.train(rb, B, iterations=6)
+        torch.cuda.synchronize()
+        return [{k: {n: v.clone() for n, v in pop.agent_state_dict(k, i).items()} for k in NETS} for i in range(count)], \
+            pop.last_critic_loss.cpu().numpy().copy()
+
+    torch.manual_seed(11)
+    donor = TD3(obs, act, n_agents=total, precision="tf32", seed=1, **KW)
+    init = [{k: {n: v.clone() for n, v in donor.agent_state_dict(k, i).items()} for k in NETS} for i in range(total)]
+    whole, loss_whole = run(0, total, init)
+    parts, losses = [], []
+    for r in range(2):
+        a, b = shard_range(total, 2, r)
+        p, l = run(a, b - a, init)
+        parts += p
+        losses += list(l)
+    assert np.array_equal(np.asarray(losses), loss_whole)
+    for g in range(total):
+        for k in NETS:
+            for n in whole[g][k]:
+                assert torch.equal(whole[g][k][n], parts[g][k][n]), (g, k, n)
