@@ -157,7 +157,7 @@ class ClockSampler:
 # --------------------------------------------------------------------------- builders
 def build_ours(w, seed, rows=None, n_agents=1, rng_seed=None):
     import torch
-    from oracle import td3_oracle as O              # synthetic-data generator only (inputs, not the measured path)
+    from td3_b200 import synthetic as O             # inputs of the named shapes; nothing on this arm touches oracle/
     rows = rows or w["rows"]
     if w["kind"] == "featured":
         from td3_b200.TD3_featured import TD3
@@ -168,7 +168,7 @@ def build_ours(w, seed, rows=None, n_agents=1, rng_seed=None):
                     seed=seed + 1 if rng_seed is None else rng_seed, max_action=1, n_agents=n_agents, **HYPER)
         rb = ReplayBuffer_featured(obs, act, max_size=rows, n_agents=n_agents)
         for i in range(n_agents):
-            rb.add_batch(agent=i, **O.synthetic_transitions_featured(rows, w["S"], w["A"], seed=i))
+            rb.add_batch(agent=i, **O.transitions_featured(rows, w["S"], w["A"], seed=i))
     else:
         from td3_b200.TD3_particles import TD3
         from td3_b200.my_replay_buffer import ReplayBuffer_particles
@@ -176,7 +176,7 @@ def build_ours(w, seed, rows=None, n_agents=1, rng_seed=None):
         torch.manual_seed(seed)
         agent = TD3(obs, act, lr=1e-4, norm=w["norm"], seed=seed + 1, **HYPER)
         rb = ReplayBuffer_particles(obs, act, max_size=rows)
-        rb.add_batch(**O.synthetic_transitions_particles(rows, w["F"], w["N"], w["D"], w["A"], seed=0))
+        rb.add_batch(**O.transitions_particles(rows, w["F"], w["N"], w["D"], w["A"], seed=0))
     return agent, rb
 
 

@@ -83,3 +83,14 @@ def test_oracle_matches_live_reference(name):
     res = MG.run_case(name, MG.CASES[name], RF, RP, RB)               # asserts bit-equality internally
     z, _ = _load(name)
     assert np.array_equal(res["critic_loss"], z["critic_loss"])
+
+
+def test_package_and_oracle_generate_the_same_synthetic_inputs():
+    """bench.py feeds the CUDA arm from td3_b200/synthetic.py and the CPU arm from the oracle's own generators (the
+    measured path never imports oracle/): both must be the same bytes."""
+    from oracle import td3_oracle as O
+    from td3_b200 import synthetic as Syn
+    a, b = O.synthetic_transitions_featured(64, 17, 6, seed=3), Syn.transitions_featured(64, 17, 6, seed=3)
+    assert a.keys() == b.keys() and all(np.array_equal(a[k], b[k]) for k in a)
+    a, b = O.synthetic_transitions_particles(8, 8, 16, 6, 3, seed=1), Syn.transitions_particles(8, 8, 16, 6, 3, seed=1)
+    assert a.keys() == b.keys() and all(np.array_equal(a[k], b[k]) and a[k].dtype == b[k].dtype for k in a)

@@ -5,7 +5,7 @@
 import json, os, sys
 import numpy as np, torch, torch.distributed as dist
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from oracle import td3_oracle as O
+from td3_b200 import synthetic as O
 from td3_b200.TD3_featured import TD3
 from td3_b200.my_replay_buffer import ReplayBuffer_featured
 from td3_b200.data_parallel import DataParallelTD3
@@ -15,7 +15,7 @@ torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 S, A, ROWS = 17, 6, 65536
 obs, act = O.Space(S), O.Space(A)
-data = O.synthetic_transitions_featured(ROWS, S, A, seed=0)
+data = O.transitions_featured(ROWS, S, A, seed=0)
 
 
 def make(precision):
