@@ -95,3 +95,20 @@ def test_dropin_module_names_resolve():
         sys.path.remove(os.path.join(ROOT, "dropin"))
         for name in ("TD3_base", "TD3_featured", "TD3_particles", "my_replay_buffer"):
             sys.modules.pop(name, None)
+
+
+@pytest.mark.parametrize("S,A,aw,qw", [(17, 6, (400, 300), (400, 300)), (17, 6, (500, 400, 300), (500, 400, 200)),
+                                        (32, 0, (64, 64), (64, 64)), (3, 1, (400, 300), (400, 300))])
+def test_plain_mlp_layouts_meet_the_tail_fusion_preconditions(S, A, aw, qw):
+    """engine.cu fuses the first layer's dW into the optimiser launch only when the first layer sits at the head of each
+    network's packed block, 16-byte aligned, with K <= 32 and a width that is a multiple of 4 (plan_agent: l0_fusable).
+    The packing of the plain MLPs must keep satisfying that, or the fast path silently turns itself off."""
+    from td3_b200.packing import MlpActor, MlpCritic, net_layout
+    A = max(A, 1)
+    for net, k0 in ((MlpActor(S, A, 1.0, None, aw), S), (MlpCritic(S, A, None, qw).q1, S + A)):
+        lay = net_layout(net)
+        n, d0, d1 = lay.n_linear, lay.dims[0], lay.dims[1]
+        assert d0 == k0 and n >= 2
+        fusable = (d0 <= 32 and d1 % 4 == 0 and lay.w_off[0] == 0 and lay.w_off[1] % 4 == 0 and lay.b_off[0] >= d0 * d1 and
+                   lay.w_off[1] >= lay.b_off[0] + d1 and lay.n_floats % 4 == 0)
+        assert fusable == (k0 <= 32), (S, A, d0, d1, lay.w_off[0], lay.b_off[0], lay.w_off[1], lay.n_floats)
