@@ -130,3 +130,37 @@ def test_buffer_save_load_reference_format(tmp_path):
     rb2 = ReplayBuffer_featured(O.Space(4), O.Space(2), max_size=64, load_folder=str(tmp_path))
     assert (rb2.ptr, rb2.size) == (40, 40)
     assert torch.equal(rb2._rows, rb._rows)
+
+
+def test_device_rng_statistics():
+    """T5: what the on-device Philox stream feeds an update -- replay indices uniform over [0, size)
+    (chi-square over 64 bins, range), smoothing noise = clip(N(0, policy_noise^2), +-noise_clip) with the mean, standard
+    deviation and clip fraction of that distribution (TD3_featured.py:131-133)."""
+    import math
+    from helpers import make_featured
+    rows, B, n_upd = 4096, 4096, 8
+    _, _, ours, rb = make_featured(rows=rows, actor_widths=(64, 64), q_widths=(64, 64), policy_noise=0.2, noise_clip=0.5)
+    idx, eps = [], []
+    for _ in range(n_upd):
+        ours.train(rb, B)
+        torch.cuda.synchronize()
+        d = ours.debug_tensors()
+        idx.append(d["indices"].cpu().numpy().reshape(-1).copy())
+        eps.append(d["eps"].cpu().numpy().reshape(-1).copy())
+    idx, eps = np.concatenate(idx), np.concatenate(eps).astype(np.float64)
+    assert idx.min() >= 0 and idx.max() < rows
+    assert len(np.unique(idx[:B])) < B and not np.array_equal(idx[:B], idx[B:2 * B])     # with replacement, fresh per update
+    counts = np.bincount(idx * 64 // rows, minlength=64)
+    chi2 = float(((counts - len(idx) / 64) ** 2 / (len(idx) / 64)).sum())
+    assert chi2 < 63 + 6 * math.sqrt(2 * 63), chi2                                       # 6 sigma of chi-square(63)
+    n = len(eps)
+    assert abs(eps).max() <= 0.5 + 1e-7
+    clip_frac = float((np.abs(eps) >= 0.5 - 1e-7).mean())
+    want_clip = math.erfc(2.5 / math.sqrt(2))                                            # P(|z| > 2.5) = 1.24 %
+    assert abs(clip_frac - want_clip) < 6 * math.sqrt(want_clip / n), (clip_frac, want_clip)
+    assert abs(eps.mean()) < 6 * 0.2 / math.sqrt(n)
+    # variance of a normal clipped at c = 2.5 sigma: sigma^2 (1 - 2 c phi(c) - 2 (1 - c^2) Q(c)) with Q the upper tail
+    c = 2.5
+    phi, Q = math.exp(-c * c / 2) / math.sqrt(2 * math.pi), 0.5 * math.erfc(c / math.sqrt(2))
+    want_std = 0.2 * math.sqrt(1 - 2 * c * phi - 2 * (1 - c * c) * Q)
+    assert abs(eps.std() - want_std) < 0.01 * want_std, (eps.std(), want_std)
