@@ -226,3 +226,17 @@ def test_tail_fused_update_matches_the_unfused_sequences(monkeypatch):
                 x, y = a[k][name].double(), b[k][name].double()
                 rel = float((x - y).norm() / y.norm().clamp_min(1e-30))
                 assert rel <= tol, f"{k}.{name}: fused vs unfused rel {rel:.3e} > {tol}"
+
+
+@pytest.mark.parametrize("unfused", [False, True])
+@pytest.mark.parametrize("aw,qw", [((64,), (48,)), ((96, 64, 48, 32), (80, 64, 48, 32))])
+def test_shallow_and_deep_networks_match_oracle(monkeypatch, unfused, aw, qw):
+    """Two-layer networks (one hidden layer: the output layer's dW rides with the first layer's stage) and five-layer
+    ones, through the tail-fused and the unfused sequences, against the fp32 oracle."""
+    if unfused:
+        monkeypatch.setenv("TD3_NO_TAIL_FUSION", "1")
+    else:
+        monkeypatch.delenv("TD3_NO_TAIL_FUSION", raising=False)
+    ora, orb, ours, rb = make_featured(norm=None, actor_widths=aw, q_widths=qw, lr=1e-3, precision="fp32")
+    worst = _run(ora, orb, ours, rb, B=64, steps=8, A=6, rows=512, lr=1e-3, tol_params=2e-4)
+    print(f"featured widths={aw}/{qw} unfused={unfused}: worst param rel err {worst}")
