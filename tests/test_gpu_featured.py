@@ -240,3 +240,12 @@ def test_shallow_and_deep_networks_match_oracle(monkeypatch, unfused, aw, qw):
     ora, orb, ours, rb = make_featured(norm=None, actor_widths=aw, q_widths=qw, lr=1e-3, precision="fp32")
     worst = _run(ora, orb, ours, rb, B=64, steps=8, A=6, rows=512, lr=1e-3, tol_params=2e-4)
     print(f"featured widths={aw}/{qw} unfused={unfused}: worst param rel err {worst}")
+
+
+def test_ragged_batch_and_small_dims_through_the_fused_path():
+    """B = 37 (partial row blocks in the front / head / first-layer tiles), S = 5, A = 2, widths that are not
+    multiples of 16, policy update every step: the tail-fused default path against the fp32 oracle."""
+    ora, orb, ours, rb = make_featured(S=5, A=2, rows=300, norm=None, actor_widths=(40, 24), q_widths=(44, 20), lr=1e-3,
+                                       precision="fp32", policy_freq=1)
+    worst = _run(ora, orb, ours, rb, B=37, steps=6, A=2, rows=300, lr=1e-3, tol_params=2e-4)
+    print(f"ragged featured: worst param rel err {worst}")
