@@ -509,7 +509,7 @@ def main():
         whole = {"bound": bound, "achieved": achieved, "peak": peak, "unit": unit, "frac": achieved / peak,
                  "us_per_update": t_update_us, "hbm_floor_us": hbm_floor_us, "tensor_floor_us": tensor_floor_us, "kernel": kernel}
         note = ("single-agent MLP updates are bound by the dependency chain of 7-14 launches (cold code, first-operand "
-                "latency, a K loop one SM's tensor pipe walks at ~100 cycles per K=8 MMA), not by HBM or tensor throughput "
+                "latency, a K loop that is bound by the ~50-cycle issue rate of tcgen05.mma from one thread plus barrier rounds), not by HBM or tensor throughput "
                 "(SURVEY.md 8d, DESIGN.md 5); fractions are reported against the floors anyway")
         if stage_info and stage_info["n_stage"] > 0:
             # dominant kernel: td3::stage_kernel<true>, the tcgen05 TF32 GEMM stages (hidden-layer contractions of all
