@@ -12,8 +12,17 @@ batch 256, 1M-row device-resident replay buffer, one agent per GPU.
          stage kernels -- or one cooperative launch of the persistent update kernel with --exec-mode
          persistent -- CUDA-event timed, max over ranks).
   e2e    the same metric through the public Python API the reference's main.py loop uses, per step:
-         replay_buffer.add(one host transition -> pinned -> H2D), policy.train(replay_buffer, 256),
-         and a synchronous D2H read of the critic loss.
+         replay_buffer.add(one host transition -> pinned -> H2D), policy.train(replay_buffer, 256), and
+         policy.wait_critic_loss(): the host blocks until THIS step's critic loss (an 8-byte word the critic-head
+         kernel stores to pinned host memory) has landed, then enqueues the next step behind the optimiser kernels
+         still running; the timed region ends with a full device synchronise.  e2e.drain_value is the same loop
+         with a D2H copy behind the whole update and a stream synchronise every step.
+  roofline  the dominant kernel (the tcgen05 GEMM stage kernel): algorithmic flops of its launches in one
+         policy_freq cycle / their in-situ duration (CUDA events around graph replays of the first k launches,
+         td3_debug_prefix_times), against the TF32 peak from MEASURED_PEAKS.json; whole-update floors beside it.
+  torch_eager_gpu  the oracle port of the reference with its networks on the GPU (eager PyTorch): a comparator.
+  population  8 independent agents per GPU in lock-step (BASELINE config 5) + the HBM-side roofline of its
+         optimiser launch.
   --impl reference times the CPU oracle port of the reference (oracle/td3_oracle.py, torch CPU ops --
          /root/reference is not present on the GPU box) on the host cores with the same config.
 With N > 1 (torchrun) every rank runs an independent agent/seed on its own GPU (weak scaling, no
