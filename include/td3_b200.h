@@ -186,6 +186,12 @@ int td3_agent_bind_state(td3_agent* agent, void* state_dev, int64_t n_bytes);
  * whenever the critic head is fused: output width <= 4, last hidden width <= 512). */
 int td3_agent_bind_host_status(td3_agent* agent, void* host_words);
 int td3_agent_host_status_live(const td3_agent* agent);
+/* precision = TD3_PRECISION_TF32 keeps round-to-nearest TF32 copies of the four packed parameter buffers for the tensor
+ * cores (tcgen05 kind::tf32 truncates its operands; a pre-rounded operand is read exactly, which removes the bias of
+ * truncation).  The optimiser kernels keep them current.  Whoever writes the parameter buffers from outside -- the
+ * host mirror's load_state_dict / load (TD3_base.py:37-50), or any in-place edit of a state_dict view -- calls this
+ * afterwards; the next entry point that runs an update rebuilds the copies first (one launch). */
+int td3_agent_params_changed(td3_agent* agent);
 /* Workspace (activations, batch staging) for a given batch size, in floats. */
 int64_t td3_agent_workspace_floats(const td3_agent* agent, int64_t batch);
 /* Bind the workspace and build the launch plan for `batch`.  Drops captured graphs. */

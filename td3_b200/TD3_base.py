@@ -53,6 +53,14 @@ class TD3_base(object):
             self.actor_target.load_state_dict(rd("actor_target"))
         else:
             self._actor_family.rebind_target(self.actor)
+        self.params_changed()
+
+    def params_changed(self):
+        """Tell the engine that parameter values were written from outside its kernels (``load_state_dict`` and
+        ``load`` call this themselves; call it after editing a ``state_dict()`` view in place): in TF32 mode the
+        tensor cores read round-to-nearest copies of the weights, which are rebuilt before the next update."""
+        if getattr(self, "_handle", None) is not None:
+            _lib.check(self._lib.td3_agent_params_changed(self._handle))
 
     # ------------------------------------------------------------------ engine plumbing
     def _engine_init(self, cfg: _lib.AgentConfig, actor_family: PackedFamily, critic_family: PackedFamily,
@@ -199,6 +207,7 @@ class TD3_base(object):
     def load_agent_state_dict(self, net: str, agent: int, state_dict):
         fam = self._actor_family if net.startswith("actor") else self._critic_family
         fam.load_agent(int(agent), state_dict, which="target" if net.endswith("_target") else "online")
+        self.params_changed()
 
     # ------------------------------------------------------------------ diagnostics (device tensors, no sync)
     @property

@@ -31,6 +31,7 @@ struct DwParams {
   const float* dz; long long dz_go, dz_gi;      // gradient w.r.t. the layer's pre-activation [B, N] (ReLU mask applied)
   const float* x; long long x_go, x_gi;         // the layer's input [B, ldx]
   float* p; float* g; float* m; float* v; float* tgt;    // packed buffers of the family
+  float* p_sh; float* tgt_sh;                    // optional TF32-rounded shadows of p / tgt (tensor-core operands)
   long long p_go, p_gi, w_off, b_off;           // agent stride, twin stride, offsets of W_0 / b_0 inside a network
   const float* sc_ptr;                          // device-resident {step_size, sqrt(1 - beta2^t)} (adam_tick)
 };
@@ -134,7 +135,12 @@ __device__ __forceinline__ void dw_adam_body(const DwParams& D, const EwParams& 
     D.m[pi[j]] = mv[j];
     D.v[pi[j]] = vv[j];
     D.p[pi[j]] = pn;
-    if (D.do_polyak) D.tgt[pi[j]] = __fadd_rn(__fmul_rn(tau, pn), __fmul_rn(omt, tv[j]));
+    if (D.p_sh) D.p_sh[pi[j]] = rn_tf32(pn);
+    if (D.do_polyak) {
+      const float tn = __fadd_rn(__fmul_rn(tau, pn), __fmul_rn(omt, tv[j]));
+      D.tgt[pi[j]] = tn;
+      if (D.tgt_sh) D.tgt_sh[pi[j]] = rn_tf32(tn);
+    }
   }
 }
 

@@ -315,6 +315,7 @@ void finalize_problem(Problem& p, GroupShape gs) {
       };
       p.use_tc = g_tc_mode && p.K >= 64 && !(p.aux1 && p.epi == EPI_STORE) && tma_ok(p.A, p.lda, p.a_go, p.a_gi) &&
                  tma_ok(p.B, p.ldb, p.b_go, p.b_gi) && encode_tiled_fn() != nullptr && !getenv("TD3_NO_TMA");
+      if (!p.use_tc && p.B_master) { p.B = p.B_master; p.B_master = nullptr; }   // FFMA tiles read the fp32 master weights
       if (p.use_tc) {
         p.tiles_m = (p.M + 127) / 128;
         int nt = p.N <= 16 ? 16 : 32;
@@ -567,7 +568,16 @@ struct OutSpec {
 struct ParamRef {   // packed parameters of `n_inner` networks per agent
   const float* base = nullptr;
   long long go = 0, gi = 0;
+  const float* tc = nullptr;   // TF32 mode: round-to-nearest shadow of `base` (same layout) for the tensor-core tiles
 };
+
+// weight matrix at `off` as the B operand of a contraction: the TF32 shadow when there is one (finalize_problem
+// switches back to the master copy if the problem ends up on the FFMA tile)
+void weight_operand(Problem& p, const ParamRef& W, long long off) {
+  p.B = W.base + off;
+  p.B_master = nullptr;
+  if (W.tc) { p.B = W.tc + off; p.B_master = W.base + off; }
+}
 
 struct GradRef {
   float* base = nullptr;
@@ -600,6 +610,12 @@ struct td3_agent {
   PassBuf pb_at, pb_ct, pb_c, pb_a, pb_q1;
   // weight normalisation: effective parameters (W = g v / ||v|| in every weight_v slot) the contractions read
   float *eff_a = nullptr, *eff_at = nullptr, *eff_c = nullptr, *eff_ct = nullptr;
+  // TF32 mode without weight normalisation: round-to-nearest shadows of the four packed parameter buffers, read by the
+  // tensor-core tiles (tcgen05 truncates its operands; a rounded operand is read exactly).  Kept current by the
+  // optimiser kernels (Adam / Polyak / apply write master and shadow together); rebuilt from the masters when the
+  // caller says the parameters changed under us (td3_agent_params_changed) and after every plan.
+  float *sh_a = nullptr, *sh_at = nullptr, *sh_c = nullptr, *sh_ct = nullptr;
+  bool shadow_dirty = true;
   // row-local front kernels (front.cuh): template of the sampling launch (gather + first layers), filled by plan_sample
   bool front_on = false;
   FrontParams front_sample{};
@@ -631,7 +647,7 @@ struct td3_agent {
   StageRec* prog_dev = nullptr;
   long long* prof_dev = nullptr;
   CUtensorMap* tmaps_dev = nullptr;
-  int n_prog_critic = 0, n_prog_policy = 0;
+  int n_prog_critic = 0, n_prog_policy = 0, n_bar_critic = 0, n_bar_policy = 0;
   bool prog_dirty = true;
   int persist_grid = 0;
   int cluster_mode = 1;                      // stage launches use clusters (graph / launches modes); the persistent kernel does not
@@ -663,6 +679,9 @@ std::vector<ProblemList> build_forward(const td3_agent_config& cfg, const td3_ne
   const bool ln = cfg.norm == TD3_NORM_LAYER;
   const bool enc = cfg.variant == TD3_VARIANT_PARTICLES;
   const int L = net.n_linear;
+  // TF32 mode: whatever a later tensor-core contraction reads as an operand is stored rounded to nearest TF32 by its
+  // producer (stage.cuh: Problem::rn_out), and weights come from the rounded shadows (ParamRef::tc)
+  const int tf = g_tc_mode ? 1 : 0;
   if (enc) {
     const int rows = B * cfg.n_particles;
     // conv1 == per-particle linear D -> enc_hidden (TD3_particles.py:29,54)
@@ -671,6 +690,7 @@ std::vector<ProblemList> build_forward(const td3_agent_config& cfg, const td3_ne
     set_groups(e1, pb.P_go, 0, W.go, W.gi, pb.h1_go, pb.h1_gi);
     e1.bias = W.base + net.c1b_off; e1.bias_go = W.go; e1.bias_gi = W.gi;
     if (cfg.particle_dim <= 8) e1.kind = PK_SMALLK_FWD;   // D-long reduction: dedicated HBM-write-bound tile
+    e1.rn_out = tf;
     finalize_problem(e1, gs);
     st.push_back({e1});
     // conv2 (1x1) == linear enc_hidden -> enc_out (:30,56)
@@ -678,6 +698,7 @@ std::vector<ProblemList> build_forward(const td3_agent_config& cfg, const td3_ne
                            net.enc_hidden, true, pb.h2, net.enc_out, EPI_BIAS_RELU);
     set_groups(e2, pb.h1_go, pb.h1_gi, W.go, W.gi, pb.h2_go, pb.h2_gi);
     e2.bias = W.base + net.c2b_off; e2.bias_go = W.go; e2.bias_gi = W.gi;
+    weight_operand(e2, W, net.c2w_off);
     finalize_problem(e2, gs);
     st.push_back({e2});
     // avg_pool over particles + relu, written into the first enc_out columns of the trunk input (:57-59)
@@ -686,6 +707,7 @@ std::vector<ProblemList> build_forward(const td3_agent_config& cfg, const td3_ne
     pl.A = pb.h2; pl.lda = net.enc_out; pl.a_go = pb.h2_go; pl.a_gi = pb.h2_gi;
     pl.C = pb.x0; pl.ldc = pb.ld0; pl.c_go = pb.x0_go; pl.c_gi = pb.x0_gi;
     pl.c_dups = pool_dups; pl.c_dup_stride = pool_dup_stride;
+    pl.rn_out = tf;
     finalize_problem(pl, gs);
     st.push_back({pl});
   }
@@ -701,6 +723,7 @@ std::vector<ProblemList> build_forward(const td3_agent_config& cfg, const td3_ne
     p.C = pb.x0n; p.ldc = pb.ld0; p.c_go = pb.x0n_go; p.c_gi = pb.x0n_gi;
     p.aux2 = pb.mean0; p.aux3 = pb.rstd0; p.aux2_go = p.aux3_go = pb.s_go; p.aux2_gi = p.aux3_gi = pb.s_gi;
     p.f0 = 1e-5f;
+    p.rn_out = tf;
     finalize_problem(p, gs);
     st.push_back({p});
     in = pb.x0n; in_go = pb.x0n_go; in_gi = pb.x0n_gi;
@@ -718,6 +741,10 @@ std::vector<ProblemList> build_forward(const td3_agent_config& cfg, const td3_ne
       g.f0 = out.f0; g.f1 = out.f1;
       g.c_dups = out.dups; g.c_dup_stride = out.dup_stride;
     }
+    weight_operand(g, W, net.w_off[l]);
+    // hidden activations feed the next layer's contraction (through LayerNorm when there is one: then its output is
+    // the operand); an action written into a network input feeds that network's first layer; Q values are results
+    g.rn_out = tf && (last ? out.epi != EPI_BIAS : !ln);
     finalize_problem(g, gs);
     if (!(l == 0 && skip_first)) st.push_back({g});
     if (last) break;
@@ -731,6 +758,7 @@ std::vector<ProblemList> build_forward(const td3_agent_config& cfg, const td3_ne
       p.C = pb.n[l]; p.ldc = N; p.c_go = pb.h_go[l]; p.c_gi = pb.h_gi[l];
       p.aux2 = pb.mean[l]; p.aux3 = pb.rstd[l]; p.aux2_go = p.aux3_go = pb.s_go; p.aux2_gi = p.aux3_gi = pb.s_gi;
       p.f0 = 1e-5f;
+      p.rn_out = tf;
       finalize_problem(p, gs);
       st.push_back({p});
       in = pb.n[l];
@@ -789,6 +817,7 @@ std::vector<ProblemList> build_backward(const td3_agent_config& cfg, const td3_n
   const bool enc = cfg.variant == TD3_VARIANT_PARTICLES;
   const int L = net.n_linear;
   const int groups = gs.n_outer * gs.n_inner;
+  const int tf = g_tc_mode ? 1 : 0;      // gradients w.r.t. activations are operands of the next dW / dX contractions
   const float* dz = dout;
   int ld_dz = ld_dout;
   long long dz_go = dout_go, dz_gi = dout_gi;
@@ -840,6 +869,8 @@ std::vector<ProblemList> build_backward(const td3_agent_config& cfg, const td3_n
                               mask_now ? EPI_RELU_MASK : EPI_STORE);
         set_groups(p, dz_go, dz_gi, W.go, W.gi, sc.go, sc.gi);
         if (mask_now) { p.aux0 = pb.r[l - 1]; p.ldaux = K; p.aux0_go = pb.h_go[l - 1]; p.aux0_gi = pb.h_gi[l - 1]; }
+        weight_operand(p, W, net.w_off[l]);
+        p.rn_out = tf && mask_now;        // with LayerNorm the fp32 LN-backward tile consumes this and rounds its own output
         finalize_problem(p, gs);
         stage.push_back(p);
       }
@@ -855,6 +886,7 @@ std::vector<ProblemList> build_backward(const td3_agent_config& cfg, const td3_n
         rr.aux2 = pb.mean[l - 1]; rr.aux3 = pb.rstd[l - 1];
         rr.aux2_go = rr.aux3_go = pb.s_go; rr.aux2_gi = rr.aux3_gi = pb.s_gi;
         rr.C = sc.dz[pp]; rr.ldc = K; rr.c_go = sc.go; rr.c_gi = sc.gi;
+        rr.rn_out = tf;
         finalize_problem(rr, gs);
         s2.push_back(rr);
         if (want_dw) {
@@ -885,6 +917,8 @@ std::vector<ProblemList> build_backward(const td3_agent_config& cfg, const td3_n
                             dx0.epi);
       set_groups(p, dz_go, dz_gi, W.go, W.gi, dx0.go, dx0.gi);
       p.aux0 = dx0.aux0; p.ldaux = dx0.ldaux; p.aux0_go = dx0.aux0_go; p.aux0_gi = dx0.aux0_gi; p.f0 = dx0.f0;
+      weight_operand(p, W, net.w_off[0] + dx0.col0);
+      p.rn_out = tf;
       finalize_problem(p, gs);
       stage.push_back(p);
       st.push_back(stage);
@@ -895,6 +929,7 @@ std::vector<ProblemList> build_backward(const td3_agent_config& cfg, const td3_n
       const int ldd = lnin ? K : pb.ld0;
       Problem p = make_gemm(B, K, N, dz, ld_dz, true, W.base + net.w_off[0], K, false, dst, ldd, EPI_STORE);
       set_groups(p, dz_go, dz_gi, W.go, W.gi, lnin ? sc.go : sc.dx0_full_go, lnin ? sc.gi : sc.dx0_full_gi);
+      weight_operand(p, W, net.w_off[0]);
       finalize_problem(p, gs);
       stage.push_back(p);
     }
@@ -934,6 +969,7 @@ std::vector<ProblemList> build_backward(const td3_agent_config& cfg, const td3_n
       pbk.aux0 = pb.x0; pbk.ldaux = pb.ld0; pbk.aux0_go = pb.x0_go; pbk.aux0_gi = pb.x0_gi;
       pbk.aux1 = pb.h2; pbk.ldb = O; pbk.aux1_go = pb.h2_go; pbk.aux1_gi = pb.h2_gi;
       pbk.C = sc.dh2; pbk.ldc = O; pbk.c_go = sc.dh2_go; pbk.c_gi = sc.dh2_gi;
+      pbk.rn_out = tf;
       finalize_problem(pbk, gs);
       st.push_back({pbk});
       // conv2: dW2 = dH2^T H1 (split-K over B*N), dH1 = (dH2 W2) * (H1 > 0)
@@ -962,6 +998,8 @@ std::vector<ProblemList> build_backward(const td3_agent_config& cfg, const td3_n
       Problem dx2 = make_gemm(rows, H, O, sc.dh2, O, true, W.base + net.c2w_off, H, false, sc.dh1, H, EPI_RELU_MASK);
       set_groups(dx2, sc.dh2_go, sc.dh2_gi, W.go, W.gi, sc.dh1_go, sc.dh1_gi);
       dx2.aux0 = pb.h1; dx2.ldaux = H; dx2.aux0_go = pb.h1_go; dx2.aux0_gi = pb.h1_gi;
+      weight_operand(dx2, W, net.c2w_off);
+      dx2.rn_out = tf;
       finalize_problem(dx2, gs);
       if (dw2_tc) st.push_back({dw2, dx2, cs2});
       else st.push_back({dw2, dx2});
@@ -1093,9 +1131,10 @@ Problem make_slice(int B, int ncols, const float* in, int ld_in, const float* ey
 
 // ---- row-local front kernels (front.cuh) ----
 // first layer of `net` as a front job: out = relu(x[:, :K] W_0^T + b_0) into the pass's r[0]
-FrontNet front_first_layer(const td3_net_layout& net, ParamRef W, int n_inner, const PassBuf& pb) {
+FrontNet front_first_layer(const td3_net_layout& net, ParamRef W, int n_inner, const PassBuf& pb, int rn_out = 0) {
   FrontNet n;
   memset(&n, 0, sizeof(n));
+  n.rn_out = rn_out;
   n.W = W.base + net.w_off[0]; n.bias = W.base + net.b_off[0]; n.w_go = W.go; n.w_gi = W.gi;
   n.ws_c = net.dims[0]; n.ws_k = 1;
   n.out = pb.r[0]; n.out_go = pb.h_go[0]; n.out_gi = pb.h_gi[0]; n.ldo = net.dims[1];
@@ -1160,6 +1199,7 @@ bool make_wn_launch(const td3_agent_config& c, int mode, std::initializer_list<W
   WnParams& P = L.wn;
   memset(&P, 0, sizeof(P));
   P.mode = mode; P.rows_per_tile = 8;
+  P.rn_out = (mode == 0 && g_tc_mode) ? 1 : 0;
   if (!make_wn_layout(c.actor, mode == 0, P.lay[0]) || !make_wn_layout(c.q, mode == 0, P.lay[1])) return false;
   int tiles = 0;
   for (const WnJobSpec& j : jobs) {
@@ -1254,6 +1294,14 @@ int plan_agent(td3_agent* a, long long batch) {
     a->eff_c = ws.take((long long)nA * nq * c.q.n_floats, "effective_critic");
     a->eff_ct = ws.take((long long)nA * nq * c.q.n_floats, "effective_critic_target");
   }
+  const bool tf = g_tc_mode != 0;
+  a->sh_a = a->sh_at = a->sh_c = a->sh_ct = nullptr;
+  if (tf && !wn) {
+    a->sh_a = ws.take((long long)nA * c.actor.n_floats, "tf32_actor");
+    a->sh_at = ws.take((long long)nA * c.actor.n_floats, "tf32_actor_target");
+    a->sh_c = ws.take((long long)nA * nq * c.q.n_floats, "tf32_critic");
+    a->sh_ct = ws.take((long long)nA * nq * c.q.n_floats, "tf32_critic_target");
+  }
   a->prof_dev = reinterpret_cast<long long*>(ws.take(2LL * 2 * 128 * 3, "prof"));
   a->tmaps_dev = reinterpret_cast<CUtensorMap*>(ws.take((long long)kMaxTensorMaps * (long long)(sizeof(CUtensorMap) / 4), "tensor_maps"));
   a->prog_dev = reinterpret_cast<StageRec*>(ws.take(2LL * kMaxProgStages * (long long)(sizeof(StageRec) / 4), "program"));
@@ -1295,9 +1343,9 @@ int plan_agent(td3_agent* a, long long batch) {
   const float* pat_w = wn ? a->eff_at : a->actor.target;
   const float* pc_w = wn ? a->eff_c : a->critic.params;
   const float* pct_w = wn ? a->eff_ct : a->critic.target;
-  ParamRef Wa{pa_w, an, 0}, Wat{pat_w, an, 0};
-  ParamRef Wc{pc_w, qn * nq, qn}, Wct{pct_w, qn * nq, qn};
-  ParamRef Wq1{pc_w, qn * nq, 0};
+  ParamRef Wa{pa_w, an, 0, a->sh_a}, Wat{pat_w, an, 0, a->sh_at};
+  ParamRef Wc{pc_w, qn * nq, qn, a->sh_c}, Wct{pct_w, qn * nq, qn, a->sh_ct};
+  ParamRef Wq1{pc_w, qn * nq, 0, a->sh_c};
   GradRef Ga{a->actor.grad, an, 0}, Gc{a->critic.grad, qn * nq, qn};
 
   a->seq_sample.clear(); a->seq_target.clear(); a->seq_critic_fb.clear(); a->seq_critic_apply.clear();
@@ -1314,10 +1362,13 @@ int plan_agent(td3_agent* a, long long batch) {
     return n.n_linear >= 2 && n.dims[0] <= kDwMaxK && (n.dims[1] & 3) == 0 && n.w_off[0] == 0 && (n.w_off[1] & 3) == 0 &&
            n.b_off[0] >= (long long)n.dims[0] * n.dims[1] && n.w_off[1] >= n.b_off[0] + n.dims[1] && (n.n_floats & 3) == 0;
   };
-  const bool fuse_tail = front && !ln && !wn && a->cluster_mode && l0_fusable(c.q) && l0_fusable(c.actor) && (ld_q & 3) == 0 &&
+  const bool fuse_tail = front && !ln && !wn && l0_fusable(c.q) && l0_fusable(c.actor) && (ld_q & 3) == 0 &&
                          Lq >= 2 && qw <= kHeadMaxQw && c.q.dims[Lq - 1] <= kHeadMaxW && !getenv("TD3_NO_HEAD_FUSION") &&
                          !getenv("TD3_NO_TAIL_FUSION");
   a->tail_fused = fuse_tail;
+  // first-layer outputs of the front kernels feed the second layers' tensor-core tiles (through LayerNorm when on,
+  // whose own output is then the rounded operand)
+  const int rn_front = tf && !ln ? 1 : 0;
   std::vector<Launch> v_cb, v_abf, v_tp;     // fused-mode pieces: critic head + backward, actor backward, target pass + actor forward
   std::vector<ProblemList> s_abf;
   Dz0Info dz0_c, dz0_a;
@@ -1329,9 +1380,9 @@ int plan_agent(td3_agent* a, long long batch) {
     memset(&F, 0, sizeof(F));
     F.gather = 1; F.A = A;
     F.n_nets = 2;
-    F.net[0] = front_first_layer(c.q, Wc, nq, cc);      // x_off 0 first: job 0 stages (and scatters) the whole row
+    F.net[0] = front_first_layer(c.q, Wc, nq, cc, rn_front);      // x_off 0 first: job 0 stages (and scatters) the whole row
     F.net[0].x_off = 0;
-    F.net[1] = front_first_layer(c.actor, Wat, 1, at);
+    F.net[1] = front_first_layer(c.actor, Wat, 1, at, rn_front);
     F.net[1].x_off = S + A;
     front_finish(L, B, nA);
     a->front_sample = F;
@@ -1376,7 +1427,7 @@ int plan_agent(td3_agent* a, long long batch) {
       F.a_out = a->xq2 + S; F.a_go = a->xq_go; F.a_ld = ld_q;
       F.f0 = o.f0; F.f1 = o.f1;
       F.n_nets = 1;
-      F.net[0] = front_first_layer(c.q, Wct, nq, ct);
+      F.net[0] = front_first_layer(c.q, Wct, nq, ct, rn_front);
       F.net[0].x = a->xq2; F.net[0].x_go = a->xq_go; F.net[0].ldx = ld_q; F.net[0].x_off = 0; F.net[0].act_col = S;
       front_finish(L, B, nA);
       a->seq_target.push_back(L);
@@ -1395,6 +1446,7 @@ int plan_agent(td3_agent* a, long long batch) {
     lp.discount = c.discount;
     lp.inv_norm = 1.f / (float)((a->global_batch > 0 ? a->global_batch : batch) * qw);
     lp.tick = AdamTick{a->state_u64, 0, 0, c.lr_critic, c.beta1, c.beta2};
+    lp.rn_out = tf ? 1 : 0;
     if (fuse_heads) {       // both heads + loss + head backward in one launch
       const float inv_norm = lp.inv_norm;
       const AdamTick tick = lp.tick;
@@ -1415,6 +1467,7 @@ int plan_agent(td3_agent* a, long long batch) {
       H.part = head_part; H.part_go = head_part_go; H.counter = head_counter; H.loss = a->state_f32;
       H.batch = B; H.w = wq_last; H.qw = qw; H.n_q = nq; H.ldh = wq_last; H.lddz = wq_last; H.n_cta = head_ctas;
       H.mode = 0; H.relu_mask = ln ? 0 : 1; H.skip_dw = head_dw_in_stage ? 1 : 0;
+      H.rn_out = tf ? 1 : 0;
       H.discount = c.discount; H.inv_norm = inv_norm; H.tick = tick;
       H.host_status = a->host_status_live ? a->host_status : nullptr; H.seq = head_seq;
       L.grid_x = nA * head_ctas;
@@ -1449,6 +1502,7 @@ int plan_agent(td3_agent* a, long long batch) {
     EwRange& r = e.r[0];
     r.p = a->critic.params; r.g = a->critic.grad; r.m = a->critic.exp_avg; r.v = a->critic.exp_avg_sq; r.tgt = nullptr;
     r.n = qn * nq * nA; r.blk_begin = 0; r.sc_ptr = reinterpret_cast<const float*>(a->state_u64 + 10); r.do_adam = 1; r.do_polyak = 0;
+    r.p_sh = a->sh_c;
     L.grid_x = (int)((r.n + kEwPerBlock - 1) / kEwPerBlock);
     a->seq_critic_apply.push_back(L);
   }
@@ -1482,7 +1536,7 @@ int plan_agent(td3_agent* a, long long batch) {
       F.a_out = a->xpi + S; F.a_go = a->xpi_go; F.a_ld = ld_q;
       F.f0 = o.f0;
       F.n_nets = 1;
-      F.net[0] = front_first_layer(c.q, Wq1, 1, q1);
+      F.net[0] = front_first_layer(c.q, Wq1, 1, q1, rn_front);
       F.net[0].x = a->xpi; F.net[0].x_go = a->xpi_go; F.net[0].ldx = ld_q; F.net[0].x_off = 0; F.net[0].act_col = S;
       front_finish(L, B, nA);
       a->seq_actor_fb.push_back(L);
@@ -1502,6 +1556,7 @@ int plan_agent(td3_agent* a, long long batch) {
       H.part = head_part + nA * head_part_go; H.part_go = head_part_go; H.counter = head_counter + nA; H.loss = a->state_f32 + nA;
       H.batch = B; H.w = wq_last; H.qw = qw; H.n_q = 1; H.ldh = wq_last; H.lddz = wq_last; H.n_cta = head_ctas;
       H.mode = 1; H.relu_mask = ln ? 0 : 1;
+      H.rn_out = tf ? 1 : 0;
       H.inv_norm = 1.f / (float)((a->global_batch > 0 ? a->global_batch : batch) * qw);
       H.tick = AdamTick{a->state_u64, 1, 0, c.lr_actor, c.beta1, c.beta2};
       L.grid_x = nA * head_ctas;
@@ -1547,6 +1602,7 @@ int plan_agent(td3_agent* a, long long batch) {
         n.out = sc_a.dz[0]; n.out_go = sc_a.go; n.out_gi = sc_a.gi; n.ldo = c.actor.dims[La - 1];
         n.mask = pa.r[La - 2]; n.mask_go = pa.h_go[La - 2]; n.mask_gi = pa.h_gi[La - 2];
         n.K = A; n.N = c.actor.dims[La - 1]; n.n_inner = 1; n.act_col = 0;
+        n.rn_out = tf ? 1 : 0;
         front_finish(L, B, nA);
         a->seq_actor_fb.push_back(L);
       }
@@ -1555,6 +1611,7 @@ int plan_agent(td3_agent* a, long long batch) {
         Problem sl = make_slice(B, A, sc_q1.dx0_full + E + S, ld_q, eye, da, A, EPI_TANH_GRAD);
         set_groups(sl, sc_q1.dx0_full_go, 0, 0, 0, (long long)B * A, 0);
         sl.aux0 = a->tanh_y; sl.ldaux = A; sl.aux0_go = (long long)B * A; sl.f0 = 1.f;
+        sl.rn_out = tf ? 1 : 0;
         finalize_problem(sl, g_q1);
         emit_stage(a->seq_actor_fb, {sl});
       }
@@ -1592,11 +1649,13 @@ int plan_agent(td3_agent* a, long long batch) {
     EwRange& r0 = e.r[0];
     r0.p = a->critic.params; r0.tgt = a->critic.target; r0.n = qn * nq * nA; r0.blk_begin = 0;
     r0.do_adam = 0; r0.do_polyak = 1;
+    r0.tgt_sh = a->sh_ct;
     const long long b0 = (r0.n + kEwPerBlock - 1) / kEwPerBlock;
     EwRange& r1 = e.r[1];
     r1.p = a->actor.params; r1.g = a->actor.grad; r1.m = a->actor.exp_avg; r1.v = a->actor.exp_avg_sq;
     r1.tgt = a->actor.target; r1.n = an * nA; r1.blk_begin = b0; r1.sc_ptr = reinterpret_cast<const float*>(a->state_u64 + 11);
     r1.do_adam = 1; r1.do_polyak = 1;
+    r1.p_sh = a->sh_a; r1.tgt_sh = a->sh_at;
     L.grid_x = (int)(b0 + (r1.n + kEwPerBlock - 1) / kEwPerBlock);
     a->seq_actor_apply.push_back(L);
   }
@@ -1625,7 +1684,7 @@ int plan_agent(td3_agent* a, long long batch) {
       Launch m = L;
       if (L.kind == Launch::FRONT && ai == 0 && a->n_actor_fwd >= 1 && L.front.n_nets < kFrontMaxNets && !L.front.gather) {
         FrontNet& n = m.front.net[m.front.n_nets++];
-        n = front_first_layer(c.actor, Wa, 1, pa);
+        n = front_first_layer(c.actor, Wa, 1, pa, rn_front);
         n.x = a->xpi; n.x_go = a->xpi_go; n.ldx = ld_q; n.x_off = 0; n.act_col = -1;
         front_finish(m, B, nA);
         l1_in_front = true;
@@ -1654,7 +1713,7 @@ int plan_agent(td3_agent* a, long long batch) {
   };
   if (fuse_tail) {
     auto fill_dw = [&](DwParams& D, const td3_net_layout& n, const Dz0Info& z, const PassBuf& pb, const td3_param_set& ps,
-                       int n_inner, long long net_floats, const float* sc_ptr, bool polyak) {
+                       int n_inner, long long net_floats, const float* sc_ptr, bool polyak, float* sh, float* sh_t) {
       memset(&D, 0, sizeof(D));
       D.batch = B; D.n_agents = nA; D.n_inner = n_inner; D.N = n.dims[1]; D.K = n.dims[0];
       D.col_blocks = (D.N + kDwCols - 1) / kDwCols;
@@ -1663,15 +1722,16 @@ int plan_agent(td3_agent* a, long long batch) {
       D.x = pb.x0; D.ldx = pb.ld0; D.x_go = pb.x0_go; D.x_gi = pb.x0_gi;
       D.p = ps.params; D.g = ps.grad; D.m = ps.exp_avg; D.v = ps.exp_avg_sq; D.tgt = polyak ? ps.target : nullptr;
       D.do_polyak = polyak ? 1 : 0;
+      D.p_sh = sh; D.tgt_sh = polyak ? sh_t : nullptr;
       D.p_go = net_floats * n_inner; D.p_gi = net_floats; D.w_off = n.w_off[0]; D.b_off = n.b_off[0];
       D.sc_ptr = sc_ptr;
     };
     Launch apply_c = a->seq_critic_apply[0];
     apply_c.ew.r[0].skip_period = qn; apply_c.ew.r[0].skip_len = c.q.w_off[1];
-    fill_dw(apply_c.dw, c.q, dz0_c, cc, a->critic, nq, qn, reinterpret_cast<const float*>(a->state_u64 + 10), false);
+    fill_dw(apply_c.dw, c.q, dz0_c, cc, a->critic, nq, qn, reinterpret_cast<const float*>(a->state_u64 + 10), false, a->sh_c, a->sh_ct);
     Launch apply_a = a->seq_actor_apply[0];
     apply_a.ew.r[1].skip_period = an; apply_a.ew.r[1].skip_len = c.actor.w_off[1];
-    fill_dw(apply_a.dw, c.actor, dz0_a, pa, a->actor, 1, an, reinterpret_cast<const float*>(a->state_u64 + 11), true);
+    fill_dw(apply_a.dw, c.actor, dz0_a, pa, a->actor, 1, an, reinterpret_cast<const float*>(a->state_u64 + 11), true, a->sh_a, a->sh_at);
     if (!dz0_c.dz || !dz0_a.dz || (dz0_c.ld & 3) || (dz0_a.ld & 3))
       return fail(TD3_ERR_STATE, "tail fusion: first-layer gradient not located");
     append(a->seq_run_critic, a->seq_target);
@@ -1703,6 +1763,7 @@ int plan_agent(td3_agent* a, long long batch) {
   a->plan_rows = nullptr;
   a->plan_rng_mode = -1;
   a->prog_dirty = true;
+  a->shadow_dirty = true;
   drop_graphs(a);
   return TD3_OK;
 }
@@ -1729,8 +1790,13 @@ int plan_sample(td3_agent* a, const td3_replay_view* rb, int rng_mode) {
   G.policy_noise = c.policy_noise; G.noise_clip = c.noise_clip;
   G.elem_offset = (int)a->batch_offset;
   int n = 0;
-  auto seg = [&](int off, int len, float* dst, int ld, long long astride) {
-    G.seg_off[n] = off; G.seg_len[n] = len; G.dst[n] = dst; G.dst_ld[n] = ld; G.dst_agent_stride[n] = astride; ++n;
+  // TF32 mode, plain gather launch: the network inputs (not the particle sets, rewards or flags) are operands of
+  // tensor-core first layers -> stored rounded to nearest TF32.  The front kernel's first layers are fp32 FFMA.
+  const bool rn_inputs = c.precision == TD3_PRECISION_TF32 && !a->front_on;
+  auto seg = [&](int off, int len, float* dst, int ld, long long astride, bool net_input = true) {
+    G.seg_off[n] = off; G.seg_len[n] = len; G.dst[n] = dst; G.dst_ld[n] = ld; G.dst_agent_stride[n] = astride;
+    if (net_input && rn_inputs && n < 32) G.seg_rn |= 1u << n;
+    ++n;
   };
   const int xq_inner = enc ? nq : 1;
   if (!enc) {
@@ -1739,8 +1805,8 @@ int plan_sample(td3_agent* a, const td3_replay_view* rb, int rng_mode) {
     seg(0, S, a->xpi, ld_q, a->xpi_go);
     seg(S, A, a->xq + S, ld_q, a->xq_go);
     seg(S + A, S, a->xq2, ld_q, a->xq_go);
-    seg(2 * S + A, 1, a->r, 1, B);
-    seg(2 * S + A + 1, 1, a->nd, 1, B);
+    seg(2 * S + A, 1, a->r, 1, B, false);
+    seg(2 * S + A + 1, 1, a->nd, 1, B, false);
   } else {
     // row = [f | particles | a | f2 | particles2 | r | nd]
     const int PN = c.n_particles * c.particle_dim;
@@ -1751,10 +1817,10 @@ int plan_sample(td3_agent* a, const td3_replay_view* rb, int rng_mode) {
     for (int g = 0; g < xq_inner; ++g) seg(o_a, A, a->xq + g * a->xq_gi + E + S, ld_q, a->xq_go);
     seg(o_f2, S, a->xa2 + E, ld_a, a->xa_go);
     for (int g = 0; g < xq_inner; ++g) seg(o_f2, S, a->xq2 + g * a->xq_gi + E, ld_q, a->xq_go);
-    seg(o_p, PN, a->P, PN, (long long)B * PN);
-    seg(o_p2, PN, a->P2, PN, (long long)B * PN);
-    seg(o_r, 1, a->r, 1, B);
-    seg(o_r + 1, 1, a->nd, 1, B);
+    seg(o_p, PN, a->P, PN, (long long)B * PN, false);
+    seg(o_p2, PN, a->P2, PN, (long long)B * PN, false);
+    seg(o_r, 1, a->r, 1, B, false);
+    seg(o_r + 1, 1, a->nd, 1, B, false);
   }
   if (n > kMaxSeg) return fail(TD3_ERR_INVALID, "too many gather segments (%d)", n);
   G.n_seg = n;
@@ -1805,6 +1871,7 @@ int append_records(std::vector<StageRec>& prog, const std::vector<Launch>& seq, 
         break;
       case Launch::EW:
         r.kind = SK_EW_ONLY; r.ew = L.ew; r.ew_tiles = L.grid_x;
+        if (L.dw.n_tiles > 0) { r.kind = SK_APPLY; r.u.d = L.dw; r.main_tiles = L.dw.n_tiles; }
         break;
       case Launch::HEAD:
         r.kind = SK_HEAD; r.u.h = L.head; r.main_tiles = L.grid_x;
@@ -1826,15 +1893,21 @@ int build_programs(td3_agent* a, cudaStream_t s) {
   if (!a->prog_dirty) return TD3_OK;
   std::vector<StageRec> pc, pp;
   AdamTick pend{};
-  for (auto* seq : {&a->seq_sample, &a->seq_target, &a->seq_critic_fb, &a->seq_critic_apply}) append_records(pc, *seq, &pend);
-  for (auto* seq : {&a->seq_sample, &a->seq_target, &a->seq_policy_mid}) append_records(pp, *seq, &pend);
-  append_records(pp, a->seq_actor_apply, &pend);
+  // the same sequences the CUDA graphs replay (tail-fused where the plan allows it)
+  for (auto* seq : {&a->seq_sample, &a->seq_run_critic}) append_records(pc, *seq, &pend);
+  for (auto* seq : {&a->seq_sample, &a->seq_run_policy}) append_records(pp, *seq, &pend);
   if (pc.empty() || pp.empty() || (int)pc.size() > kMaxProgStages || (int)pp.size() > kMaxProgStages)
     return fail(TD3_ERR_STATE, "persistent program has %zu / %zu stages (max %d)", pc.size(), pp.size(), kMaxProgStages);
-  // the stage after the last one of an update is the next update's gather, which touches nothing the
-  // optimiser stage touches: no barrier between them (the one after the gather covers the parameters)
-  pc.back().barrier_after = 0;
-  pp.back().barrier_after = 0;
+  // When the first stage of an update is a plain gather it touches nothing the optimiser stage before it writes (the
+  // barrier after the gather covers the parameters): no barrier between updates.  A front sampling stage also runs
+  // first layers, i.e. it READS parameters the previous update's optimiser stage is still writing on other CTAs.
+  if (pc.front().kind == SK_GATHER) {
+    pc.back().barrier_after = 0;
+    pp.back().barrier_after = 0;
+  }
+  a->n_bar_critic = a->n_bar_policy = 0;
+  for (auto& r : pc) a->n_bar_critic += r.barrier_after;
+  for (auto& r : pp) a->n_bar_policy += r.barrier_after;
   CUDA_TRY(cudaMemcpyAsync(a->prog_dev, pc.data(), pc.size() * sizeof(StageRec), cudaMemcpyHostToDevice, s));
   CUDA_TRY(cudaMemcpyAsync(a->prog_dev + kMaxProgStages, pp.data(), pp.size() * sizeof(StageRec), cudaMemcpyHostToDevice, s));
   a->n_prog_critic = (int)pc.size();
@@ -1877,7 +1950,7 @@ int launch_persistent(td3_agent* a, long long total_it, int iterations, cudaStre
   {   // barriers this launch will execute: one per stage except the last of every update
     const long long pf = a->cfg.policy_freq;
     const long long n_pol = (total_it + iterations) / pf - total_it / pf;
-    const long long n_bar = n_pol * (a->n_prog_policy - 1) + ((long long)iterations - n_pol) * (a->n_prog_critic - 1);
+    const long long n_bar = n_pol * a->n_bar_policy + ((long long)iterations - n_pol) * a->n_bar_critic;
     bar_add = (unsigned int)(n_bar * a->persist_grid);
   }
   static const bool want_prof = getenv("TD3_PERSIST_PROF") != nullptr;
@@ -1904,6 +1977,31 @@ int run_seq(const std::vector<Launch>& seq, cudaStream_t s) {
 }
 
 __global__ void set_u64_kernel(unsigned long long* p, unsigned long long v) { *p = v; }
+
+// TF32 shadows of the parameters: rebuilt from the masters whenever they may have changed outside the optimiser kernels
+int ensure_shadows(td3_agent* a, cudaStream_t s) {
+  if (!a->shadow_dirty) return TD3_OK;
+  if (a->sh_a && a->ws.base) {
+    const td3_agent_config& c = a->cfg;
+    const long long an = (long long)c.n_agents * c.actor.n_floats, cn = (long long)c.n_agents * c.n_q * c.q.n_floats;
+    RoundCopyParams R;
+    memset(&R, 0, sizeof(R));
+    const float* src[4] = {a->actor.params, a->actor.target, a->critic.params, a->critic.target};
+    float* dst[4] = {a->sh_a, a->sh_at, a->sh_c, a->sh_ct};
+    const long long n[4] = {an, an, cn, cn};
+    long long blk = 0;
+    for (int i = 0; i < 4; ++i) {
+      R.src[i] = src[i]; R.dst[i] = dst[i]; R.n[i] = n[i]; R.blk_begin[i] = blk;
+      blk += (n[i] + kEwPerBlock - 1) / kEwPerBlock;
+    }
+    R.n_ranges = 4;
+    round_copy_kernel<<<(unsigned)blk, kEwThreads, 0, s>>>(R);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    CUDA_TRY(cudaGetLastError());
+  }
+  a->shadow_dirty = false;
+  return TD3_OK;
+}
 
 int check_ready(td3_agent* a, bool need_plan = true) {
   if (!a) return fail(TD3_ERR_INVALID, "null agent");
@@ -2175,6 +2273,12 @@ int td3_agent_bind_host_status(td3_agent* a, void* host_words) {
 
 int td3_agent_host_status_live(const td3_agent* a) { return a && a->host_status_live ? 1 : 0; }
 
+int td3_agent_params_changed(td3_agent* a) {
+  if (!a) return fail(TD3_ERR_INVALID, "td3_agent_params_changed: null agent");
+  a->shadow_dirty = true;
+  return TD3_OK;
+}
+
 int64_t td3_agent_workspace_floats(const td3_agent* agent, int64_t batch) {
   if (!agent || batch <= 0) return -1;
   td3_agent tmp;
@@ -2222,17 +2326,20 @@ int td3_sample_batch(td3_agent* a, const td3_replay_view* rb, int32_t rng_mode, 
   if (rc == TD3_OK) rc = check_rb(a, rb);
   if (rc == TD3_OK) rc = plan_sample(a, rb, rng_mode);
   if (rc == TD3_OK) rc = sync_rb_size(a, rb, (cudaStream_t)stream);
+  if (rc == TD3_OK) rc = ensure_shadows(a, (cudaStream_t)stream);
   if (rc == TD3_OK) rc = run_seq(a->seq_sample, (cudaStream_t)stream);
   return rc;
 }
 
 int td3_target_step(td3_agent* a, void* stream) {
   int rc = check_ready(a);
+  if (rc == TD3_OK) rc = ensure_shadows(a, (cudaStream_t)stream);
   return rc == TD3_OK ? run_seq(a->seq_target, (cudaStream_t)stream) : rc;
 }
 
 int td3_critic_step(td3_agent* a, int32_t apply, void* stream) {
   int rc = check_ready(a);
+  if (rc == TD3_OK) rc = ensure_shadows(a, (cudaStream_t)stream);
   if (rc == TD3_OK) rc = run_seq(a->seq_critic_fb, (cudaStream_t)stream);
   if (rc == TD3_OK && apply) rc = run_seq(a->seq_critic_apply, (cudaStream_t)stream);
   return rc;
@@ -2245,6 +2352,7 @@ int td3_critic_apply(td3_agent* a, void* stream) {
 
 int td3_actor_step(td3_agent* a, int32_t apply, void* stream) {
   int rc = check_ready(a);
+  if (rc == TD3_OK) rc = ensure_shadows(a, (cudaStream_t)stream);
   if (rc == TD3_OK) rc = run_seq(a->seq_actor_fb, (cudaStream_t)stream);
   if (rc == TD3_OK && apply) rc = run_seq(a->seq_actor_apply, (cudaStream_t)stream);
   return rc;
@@ -2275,6 +2383,7 @@ int td3_train_n(td3_agent* a, const td3_replay_view* rb, int64_t total_it, int32
   }
   rc = plan_sample(a, rb, rng_mode);
   if (rc == TD3_OK) rc = sync_rb_size(a, rb, s);
+  if (rc == TD3_OK) rc = ensure_shadows(a, s);
   if (rc != TD3_OK) return rc;
   if (use_graph == 2) {            // persistent kernel: all `iterations` updates in cooperative launches
     rc = build_programs(a, s);
@@ -2325,6 +2434,7 @@ int td3_debug_prefix_times(td3_agent* a, const td3_replay_view* rb, int32_t with
   if (!a->cap_stream) CUDA_TRY(cudaStreamCreateWithFlags(&a->cap_stream, cudaStreamNonBlocking));
   cudaStream_t s = a->cap_stream;
   rc = sync_rb_size(a, rb, s);
+  if (rc == TD3_OK) rc = ensure_shadows(a, s);
   if (rc != TD3_OK) return rc;
   std::vector<Launch> all = a->seq_sample;
   for (const Launch& L : (with_actor ? a->seq_run_policy : a->seq_run_critic)) all.push_back(L);

@@ -52,6 +52,7 @@ struct FrontNet {
   int ldo, K, N, n_inner;
   int act_col;               // >= 0: input columns [act_col, act_col + A) are the head's output
   int job_begin, col_blocks;
+  int rn_out, pad_n;         // out stored rounded to nearest TF32 (operand of a tensor-core contraction)
 };
 
 struct FrontParams {
@@ -250,7 +251,8 @@ __device__ __forceinline__ void front_body(const FrontParams& P, int tile, float
             v = fmaf(x4.z, w[4 * k4 + 2], v);
             v = fmaf(x4.w, w[4 * k4 + 3], v);
           }
-        out[o] = mask ? (m > 0.f ? v : 0.f) : fmaxf(v, 0.f);
+        const float ov = mask ? (m > 0.f ? v : 0.f) : fmaxf(v, 0.f);
+        out[o] = N.rn_out ? rn_tf32(ov) : ov;
       }
     }
   }

@@ -12,6 +12,15 @@ namespace td3 {
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
 
+// fp32 -> nearest TF32-representable fp32 (10 mantissa bits, ties away from zero).  tcgen05 kind::tf32 reads only the
+// upper 19 bits of an operand word, i.e. it TRUNCATES; an operand stored through this function is read exactly, so
+// the contraction sees round-to-nearest operands (unbiased, half the worst-case error) at no cost in the GEMM itself.
+__device__ __forceinline__ float rn_tf32(float x) {
+  unsigned int u;
+  asm("cvt.rna.tf32.f32 %0, %1;\n" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
+
 // ------------------------------------------------------------------------------------
 // Philox4x32-10 (Salmon et al., SC'11).  Counter-based: every draw is a pure function of
 // (seed, stream, step, element), so a captured CUDA graph replays correctly from a
@@ -90,6 +99,7 @@ struct GatherParams {
   const float* noise_in;          // N(0,1) draws (injected mode), same shape
   int action_dim, slices;         // slices = gridDim.y
   int elem_offset, row_floats;    // data-parallel shard: local row b is element b + elem_offset of the global batch
+  unsigned int seg_rn, pad_g;     // bit s: segment s feeds a tensor-core contraction -> stored rounded to nearest TF32
   float policy_noise, noise_clip;
 };
 
@@ -134,11 +144,22 @@ __device__ __forceinline__ void gather_row(const GatherParams& G, int agent, int
       const int lo = slice * per, hi = min(n4, lo + per);
       const float4* s4 = reinterpret_cast<const float4*>(sp);
       float4* d4 = reinterpret_cast<float4*>(d);
-      for (int i = lo + lane; i < hi; i += 32) d4[i] = __ldg(s4 + i);
+      if ((G.seg_rn >> s) & 1u) {
+        for (int i = lo + lane; i < hi; i += 32) {
+          const float4 v = __ldg(s4 + i);
+          d4[i] = make_float4(rn_tf32(v.x), rn_tf32(v.y), rn_tf32(v.z), rn_tf32(v.w));
+        }
+      } else {
+        for (int i = lo + lane; i < hi; i += 32) d4[i] = __ldg(s4 + i);
+      }
     } else {
       const int per = (len + G.slices - 1) / G.slices;
       const int lo = slice * per, hi = min(len, lo + per);
-      for (int i = lo + lane; i < hi; i += 32) d[i] = __ldg(sp + i);
+      const bool rn = (G.seg_rn >> s) & 1u;
+      for (int i = lo + lane; i < hi; i += 32) {
+        const float v = __ldg(sp + i);
+        d[i] = rn ? rn_tf32(v) : v;
+      }
     }
   }
 }
@@ -226,6 +247,7 @@ struct LossParams {
   long long q_gi, q_go;            // strides between twins / agents in q, tq, dq
   long long y_go, r_go;
   float discount, inv_norm;        // inv_norm = 1 / (global_batch * width)
+  int rn_out, pad_l;               // dq stored rounded to nearest TF32 (operand of tensor-core contractions)
   AdamTick tick;                   // critic optimiser step (and [0] sample step += 1) done here by one thread
 };
 
@@ -247,7 +269,8 @@ __device__ __forceinline__ void loss_body(const LossParams& L, int agent, float*
     y[o] = yy;
     for (int g = 0; g < L.n_q; ++g) {
       const float d = __ldcg(q + g * L.q_gi + o) - yy;
-      dq[g * L.q_gi + o] = 2.f * L.inv_norm * d;
+      const float dqv = 2.f * L.inv_norm * d;
+      dq[g * L.q_gi + o] = L.rn_out ? rn_tf32(dqv) : dqv;
       acc = fmaf(d, d, acc);
     }
   }
@@ -302,6 +325,7 @@ struct HeadParams {
   float* loss;                                // loss[agent]
   int batch, w, qw, n_q, ldh, lddz, n_cta, mode, relu_mask;
   int skip_dw;                                // 1: dW/db of the head are a GEMM problem of the next stage (from dq and h)
+  int rn_out;                                 // dz / dq stored rounded to nearest TF32 (operands of tensor-core contractions)
   float discount, inv_norm;
   AdamTick tick;                              // critic optimiser tick + sampling step (mode 0), done by the finishing CTA
   // optional host mirror of the loss (mode 0): the finishing CTA of agent i bumps seq[i] and stores the 8-byte word
@@ -435,7 +459,7 @@ __device__ __forceinline__ void head_body_t(const HeadParams& H, int tile, float
             dqv[j] = -H.inv_norm;
             pair_loss += d;
           }
-          if (lane == 0 && H.dq) H.dq[qo] = dqv[j];
+          if (lane == 0 && H.dq) H.dq[qo] = H.rn_out ? rn_tf32(dqv[j]) : dqv[j];
         }
       }
       float* dzr = H.dz + agent * H.dz_go + g * H.dz_gi + (size_t)row * H.lddz;
@@ -450,7 +474,8 @@ __device__ __forceinline__ void head_body_t(const HeadParams& H, int tile, float
               sacc = fmaf(dqv[j], Ws[(g * qw + j) * w + k], sacc);
               if (want_dw) red[(rl * nq + g) * per_g + j * w + k] = dqv[j] * hv[i];
             }
-          dzr[k] = (H.relu_mask && !(hv[i] > 0.f)) ? 0.f : sacc;
+          const float dzv = (H.relu_mask && !(hv[i] > 0.f)) ? 0.f : sacc;
+          dzr[k] = H.rn_out ? rn_tf32(dzv) : dzv;
         }
       }
       if (want_dw && lane < qw) {
@@ -581,6 +606,7 @@ struct WnJob {
 
 struct WnParams {
   int mode, n_jobs, rows_per_tile, total_tiles;
+  int rn_out, pad_w;      // mode 0: effective weights stored rounded to nearest TF32 (tensor-core operands)
   WnJob job[kWnMaxJobs];
   WnLayout lay[2];
 };
@@ -630,7 +656,10 @@ __device__ __forceinline__ void wn_body(const WnParams& P, int tile) {
   const float nrm = sqrtf(ss);
   if (P.mode == 0) {
     const float sc = g / nrm;
-    for (int k = lane; k < K; k += 32) o[k] = v[k] * sc;
+    for (int k = lane; k < K; k += 32) {
+      const float w = v[k] * sc;
+      o[k] = P.rn_out ? rn_tf32(w) : w;
+    }
   } else {
     const float dg = dot / nrm, sc = g / nrm, back = dg / nrm;
     for (int k = lane; k < K; k += 32) o[k] = sc * (o[k] - back * v[k]);
@@ -662,6 +691,7 @@ __global__ void adam_tick_kernel(const __grid_constant__ AdamTick T) {
 // ------------------------------------------------------------------------------------
 struct EwRange {
   float* p; const float* g; float* m; float* v; float* tgt;
+  float* p_sh; float* tgt_sh;        // optional TF32-rounded shadows of p / tgt (what the tensor-core contractions read)
   long long n, blk_begin;
   const float* sc_ptr;               // device-resident {step_size, sqrt(1 - beta2^t)} written by adam_tick, or
   float step_size, bc2_sqrt;         // host-supplied scalars when sc_ptr == nullptr
@@ -736,12 +766,43 @@ __device__ __forceinline__ void adam_polyak_body(const EwParams& E, long long bx
     ew_store4(R.m, e, R.n, mv);
     ew_store4(R.v, e, R.n, vv);
     ew_store4(R.p, e, R.n, pv);
+    if (R.p_sh) {
+      float sv[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) sv[k] = rn_tf32(pv[k]);
+      ew_store4(R.p_sh, e, R.n, sv);
+    }
   }
   if (R.do_polyak) {
 #pragma unroll
     for (int k = 0; k < 4; ++k) tv[k] = __fadd_rn(__fmul_rn(tau, pv[k]), __fmul_rn(omt, tv[k]));
     ew_store4(R.tgt, e, R.n, tv);
+    if (R.tgt_sh) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) tv[k] = rn_tf32(tv[k]);
+      ew_store4(R.tgt_sh, e, R.n, tv);
+    }
   }
+}
+
+// dst[e] = rn_tf32(src[e]): (re)builds the TF32 shadow of a packed parameter buffer after the caller changed it
+struct RoundCopyParams {
+  int n_ranges, pad;
+  const float* src[4]; float* dst[4];
+  long long n[4], blk_begin[4];
+};
+
+__global__ void __launch_bounds__(kEwThreads) round_copy_kernel(const __grid_constant__ RoundCopyParams R) {
+  int ri = 0;
+  for (int q = 1; q < 4; ++q)
+    if (q < R.n_ranges && (long long)blockIdx.x >= R.blk_begin[q]) ri = q;
+  const long long e = ((long long)blockIdx.x - R.blk_begin[ri]) * kEwPerBlock + (long long)threadIdx.x * 4;
+  if (e >= R.n[ri]) return;
+  float v[4];
+  ew_load4(R.src[ri], e, R.n[ri], v);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) v[k] = rn_tf32(v[k]);
+  ew_store4(R.dst[ri], e, R.n[ri], v);
 }
 
 __global__ void __launch_bounds__(kEwThreads) adam_polyak_kernel(const __grid_constant__ EwParams E) {

@@ -10,6 +10,7 @@
 #include "stage.cuh"
 #include "tc.cuh"
 #include "front.cuh"
+#include "apply.cuh"
 
 namespace td3 {
 
@@ -80,7 +81,8 @@ __global__ void __launch_bounds__(kStageThreads, 1) stage_kernel(const __grid_co
   }
 }
 
-enum StageKind : int { SK_STAGE = 0, SK_GATHER = 1, SK_LOSS = 2, SK_EW_ONLY = 3, SK_HEAD = 4, SK_WN = 5, SK_FRONT = 6 };
+enum StageKind : int { SK_STAGE = 0, SK_GATHER = 1, SK_LOSS = 2, SK_EW_ONLY = 3, SK_HEAD = 4, SK_WN = 5, SK_FRONT = 6,
+                       SK_APPLY = 7 };   // SK_APPLY: first-layer dW + optimiser tiles (apply.cuh) followed by element-wise blocks
 
 struct alignas(16) StageRec {
   int kind;
@@ -96,6 +98,7 @@ struct alignas(16) StageRec {
     HeadParams h;
     WnParams w;
     FrontParams f;
+    DwParams d;
   } u;
   EwParams ew;
 };
@@ -181,6 +184,9 @@ __global__ void __launch_bounds__(kStageThreads, 1) persistent_update_kernel(con
           wn_body(R.u.w, tile);
         } else if (R.kind == SK_FRONT) {
           front_body(R.u.f, tile, reinterpret_cast<float*>(ring));
+        } else if (R.kind == SK_APPLY) {
+          __syncthreads();
+          dw_adam_body(R.u.d, R.ew, tile, reinterpret_cast<float*>(ring));
         }
       }
       // descriptor of the next stage (static data) while the others are still working

@@ -12,6 +12,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "misc.cuh"
+
 namespace td3 {
 
 enum ProblemKind : int {
@@ -51,12 +53,16 @@ struct Problem {
   int c_dups;                     // epilogue writes C to c_dups destinations c_dup_stride apart
   int use_tc;                     // 1: tcgen05 TF32 tile (128 x tc_nt) instead of the fp32 FFMA tile (32 x 32)
   int tc_nt, c_vec, aux_vec;      // TC tile width; 16-byte stores to C / loads from aux0 are legal
-  int tc_cluster, pad_p;          // > 1: this many consecutive N tiles (one cluster) multicast their common A panel
+  int tc_cluster, rn_out;         // > 1: this many consecutive N tiles (one cluster) multicast their common A panel;
+                                  // rn_out: the output is an operand of a later tensor-core contraction -> store it rounded to
+                                  // nearest TF32 (the tensor core itself would truncate the low 13 mantissa bits)
   int map_a, map_b;               // >= 0: first tensor map of operand A / B inside StageParams::maps (kernel-parameter space:
                                   // the TMA unit reads the descriptor without a global-memory round trip); < 0: tmapA / tmapB
   long long c_split, c_dup_stride;
   const float* A; const float* B; float* C; const float* bias;
   const void* tmapA; const void* tmapB;   // device arrays of CUtensorMap (one per group) when the operand is TMA-loadable
+  const float* B_master;                  // host-side planning only: B points at a TF32-rounded shadow of this buffer, which
+                                          // only the tensor-core tile should read (finalize_problem puts it back otherwise)
   float* aux0; float* aux1; float* aux2; float* aux3;
   // per-group pointer strides (floats): *_go outer group (agent), *_gi inner group (twin)
   long long a_go, a_gi, b_go, b_gi, c_go, c_gi, bias_go, bias_gi;
@@ -242,6 +248,7 @@ __device__ __forceinline__ void ffma_epilogue(const Problem& P, float* __restric
       float aux_out = 0.f;
       v = epi_apply<EPI>(v, has_bias ? bias_s[jl] : 0.f, aux_read ? aux_s[il * kLd + jl] : 0.f, P.f0, P.f1, aux_out);
       if (EPI == EPI_BIAS_TANH) aux0[(size_t)i * P.ldaux + j] = aux_out;
+      if (P.rn_out) v = rn_tf32(v);
 #pragma unroll 1
       for (int d = 0; d < P.c_dups; ++d) C[d * P.c_dup_stride + (size_t)i * P.ldc + j] = v;
     }
@@ -417,7 +424,10 @@ __device__ __forceinline__ void ln_fwd_tile(const Problem& P, int tile) {
   const float var = warp_sum(ss) / (float)P.N;
   const float rstd = 1.f / sqrtf(var + P.f0);
   #pragma unroll 2
-  for (int j = lane; j < P.N; j += 32) y[j] = (x[j] - mean) * rstd * gamma[j] + beta[j];
+  for (int j = lane; j < P.N; j += 32) {
+    const float v = (x[j] - mean) * rstd * gamma[j] + beta[j];
+    y[j] = P.rn_out ? rn_tf32(v) : v;
+  }
   if (lane == 0) {
     (P.aux2 + go * P.aux2_go + gi * P.aux2_gi)[row] = mean;
     (P.aux3 + go * P.aux3_go + gi * P.aux3_gi)[row] = rstd;
@@ -457,7 +467,7 @@ __device__ __forceinline__ void ln_bwd_rows_tile(const Problem& P, int tile) {
     const float xh = (xv - mean) * rstd;
     float d = rstd * (gdy - s1 - xh * s2);
     if (P.epi == EPI_RELU_MASK && !(xv > 0.f)) d = 0.f;
-    dx[j] = d;
+    dx[j] = P.rn_out ? rn_tf32(d) : d;
   }
 }
 
@@ -539,7 +549,8 @@ __device__ __forceinline__ void pool_fwd_tile(const Problem& P, int tile, float*
       tot.x += v.x; tot.y += v.y; tot.z += v.z; tot.w += v.w;
     }
     const float inv = 1.f / (float)P.K;
-    const float4 o = make_float4(fmaxf(tot.x * inv, 0.f), fmaxf(tot.y * inv, 0.f), fmaxf(tot.z * inv, 0.f), fmaxf(tot.w * inv, 0.f));
+    float4 o = make_float4(fmaxf(tot.x * inv, 0.f), fmaxf(tot.y * inv, 0.f), fmaxf(tot.z * inv, 0.f), fmaxf(tot.w * inv, 0.f));
+    if (P.rn_out) o = make_float4(rn_tf32(o.x), rn_tf32(o.y), rn_tf32(o.z), rn_tf32(o.w));
     float* C = P.C + go * P.c_go + gi * P.c_gi;
     for (int d = 0; d < P.c_dups; ++d) {
       float* cp = C + d * P.c_dup_stride + (size_t)b * P.ldc + c4 * 4;
@@ -578,7 +589,10 @@ __device__ __forceinline__ void pool_bwd_tile(const Problem& P, int tile) {
     if (b != b_cur) {
       b_cur = b;
 #pragma unroll
-      for (int e = 0; e < 4; ++e) gsc[e] = poolb[(size_t)b * P.ldaux + e] > 0.f ? dpb[(size_t)b * P.lda + e] * inv : 0.f;
+      for (int e = 0; e < 4; ++e) {
+        gsc[e] = poolb[(size_t)b * P.ldaux + e] > 0.f ? dpb[(size_t)b * P.lda + e] * inv : 0.f;
+        if (P.rn_out) gsc[e] = rn_tf32(gsc[e]);
+      }
     }
     const float4 hv = *reinterpret_cast<const float4*>(h2 + (size_t)row * P.ldb);
     float4 o;
@@ -637,7 +651,8 @@ __device__ __forceinline__ void smallk_fwd_tile(const Problem& P, int tile, floa
 #pragma unroll
       for (int d = 0; d < 8; ++d)
         if (d < K) v = fmaf(smem[r * 8 + d], w[d], v);
-      C[(size_t)(r0 + r) * P.ldc + c] = fmaxf(v, 0.f);
+      v = fmaxf(v, 0.f);
+      C[(size_t)(r0 + r) * P.ldc + c] = P.rn_out ? rn_tf32(v) : v;
     }
   }
   __syncthreads();

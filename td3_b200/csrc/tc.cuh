@@ -309,6 +309,7 @@ __device__ __forceinline__ void tc_epilogue_group(const Problem& P, float* __res
       const float v = have_acc ? __uint_as_float(r[4 * q + e]) : 0.f;
       o[e] = epi_apply<EPI>(v, has_bias ? bias_s[jl + 4 * q + e] : 0.f, ax[4 * q + e], P.f0, P.f1, aux_out);
       if (EPI == EPI_BIAS_TANH && jq + e < P.N) aux0[(size_t)i * P.ldaux + jq + e] = aux_out;
+      if (P.rn_out) o[e] = rn_tf32(o[e]);
     }
 #pragma unroll 1
     for (int d = 0; d < P.c_dups; ++d) {

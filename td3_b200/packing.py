@@ -41,6 +41,14 @@ class _Net(nn.Module):
         object.__setattr__(self, "_owner", owner)
         object.__setattr__(self, "_which", which)
 
+    def load_state_dict(self, state_dict, *args, **kwargs):
+        # the values land in the packed device buffers through the Parameter views; the engine's TF32 copies of
+        # them (csrc/engine.cu: ensure_shadows) have to be rebuilt before the next update
+        out = super().load_state_dict(state_dict, *args, **kwargs)
+        if self._owner is not None:
+            self._owner.params_changed()
+        return out
+
     def _check_norm(self, norm, allow_weight_norm=False):
         if norm == "weight_normalization" and allow_weight_norm:
             return
