@@ -45,6 +45,8 @@ WORKLOADS = {
     # name: description of the synthetic job
     "cfg1": dict(kind="featured", S=17, A=6, aw=(400, 300), qw=(400, 300), norm=None, B=100, rows=10_000),
     "cfg2": dict(kind="featured", S=17, A=6, aw=(400, 300), qw=(400, 300), norm=None, B=256, rows=1_000_000),
+    "cfg2_S32": dict(kind="featured", S=32, A=6, aw=(400, 300), qw=(400, 300), norm=None, B=256, rows=200_000),
+    "cfg5b": dict(kind="featured", S=17, A=6, aw=(400, 300), qw=(400, 300), norm=None, B=8192, rows=1_000_000),
     "cfg3": dict(kind="featured", S=17, A=6, aw=(500, 400, 300), qw=(500, 400, 200), norm=None, B=256, rows=1_000_000),
     "cfg3_layer": dict(kind="featured", S=17, A=6, aw=(500, 400, 300), qw=(500, 400, 200), norm="layer", B=256,
                        rows=1_000_000),
@@ -113,6 +115,148 @@ def measured_peaks():
                     source="measured (MEASURED_PEAKS.json)")
     except Exception:
         return dict(hbm=6650.0, bf16=1590.0, bf16_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+# fp32 FFMA peak of the chip: 148 SMs x 128 FMA lanes x 2 flop x 1.965 GHz (nominal, at the maximum SM clock)
+FFMA_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12
+
+
+def measure_tf32_peak():
+    """TF32 tensor-core peak of THIS GPU, measured the way MEASURED_PEAKS.json measures bf16: cuBLAS matmul 8192^3 with
+    allow_tf32, best of 5, CUDA events (a library GEMM used as a yardstick only; nothing on the product path calls it)."""
+    import torch
+    try:
+        old = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = True
+        n = 8192
+        a = torch.randn(n, n, device="cuda")
+        b = torch.randn(n, n, device="cuda")
+        best = 0.0
+        for _ in range(6):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            a @ b
+            e1.record()
+            torch.cuda.synchronize()
+            best = max(best, 2.0 * n ** 3 / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+        torch.backends.cuda.matmul.allow_tf32 = old
+        del a, b
+        torch.cuda.empty_cache()
+        return best
+    except Exception:
+        return None
+
+
+def hbm_kernel_rooflines(peaks):
+    """Achieved HBM GB/s of the bandwidth-bound kernels of the path, each launched through the C ABI on buffers larger
+    than the 126 MB L2 and timed with CUDA events on the launching stream: replay gather (cfg2 and cfg4 row shapes,
+    algorithmic bytes = 2 x row bytes x batch: every sampled row is read once and written once), Adam (28 B / parameter),
+    Polyak (12 B / parameter)."""
+    import ctypes as C
+    import numpy as np
+    import torch
+    from td3_b200 import _lib as L_, synthetic as O
+    from td3_b200.my_replay_buffer import ReplayBuffer_featured, ReplayBuffer_particles
+    lib = L_.require_cuda()
+    out = {}
+
+    def timed(fn, reps):
+        fn()
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for _ in range(reps):
+                fn()
+        g.replay()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) * 1e3 / reps            # us per launch
+
+    # ---- replay gather ----
+    for name, rb, B in (("gather_cfg2_rows", ReplayBuffer_featured(O.Space(17), O.Space(6), max_size=1_000_000), 256),
+                        ("gather_cfg4_rows", ReplayBuffer_particles((O.Space(8), O.Space(1024, 6)), O.Space(3), max_size=8192), 256)):
+        rb._all_rows.normal_()
+        rb.size = rb.max_size
+        g = torch.Generator(device="cuda")
+        g.manual_seed(1)
+        idxs = [torch.randint(0, rb.max_size, (B,), device="cuda", generator=g) for _ in range(16)]
+        it = [0]
+
+        def one():
+            rb.sample(B, indices=idxs[it[0] % 16])
+            it[0] += 1
+        us = timed(one, 16)
+        nbytes = 2.0 * rb.row_floats * 4 * B
+        out[name] = {"kernel": "td3::gather_kernel" + (" (cp.async.bulk staging of the particle sets)" if "cfg4" in name else ""),
+                     "bound": "hbm", "us_per_launch": us, "algorithmic_mb_per_launch": nbytes / 1e6,
+                     "achieved": nbytes / (us * 1e-6) / 1e9, "peak": peaks["hbm"], "unit": "GB/s",
+                     "frac": nbytes / (us * 1e-6) / 1e9 / peaks["hbm"],
+                     "buffer_mb": rb._all_rows.numel() * 4 / 1e6, "rows_per_launch": B}
+        del rb
+    # ---- Adam / Polyak over a packed buffer of 48 M parameters (192 MB per array) ----
+    n = 48 * 1024 * 1024
+    p, gr, m, v, t = (torch.randn(n, device="cuda") * 0.01 for _ in range(5))
+    v.abs_()
+    s = L_.stream_ptr
+    vp = lambda x: C.c_void_p(x.data_ptr())
+    for name, args, bpp in (("adam", (vp(p), vp(gr), vp(m), vp(v), None), 28.0), ("polyak", (vp(p), None, None, None, vp(t)), 12.0),
+                            ("adam_polyak_fused", (vp(p), vp(gr), vp(m), vp(v), vp(t)), 40.0)):
+        def one():
+            L_.check(lib.adam_polyak_step(*args, n, 10, 1e-4, 0.9, 0.999, 1e-8, 0.005, s()))
+        us = timed(one, 4)
+        nbytes = bpp * n
+        out[name] = {"kernel": "td3::adam_polyak_kernel", "bound": "hbm", "us_per_launch": us,
+                     "algorithmic_mb_per_launch": nbytes / 1e6, "achieved": nbytes / (us * 1e-6) / 1e9, "peak": peaks["hbm"],
+                     "unit": "GB/s", "frac": nbytes / (us * 1e-6) / 1e9 / peaks["hbm"], "parameters": n}
+    del p, gr, m, v, t
+    torch.cuda.empty_cache()
+    return out
+
+
+def time_dp_critic(rank, world, K):
+    """BASELINE config 5b: ONE 400-300 agent at global batch 8192, the batch sharded over the ranks, one sum-all-reduce of
+    the packed critic gradient per update (+ one of the actor gradient on policy steps).  Strong scaling: total work is
+    fixed.  Returns per-update times with and without the collectives (the latter is timing only: replicas diverge)."""
+    import torch
+    import torch.distributed as dist
+    from td3_b200.data_parallel import DataParallelTD3
+    w = WORKLOADS["cfg5b"]
+    if w["B"] % world:
+        return None
+    agent, rb = build_ours(w, seed=4242, rows=200_000)        # same seed on every rank: replicas
+    dp = DataParallelTD3(agent)
+    res = {}
+    for label, comm in (("with_allreduce", True), ("compute_only", False)):
+        dp.communicate = comm
+        for _ in range(10):
+            dp.train(rb, w["B"])
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(K):
+            dp.train(rb, w["B"])
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        res[label] = float(t[0]) / K                       # ms per update, max over ranks
+    pc, pa = int(agent._critic_family.params.numel()), int(agent._actor_family.params.numel())
+    out = {"value": 1000.0 / res["with_allreduce"], "unit": "updates/s", "global_batch": w["B"], "rows_per_rank": w["B"] // world,
+           "ms_per_update": res["with_allreduce"], "ms_per_update_compute_only": res["compute_only"],
+           "collective_share": max(0.0, 1.0 - res["compute_only"] / res["with_allreduce"]), "steps": K, "scaling": "strong",
+           "allreduce_bytes_per_update": 4 * pc + 4 * pa / HYPER["policy_freq"], "mode": dp.mode,
+           "what": "one agent, global batch 8192 split over the ranks (world-size-invariant Philox batch), gradients summed "
+                   "across ranks before identical Adam steps; value = updates/s of the whole job (max over ranks)"}
+    del agent, rb, dp
+    torch.cuda.empty_cache()
+    return out
 
 
 # --------------------------------------------------------------------------- clocks
@@ -268,6 +412,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-dp", action="store_true", help="skip the batch-8192 data-parallel update (config 5b) at N = 1")
     ap.add_argument("--precision", default=os.environ.get("TD3_PRECISION", "tf32"), choices=["tf32", "fp32"],
                     help="tf32: layer GEMMs on tcgen05 tensor cores (default); fp32: strict-fp32 FFMA tiles")
     ap.add_argument("--population", type=int, default=8,
@@ -293,13 +438,13 @@ def main():
               "the parameters are re-used across steps by the algorithm itself"}
 
     ncpu = os.cpu_count() or 1
-    threads_list = sorted({1, min(4, ncpu), ncpu})
+    threads_list = sorted({t for t in (1, 4, 8, 16, ncpu) if t <= ncpu})
 
     if args.impl == "reference":
         if rank != 0:
             return
         cpu_rows = min(w["rows"], 100_000)            # float64 host buffer; sampling cost does not depend on rows
-        steps = min(K, 300 if w["kind"] == "featured" else 5)
+        steps = max(150, min(K, 300)) if w["kind"] == "featured" else min(max(K, 3), 5)     # >= 150 updates: a 20-step sample is noise
         warm = min(W, 30 if w["kind"] == "featured" else 1)
         ups, th, dt = time_cpu(w, steps, warm, threads_list, cpu_rows)
         line = {"impl": "reference", "metric": "TD3 gradient updates/sec (batch 256)", "value": ups, "unit": "updates/s",
@@ -435,8 +580,8 @@ def main():
         first_agent, _ = shard_range(world * n_pop, world, rank)
         pop, prb = build_ours(w, seed=1000 + 64 * rank, rows=min(w["rows"], 100_000), n_agents=n_pop,
                               rng_seed=shard_seed(1001, first_agent))
-        Kp = max(3, K // 4)
-        pop.train(prb, B, iterations=max(3, W // 4))
+        Kp = max(200, K // 4)                          # >= 200 timed lock-step updates whatever --steps says
+        pop.train(prb, B, iterations=max(20, W // 4))
         barrier()
         p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         p0.record()
@@ -466,11 +611,81 @@ def main():
                                    "CUDA events, 300 graph replays each (a replay is quantised to ~2 us by the GPU front end)"}
             torch.cuda.synchronize()
 
+    if n_pop > 1:
+        del pop, prb
+    else:
+        del agent, rb
+    torch.cuda.empty_cache()
+
+    # ---------------- the same workload in strict fp32 (FFMA tiles; what the parity suite runs by default) ----------------
+    fp32_ms = fp32_e2e_s = 0.0
+    Kf = min(K, 500)
+    if args.precision != "fp32" and args.workload == "cfg2":
+        os.environ["TD3_PRECISION"] = "fp32"
+        fa, frb = build_ours(w, seed=100 + rank, rows=200_000)
+        os.environ["TD3_PRECISION"] = args.precision
+        fa.train(frb, B, iterations=max(W, 20))
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        fa.train(frb, B, iterations=Kf)
+        f1.record()
+        barrier()
+        fp32_ms = f0.elapsed_time(f1)
+        for i in range(20):
+            frb.add(*new_rows[i % len(new_rows)]); fa.train(frb, B); fa.wait_critic_loss()
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(Kf):
+            frb.add(*new_rows[i % len(new_rows)]); fa.train(frb, B); fa.wait_critic_loss()
+        torch.cuda.synchronize()
+        fp32_e2e_s = time.perf_counter() - t0
+        barrier()
+        del fa, frb
+        torch.cuda.empty_cache()
+
+    # ---------------- a wider observation (S = 32): S + A > 32 takes the first layers off the row-local front kernels ----------------
+    wide = None
+    if args.workload == "cfg2":
+        ww = WORKLOADS["cfg2_S32"]
+        wa, wrb = build_ours(ww, seed=300 + rank)
+        wa.train(wrb, ww["B"], iterations=max(W, 20))
+        barrier()
+        l0 = lib.td3_launch_count()
+        w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w0.record()
+        wa.train(wrb, ww["B"], iterations=Kf)
+        w1.record()
+        torch.cuda.synchronize()
+        wide = {"workload": "cfg2 with S = 32 (SURVEY 8d's wider synthetic observation)", "ms_per_step": w0.elapsed_time(w1) / Kf,
+                "value": Kf / (w0.elapsed_time(w1) / 1000.0), "unit": "updates/s (this rank)", "steps": Kf,
+                "launches_per_update": (lib.td3_launch_count() - l0) / Kf}
+        del wa, wrb
+        torch.cuda.empty_cache()
+
+    # ---------------- BASELINE config 5b: data-parallel update at global batch 8192 over all ranks ----------------
+    dp_line = None
+    if args.workload == "cfg2" and (world > 1 or not args.no_dp):
+        if world == 1 and not dist.is_initialized():
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            os.environ.setdefault("MASTER_PORT", "29531")
+            dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device("cuda", local_rank))
+        try:
+            dp_line = time_dp_critic(rank, world, max(50, min(K, 200)))
+        except Exception as exc:
+            dp_line = {"unavailable": repr(exc)[:300]}
+
     # ---------------- reduce over ranks ----------------
     if world > 1:
-        t = torch.tensor([ms, e2e_s, pop_ms, e2e_drain_s], device="cuda", dtype=torch.float64)
+        t = torch.tensor([ms, e2e_s, pop_ms, e2e_drain_s, fp32_ms, fp32_e2e_s], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, e2e_s, pop_ms, e2e_drain_s = float(t[0]), float(t[1]), float(t[2]), float(t[3])
+        ms, e2e_s, pop_ms, e2e_drain_s, fp32_ms, fp32_e2e_s = (float(x) for x in t)
+    if dist.is_initialized():
+        # the other ranks are done: they leave here instead of spinning in an NCCL barrier while rank 0 times the CPU arms
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return
     value = world * K / (ms / 1000.0)
     e2e = world * Ke / e2e_s
     t_update_us = ms * 1000.0 / K
@@ -490,6 +705,16 @@ def main():
                     "drain_what": "same loop with a D2H copy of the loss behind the whole update and a stream "
                                   "synchronise every step (the GPU idles while the host prepares the next step)"},
             "gpu_launches": int(launches)}
+    if fp32_ms > 0:
+        line["fp32_mode"] = {"value": world * Kf / (fp32_ms / 1000.0), "e2e": world * Kf / fp32_e2e_s, "unit": "updates/s", "steps": Kf,
+                             "ffma_peak_tflops": FFMA_PEAK_TFLOPS,
+                             "frac_of_ffma_peak": gflop * 1e9 / (fp32_ms / Kf * 1e-3) / 1e12 / FFMA_PEAK_TFLOPS,
+                             "what": "the same workload with precision='fp32': every contraction on fp32 FFMA tiles (the mode "
+                                     "the parity suite compares with the CPU oracle at 2e-5); peak = 148 SMs x 128 lanes x 2 x 1.965 GHz"}
+    if wide:
+        line["wide_state"] = wide
+    if dp_line:
+        line["dp_critic"] = dp_line
     if n_pop > 1 and pop_ms > 0:
         line["population"] = {"adam_kernel_roofline": pop_adam, "agents_per_gpu": n_pop, "value": world * n_pop * Kp / (pop_ms / 1000.0), "unit": "updates/s",
                               "ms_per_lockstep_update": pop_ms / Kp, "steps": Kp,
@@ -499,7 +724,16 @@ def main():
 
     if rank == 0:
         hbm_floor_us = mbytes * 1e6 / (peaks["hbm"] * 1e9) * 1e6
-        tf32_peak = peaks["bf16_sustained"] / 2.0
+        tf32_measured = measure_tf32_peak()
+        tf32_peak = tf32_measured if tf32_measured else peaks["bf16_sustained"] / 2.0
+        tf32_src = ("measured in this run: cuBLAS TF32 matmul 8192^3, best of 6 (MEASURED_PEAKS.json bf16 sustained / 2 = "
+                    f"{peaks['bf16_sustained'] / 2.0:.1f})") if tf32_measured else peaks["source"] + " (bf16 sustained / 2 for kind::tf32)"
+        if args.precision == "fp32":
+            tf32_peak, tf32_src = FFMA_PEAK_TFLOPS, "fp32 FFMA peak: 148 SMs x 128 lanes x 2 flop x 1.965 GHz"
+        try:
+            line["hbm_kernels"] = hbm_kernel_rooflines(peaks)
+        except Exception as exc:
+            line["hbm_kernels"] = {"unavailable": repr(exc)[:300]}
         tensor_floor_us = gflop * 1e9 / (tf32_peak * 1e12) * 1e6
         bound = "hbm" if hbm_floor_us >= tensor_floor_us else "tensor"
         if bound == "hbm":
@@ -530,13 +764,14 @@ def main():
             line["roofline"] = {
                 "bound": "tensor", "achieved": ach, "peak": tf32_peak, "unit": "TFLOP/s", "frac": ach / tf32_peak,
                 "traffic": traffic,
-                "kernel": "td3::stage_kernel<true> (tcgen05 kind::tf32 GEMM stages)",
+                "kernel": "td3::stage_kernel<true> (tcgen05 kind::tf32 GEMM stages)" if args.precision == "tf32"
+                          else "td3::stage_kernel<false> (fp32 FFMA GEMM stages)",
                 "launches_per_cycle": stage_info["n_stage"], "us_per_launch": stage_info["stage_us"] / stage_info["n_stage"],
                 "share_of_update_time": stage_info["stage_us"] / stage_info["cycle_us"],
                 "algorithmic_gflop_per_launch": sg / stage_info["n_stage"],
                 "how": "CUDA events around graph replays of the first k launches of a critic-only and a policy update, "
                        "k = 1..n (td3_debug_prefix_times, on the replay stream); a launch's duration = prefix(k) - prefix(k-1)",
-                "peak_source": peaks["source"] + " (bf16 sustained / 2 for kind::tf32)", "whole_update": whole, "note": note}
+                "peak_source": tf32_src, "whole_update": whole, "note": note}
         else:
             whole.update({"traffic": traffic, "per": "update", "peak_source": peaks["source"], "note": note})
             line["roofline"] = whole
@@ -558,9 +793,6 @@ def main():
                                               f"port of the reference on torch CPU, best of threads {threads_list}, "
                                               f"os.cpu_count()={ncpu}"}
         print(json.dumps(line))
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -109,7 +109,8 @@ typedef struct td3_agent_config {
 
 /* Device-resident replay buffer view: array-of-rows, one transition per row.
  * Row = [state | action | next_state | reward | not_done] (featured) or
- *       [feat | particles | action | next_feat | next_particles | reward | not_done] (particles),
+ *       [particles | next_particles | feat | action | next_feat | reward | not_done] (particles; each particle set
+ *        padded to a multiple of 4 floats, so both start 16-byte aligned: the gather stages them with cp.async.bulk),
  * fp32, row_stride floats apart.  Replaces the five/seven float64 NumPy arrays of
  * my_replay_buffer.py:16-22,81-85 (fp32 round-to-nearest at add == FloatTensor(float64) at sample). */
 typedef struct td3_replay_view {
@@ -192,6 +193,29 @@ int td3_agent_host_status_live(const td3_agent* agent);
  * host mirror's load_state_dict / load (TD3_base.py:37-50), or any in-place edit of a state_dict view -- calls this
  * afterwards; the next entry point that runs an update rebuilds the copies first (one launch). */
 int td3_agent_params_changed(td3_agent* agent);
+/* Things an update does lazily on entry -- publishing rb->size to the device word the sampling kernel reads, rebuilding
+ * the TF32 copies after td3_agent_params_changed -- done now, on `stream`.  A caller that replays a captured CUDA graph
+ * of the phase calls below (td3_b200/data_parallel.py) calls this before every replay. */
+int td3_agent_prepare(td3_agent* agent, const td3_replay_view* rb, void* stream);
+
+/* ---- data-parallel update over one NVLink domain (BASELINE config 5b; the reference is single-device) ------------
+ * The batch of ONE agent is split over `world` ranks (td3_agent_set_global_batch); what has to be exchanged is the sum
+ * of the packed gradients before each Adam step (the step being sharded: TD3_featured.py:151-153 and :162-164).
+ *
+ * dp_allreduce_grads: out[e] = sum over r of peer_grads[r][e], added in rank order, read through peer mappings (or plain
+ * device pointers on one GPU).  The caller orders it after the producers (stream order / its own flags).
+ *
+ * td3_dp_bind_peers + td3_dp_set_fused_reduce(1): the same sum folded INTO the optimiser kernels -- critic_grad_peers /
+ * actor_grad_peers are the `world` ranks' gradient buffers (this rank's own td3_param_set::grad among them, all in
+ * symmetric, peer-mapped memory), flag_peers their 64-word flag arrays (zero-initialised).  td3_critic_apply /
+ * td3_actor_apply then run [signal "my gradient is complete" + wait for every rank's] -> Adam reading the peers'
+ * gradients over NVLink -> [signal "done reading"], and td3_critic_step / td3_actor_step wait for every rank's "done
+ * reading" before they overwrite the gradient.  No all-reduce pass, no reduced copy, bit-identical sums on all ranks.
+ * Needs the unfused phase calls (td3_sample_batch .. td3_actor_apply); counters live in the bound state block. */
+int dp_allreduce_grads(float* out, const float* const* peer_grads, int32_t world, int64_t n, void* stream);
+int td3_dp_bind_peers(td3_agent* agent, int32_t world, int32_t rank, float* const* critic_grad_peers,
+                      float* const* actor_grad_peers, uint32_t* const* flag_peers);
+int td3_dp_set_fused_reduce(td3_agent* agent, int32_t on);
 /* Workspace (activations, batch staging) for a given batch size, in floats. */
 int64_t td3_agent_workspace_floats(const td3_agent* agent, int64_t batch);
 /* Bind the workspace and build the launch plan for `batch`.  Drops captured graphs. */

@@ -84,6 +84,10 @@ SIGNATURES = {
     "td3_agent_bind_host_status": (C.c_int, [_vp, _vp]),
     "td3_agent_host_status_live": (C.c_int, [_vp]),
     "td3_agent_params_changed": (C.c_int, [_vp]),
+    "td3_agent_prepare": (C.c_int, [_vp, _P(ReplayView), _vp]),
+    "dp_allreduce_grads": (C.c_int, [_vp, _P(_vp), _i32, _i64, _vp]),
+    "td3_dp_bind_peers": (C.c_int, [_vp, _i32, _i32, _P(_vp), _P(_vp), _P(_vp)]),
+    "td3_dp_set_fused_reduce": (C.c_int, [_vp, _i32]),
     "td3_agent_workspace_floats": (_i64, [_vp, _i64]),
     "td3_agent_plan": (C.c_int, [_vp, _i64, _vp, _i64, _vp]),
     "td3_agent_region": (C.c_int, [_vp, C.c_char_p, _P(_i64), _P(_i64)]),

@@ -57,7 +57,8 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 // launch list
 // ------------------------------------------------------------------------------------
 struct Launch {
-  enum Kind { STAGE, GATHER, LOSS, EW, TICK, HEAD, WN, FRONT } kind = STAGE;
+  enum Kind { STAGE, GATHER, LOSS, EW, TICK, HEAD, WN, FRONT, DPSYNC } kind = STAGE;
+  DpSyncParams dpsync{};
   HeadParams head{};
   WnParams wn{};
   FrontParams front{};
@@ -122,9 +123,16 @@ int run_launch(const Launch& L, cudaStream_t s) {
       else e = launch_pdl(stage_kernel<false>, dim3(L.stage.total_tiles), dim3(kStageThreads), kSmemBytes + 1024, s, L.stage);
       break;
     }
-    case Launch::GATHER:
-      e = launch_pdl(gather_kernel, dim3(L.grid_x, L.grid_y), dim3(256), 0, s, L.gather);
+    case Launch::GATHER: {
+      // rows with a long 16-byte aligned segment (particle sets): bulk-copy staging through shared memory
+      int bulk = 0;
+      for (int i = 0; i < L.gather.n_seg; ++i) bulk |= L.gather.seg_len[i] >= kGatherBulkMinFloats;
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3(L.grid_x, L.grid_y); cfg.blockDim = dim3(256); cfg.stream = s;
+      cfg.dynamicSmemBytes = bulk ? 8 * kGatherBulkBytes : 0;
+      e = cudaLaunchKernelEx(&cfg, gather_kernel, L.gather, bulk);
       break;
+    }
     case Launch::LOSS:
       e = launch_pdl(loss_kernel, dim3(L.grid_x), dim3(256), 0, s, L.loss);
       break;
@@ -160,6 +168,10 @@ int run_launch(const Launch& L, cudaStream_t s) {
       e = launch_pdl(front_kernel, dim3(L.grid_x), dim3(256), (size_t)kFrontSmemBytes, s, L.front);
       break;
     }
+    case Launch::DPSYNC:
+      dp_signal_wait_kernel<<<1, 32, 0, s>>>(L.dpsync);
+      e = cudaGetLastError();
+      break;
   }
   if (e != cudaSuccess) return fail(TD3_ERR_CUDA, "kernel launch: %s", cudaGetErrorString(e));
   g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -616,6 +628,12 @@ struct td3_agent {
   // caller says the parameters changed under us (td3_agent_params_changed) and after every plan.
   float *sh_a = nullptr, *sh_at = nullptr, *sh_c = nullptr, *sh_ct = nullptr;
   bool shadow_dirty = true;
+  // data-parallel update over peer-mapped gradient buffers (td3_dp_bind_peers): the Adam launches sum the ranks' gradients
+  int dp_world = 0, dp_rank = 0;
+  bool dp_fused = false;
+  const float* dp_critic_grads[kMaxPeers] = {};
+  const float* dp_actor_grads[kMaxPeers] = {};
+  unsigned int* dp_flags[kMaxPeers] = {};
   // row-local front kernels (front.cuh): template of the sampling launch (gather + first layers), filled by plan_sample
   bool front_on = false;
   FrontParams front_sample{};
@@ -1214,6 +1232,17 @@ bool make_wn_launch(const td3_agent_config& c, int mode, std::initializer_list<W
   return tiles > 0;
 }
 
+Launch dp_sync_launch(const td3_agent* a, int signal_slot, int wait_slot) {
+  Launch L;
+  L.kind = Launch::DPSYNC;
+  DpSyncParams& P = L.dpsync;
+  memset(&P, 0, sizeof(P));
+  for (int i = 0; i < a->dp_world; ++i) P.peer_flags[i] = a->dp_flags[i];
+  P.counts = reinterpret_cast<unsigned int*>(a->state_u64 + 12);     // four 32-bit counters in the reserved state words
+  P.world = a->dp_world; P.rank = a->dp_rank; P.signal_slot = signal_slot; P.wait_slot = wait_slot;
+  return L;
+}
+
 int plan_agent(td3_agent* a, long long batch) {
   const td3_agent_config& c = a->cfg;
   const int B = (int)batch, nA = c.n_agents, nq = c.n_q;
@@ -1362,7 +1391,8 @@ int plan_agent(td3_agent* a, long long batch) {
     return n.n_linear >= 2 && n.dims[0] <= kDwMaxK && (n.dims[1] & 3) == 0 && n.w_off[0] == 0 && (n.w_off[1] & 3) == 0 &&
            n.b_off[0] >= (long long)n.dims[0] * n.dims[1] && n.w_off[1] >= n.b_off[0] + n.dims[1] && (n.n_floats & 3) == 0;
   };
-  const bool fuse_tail = front && !ln && !wn && l0_fusable(c.q) && l0_fusable(c.actor) && (ld_q & 3) == 0 &&
+  const bool dp_fused = a->dp_fused && a->dp_world >= 1;
+  const bool fuse_tail = front && !dp_fused && !ln && !wn && l0_fusable(c.q) && l0_fusable(c.actor) && (ld_q & 3) == 0 &&
                          Lq >= 2 && qw <= kHeadMaxQw && c.q.dims[Lq - 1] <= kHeadMaxW && !getenv("TD3_NO_HEAD_FUSION") &&
                          !getenv("TD3_NO_TAIL_FUSION");
   a->tail_fused = fuse_tail;
@@ -1435,6 +1465,7 @@ int plan_agent(td3_agent* a, long long batch) {
     for (auto& st : s_ct) emit_stage(a->seq_target, st);
   }
   // ---- critic loss + backward (:145-152) ----
+  if (dp_fused) a->seq_critic_fb.push_back(dp_sync_launch(a, -1, 1));   // every rank is done reading my previous critic gradient
   {
     Launch L;
     L.kind = Launch::LOSS;
@@ -1504,7 +1535,15 @@ int plan_agent(td3_agent* a, long long batch) {
     r.n = qn * nq * nA; r.blk_begin = 0; r.sc_ptr = reinterpret_cast<const float*>(a->state_u64 + 10); r.do_adam = 1; r.do_polyak = 0;
     r.p_sh = a->sh_c;
     L.grid_x = (int)((r.n + kEwPerBlock - 1) / kEwPerBlock);
-    a->seq_critic_apply.push_back(L);
+    if (dp_fused) {
+      for (int i = 0; i < a->dp_world; ++i) r.g_peer[i] = a->dp_critic_grads[i];
+      r.n_peer = a->dp_world;
+      a->seq_critic_apply.push_back(dp_sync_launch(a, 0, 0));     // my gradient is complete; wait for everybody's
+      a->seq_critic_apply.push_back(L);
+      a->seq_critic_apply.push_back(dp_sync_launch(a, 1, -1));    // done reading the peers' gradients
+    } else {
+      a->seq_critic_apply.push_back(L);
+    }
   }
   // ---- actor step (:159-163): actor fwd, Q1 fwd with the stepped critic, -mean, backward ----
   {
@@ -1515,6 +1554,7 @@ int plan_agent(td3_agent* a, long long batch) {
     auto s_a = build_forward(c, c.actor, Wa, g_actor, B, pa, o, 1, 0, front);
     for (auto& st : s_a) emit_stage(a->seq_actor_fb, st);
     a->n_actor_fwd = (int)a->seq_actor_fb.size();
+    if (dp_fused) a->seq_actor_fb.push_back(dp_sync_launch(a, -1, 3));   // every rank is done reading my previous actor gradient
     if (wn) {     // Q1 below reads the critic the Adam step just changed
       Launch Lw;
       if (!make_wn_launch(c, 0, {{a->critic.params, a->eff_c, qn, nA * nq, 1}}, Lw))
@@ -1657,7 +1697,15 @@ int plan_agent(td3_agent* a, long long batch) {
     r1.do_adam = 1; r1.do_polyak = 1;
     r1.p_sh = a->sh_a; r1.tgt_sh = a->sh_at;
     L.grid_x = (int)(b0 + (r1.n + kEwPerBlock - 1) / kEwPerBlock);
-    a->seq_actor_apply.push_back(L);
+    if (dp_fused) {
+      for (int i = 0; i < a->dp_world; ++i) r1.g_peer[i] = a->dp_actor_grads[i];
+      r1.n_peer = a->dp_world;
+      a->seq_actor_apply.push_back(dp_sync_launch(a, 2, 2));
+      a->seq_actor_apply.push_back(L);
+      a->seq_actor_apply.push_back(dp_sync_launch(a, 3, -1));
+    } else {
+      a->seq_actor_apply.push_back(L);
+    }
   }
   // The actor's forward pass (TD3_featured.py:159, actor(state)) reads nothing the critic update writes, so in the
   // fused policy update its layers ride along with the critic's backward stages instead of owning barriers.
@@ -1808,9 +1856,9 @@ int plan_sample(td3_agent* a, const td3_replay_view* rb, int rng_mode) {
     seg(2 * S + A, 1, a->r, 1, B, false);
     seg(2 * S + A + 1, 1, a->nd, 1, B, false);
   } else {
-    // row = [f | particles | a | f2 | particles2 | r | nd]
-    const int PN = c.n_particles * c.particle_dim;
-    const int o_f = 0, o_p = S, o_a = S + PN, o_f2 = o_a + A, o_p2 = o_f2 + S, o_r = o_p2 + PN;
+    // row = [particles | particles2 | f | a | f2 | r | nd], the particle sets padded to 16-byte multiples (bulk copies)
+    const int PN = c.n_particles * c.particle_dim, PNp = (PN + 3) / 4 * 4;
+    const int o_p = 0, o_p2 = PNp, o_f = 2 * PNp, o_a = o_f + S, o_f2 = o_a + A, o_r = o_f2 + S;
     seg(o_f, S, a->xa + E, ld_a, a->xa_go);
     seg(o_f, S, a->xpi + E, ld_q, a->xpi_go);
     for (int g = 0; g < xq_inner; ++g) seg(o_f, S, a->xq + g * a->xq_gi + E, ld_q, a->xq_go);
@@ -2015,7 +2063,7 @@ int check_rb(td3_agent* a, const td3_replay_view* rb) {
   if (rb->size <= 0) return fail(TD3_ERR_INVALID, "cannot sample from an empty replay buffer (size=%lld)", (long long)rb->size);
   const td3_agent_config& c = a->cfg;
   long long want = c.variant == TD3_VARIANT_PARTICLES
-                       ? 2LL * (c.state_dim + (long long)c.n_particles * c.particle_dim) + c.action_dim + 2
+                       ? 2LL * (c.state_dim + ((long long)c.n_particles * c.particle_dim + 3) / 4 * 4) + c.action_dim + 2
                        : 2LL * c.state_dim + c.action_dim + 2;
   if (rb->row_floats != want) return fail(TD3_ERR_INVALID, "replay row has %lld floats, agent expects %lld", (long long)rb->row_floats, want);
   return TD3_OK;
@@ -2272,6 +2320,60 @@ int td3_agent_bind_host_status(td3_agent* a, void* host_words) {
 }
 
 int td3_agent_host_status_live(const td3_agent* a) { return a && a->host_status_live ? 1 : 0; }
+
+int td3_dp_bind_peers(td3_agent* a, int32_t world, int32_t rank, float* const* critic_grad_peers, float* const* actor_grad_peers,
+                      uint32_t* const* flag_peers) {
+  if (!a || world < 1 || world > kMaxPeers || rank < 0 || rank >= world || !critic_grad_peers || !actor_grad_peers || !flag_peers)
+    return fail(TD3_ERR_INVALID, "td3_dp_bind_peers: bad arguments (world %d, at most %d ranks of one NVLink domain)", world, kMaxPeers);
+  for (int i = 0; i < world; ++i) {
+    if (!critic_grad_peers[i] || !actor_grad_peers[i] || !flag_peers[i] || !aligned16(critic_grad_peers[i]) || !aligned16(actor_grad_peers[i]))
+      return fail(TD3_ERR_INVALID, "td3_dp_bind_peers: null or misaligned peer buffer of rank %d", i);
+    a->dp_critic_grads[i] = critic_grad_peers[i];
+    a->dp_actor_grads[i] = actor_grad_peers[i];
+    a->dp_flags[i] = flag_peers[i];
+  }
+  a->dp_world = world; a->dp_rank = rank;
+  a->batch = 0;                  // the Adam launches carry the peer pointers: plan again
+  drop_graphs(a);
+  return TD3_OK;
+}
+
+int td3_dp_set_fused_reduce(td3_agent* a, int32_t on) {
+  if (!a) return fail(TD3_ERR_INVALID, "td3_dp_set_fused_reduce: null agent");
+  const bool want = on != 0;
+  if (want && a->dp_world < 1) return fail(TD3_ERR_STATE, "td3_dp_set_fused_reduce: td3_dp_bind_peers not called");
+  if (want == a->dp_fused) return TD3_OK;
+  a->dp_fused = want;
+  drop_graphs(a);
+  if (a->batch > 0 && a->ws.base) {
+    CUDA_TRY(cudaDeviceSynchronize());
+    return plan_agent(a, a->batch);
+  }
+  return TD3_OK;
+}
+
+int dp_allreduce_grads(float* out, const float* const* peer_grads, int32_t world, int64_t n, void* stream) {
+  if (!out || !peer_grads || world < 1 || world > kMaxPeers || n <= 0) return fail(TD3_ERR_INVALID, "dp_allreduce_grads: bad arguments");
+  PeerSumParams P;
+  memset(&P, 0, sizeof(P));
+  for (int i = 0; i < world; ++i) {
+    if (!peer_grads[i] || !aligned16(peer_grads[i])) return fail(TD3_ERR_INVALID, "dp_allreduce_grads: null or misaligned buffer of rank %d", i);
+    P.peer[i] = peer_grads[i];
+  }
+  P.out = out; P.n = n; P.world = world;
+  peer_sum_kernel<<<(unsigned)((n + kEwPerBlock - 1) / kEwPerBlock), kEwThreads, 0, (cudaStream_t)stream>>>(P);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  CUDA_TRY(cudaGetLastError());
+  return TD3_OK;
+}
+
+int td3_agent_prepare(td3_agent* a, const td3_replay_view* rb, void* stream) {
+  int rc = check_ready(a);
+  if (rc == TD3_OK) rc = check_rb(a, rb);
+  if (rc == TD3_OK) rc = sync_rb_size(a, rb, (cudaStream_t)stream);
+  if (rc == TD3_OK) rc = ensure_shadows(a, (cudaStream_t)stream);
+  return rc;
+}
 
 int td3_agent_params_changed(td3_agent* a) {
   if (!a) return fail(TD3_ERR_INVALID, "td3_agent_params_changed: null agent");

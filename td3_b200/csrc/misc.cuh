@@ -112,9 +112,29 @@ __device__ __forceinline__ long long gather_index(const GatherParams& G, int age
                       (uint32_t)(b + G.elem_offset), size);
 }
 
+// ---- bulk-copy (TMA engine, non-tensor form) staging of large row segments -----------------------------------------
+// A particle set is 24 KB of contiguous floats per sampled row.  Instead of every lane issuing 16-byte loads and
+// stores, one lane hands the warp's slice to the copy engine: cp.async.bulk global -> shared (completion on an
+// mbarrier), then cp.async.bulk shared -> global.  No registers carry data, a warp has its whole slice in flight, and
+// the SM's load/store pipes stay free.  Needs 16-byte aligned addresses and sizes (the row layout guarantees it).
+constexpr int kGatherBulkBytes = 4096;            // staging bytes per warp (8 warps per CTA: 32 KB of dynamic shared memory)
+constexpr int kGatherBulkMinFloats = 1024;        // segments at least this long take the bulk path
+
+__device__ __forceinline__ void bulk_g2s(unsigned int dst_smem, const void* src, unsigned int bytes, unsigned int bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(dst_smem), "l"(src),
+               "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* dst, unsigned int src_smem, unsigned int bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(dst), "r"(src_smem), "r"(bytes) : "memory");
+}
+
 // one warp scatters (its slice of) transition `idx` to every destination segment; slice 0 also records the index and
-// draws the row's clipped smoothing noise
-__device__ __forceinline__ void gather_row(const GatherParams& G, int agent, int b, long long idx, int slice, int lane) {
+// draws the row's clipped smoothing noise.  stage / bar: this warp's bulk staging area and mbarrier in shared memory
+// (nullptr: no bulk path), phase: the barrier's parity, advanced for every bulk load
+__device__ __forceinline__ void gather_row(const GatherParams& G, int agent, int b, long long idx, int slice, int lane,
+                                           unsigned char* stage = nullptr, unsigned long long* bar = nullptr,
+                                           unsigned int* phase = nullptr) {
   const long long job = (long long)agent * G.batch + b;
   if (slice == 0) {
     if (lane == 0) G.idx_out[job] = idx;
@@ -138,7 +158,32 @@ __device__ __forceinline__ void gather_row(const GatherParams& G, int agent, int
     // this slice's part of the segment, in units of 4 floats where alignment allows
     const bool vec = ((G.seg_off[s] | len | G.dst_ld[s]) & 3) == 0 &&
                      ((reinterpret_cast<uintptr_t>(d) | reinterpret_cast<uintptr_t>(sp)) & 15) == 0;
-    if (vec) {
+    if (vec && stage && len >= kGatherBulkMinFloats && !((G.seg_rn >> s) & 1u)) {
+      // this slice's part of the segment, in 16-byte units, moved kGatherBulkBytes at a time by the copy engine
+      const int n4 = len >> 2;
+      const int per = (n4 + G.slices - 1) / G.slices;
+      const int lo = slice * per, hi = min(n4, lo + per);
+      const unsigned int st = (unsigned int)__cvta_generic_to_shared(stage), br = (unsigned int)__cvta_generic_to_shared(bar);
+      for (int at = lo; at < hi; at += kGatherBulkBytes / 16) {
+        const unsigned int bytes = (unsigned int)(min(hi - at, kGatherBulkBytes / 16) * 16);
+        if (lane == 0) {
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(br), "r"(bytes) : "memory");
+          bulk_g2s(st, reinterpret_cast<const float4*>(sp) + at, bytes, br);
+          unsigned int done = 0;
+          while (!done) {
+            asm volatile(
+                "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                : "=r"(done)
+                : "r"(br), "r"(*phase & 1u)
+                : "memory");
+          }
+          bulk_s2g(reinterpret_cast<float4*>(d) + at, st, bytes);
+          asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+          asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");     // the staging area may be overwritten
+        }
+        *phase += 1;
+      }
+    } else if (vec) {
       const int n4 = len >> 2;
       const int per = (n4 + G.slices - 1) / G.slices;
       const int lo = slice * per, hi = min(n4, lo + per);
@@ -185,19 +230,32 @@ __device__ __forceinline__ void gather_scatter(const GatherParams& G, int agent,
   }
 }
 
-__device__ __forceinline__ void gather_body(const GatherParams& G, int bx, int by) {
+__device__ __forceinline__ void gather_body(const GatherParams& G, int bx, int by, unsigned char* stage = nullptr,
+                                            unsigned long long* bars = nullptr) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
   const long long job = (long long)bx * warps_per_block + warp;   // (agent, b)
   if (job >= (long long)G.n_agents * G.batch) return;
   const int agent = (int)(job / G.batch), b = (int)(job - (long long)agent * G.batch);
-  gather_row(G, agent, b, gather_index(G, agent, b), by, lane);
+  unsigned int phase = 0;
+  gather_row(G, agent, b, gather_index(G, agent, b), by, lane, stage ? stage + warp * kGatherBulkBytes : nullptr,
+             bars ? bars + warp : nullptr, &phase);
 }
 
-__global__ void __launch_bounds__(256) gather_kernel(const __grid_constant__ GatherParams G) {
+// bulk != 0: launched with 8 * kGatherBulkBytes of dynamic shared memory; large aligned segments go through the copy engine
+__global__ void __launch_bounds__(256) gather_kernel(const __grid_constant__ GatherParams G, int bulk) {
+  extern __shared__ __align__(128) unsigned char gather_stage[];
+  __shared__ unsigned long long gather_bars[8];
   pdl_launch_dependents();
+  if (bulk) {
+    if (threadIdx.x < 8) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"((unsigned int)__cvta_generic_to_shared(&gather_bars[threadIdx.x])) : "memory");
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    __syncthreads();
+  }
   pdl_wait();
-  gather_body(G, blockIdx.x, blockIdx.y);
+  gather_body(G, blockIdx.x, blockIdx.y, bulk ? gather_stage : nullptr, bulk ? gather_bars : nullptr);
 }
 
 __global__ void philox_indices_kernel(long long* idx, long long batch, long long size, unsigned long long seed,
@@ -689,9 +747,20 @@ __global__ void adam_tick_kernel(const __grid_constant__ AdamTick T) {
 // Polyak (TD3_featured.py:167-171): t = tau*p + (1-tau)*t with both products rounded first.
 // Up to three ranges per launch (actor Adam+Polyak and critic Polyak fuse into one kernel).
 // ------------------------------------------------------------------------------------
+constexpr int kMaxPeers = 8;       // one NVSwitch domain
+
+// 16 bytes from a peer GPU's memory: system-scope relaxed load (never served from a stale local cache line)
+__device__ __forceinline__ void peer_load4(const float* p, float (&v)[4]) {
+  asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];\n" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "l"(p) : "memory");
+}
+
 struct EwRange {
   float* p; const float* g; float* m; float* v; float* tgt;
   float* p_sh; float* tgt_sh;        // optional TF32-rounded shadows of p / tgt (what the tensor-core contractions read)
+  // data-parallel update: n_peer > 0 -> the gradient is the sum over the ranks' buffers g_peer[0..n_peer), read over
+  // NVLink peer mappings and added in rank order (every replica forms the bit-identical sum; no all-reduce pass)
+  const float* g_peer[kMaxPeers];
+  int n_peer, pad_e;
   long long n, blk_begin;
   const float* sc_ptr;               // device-resident {step_size, sqrt(1 - beta2^t)} written by adam_tick, or
   float step_size, bc2_sqrt;         // host-supplied scalars when sc_ptr == nullptr
@@ -750,7 +819,22 @@ __device__ __forceinline__ void adam_polyak_body(const EwParams& E, long long bx
   float pv[4], gv[4], mv[4], vv[4], tv[4];
   ew_load4(R.p, e, R.n, pv);
   if (R.do_adam) {
-    ew_load4(R.g, e, R.n, gv);
+    if (R.n_peer > 0) {              // sum of the ranks' gradients, in rank order (n is a multiple of 4: packed layout)
+      float pg[kMaxPeers][4];
+#pragma unroll
+      for (int r = 0; r < kMaxPeers; ++r)
+        if (r < R.n_peer) peer_load4(R.g_peer[r] + e, pg[r]);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) gv[k] = pg[0][k];
+#pragma unroll
+      for (int r = 1; r < kMaxPeers; ++r)
+        if (r < R.n_peer) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) gv[k] = __fadd_rn(gv[k], pg[r][k]);
+        }
+    } else {
+      ew_load4(R.g, e, R.n, gv);
+    }
     ew_load4(R.m, e, R.n, mv);
     ew_load4(R.v, e, R.n, vv);
   }
@@ -783,6 +867,78 @@ __device__ __forceinline__ void adam_polyak_body(const EwParams& E, long long bx
       ew_store4(R.tgt_sh, e, R.n, tv);
     }
   }
+}
+
+// ------------------------------------------------------------------------------------
+// Data-parallel update, p2p mode: the ranks meet at flag words in each other's (symmetric) memory.
+//   flags of rank r: [slot][sender] 32-bit counters, written by the senders with system-scope release stores.
+//   signal(slot): my count for the slot += 1, stored to flags[slot][my rank] on every rank.
+//   wait(slot):   spin until flags[slot][r] on MY device has reached my own count for every r (all ranks signal
+//                 the same number of times, so "my count" is what everybody must have reached).
+// Slots: "gradient complete" before the peer reads of an Adam kernel, "done reading" before the next backward pass
+// overwrites the gradient (one pair for the critic family, one for the actor family).
+// ------------------------------------------------------------------------------------
+struct DpSyncParams {
+  unsigned int* peer_flags[kMaxPeers];   // flag arrays of all ranks (mine included), peer-mapped
+  unsigned int* counts;                  // my per-slot signal counts (device-resident: graph replays need no host)
+  int world, rank, signal_slot, wait_slot;   // slot < 0: skip that half
+};
+
+__global__ void dp_signal_wait_kernel(const __grid_constant__ DpSyncParams P) {
+  const int r = threadIdx.x;
+  __shared__ unsigned int s_cnt[2];
+  if (r == 0) {
+    if (P.signal_slot >= 0) {
+      s_cnt[0] = P.counts[P.signal_slot] + 1u;
+      P.counts[P.signal_slot] = s_cnt[0];
+    }
+    if (P.wait_slot >= 0) s_cnt[1] = P.wait_slot == P.signal_slot ? s_cnt[0] : P.counts[P.wait_slot];
+    __threadfence_system();              // everything earlier launches wrote is visible system-wide before the flag is
+  }
+  __syncthreads();
+  if (r < P.world) {
+    if (P.signal_slot >= 0) {
+      unsigned int* f = P.peer_flags[r] + P.signal_slot * kMaxPeers + P.rank;
+      asm volatile("st.release.sys.global.u32 [%0], %1;\n" ::"l"(f), "r"(s_cnt[0]) : "memory");
+    }
+    if (P.wait_slot >= 0) {
+      const unsigned int* f = P.peer_flags[P.rank] + P.wait_slot * kMaxPeers + r;
+      unsigned int v;
+      do {
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];\n" : "=r"(v) : "l"(f) : "memory");
+      } while ((int)(v - s_cnt[1]) < 0);
+    }
+  }
+}
+
+// out[e] = sum over r of peer[r][e], in rank order (the reduction the fused Adam kernel performs, on its own)
+struct PeerSumParams {
+  const float* peer[kMaxPeers];
+  float* out;
+  long long n;
+  int world, pad;
+};
+
+__global__ void __launch_bounds__(kEwThreads) peer_sum_kernel(const __grid_constant__ PeerSumParams P) {
+  const long long e = (long long)blockIdx.x * kEwPerBlock + (long long)threadIdx.x * 4;
+  if (e >= P.n) return;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  if (e + 4 <= P.n) {
+    for (int r = 0; r < P.world; ++r) {
+      float v[4];
+      peer_load4(P.peer[r] + e, v);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) acc[k] = r == 0 ? v[k] : __fadd_rn(acc[k], v[k]);
+    }
+  } else {
+    for (int r = 0; r < P.world; ++r)
+      for (int k = 0; k < 4; ++k)
+        if (e + k < P.n) {
+          const float v = *reinterpret_cast<const volatile float*>(P.peer[r] + e + k);
+          acc[k] = r == 0 ? v : __fadd_rn(acc[k], v);
+        }
+  }
+  ew_store4(P.out, e, P.n, acc);
 }
 
 // dst[e] = rn_tf32(src[e]): (re)builds the TF32 shadow of a packed parameter buffer after the caller changed it

@@ -34,7 +34,7 @@ class _DeviceReplay(object):
         self.n_agents = int(n_agents)
         self.store_pkl = ["ptr", "size"]
         self.device = torch.device("cuda", torch.cuda.current_device())
-        self.row_floats = sum(int(np.prod(shape)) for _, shape in self._fields.values())
+        self.row_floats = max(off + int(np.prod(shape)) for off, shape in self._fields.values())
         self.row_stride = (self.row_floats + 7) // 8 * 8          # rows start on 32-byte sector boundaries
         # population (n_agents > 1): one ring per member, a constant stride apart; self._rows is member 0's ring
         self._all_rows = torch.zeros(self.n_agents, self.max_size, self.row_stride, dtype=torch.float32, device=self.device)
@@ -225,16 +225,22 @@ class ReplayBuffer_featured(_DeviceReplay):
 
 
 class ReplayBuffer_particles(_DeviceReplay):
-    """Row = [features | particles | action | next_features | next_particles | reward | not_done]
-    (my_replay_buffer.py:6-69)."""
+    """Fields of my_replay_buffer.py:6-69.  Row = [particles | next_particles | features | action | next_features | reward |
+    not_done]: the two particle sets (N*D floats each, padded to a multiple of 4) lead the row so that both start on a
+    16-byte boundary -- what the gather kernel's bulk-copy (cp.async.bulk) staging of large rows needs
+    (csrc/misc.cuh: gather_row)."""
 
     def __init__(self, obs_space, action_space, max_size=int(1e6), load_folder=None):
         F, pshape, A = obs_space[0].shape[0], tuple(obs_space[1].shape), action_space.shape[0]
         self.store_np = ["state_features", "state_particles", "action", "next_state_features", "next_state_particles",
                          "reward", "not_done"]
-        self._fields = _layout([("state_features", (F,)), ("state_particles", pshape), ("action", (A,)),
-                                ("next_state_features", (F,)), ("next_state_particles", pshape), ("reward", (1,)),
-                                ("not_done", (1,))])
+        pn = int(np.prod(pshape))
+        pnp = (pn + 3) // 4 * 4
+        o_f = 2 * pnp
+        # dict order = the reference's sample() order (:61-69); offsets = the device row layout above
+        self._fields = {"state_features": (o_f, (F,)), "state_particles": (0, pshape), "action": (o_f + F, (A,)),
+                        "next_state_features": (o_f + F + A, (F,)), "next_state_particles": (pnp, pshape),
+                        "reward": (o_f + 2 * F + A, (1,)), "not_done": (o_f + 2 * F + A + 1, (1,))}
         self._init_storage(max_size, load_folder)
 
     def add(self, state, action, next_state, reward, done):

@@ -14,7 +14,7 @@ from oracle import td3_oracle as O
 def _declared_symbols():
     text = open(os.path.join(ROOT, "include", "td3_b200.h")).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b((?:td3|rb|adam)_[a-z0-9_]+)\s*\(", text)))
+    return sorted(set(re.findall(r"\b((?:td3|rb|adam|dp|set_encoder)_[a-z0-9_]+)\s*\(", text)))
 
 
 def test_library_exports_every_declared_symbol():

@@ -25,45 +25,61 @@ def make(precision):
     rb.add_batch(**data)
     return a, rb
 
-# ---- 1. parity (fp32 tiles: differences are summation order only) ----
-a, rb = make("fp32")
-dp = DataParallelTD3(a)
-for _ in range(6):
-    dp.train(rb, 256)
-loss = float(dp.global_critic_loss()[0].item())
-if rank == 0:
-    ref, rrb = make("fp32")
-    ref.exec_mode = "launches"
+# ---- 1. parity (fp32 tiles: differences are summation order only), both ways of forming the gradient sum ----
+ref_state = None
+for mode in ("p2p", "nccl"):
+    a, rb = make("fp32")
+    dp = DataParallelTD3(a, mode=mode)
     for _ in range(6):
-        ref.train(rrb, 256)
-    worst = 0.0
-    for k in ("actor", "critic", "actor_target", "critic_target"):
-        for (n, v), w in zip(getattr(a, k).state_dict().items(), getattr(ref, k).state_dict().values()):
-            worst = max(worst, float((v - w).norm() / max(float(w.norm()), 1e-12)))
-    want = float(ref.last_critic_loss[0].item())
-    ok = worst <= 1e-4 and abs(loss - want) <= 1e-4 * max(1.0, abs(want))
-    print(json.dumps({"check": "dp_parity", "world": world, "global_batch": 256, "updates": 6, "worst_param_rel_l2": worst,
-                      "critic_loss_dp": loss, "critic_loss_single": want, "ok": ok}))
-    assert ok
-dist.barrier()
+        dp.train(rb, 256)
+    loss = float(dp.global_critic_loss()[0].item())
+    # replicas must hold bit-identical parameters after the updates (identical sums on every rank)
+    flat = torch.cat([a._critic_family.params, a._actor_family.params])
+    gathered = [torch.empty_like(flat) for _ in range(world)]
+    dist.all_gather(gathered, flat)
+    replicas_identical = all(torch.equal(gathered[0], g) for g in gathered)
+    if rank == 0:
+        if ref_state is None:
+            ref, rrb = make("fp32")
+            ref.exec_mode = "launches"
+            for _ in range(6):
+                ref.train(rrb, 256)
+            ref_state = ({k: [w.clone() for w in getattr(ref, k).state_dict().values()] for k in ("actor", "critic", "actor_target", "critic_target")},
+                         float(ref.last_critic_loss[0].item()))
+        worst = 0.0
+        for k in ("actor", "critic", "actor_target", "critic_target"):
+            for (n, v), w in zip(getattr(a, k).state_dict().items(), ref_state[0][k]):
+                worst = max(worst, float((v - w).norm() / max(float(w.norm()), 1e-12)))
+        want = ref_state[1]
+        ok = worst <= 1e-4 and abs(loss - want) <= 1e-4 * max(1.0, abs(want)) and replicas_identical
+        print(json.dumps({"check": "dp_parity", "mode": dp.mode, "requested_mode": mode, "world": world, "global_batch": 256, "updates": 6,
+                          "worst_param_rel_l2": worst, "critic_loss_dp": loss, "critic_loss_single": want,
+                          "replicas_bit_identical": replicas_identical, "graph_replay": dp.use_graph,
+                          "p2p_unavailable": getattr(dp, "p2p_unavailable", None), "ok": ok}))
+        assert ok
+    dist.barrier()
+    del dp, a, rb
 
 # ---- 2. timing at global batch 8192 ----
-a, rb = make("tf32")
-dp = DataParallelTD3(a)
-for _ in range(20):
-    dp.train(rb, 8192)
-torch.cuda.synchronize(); dist.barrier()
-e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-K = 200
-e0.record()
-for _ in range(K):
-    dp.train(rb, 8192)
-e1.record()
-torch.cuda.synchronize()
-t = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
-dist.all_reduce(t, op=dist.ReduceOp.MAX)
-if rank == 0:
-    print(json.dumps({"check": "dp_timing", "workload": "cfg5b: 400-300 networks, global batch 8192, policy_freq 2", "world": world,
-                      "updates_per_s": K / (float(t[0]) / 1e3), "ms_per_update": float(t[0]) / K, "scaling": "strong",
-                      "collectives_per_update": "1 all-reduce(critic grad 1.04 MB) + 0.5 all-reduce(actor grad 0.52 MB)"}))
+for mode in ("p2p", "nccl"):
+    a, rb = make("tf32")
+    dp = DataParallelTD3(a, mode=mode)
+    for _ in range(20):
+        dp.train(rb, 8192)
+    torch.cuda.synchronize(); dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    K = 200
+    e0.record()
+    for _ in range(K):
+        dp.train(rb, 8192)
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        print(json.dumps({"check": "dp_timing", "mode": dp.mode, "workload": "cfg5b: 400-300 networks, global batch 8192, policy_freq 2",
+                          "world": world, "updates_per_s": K / (float(t[0]) / 1e3), "ms_per_update": float(t[0]) / K, "scaling": "strong",
+                          "reductions_per_update": "1 x critic gradient (1.04 MB) + 0.5 x actor gradient (0.52 MB)"}))
+    dist.barrier()
+    del dp, a, rb
 dist.destroy_process_group()
