@@ -21,6 +21,7 @@ namespace td3 {
 
 constexpr int kDwCols = 16;      // output channels (rows of W_0) per tile
 constexpr int kDwRows = 256;     // batch rows staged per pass
+constexpr int kDwRowsSmall = 128;
 constexpr int kDwMaxK = 32;      // input width of the layer (<= kFrontMaxK)
 constexpr int kDwThreads = kEwThreads;
 
@@ -28,6 +29,8 @@ struct DwParams {
   int n_tiles;                   // 0: plain Adam/Polyak launch
   int batch, n_agents, n_inner, col_blocks;
   int N, K, ld_dz, ldx, do_polyak;
+  int rows_per_pass, pad_d;      // batch rows staged per pass: kDwRows (one agent: shortest chain) or kDwRowsSmall (populations:
+                                 // half the shared memory per block doubles the resident element-wise blocks of the launch)
   const float* dz; long long dz_go, dz_gi;      // gradient w.r.t. the layer's pre-activation [B, N] (ReLU mask applied)
   const float* x; long long x_go, x_gi;         // the layer's input [B, ldx]
   float* p; float* g; float* m; float* v; float* tgt;    // packed buffers of the family
@@ -42,12 +45,13 @@ struct DwParams {
 // rows of W_0, i.e. one contiguous run of 16 K floats, plus 16 biases -- with consecutive threads on consecutive
 // addresses; their p / m / v / target values were requested before the first operand was staged.
 constexpr int kDwSlices = 4, kDwPartLd = kDwMaxK + 4;      // partial tile [slice][16][36]: 32 dW columns + the bias sum + pad
-static_assert(kDwSlices * kDwCols * kDwPartLd <= kDwRows * kDwCols, "slice partials reuse the dz buffer");
+static_assert(kDwSlices * kDwCols * kDwPartLd <= kDwRowsSmall * (kDwCols + kDwMaxK), "slice partials reuse the staging buffers");
 constexpr int kDwElems = 2;                                  // optimiser elements per thread: 16 * (32 + 1) <= 2 * 256 + 16
 
 __device__ __forceinline__ void dw_adam_body(const DwParams& D, const EwParams& E, int tile, float* smem) {
-  float* dzs = smem;                              // [kDwRows][kDwCols]
-  float* xs = smem + kDwRows * kDwCols;           // [kDwRows][kDwMaxK]
+  const int RP = D.rows_per_pass;
+  float* dzs = smem;                              // [RP][kDwCols]
+  float* xs = smem + RP * kDwCols;                // [RP][kDwMaxK]
   const int tid = threadIdx.x;
   const int per_agent = D.n_inner * D.col_blocks;
   const int agent = tile / per_agent;
@@ -77,8 +81,8 @@ __device__ __forceinline__ void dw_adam_body(const DwParams& D, const EwParams& 
   const int kg = (K + 3) >> 2;                    // 16-byte granules per input row
   float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}}, accb[2] = {0.f, 0.f};
 #pragma unroll 1
-  for (int b0 = 0; b0 < D.batch; b0 += kDwRows) {
-    const int rows = min(kDwRows, D.batch - b0);
+  for (int b0 = 0; b0 < D.batch; b0 += RP) {
+    const int rows = min(RP, D.batch - b0);
     if (b0 > 0) __syncthreads();
 #pragma unroll 1
     for (int i = tid; i < rows * (kDwCols / 4); i += kDwThreads) {
@@ -144,11 +148,11 @@ __device__ __forceinline__ void dw_adam_body(const DwParams& D, const EwParams& 
   }
 }
 
-constexpr int kDwSmemBytes = (kDwRows * kDwCols + kDwRows * kDwMaxK) * 4;
+constexpr int dw_smem_bytes(int rows_per_pass) { return rows_per_pass * (kDwCols + kDwMaxK) * 4; }
 
 // blocks [0, n_tiles): first-layer gradient + step; the rest: element-wise Adam / Polyak over the family's other tensors
 __global__ void __launch_bounds__(kDwThreads) apply_kernel(const __grid_constant__ EwParams E, const __grid_constant__ DwParams D) {
-  __shared__ __align__(16) float apply_smem[kDwSmemBytes / 4];
+  extern __shared__ __align__(16) float apply_smem[];
   pdl_launch_dependents();
   pdl_wait();
   if ((int)blockIdx.x < D.n_tiles) dw_adam_body(D, E, blockIdx.x, apply_smem);

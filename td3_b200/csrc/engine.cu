@@ -140,7 +140,7 @@ int run_launch(const Launch& L, cudaStream_t s) {
       if (L.dw.n_tiles > 0) {
         static const bool use_pdl = getenv("TD3_PDL") != nullptr;
         cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3(L.dw.n_tiles + L.grid_x); cfg.blockDim = dim3(kDwThreads); cfg.dynamicSmemBytes = 0; cfg.stream = s;
+        cfg.gridDim = dim3(L.dw.n_tiles + L.grid_x); cfg.blockDim = dim3(kDwThreads); cfg.dynamicSmemBytes = (size_t)dw_smem_bytes(L.dw.rows_per_pass); cfg.stream = s;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr[0].val.programmaticStreamSerializationAllowed = 1;
@@ -165,7 +165,7 @@ int run_launch(const Launch& L, cudaStream_t s) {
     case Launch::FRONT: {
       int rc = ensure_kernel_attrs();
       if (rc != TD3_OK) return rc;
-      e = launch_pdl(front_kernel, dim3(L.grid_x), dim3(256), (size_t)kFrontSmemBytes, s, L.front);
+      e = launch_pdl(front_kernel, dim3(L.grid_x), dim3(256), (size_t)front_smem_bytes(L.front.rows_per_tile, L.front.head != 0), s, L.front);
       break;
     }
     case Launch::DPSYNC:
@@ -1163,7 +1163,10 @@ FrontNet front_first_layer(const td3_net_layout& net, ParamRef W, int n_inner, c
 // job table + grid of a front launch
 void front_finish(Launch& L, int B, int nA) {
   FrontParams& F = L.front;
-  F.batch = B; F.n_agents = nA; F.row_blocks = (B + kFrontRows - 1) / kFrontRows;
+  // thousands of rows (a population, or a large data-parallel batch): 32-row tiles amortise the weight block; one agent
+  // at batch 256 keeps 8-row tiles (more CTAs in flight on a path that is pure latency)
+  F.rows_per_tile = (long long)nA * B >= 1024 && !getenv("TD3_FRONT_ROWS8") ? kFrontRowsWide : kFrontRows;
+  F.batch = B; F.n_agents = nA; F.row_blocks = (B + F.rows_per_tile - 1) / F.rows_per_tile;
   int jobs = 0;
   for (int i = 0; i < F.n_nets; ++i) {
     F.net[i].job_begin = jobs;
@@ -1764,6 +1767,7 @@ int plan_agent(td3_agent* a, long long batch) {
                        int n_inner, long long net_floats, const float* sc_ptr, bool polyak, float* sh, float* sh_t) {
       memset(&D, 0, sizeof(D));
       D.batch = B; D.n_agents = nA; D.n_inner = n_inner; D.N = n.dims[1]; D.K = n.dims[0];
+      D.rows_per_pass = nA > 1 ? kDwRowsSmall : kDwRows;
       D.col_blocks = (D.N + kDwCols - 1) / kDwCols;
       D.n_tiles = nA * n_inner * D.col_blocks;
       D.dz = z.dz; D.ld_dz = z.ld; D.dz_go = z.go; D.dz_gi = z.gi;

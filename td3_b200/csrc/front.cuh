@@ -31,14 +31,17 @@
 namespace td3 {
 
 constexpr int kFrontRows = 8, kFrontCols = 128, kFrontMaxK = 32, kFrontMaxA = 8, kFrontMaxNets = 4;
+constexpr int kFrontRowsWide = 32;                  // rows per tile when there are thousands of rows (populations, large batches):
+                                                    // the tile's weight block is staged once per 32 rows instead of once per 8
 constexpr int kFrontMaxKh = 512;                    // head reduction length (hidden width)
 constexpr int kFrontXs = 72;                        // staged row: a transition prefix [s | a | s'] (<= 2*32 + 8 floats)
 constexpr int kFrontWs = kFrontMaxK + 1;            // odd stride: column-per-thread reads are conflict-free
 constexpr int kFrontWh = kFrontMaxKh + 4;
 // shared memory: staged rows, weight block, bias strip, head weights, head input rows
-constexpr int kFrontSmemFloats = kFrontRows * kFrontXs + kFrontCols * kFrontWs + kFrontCols + kFrontMaxA * kFrontWh +
-                                 kFrontRows * kFrontWh;
-constexpr int kFrontSmemBytes = kFrontSmemFloats * 4;
+constexpr int front_smem_bytes(int rows, bool head) {
+  return (rows * kFrontXs + kFrontCols * kFrontWs + kFrontCols + (head ? kFrontMaxA * kFrontWh + rows * kFrontWh : 0)) * 4;
+}
+constexpr int kFrontSmemBytes = front_smem_bytes(kFrontRowsWide, true);      // the largest configuration (kernel attribute)
 
 struct FrontNet {
   const float* x;            // input rows [B, ldx] (nullptr: the sampled transition, or the head output alone)
@@ -58,6 +61,7 @@ struct FrontNet {
 struct FrontParams {
   int gather, head, n_nets, jobs;
   int batch, n_agents, row_blocks, A;
+  int rows_per_tile, pad_r;                   // kFrontRows (latency: one agent, batch 256) or kFrontRowsWide
   GatherParams g;
   // head
   const float* h; long long h_go; int ldh, Kh;
@@ -86,11 +90,12 @@ __device__ __forceinline__ void front_copy(float* dst, const float* src, int n, 
 }
 
 __device__ __forceinline__ void front_body(const FrontParams& P, int tile, float* smem) {
-  float* xs = smem;                                   // [kFrontRows][kFrontXs]
-  float* ws = smem + kFrontRows * kFrontXs;           // [kFrontCols][ws_ld]
+  const int R = P.rows_per_tile;
+  float* xs = smem;                                   // [R][kFrontXs]
+  float* ws = smem + R * kFrontXs;                    // [kFrontCols][ws_ld]
   float* bs = ws + kFrontCols * kFrontWs;             // [kFrontCols]
   float* whs = bs + kFrontCols;                       // [kFrontMaxA][h_ld]
-  float* hs = whs + kFrontMaxA * kFrontWh;            // [kFrontRows][h_ld]
+  float* hs = whs + kFrontMaxA * kFrontWh;            // [R][h_ld]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nthr = blockDim.x;
   const int per_agent = P.row_blocks * P.jobs;
   const int agent = tile / per_agent;
@@ -103,11 +108,11 @@ __device__ __forceinline__ void front_body(const FrontParams& P, int tile, float
   const FrontNet& N = P.net[ni];
   const int lj = job - N.job_begin;
   const int inner = lj / N.col_blocks, c0 = (lj - inner * N.col_blocks) * kFrontCols;
-  const int r0 = rb * kFrontRows;
+  const int r0 = rb * R;
   const bool writer = job == 0;                       // net[0].x_off == 0 (host): the writer's rows are staged unshifted
   const int nc = min(kFrontCols, N.N - c0), K = N.K;
   const int A = P.A, Kh = P.Kh;
-  const int nrows = min(kFrontRows, P.batch - r0);
+  const int nrows = min(R, P.batch - r0);
   const int h_ld = (Kh + 3) & ~3;                     // rows of hs / whs (a flat copy when the source is dense)
   const int ws_ld = K;                                // weight block [nc][K], flat
   const bool do_head = P.head && (writer || N.act_col >= 0);   // tiles of a network that does not consume the head skip it
@@ -235,7 +240,7 @@ __device__ __forceinline__ void front_body(const FrontParams& P, int tile, float
       const float bias = N.bias ? bs[c] : 0.f;
       float* out = N.out + (long long)agent * N.out_go + (long long)inner * N.out_gi;
       const float* mask = N.mask ? N.mask + (long long)agent * N.mask_go + (long long)inner * N.mask_gi : nullptr;
-      const int rbeg = half * (kFrontRows / 2), rend = min(nrows, rbeg + kFrontRows / 2);
+      const int rbeg = half * (R / 2), rend = min(nrows, rbeg + R / 2);
 #pragma unroll 1
       for (int r = rbeg; r < rend; ++r) {
         const long long o = (long long)(r0 + r) * N.ldo + c0 + c;
