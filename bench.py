@@ -663,6 +663,20 @@ def main():
         del wa, wrb
         torch.cuda.empty_cache()
 
+    # ---------------- B = 1 latency of select_action / eval_q (the calls main.py makes every env step) ----------------
+    b1 = None
+    if rank == 0 and args.workload == "cfg2":
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import latency_b1
+            b1 = latency_b1.measure("cfg2", n=1000, with_eager=not args.no_cpu_baseline)
+            b1["what"] = ("host call -> host result of policy.select_action(state) / policy.eval_q(state, action) at batch 1: one kernel "
+                          "per call reading the row from pinned host memory and writing the result back (csrc/infer.cuh); "
+                          "torch_eager_gpu = the oracle port of the reference with its networks on this GPU")
+        except Exception as exc:
+            b1 = {"unavailable": repr(exc)[:300]}
+        torch.cuda.empty_cache()
+
     # ---------------- BASELINE config 5b: data-parallel update at global batch 8192 over all ranks ----------------
     dp_line = None
     if args.workload == "cfg2" and (world > 1 or not args.no_dp):
@@ -711,6 +725,8 @@ def main():
                              "frac_of_ffma_peak": gflop * 1e9 / (fp32_ms / Kf * 1e-3) / 1e12 / FFMA_PEAK_TFLOPS,
                              "what": "the same workload with precision='fp32': every contraction on fp32 FFMA tiles (the mode "
                                      "the parity suite compares with the CPU oracle at 2e-5); peak = 148 SMs x 128 lanes x 2 x 1.965 GHz"}
+    if b1:
+        line["b1_latency"] = b1
     if wide:
         line["wide_state"] = wide
     if dp_line:

@@ -256,6 +256,15 @@ int td3_actor_forward(td3_agent* agent, int32_t which, int32_t agent_index, cons
                       int64_t batch, float* action_out, void* stream);
 int td3_critic_forward(td3_agent* agent, int32_t which, int32_t agent_index, const float* state, const float* particles,
                        const float* action, int64_t batch, float* q_out, void* stream);
+/* select_action / eval_q at batch 1 (TD3_featured.py:113-121; main.py:44-45,250), plain-MLP networks: ONE kernel per
+ * call.  host_in = the input row ([state] for net 0 = actor, [state | action] for net 1 = the twin critics), host_out =
+ * [n_nets * out_dim results][n_nets sequence words], both in page-locked host memory the device can address: the kernel
+ * reads the row over PCIe, walks the layers with activations in shared memory (strict fp32, LayerNorm as :44-46) and
+ * stores results and then `seq` into the sequence words.  td3_infer_wait spins on those words (host side, no CUDA
+ * call) until they equal seq.  Ordered after everything enqueued on `stream` before it, like the reference's .cpu(). */
+int td3_infer_b1(td3_agent* agent, int32_t net, int32_t which, int32_t agent_index, const float* host_in, float* host_out,
+                 uint32_t seq, int64_t wait_us, void* stream);   /* wait_us > 0: also td3_infer_wait(.., wait_us) before returning */
+int td3_infer_wait(const uint32_t* host_flags, int32_t n, uint32_t seq, int64_t timeout_us);
 
 /* Number of kernel launches issued by this library since load (bench.py "gpu_launches"). */
 int64_t td3_launch_count(void);

@@ -209,6 +209,112 @@ def sample_case(RB):
     return out
 
 
+SMALL_ACTOR, SMALL_Q, SMALL_PQ = (24, 16, 12), (24, 16, 8), (24, 16, 12)
+
+
+def import_reference_small():
+    """The reference's TD3_featured / TD3_particles with ONE edit made in memory: the hard-coded hidden widths
+    (TD3_featured.py:19,54; TD3_particles.py:25,77) are replaced by small ones, so that the checkpoints the reference
+    classes write (TD3_base.save, unmodified: TD3_base.py:26-34) are a few tens of KB instead of 15-20 MB and can be
+    committed.  Everything else -- module structure, state_dict keys, weight-norm reparametrisation, optimiser
+    construction, save/load -- is the reference's own code."""
+    import importlib.util
+    mods = {}
+    for name, repl in (("TD3_featured", {"(500,400,300)": repr(SMALL_ACTOR), "(500,400,200)": repr(SMALL_Q)}),
+                       ("TD3_particles", {"(500,400,300)": repr(SMALL_PQ)})):
+        src = open(os.path.join(REFERENCE, name + ".py")).read()
+        for k, v in repl.items():
+            assert k in src, (name, k)
+            src = src.replace(k, v)
+        src = src.split('if __name__ == "__main__":')[0].split("if __name__ == '__main__':")[0]
+        mod = types.ModuleType(name + "_small")
+        mod.__file__ = os.path.join(REFERENCE, name + ".py")
+        with contextlib.redirect_stdout(io.StringIO()):
+            exec(compile(src, mod.__file__, "exec"), mod.__dict__)
+        mods[name] = mod
+    return mods["TD3_featured"], mods["TD3_particles"]
+
+
+def ondisk_cases(RB):
+    """Artefacts WRITTEN BY THE REFERENCE CLASSES (tests/golden/ondisk/): replay-buffer folders of both buffer classes
+    (my_replay_buffer.py:28-36,91-99) and policy checkpoints of both agents (TD3_base.py:26-34) incl. LayerNorm and
+    weight-normalisation keys and non-empty Adam state, plus what the reference computes after loading them."""
+    import shutil
+    RFs, RPs = import_reference_small()
+    base = os.path.join(ROOT, "tests", "golden", "ondisk")
+    shutil.rmtree(base, ignore_errors=True)
+    os.makedirs(base)
+    expect = {}
+    rs = np.random.RandomState(21)
+    # ---- buffers ----
+    obs, act = O.Space(5), O.Space(2)
+    rrb = RB.ReplayBuffer_featured(obs, act, max_size=37)
+    for _ in range(50):
+        rrb.add(rs.standard_normal(5), rs.uniform(-1, 1, 2), rs.standard_normal(5), float(rs.standard_normal()), float(rs.uniform() < 0.2))
+    rrb.save(os.path.join(base, "buffer_featured"))
+    ind = rs.randint(0, 37, size=32)
+    with _Inject([ind], []):
+        got = rrb.sample(32)
+    expect["bf_indices"] = ind
+    for k, v in zip(O.ReplayFeatured.fields, got):
+        expect["bf_" + k] = v.numpy()
+    expect["bf_ptr_size"] = np.array([rrb.ptr, rrb.size])
+    pobs = (O.Space(3), O.Space(6, 4))
+    prb = RB.ReplayBuffer_particles(pobs, act, max_size=9)
+    for _ in range(14):
+        prb.add((rs.standard_normal(3), rs.standard_normal((6, 4))), rs.uniform(-1, 1, 2),
+                (rs.standard_normal(3), rs.standard_normal((6, 4))), float(rs.standard_normal()), float(rs.uniform() < 0.3))
+    prb.save(os.path.join(base, "buffer_particles"))
+    ind = rs.randint(0, 9, size=16)
+    with _Inject([ind], []):
+        got = prb.sample(16)
+    expect["bp_indices"] = ind
+    for k, v in zip(O.ReplayParticles.fields, got):
+        expect["bp_" + k] = v.numpy()
+    expect["bp_ptr_size"] = np.array([prb.ptr, prb.size])
+    # ---- checkpoints: train 3 updates (Adam state populated, one policy step), save, then one more update ----
+    torch.set_num_threads(1)
+    for tag, kind, norm in (("ckpt_featured_layer", "featured", "layer"), ("ckpt_particles_wn", "particles", "weight_normalization")):
+        torch.manual_seed(5)
+        if kind == "featured":
+            S, A, rows, B = 7, 3, 64, 16
+            o, a = O.Space(S), O.Space(A)
+            data = O.synthetic_transitions_featured(rows, S, A, seed=2)
+            with contextlib.redirect_stdout(io.StringIO()):
+                ref = RFs.TD3(o, a, norm=norm, lr=1e-3)
+            rb = RB.ReplayBuffer_featured(o, a, max_size=rows)
+            O.fill_featured(rb, data)
+            st, ac = np.linspace(-1, 1, S), np.linspace(-0.5, 0.5, A)
+            dims = dict(S=S, A=A)
+        else:
+            F, N, D, A, rows, B = 4, 16, 3, 2, 32, 8
+            o, a = (O.Space(F), O.Space(N, D)), O.Space(A)
+            data = O.synthetic_transitions_particles(rows, F, N, D, A, seed=2)
+            ref = RPs.TD3(o, a, norm=norm, lr=1e-3)
+            rb = RB.ReplayBuffer_particles(o, a, max_size=rows)
+            O.fill_particles(rb, data)
+            r2 = np.random.RandomState(3)
+            st, ac = (r2.standard_normal(F), r2.standard_normal((N, D))), np.linspace(-0.5, 0.5, A)
+            dims = dict(F=F, N=N, D=D, A=A)
+        idx = rs.randint(0, rows, size=(4, B))
+        noise = rs.standard_normal((4, B, A)).astype(np.float32)
+        with _Inject(list(idx), list(noise)):
+            for t in range(3):
+                ref.train(rb, B)
+            ref.save(os.path.join(base, tag))
+            expect[tag + "_select_action"] = ref.select_action(st)
+            expect[tag + "_eval_q"] = np.stack(ref.eval_q(st, ac))
+            ref.train(rb, B)                       # update 4 (a policy step) from the saved state
+        for net in ("actor", "critic", "actor_target", "critic_target"):
+            for k, v in getattr(ref, net).state_dict().items():
+                expect[f"{tag}_after_{net}.{k}"] = v.numpy()
+        expect[tag + "_indices"], expect[tag + "_noise"] = idx[3], noise[3]
+        expect[tag + "_meta"] = np.array(repr(dict(kind=kind, norm=norm, rows=rows, B=B, total_it_at_save=3, data_seed=2, lr=1e-3, **dims)))
+    expect["widths"] = np.array(repr(dict(actor=SMALL_ACTOR, q=SMALL_Q, pq=SMALL_PQ)))
+    np.savez_compressed(os.path.join(base, "expect.npz"), **expect)
+    return base
+
+
 def main():
     only = sys.argv[1:]                     # optional: names of the cases to (re)generate
     RF, RP, RB = import_reference()
@@ -217,6 +323,8 @@ def main():
     if not only:
         np.savez_compressed(os.path.join(gold, "replay_sample.npz"), **sample_case(RB))
         print("replay_sample: oracle == reference (bit-exact); fixture written")
+    if not only or "ondisk" in only:
+        print("reference-written buffer folders and checkpoints ->", ondisk_cases(RB))
     for name, case in CASES.items():
         if only and name not in only:
             continue

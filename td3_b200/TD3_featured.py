@@ -17,6 +17,7 @@ Same constructor keywords and methods; extra keyword-only options:
 """
 from __future__ import annotations
 
+import ctypes as C
 import os
 
 import numpy as np
@@ -74,14 +75,45 @@ class TD3(TD3_base):
         self._engine_init(cfg, fam_a, fam_c, lr, rng)
 
     # ------------------------------------------------------------------ B=1 API (TD3_featured.py:113-121)
+    def _b1_buffers(self):
+        """Pinned host I/O of the batch-1 kernel (csrc/infer.cuh): allocated once, addressed directly by the device."""
+        b = self.__dict__.get("_b1")
+        if b is None:
+            S, A = self._cfg.state_dim, self._cfg.action_dim
+            pin_in = torch.zeros(S + A, dtype=torch.float32).pin_memory()
+            pin_out = [torch.zeros(A + 4, dtype=torch.float32).pin_memory(),                 # actor: A results + 1 sequence word
+                       torch.zeros(self._cfg.n_q + 4, dtype=torch.float32).pin_memory()]     # critics: n_q results + n_q words
+            b = dict(pin_in=pin_in, pin_out=pin_out, in_np=pin_in.numpy(), out_np=[t.numpy() for t in pin_out],
+                     in_ptr=C.c_void_p(pin_in.data_ptr()), out_ptr=[C.c_void_p(t.data_ptr()) for t in pin_out], seq=0,
+                     fn=self._lib.td3_infer_b1, dev=self._device.index)
+            self.__dict__["_b1"] = b
+        return b
+
+    def _b1_call(self, net, agent, n_nets, n_out):
+        b = self._b1_buffers()
+        b["seq"] = seq = (b["seq"] + 1) & 0x7FFFFFFF
+        rc = b["fn"](self._handle, net, 0, agent, b["in_ptr"], b["out_ptr"][net], seq, 5_000_000,
+                     torch._C._cuda_getCurrentRawStream(b["dev"]))
+        if rc:
+            _lib.check(rc)
+        return b["out_np"][net]
+
     def select_action(self, state, agent=0):
-        state = torch.as_tensor(np.asarray(state, dtype=np.float32).reshape(1, -1), device=self._device)
-        return self._actor_forward(0, state, agent=agent).cpu().numpy().flatten()
+        """actor(state) for one state (TD3_featured.py:113-115): the row goes into a pinned host buffer, ONE kernel reads
+        it over PCIe, runs the whole network and writes the action back to pinned memory; no device tensors are made."""
+        S, A = self._cfg.state_dim, self._cfg.action_dim
+        b = self._b1_buffers()
+        b["in_np"][:S] = np.asarray(state, dtype=np.float32).reshape(-1)
+        return self._b1_call(0, agent, 1, A)[:A].copy()
 
     def eval_q(self, state, action, agent=0):
-        state = torch.as_tensor(np.asarray(state, dtype=np.float32).reshape(1, -1), device=self._device)
-        action = torch.as_tensor(np.asarray(action, dtype=np.float32).reshape(1, -1), device=self._device)
-        return [q.cpu().numpy().flatten() for q in self._critic_forward(0, state, action, agent=agent)]
+        """[Q1(s, a), Q2(s, a)] for one pair (TD3_featured.py:117-121), same single-kernel path."""
+        S, A, nq = self._cfg.state_dim, self._cfg.action_dim, self._cfg.n_q
+        b = self._b1_buffers()
+        b["in_np"][:S] = np.asarray(state, dtype=np.float32).reshape(-1)
+        b["in_np"][S:S + A] = np.asarray(action, dtype=np.float32).reshape(-1)
+        out = self._b1_call(1, agent, nq, 1)
+        return [out[i:i + 1].copy() for i in range(nq)]
 
     def _actor_forward(self, which, state, particles=None, agent=0):
         state = state.to(self._device, torch.float32).contiguous()

@@ -102,6 +102,8 @@ SIGNATURES = {
     "td3_actor_apply": (C.c_int, [_vp, _vp]),
     "td3_actor_forward": (C.c_int, [_vp, _i32, _i32, _vp, _vp, _i64, _vp, _vp]),
     "td3_critic_forward": (C.c_int, [_vp, _i32, _i32, _vp, _vp, _vp, _i64, _vp, _vp]),
+    "td3_infer_b1": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _vp, C.c_uint32, _i64, _vp]),
+    "td3_infer_wait": (C.c_int, [_vp, _i32, C.c_uint32, _i64]),
     "td3_launch_count": (_i64, []),
 }
 

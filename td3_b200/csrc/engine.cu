@@ -14,6 +14,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <ctime>
 #include <map>
 #include <string>
 #include <vector>
@@ -24,6 +25,7 @@
 #include "front.cuh"
 #include "apply.cuh"
 #include "persist.cuh"
+#include "infer.cuh"
 
 using namespace td3;
 
@@ -2617,6 +2619,71 @@ int td3_actor_forward(td3_agent* a, int32_t which, int32_t agent_index, const fl
   o.f0 = enc ? 1.f : c.max_action;
   for (auto& st : build_forward(c, c.actor, W, GroupShape{1, 1}, (int)batch, pb, o)) emit_stage(seq, st);
   return run_seq(seq, s);
+}
+
+int td3_infer_wait(const uint32_t* host_flags, int32_t n, uint32_t seq, int64_t timeout_us);
+
+int td3_infer_b1(td3_agent* a, int32_t net, int32_t which, int32_t agent_index, const float* host_in, float* host_out, uint32_t seq,
+                 int64_t wait_us, void* stream) {
+  if (!a || !a->params_bound) return fail(TD3_ERR_STATE, "td3_infer_b1: td3_agent_bind_params not called");
+  const td3_agent_config& c = a->cfg;
+  if (!host_in || !host_out || agent_index < 0 || agent_index >= c.n_agents || net < 0 || net > 1)
+    return fail(TD3_ERR_INVALID, "td3_infer_b1: bad arguments");
+  if (c.variant != TD3_VARIANT_FEATURED || c.norm == TD3_NORM_WEIGHT)
+    return fail(TD3_ERR_UNSUPPORTED, "td3_infer_b1: plain-MLP networks only (the particle encoder goes through td3_actor_forward / td3_critic_forward)");
+  const td3_net_layout& L = net == 0 ? c.actor : c.q;
+  for (int l = 0; l <= L.n_linear; ++l)
+    if (L.dims[l] > kInferMaxWidth) return fail(TD3_ERR_UNSUPPORTED, "td3_infer_b1: layer width %d > %d", L.dims[l], kInferMaxWidth);
+  InferParams P;
+  memset(&P, 0, sizeof(P));
+  const td3_param_set& ps = net == 0 ? a->actor : a->critic;
+  const int n_nets = net == 0 ? 1 : c.n_q;
+  P.x_host = host_in; P.out_host = host_out;
+  P.W = (which ? ps.target : ps.params) + (long long)agent_index * L.n_floats * n_nets;
+  P.net_stride = L.n_floats; P.n_nets = n_nets; P.n_linear = L.n_linear;
+  P.ln = c.norm == TD3_NORM_LAYER ? 1 : 0;
+  P.final_tanh = net == 0 ? 1 : 0;
+  P.out_scale = net == 0 ? c.max_action : 1.f;
+  P.seq = seq;
+  for (int l = 0; l <= L.n_linear; ++l) P.dims[l] = L.dims[l];
+  if (L.dims[0] <= kInferInline) {       // the row rides in the kernel parameters: the device never reads host memory
+    P.x_inline = 1;
+    memcpy(P.x, host_in, sizeof(float) * L.dims[0]);
+  }
+  for (int l = 0; l < L.n_linear; ++l) {
+    P.w_off[l] = L.w_off[l]; P.b_off[l] = L.b_off[l]; P.lng_off[l] = L.ln_g_off[l]; P.lnb_off[l] = L.ln_b_off[l];
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(n_nets * kInferCluster); cfg.blockDim = dim3(kInferThreads); cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kInferCluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  CUDA_TRY(cudaLaunchKernelEx(&cfg, infer_b1_kernel, P));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  if (wait_us > 0) return td3_infer_wait(reinterpret_cast<const uint32_t*>(host_out + (size_t)n_nets * L.dims[L.n_linear]), n_nets, seq, wait_us);
+  return TD3_OK;
+}
+
+int td3_infer_wait(const uint32_t* host_flags, int32_t n, uint32_t seq, int64_t timeout_us) {
+  if (!host_flags || n < 1) return fail(TD3_ERR_INVALID, "td3_infer_wait: bad arguments");
+  const volatile uint32_t* f = host_flags;
+  long long spins = 0;
+  timespec t0, t1;
+  clock_gettime(CLOCK_MONOTONIC, &t0);
+  for (;;) {
+    bool done = true;
+    for (int i = 0; i < n; ++i) done &= f[i] == seq;
+    if (done) return TD3_OK;
+    if ((++spins & 1023) == 0) {
+      clock_gettime(CLOCK_MONOTONIC, &t1);
+      const long long us = (t1.tv_sec - t0.tv_sec) * 1000000LL + (t1.tv_nsec - t0.tv_nsec) / 1000;
+      if (us > timeout_us) {
+        cudaError_t err = cudaGetLastError();
+        return fail(TD3_ERR_CUDA, "td3_infer_wait: result did not arrive within %lld us (%s)", (long long)timeout_us, cudaGetErrorString(err));
+      }
+    }
+  }
 }
 
 int td3_critic_forward(td3_agent* a, int32_t which, int32_t agent_index, const float* state, const float* particles,

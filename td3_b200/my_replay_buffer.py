@@ -178,14 +178,41 @@ class _DeviceReplay(object):
         for attrib in self.store_pkl:
             with open(os.path.join(folder, attrib + ".pkl"), "rb") as f:
                 setattr(self, attrib, int(pickle.load(f)))
+        arrays = {}
         for attrib in self.store_np:
             with open(os.path.join(folder, attrib + ".pkl"), "rb") as f:
-                arr = np.load(f)
-            if arr.shape[0] != self.max_size:
-                raise ValueError(f"{attrib}: stored buffer has {arr.shape[0]} rows, max_size is {self.max_size}")
+                arrays[attrib] = np.load(f)
+        n = int(next(iter(arrays.values())).shape[0])
+        if n != self.max_size:
+            # the reference adopts the stored arrays whatever max_size the constructor was given (my_replay_buffer.py:38-44:
+            # experience_injection.py builds the buffer with the default max_size and loads a smaller one): so do we
+            if self.n_agents != 1:
+                raise ValueError(f"stored buffer has {n} rows, this population's rings have {self.max_size}")
+            torch.cuda.current_stream().synchronize()
+            self.max_size = n
+            self._all_rows = torch.zeros(1, n, self.row_stride, dtype=torch.float32, device=self.device)
+            self._rows = self._all_rows[0]
+            self._rows_ptr = self._rows.data_ptr()
+            self.__dict__.pop("_cached_view", None)
+        for attrib, arr in arrays.items():
             off, shape = self._fields[attrib]
             w = int(np.prod(shape))
             self._rows[:, off:off + w] = torch.from_numpy(arr.reshape(self.max_size, w).astype(np.float32)).to(self.device)
+
+    def get_rows(self, name, start=0, stop=None) -> np.ndarray:
+        """float64 copy of rows [start, stop) of one field (``rb.state`` & co. snapshot the WHOLE ring on every access and are
+        read-only: an in-place edit of such a snapshot does not reach the device)."""
+        off, shape = self._fields[name]
+        w = int(np.prod(shape))
+        stop = self.max_size if stop is None else stop
+        return self._rows[start:stop, off:off + w].cpu().numpy().astype(np.float64).reshape(stop - start, *shape)
+
+    def set_rows(self, name, start, values):
+        """Write rows of one field in place (what ``rb.reward[i] = x`` does on the reference's NumPy arrays)."""
+        off, shape = self._fields[name]
+        w = int(np.prod(shape))
+        v = np.asarray(values, dtype=np.float64).reshape(-1, w).astype(np.float32)
+        self._rows[start:start + v.shape[0], off:off + w] = torch.from_numpy(v).to(self.device)
 
     def __getattr__(self, name):
         # float64 NumPy snapshots of the per-field arrays (reference attribute names)
