@@ -28,7 +28,7 @@ Actor, Critic = SetActor, SetCritic
 class TD3(TD3_base):
     def __init__(self, obs_space, action_space, lr=1e-4, norm=None, CDQ=True, *,
                  actor_widths=(500, 400, 300), q_widths=(500, 400, 300), rng="device", seed=None, precision=None,
-                 **kwargs):
+                 n_agents=1, **kwargs):
         _lib.require_cuda()
         F = obs_space[0].shape[0]
         N, D = obs_space[1].shape
@@ -43,8 +43,14 @@ class TD3(TD3_base):
         critic_t.load_state_dict(critic.state_dict())
         super(TD3, self).__init__(**kwargs)                                     # :151
         dev = torch.device("cuda", torch.cuda.current_device())
-        fam_a = PackedFamily(actor, actor_t, [""], dev)
-        fam_c = PackedFamily(critic, critic_t, ["q1", "q2"] if CDQ else ["q1"], dev)
+        n_agents = int(n_agents)
+        if n_agents < 1:
+            raise ValueError("n_agents must be >= 1")
+        fam_a = PackedFamily(actor, actor_t, [""], dev, n_agents)
+        fam_c = PackedFamily(critic, critic_t, ["q1", "q2"] if CDQ else ["q1"], dev, n_agents)
+        for i in range(1, n_agents):      # further members of the population: fresh default initialisations, in order
+            fam_a.load_agent(i, SetActor(F, N, D, A, norm, actor_widths).state_dict())
+            fam_c.load_agent(i, SetCritic(F, N, D, A, norm, CDQ, q_widths).state_dict())
         self.actor, self.actor_target, self.critic, self.critic_target = actor, actor_t, critic, critic_t
         for m, w in ((actor, 0), (actor_t, 1), (critic, 0), (critic_t, 1)):
             m._attach(self, w)
@@ -54,7 +60,7 @@ class TD3(TD3_base):
         cfg.norm = {None: _lib.NORM_NONE, "layer": _lib.NORM_LAYER, "weight_normalization": _lib.NORM_WEIGHT}[norm]
         cfg.n_q, cfg.state_dim, cfg.action_dim = (2 if CDQ else 1), F, A
         cfg.n_particles, cfg.particle_dim = N, D
-        cfg.clamp_target_action, cfg.n_agents = 0, 1
+        cfg.clamp_target_action, cfg.n_agents = 0, n_agents
         cfg.max_action = 1.0
         cfg.discount, cfg.tau = float(self.discount), float(self.tau)
         cfg.policy_noise, cfg.noise_clip = float(self.policy_noise), float(self.noise_clip)
@@ -72,33 +78,33 @@ class TD3(TD3_base):
         parts = np.asarray(state[1], dtype=np.float32)
         return feats, torch.as_tensor(parts.reshape(1, *parts.shape), device=self._device)
 
-    def select_action(self, state):
+    def select_action(self, state, agent=0):
         feats, parts = self._state_to_device(state)
-        return self._actor_forward(0, feats, parts).cpu().numpy().flatten()
+        return self._actor_forward(0, feats, parts, agent=agent).cpu().numpy().flatten()
 
-    def eval_q(self, state, action):
+    def eval_q(self, state, action, agent=0):
         feats, parts = self._state_to_device(state)
         action = torch.as_tensor(np.array(action, dtype=np.float32).reshape(1, -1), device=self._device)
-        return [q.cpu().numpy().flatten() for q in self._critic_forward(0, feats, action, parts)]
+        return [q.cpu().numpy().flatten() for q in self._critic_forward(0, feats, action, parts, agent=agent)]
 
-    def _actor_forward(self, which, feats, particles):
+    def _actor_forward(self, which, feats, particles, agent=0):
         feats = feats.to(self._device, torch.float32).contiguous()
         particles = particles.to(self._device, torch.float32).contiguous()
         B = feats.shape[0]
         self._ensure_plan(max(B, self._planned_batch))
         out = torch.empty(B, self._cfg.action_dim, device=self._device)
-        _lib.check(self._lib.td3_actor_forward(self._handle, which, 0, feats.data_ptr(), particles.data_ptr(), B,
+        _lib.check(self._lib.td3_actor_forward(self._handle, which, int(agent), feats.data_ptr(), particles.data_ptr(), B,
                                                out.data_ptr(), _lib.stream_ptr()))
         return out
 
-    def _critic_forward(self, which, feats, action, particles):
+    def _critic_forward(self, which, feats, action, particles, agent=0):
         feats = feats.to(self._device, torch.float32).contiguous()
         action = action.to(self._device, torch.float32).contiguous()
         particles = particles.to(self._device, torch.float32).contiguous()
         B = feats.shape[0]
         self._ensure_plan(max(B, self._planned_batch))
         out = torch.empty(self._cfg.n_q, B, self._cfg.action_dim, device=self._device)
-        _lib.check(self._lib.td3_critic_forward(self._handle, which, 0, feats.data_ptr(), particles.data_ptr(),
+        _lib.check(self._lib.td3_critic_forward(self._handle, which, int(agent), feats.data_ptr(), particles.data_ptr(),
                                                 action.data_ptr(), B, out.data_ptr(), _lib.stream_ptr()))
         return [out[i] for i in range(self._cfg.n_q)]
 

@@ -72,7 +72,16 @@ class _DeviceReplay(object):
         self._slot += 1
         return s
 
-    def _commit_row(self, slot):
+    def _commit_row(self, slot, agent=0):
+        if agent:                                            # population member >= 1: its own ring, pointer and size
+            ring = self._rows_ptr + agent * self.max_size * self.row_stride * 4
+            rc = self._lib.rb_add_rows(ring, self.row_stride, self.row_floats, self.max_size, self._ptrs[agent],
+                                       self._stage_ptr + slot * self.row_floats * 4, 1, _lib.stream_ptr())
+            if rc:
+                _lib.check(rc)
+            self._ptrs[agent] = (self._ptrs[agent] + 1) % self.max_size
+            self._sizes[agent] = min(self._sizes[agent] + 1, self.max_size)
+            return
         rc = self._lib.rb_add_rows(self._rows_ptr, self.row_stride, self.row_floats, self.max_size, self.ptr,
                                    self._stage_ptr + slot * self.row_floats * 4, 1, _lib.stream_ptr())
         if rc:
@@ -239,7 +248,7 @@ class ReplayBuffer_featured(_DeviceReplay):
         self._fields = _layout([("state", (S,)), ("action", (A,)), ("next_state", (S,)), ("reward", (1,)), ("not_done", (1,))])
         self._init_storage(max_size, load_folder, n_agents)
 
-    def add(self, state, action, next_state, reward, done):
+    def add(self, state, action, next_state, reward, done, agent=0):
         slot = self._next_slot()
         row, f = self._stage_np[slot], self._fields
         S, A = f["state"][1][0], f["action"][1][0]
@@ -248,7 +257,7 @@ class ReplayBuffer_featured(_DeviceReplay):
         row[S + A:2 * S + A] = next_state
         row[2 * S + A] = reward
         row[2 * S + A + 1] = 1. - done
-        self._commit_row(slot)
+        self._commit_row(slot, agent)
 
 
 class ReplayBuffer_particles(_DeviceReplay):
@@ -257,7 +266,7 @@ class ReplayBuffer_particles(_DeviceReplay):
     16-byte boundary -- what the gather kernel's bulk-copy (cp.async.bulk) staging of large rows needs
     (csrc/misc.cuh: gather_row)."""
 
-    def __init__(self, obs_space, action_space, max_size=int(1e6), load_folder=None):
+    def __init__(self, obs_space, action_space, max_size=int(1e6), load_folder=None, n_agents=1):
         F, pshape, A = obs_space[0].shape[0], tuple(obs_space[1].shape), action_space.shape[0]
         self.store_np = ["state_features", "state_particles", "action", "next_state_features", "next_state_particles",
                          "reward", "not_done"]
@@ -268,16 +277,16 @@ class ReplayBuffer_particles(_DeviceReplay):
         self._fields = {"state_features": (o_f, (F,)), "state_particles": (0, pshape), "action": (o_f + F, (A,)),
                         "next_state_features": (o_f + F + A, (F,)), "next_state_particles": (pnp, pshape),
                         "reward": (o_f + 2 * F + A, (1,)), "not_done": (o_f + 2 * F + A + 1, (1,))}
-        self._init_storage(max_size, load_folder)
+        self._init_storage(max_size, load_folder, n_agents)
 
-    def add(self, state, action, next_state, reward, done):
+    def add(self, state, action, next_state, reward, done, agent=0):
         slot = self._next_slot()
         row = self._stage_np[slot]
         vals = (state[0], state[1], action, next_state[0], next_state[1], reward, 1. - done)
         for (off, shape), v in zip(self._fields.values(), vals):
             w = int(np.prod(shape))
             row[off:off + w] = np.asarray(v).reshape(-1) if w > 1 else v
-        self._commit_row(slot)
+        self._commit_row(slot, agent)
 
 
 # experience_injection.py:3 imports a name the reference never defines; its environment

@@ -134,3 +134,73 @@ def test_sharded_population_equals_the_unsharded_one():
         for k in NETS:
             for n in whole[g][k]:
                 assert torch.equal(whole[g][k][n], parts[g][k][n]), (g, k, n)
+
+
+def test_particles_population_members_match_standalone_agents():
+    """TD3_particles populations (round 2): two members stepped in lock-step equal two standalone agents bit for bit, with
+    per-member add() into the members' own rings."""
+    from td3_b200.TD3_particles import TD3 as PT
+    from td3_b200.my_replay_buffer import ReplayBuffer_particles
+    F, Np, D, Ap, rows, Bp = 4, 32, 3, 2, 48, 16
+    obs, act = (O.Space(F), O.Space(Np, D)), O.Space(Ap)
+    torch.manual_seed(9)
+    pop = PT(obs, act, n_agents=2, precision="fp32", seed=5, lr=1e-3, actor_widths=(48, 32), q_widths=(48, 32))
+    rbp = ReplayBuffer_particles(obs, act, max_size=rows, n_agents=2)
+    singles = []
+    for i in range(2):
+        a = PT(obs, act, precision="fp32", seed=(5 + i * 0x9E3779B97F4A7C15) % (1 << 64), lr=1e-3, actor_widths=(48, 32), q_widths=(48, 32))
+        for k in NETS:
+            getattr(a, k).load_state_dict({n: v.clone() for n, v in pop.agent_state_dict(k, i).items()})
+        data = O.synthetic_transitions_particles(rows, F, Np, D, Ap, seed=20 + i)
+        rb = ReplayBuffer_particles(obs, act, max_size=rows)
+        for r in range(rows):       # one row at a time through add(..., agent=i): the per-member ingest path
+            row = ((data["state_features"][r], data["state_particles"][r]), data["action"][r],
+                   (data["next_state_features"][r], data["next_state_particles"][r]), float(data["reward"][r]), float(data["done"][r]))
+            rb.add(*row)
+            rbp.add(*row, agent=i)
+        singles.append((a, rb))
+    rs = np.random.RandomState(2)
+    for t in range(4):
+        idx = rs.randint(0, rows, size=(2, Bp))
+        nz = rs.standard_normal((2, Bp, Ap)).astype(np.float32)
+        pop.train(rbp, Bp, indices=idx, noise=nz)
+        for i, (a, rb) in enumerate(singles):
+            a.train(rb, Bp, indices=idx[i], noise=nz[i])
+    _assert_same(pop, singles)
+    assert np.allclose(pop.select_action((data["state_features"][0], data["state_particles"][0]), agent=1),
+                       singles[1][0].select_action((data["state_features"][0], data["state_particles"][0])))
+
+
+def test_run_population_trains_every_member_on_the_device():
+    """The population driver loop (td3_b200.population.run_population, main.py:240-289 generalised) on a toy environment:
+    three members, own rings, lock-step updates after the random phase; every member's parameters move and stay finite."""
+    from td3_b200.TD3_featured import TD3
+    from td3_b200.my_replay_buffer import ReplayBuffer_featured
+    from td3_b200.population import run_population
+
+    class Toy:
+        def __init__(self, seed):
+            self.rs, self.t = np.random.RandomState(seed), 0
+
+        def reset(self):
+            self.t, self.s = 0, self.rs.standard_normal(S)
+            return self.s
+
+        def step(self, a):
+            self.t += 1
+            self.s = 0.9 * self.s + 0.1 * self.rs.standard_normal(S)
+            return self.s, float(-np.square(a).sum()), self.t >= 25, {}
+
+    obs, act = O.Space(S), O.Space(A)
+    torch.manual_seed(1)
+    pop = TD3(obs, act, n_agents=3, seed=3, **KW)
+    rb = ReplayBuffer_featured(obs, act, max_size=512, n_agents=3)
+    before = [pop.agent_state_dict("critic", i)["q1.linears.0.weight"].clone() for i in range(3)]
+    rets = run_population(pop, rb, [Toy(i) for i in range(3)], max_timesteps=120, start_timesteps=64, batch_size=32)
+    torch.cuda.synchronize()
+    assert pop.total_it == 56 and all(len(r) == 4 for r in rets)
+    assert rb.size == 120 and rb._sizes[1] == 120 and rb._sizes[2] == 120
+    for i in range(3):
+        after = pop.agent_state_dict("critic", i)["q1.linears.0.weight"]
+        assert torch.isfinite(after).all() and not torch.equal(after, before[i])
+    assert torch.isfinite(pop.last_critic_loss).all()

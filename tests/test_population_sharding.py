@@ -76,3 +76,53 @@ def test_two_ranks_own_disjoint_agents_with_rank_independent_keys_gloo_world2():
         assert p.exitcode == 0
     assert keys == [member_seed(1001, g) for g in range(16)]
     assert t_max == 2.0
+
+
+def test_run_population_follows_the_reference_loop():
+    """Control flow of td3_b200.population.run_population (main.py:240-289 for a population) with duck-typed stand-ins:
+    random actions then policy actions + noise, one add per member per step into its own ring, one lock-step train per
+    step after start_timesteps, episode bookkeeping per member."""
+    import numpy as np
+    from td3_b200.population import run_population
+
+    class Env:
+        def __init__(self, horizon):
+            self.h, self.t = horizon, 0
+
+        def reset(self):
+            self.t = 0
+            return np.zeros(3)
+
+        def step(self, a):
+            self.t += 1
+            return np.full(3, self.t, dtype=np.float64), 1.0, self.t >= self.h, {}
+
+    class Policy:
+        n_agents, max_action = 2, 1.0
+
+        def __init__(self):
+            self.sel, self.trains = [], 0
+
+        def select_action(self, s, agent=0):
+            self.sel.append(agent)
+            return np.array([0.5, -0.5])
+
+        def train(self, rb, batch):
+            self.trains += 1
+            assert batch == 8 and all(c >= 5 for c in rb.count)
+
+    class Buffer:
+        def __init__(self):
+            self.count, self.rows = [0, 0], []
+
+        def add(self, s, a, s2, r, d, agent=0):
+            assert -1.0 <= a.min() and a.max() <= 1.0 and len(a) == 2
+            self.count[agent] += 1
+            self.rows.append((agent, float(s2[0]), d))
+
+    pol, rb = Policy(), Buffer()
+    rets = run_population(pol, rb, [Env(4), Env(6)], max_timesteps=12, start_timesteps=5, batch_size=8, action_dim=2)
+    assert rb.count == [12, 12] and pol.trains == 7
+    assert pol.sel == [0, 1] * 7                      # policy actions only after the random phase, members in order
+    assert rets == [[4.0, 4.0, 4.0], [6.0, 6.0]]
+    assert [r for r in rb.rows if r[0] == 0][3] == (0, 4.0, 1.0)      # member 0's fourth transition ends its episode
