@@ -26,6 +26,7 @@
 #include "apply.cuh"
 #include "persist.cuh"
 #include "infer.cuh"
+#include "enc.cuh"
 
 using namespace td3;
 
@@ -59,8 +60,9 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 // launch list
 // ------------------------------------------------------------------------------------
 struct Launch {
-  enum Kind { STAGE, GATHER, LOSS, EW, TICK, HEAD, WN, FRONT, DPSYNC } kind = STAGE;
+  enum Kind { STAGE, GATHER, LOSS, EW, TICK, HEAD, WN, FRONT, DPSYNC, ENC } kind = STAGE;
   DpSyncParams dpsync{};
+  EncParams enc{};
   HeadParams head{};
   WnParams wn{};
   FrontParams front{};
@@ -79,6 +81,7 @@ int ensure_kernel_attrs() {
   if (done) return TD3_OK;
   CUDA_TRY(cudaFuncSetAttribute(head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
   CUDA_TRY(cudaFuncSetAttribute(front_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFrontSmemBytes));
+  CUDA_TRY(cudaFuncSetAttribute(enc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kEncSmemBytes));
   CUDA_TRY(cudaFuncSetAttribute(stage_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynSmemBytes));
   CUDA_TRY(cudaFuncSetAttribute(stage_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynSmemBytes));
   CUDA_TRY(cudaFuncSetAttribute(persistent_update_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynSmemBytes));
@@ -174,6 +177,12 @@ int run_launch(const Launch& L, cudaStream_t s) {
       dp_signal_wait_kernel<<<1, 32, 0, s>>>(L.dpsync);
       e = cudaGetLastError();
       break;
+    case Launch::ENC: {
+      int rc = ensure_kernel_attrs();
+      if (rc != TD3_OK) return rc;
+      e = launch_pdl(enc_fwd_kernel, dim3(L.grid_x), dim3(kEncThreads), (size_t)kEncSmemBytes, s, L.enc);
+      break;
+    }
   }
   if (e != cudaSuccess) return fail(TD3_ERR_CUDA, "kernel launch: %s", cudaGetErrorString(e));
   g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -376,6 +385,9 @@ void finalize_problem(Problem& p, GroupShape gs) {
     case PK_NEG_MEAN:
       p.tiles_per_group = 1;
       break;
+    case PK_ENC_FUSED:
+      p.tiles_per_group = p.M / kEncTile;
+      break;
   }
   p.tile_count = p.tiles_per_group * groups;
 }
@@ -489,7 +501,52 @@ void layout_stage(Launch& L) {
   S.cluster = c;
 }
 
-int emit_stage(std::vector<Launch>& seq, const ProblemList& probs) {
+// the fused set-encoder forward of one pass (enc.cuh) as a launch: the problem record carries
+//   A = particles, B / bias = conv1 weight / bias (fp32 masters), aux0 = conv2 weight (the TF32 copy when there is one),
+//   aux1 = conv2 bias, aux2 / aux3 = optional h1 / h2 outputs, C = partial means, M = rows, K = D, N = particles per sample
+bool make_enc_launch(const Problem& p, Launch& L) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) return false;
+  L = Launch{};
+  L.kind = Launch::ENC;
+  EncParams& E = L.enc;
+  memset(&E, 0, sizeof(E));
+  const int groups = p.tile_count / std::max(1, p.tiles_per_group);
+  const int n_inner = std::max(1, p.groups_inner), n_outer = std::max(1, groups / n_inner);
+  if (groups > kEncMaxGroups) return false;
+  E.P = p.A; E.p_go = p.a_go;
+  E.W1 = p.B; E.b1 = p.bias; E.b2 = p.aux1; E.w_go = p.b_go; E.w_gi = p.b_gi;
+  E.h1 = p.aux2; E.h1_go = p.aux2_go; E.h1_gi = p.aux2_gi;
+  E.h2 = p.aux3; E.h2_go = p.aux3_go; E.h2_gi = p.aux3_gi;
+  E.part = p.C; E.part_go = p.c_go; E.part_gi = p.c_gi;
+  E.rows = p.M; E.D = p.K; E.n_inner = n_inner; E.n_groups = groups; E.tiles_per_group = p.tiles_per_group;
+  for (int o = 0; o < n_outer; ++o)
+    for (int i = 0; i < n_inner; ++i) {
+      CUtensorMap m;
+      cuuint64_t gdim[2] = {(cuuint64_t)kEncH, (cuuint64_t)kEncO}, gstride[1] = {(cuuint64_t)kEncH * 4};
+      cuuint32_t box[2] = {32, (cuuint32_t)kEncO}, estr[2] = {1, 1};
+      void* addr = const_cast<float*>(p.aux0 + o * p.aux0_go + i * p.aux0_gi);
+      if (enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, addr, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return false;
+      static_assert(sizeof(CUtensorMap) == sizeof(TensorMapBlob), "tensor map blob size");
+      memcpy(&E.w2_map[o * n_inner + i], &m, sizeof(m));
+    }
+  L.grid_x = std::min(g_sm_count, groups * p.tiles_per_group);
+  return true;
+}
+
+int emit_stage(std::vector<Launch>& seq, const ProblemList& probs_in) {
+  ProblemList probs;
+  for (const Problem& p : probs_in) {
+    if (p.kind == PK_ENC_FUSED) {
+      Launch L;
+      if (!make_enc_launch(p, L)) return fail(TD3_ERR_CUDA, "fused set-encoder: tensor map for conv2 could not be encoded");
+      seq.push_back(L);
+    } else {
+      probs.push_back(p);
+    }
+  }
   // split into chunks of kMaxProblemsPerStage (they stay independent, so extra launches are still correct)
   size_t i = 0;
   while (i < probs.size()) {
@@ -569,6 +626,8 @@ struct PassBuf {
   const float* P = nullptr; long long P_go = 0;       // particles [B*N, D]
   float* h1 = nullptr; float* h2 = nullptr;           // encoder activations
   long long h1_go = 0, h1_gi = 0, h2_go = 0, h2_gi = 0;
+  float* part = nullptr; long long part_go = 0, part_gi = 0;   // fused encoder: partial means [rows / 128, enc_out]
+  bool keep_enc_acts = true;                          // false: nothing reads h1 / h2 after the forward pass (target networks, Q1)
 };
 
 struct OutSpec {
@@ -702,7 +761,37 @@ std::vector<ProblemList> build_forward(const td3_agent_config& cfg, const td3_ne
   // TF32 mode: whatever a later tensor-core contraction reads as an operand is stored rounded to nearest TF32 by its
   // producer (stage.cuh: Problem::rn_out), and weights come from the rounded shadows (ParamRef::tc)
   const int tf = g_tc_mode ? 1 : 0;
-  if (enc) {
+  // K6 (enc.cuh): layer 1 -> layer 2 on tcgen05 -> partial pooling in ONE persistent launch, activations on chip
+  const bool fuse_enc = enc && tf && net.enc_hidden == kEncH && net.enc_out == kEncO && cfg.particle_dim <= 7 &&
+                        ((long long)B * cfg.n_particles) % kEncTile == 0 && cfg.n_particles % kEncTile == 0 &&
+                        gs.n_outer * gs.n_inner <= kEncMaxGroups && pb.part && encode_tiled_fn() != nullptr &&
+                        !getenv("TD3_NO_ENC_FUSION");
+  if (fuse_enc) {
+    const int rows = B * cfg.n_particles;
+    Problem ef = blank_problem(PK_ENC_FUSED);
+    ef.M = rows; ef.K = cfg.particle_dim; ef.N = cfg.n_particles;
+    ef.A = pb.P; ef.a_go = pb.P_go;
+    ef.B = W.base + net.c1w_off; ef.b_go = W.go; ef.b_gi = W.gi;
+    ef.bias = W.base + net.c1b_off; ef.bias_go = W.go; ef.bias_gi = W.gi;
+    ef.aux0 = const_cast<float*>((W.tc ? W.tc : W.base) + net.c2w_off); ef.aux0_go = W.go; ef.aux0_gi = W.gi;
+    ef.aux1 = const_cast<float*>(W.base + net.c2b_off); ef.aux1_go = W.go; ef.aux1_gi = W.gi;
+    if (pb.keep_enc_acts) {
+      ef.aux2 = pb.h1; ef.aux2_go = pb.h1_go; ef.aux2_gi = pb.h1_gi;
+      ef.aux3 = pb.h2; ef.aux3_go = pb.h2_go; ef.aux3_gi = pb.h2_gi;
+    }
+    ef.C = pb.part; ef.c_go = pb.part_go; ef.c_gi = pb.part_gi;
+    finalize_problem(ef, gs);
+    st.push_back({ef});
+    // relu(mean over the sample's N / 128 partial means), into the first enc_out columns of the trunk input (:57-59)
+    Problem pl = blank_problem(PK_POOL_FWD);
+    pl.M = B; pl.N = net.enc_out; pl.K = cfg.n_particles / kEncTile;
+    pl.A = pb.part; pl.lda = net.enc_out; pl.a_go = pb.part_go; pl.a_gi = pb.part_gi;
+    pl.C = pb.x0; pl.ldc = pb.ld0; pl.c_go = pb.x0_go; pl.c_gi = pb.x0_gi;
+    pl.c_dups = pool_dups; pl.c_dup_stride = pool_dup_stride;
+    pl.rn_out = tf;
+    finalize_problem(pl, gs);
+    st.push_back({pl});
+  } else if (enc) {
     const int rows = B * cfg.n_particles;
     // conv1 == per-particle linear D -> enc_hidden (TD3_particles.py:29,54)
     Problem e1 = make_gemm(rows, net.enc_hidden, cfg.particle_dim, pb.P, cfg.particle_dim, true, W.base + net.c1w_off,
@@ -1116,6 +1205,11 @@ void alloc_pass(Bump& ws, const td3_agent_config& cfg, const td3_net_layout& net
     pb.h1 = ws.take(groups * rows * net.enc_hidden);
     pb.h2 = ws.take(groups * rows * net.enc_out);
   }
+  if (enc) {
+    const long long tiles = ((long long)B * cfg.n_particles + kEncTile - 1) / kEncTile;
+    pb.part_gi = tiles * net.enc_out; pb.part_go = pb.part_gi * gs.n_inner;
+    pb.part = ws.take(groups * tiles * net.enc_out);
+  }
 }
 
 void alloc_bwd(Bump& ws, const td3_agent_config& cfg, const td3_net_layout& net, GroupShape gs, int B, BwdScratch& sc,
@@ -1346,6 +1440,7 @@ int plan_agent(td3_agent* a, long long batch) {
   };
   PassBuf &at = a->pb_at, &ct = a->pb_ct, &cc = a->pb_c, &pa = a->pb_a, &q1 = a->pb_q1;
   at = ct = cc = pa = q1 = PassBuf{};
+  at.keep_enc_acts = ct.keep_enc_acts = q1.keep_enc_acts = false;   // only the passes with an encoder backward (critics, actor) keep h1 / h2
   if (enc) {
     share_x0(at, a->xa2, ld_a, a->xa_go, 0);
     share_x0(pa, a->xa, ld_a, a->xa_go, 0);

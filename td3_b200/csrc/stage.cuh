@@ -27,7 +27,8 @@ enum ProblemKind : int {
   PK_NEG_MEAN = 7,      // scalar = -mean(A)      (actor loss read-back)
   PK_COLSUM = 8,        // C[j] = sum_i A[i,j]    (bias gradient next to a tensor-core dW)
   PK_SMALLK_FWD = 9,    // C[i,j] = relu(bias[j] + sum_{d<K} A[i,d] B[j,d]), K <= 8   (particle encoder layer 1: HBM-write bound)
-  PK_SMALLK_DW = 10     // C[j,d] = sum_i A[i,j] B[i,d], aux1[j] = sum_i A[i,j], N <= 8, reduction split over CTAs
+  PK_SMALLK_DW = 10,    // C[j,d] = sum_i A[i,j] B[i,d], aux1[j] = sum_i A[i,j], N <= 8, reduction split over CTAs
+  PK_ENC_FUSED = 11     // host-side planning only: the fused set-encoder forward (enc.cuh), emitted as a launch of its own
 };
 
 enum Epilogue : int {
