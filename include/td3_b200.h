@@ -187,6 +187,10 @@ int td3_agent_bind_state(td3_agent* agent, void* state_dev, int64_t n_bytes);
  * whenever the critic head is fused: output width <= 4, last hidden width <= 512). */
 int td3_agent_bind_host_status(td3_agent* agent, void* host_words);
 int td3_agent_host_status_live(const td3_agent* agent);
+/* 1 when the planned update runs as the layer-fused chain launches (csrc/chain.cuh: TD3_featured.py:129-163 as one
+ * launch per phase; opt-in through the environment variable TD3_CHAIN=1, plain MLPs in TF32 mode), 0 when it runs as
+ * the default stage-per-layer sequence. */
+int td3_agent_chain_active(const td3_agent* agent);
 /* precision = TD3_PRECISION_TF32 keeps round-to-nearest TF32 copies of the four packed parameter buffers for the tensor
  * cores (tcgen05 kind::tf32 truncates its operands; a pre-rounded operand is read exactly, which removes the bias of
  * truncation).  The optimiser kernels keep them current.  Whoever writes the parameter buffers from outside -- the

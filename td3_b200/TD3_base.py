@@ -252,6 +252,10 @@ class TD3_base(object):
         out = self.last_critic_loss.cpu().numpy()
         return float(out[0]) if nA == 1 else out
 
+    def chain_active(self) -> bool:
+        """True when the planned update runs as the layer-fused chain launches (csrc/chain.cuh, TD3_CHAIN=1)."""
+        return bool(self._lib.td3_agent_chain_active(self._handle))
+
     def debug_tensors(self):
         """Views of the last update's Q-values / Bellman target (tests)."""
         B, nq, nA = self._planned_batch, self._cfg.n_q, self._cfg.n_agents

@@ -83,6 +83,7 @@ SIGNATURES = {
     "td3_agent_bind_state": (C.c_int, [_vp, _vp, _i64]),
     "td3_agent_bind_host_status": (C.c_int, [_vp, _vp]),
     "td3_agent_host_status_live": (C.c_int, [_vp]),
+    "td3_agent_chain_active": (C.c_int, [_vp]),
     "td3_agent_params_changed": (C.c_int, [_vp]),
     "td3_agent_prepare": (C.c_int, [_vp, _P(ReplayView), _vp]),
     "dp_allreduce_grads": (C.c_int, [_vp, _P(_vp), _i32, _i64, _vp]),

@@ -27,6 +27,7 @@
 #include "persist.cuh"
 #include "infer.cuh"
 #include "enc.cuh"
+#include "chain.cuh"
 
 using namespace td3;
 
@@ -60,7 +61,8 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 // launch list
 // ------------------------------------------------------------------------------------
 struct Launch {
-  enum Kind { STAGE, GATHER, LOSS, EW, TICK, HEAD, WN, FRONT, DPSYNC, ENC } kind = STAGE;
+  enum Kind { STAGE, GATHER, LOSS, EW, TICK, HEAD, WN, FRONT, DPSYNC, ENC, CHAIN } kind = STAGE;
+  ChainParams chain{};
   DpSyncParams dpsync{};
   EncParams enc{};
   HeadParams head{};
@@ -76,12 +78,16 @@ struct Launch {
   int grid_x = 1, grid_y = 1;
 };
 
+constexpr int kChainSmemMax = 232448 - 1024;     // dynamic shared memory of a chain CTA (static barriers take the rest)
+constexpr int kChainSmemFixed = 1024 + kChX0Bytes + 2 * kChMaxW * 4 + 5 * kChRows * 4;   // alignment, X0, bias, head weights, reductions
+
 int ensure_kernel_attrs() {
   static bool done = false;
   if (done) return TD3_OK;
   CUDA_TRY(cudaFuncSetAttribute(head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
   CUDA_TRY(cudaFuncSetAttribute(front_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFrontSmemBytes));
   CUDA_TRY(cudaFuncSetAttribute(enc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kEncSmemBytes));
+  CUDA_TRY(cudaFuncSetAttribute(chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmemMax));
   CUDA_TRY(cudaFuncSetAttribute(stage_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynSmemBytes));
   CUDA_TRY(cudaFuncSetAttribute(stage_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynSmemBytes));
   CUDA_TRY(cudaFuncSetAttribute(persistent_update_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynSmemBytes));
@@ -181,6 +187,12 @@ int run_launch(const Launch& L, cudaStream_t s) {
       int rc = ensure_kernel_attrs();
       if (rc != TD3_OK) return rc;
       e = launch_pdl(enc_fwd_kernel, dim3(L.grid_x), dim3(kEncThreads), (size_t)kEncSmemBytes, s, L.enc);
+      break;
+    }
+    case Launch::CHAIN: {
+      int rc = ensure_kernel_attrs();
+      if (rc != TD3_OK) return rc;
+      e = launch_pdl(chain_kernel, dim3(L.chain.n_ctas), dim3(kChThreads), (size_t)L.smem_bytes, s, L.chain);
       break;
     }
   }
@@ -707,6 +719,10 @@ struct td3_agent {
   // -- plain MLPs -- the tail-fused form: first-layer gradient + Adam (+ Polyak) in ONE launch (apply.cuh) and the
   // actor's forward layers riding along with the target pass
   std::vector<Launch> seq_run_critic, seq_run_policy;
+  // layer-fused chains (chain.cuh): what train_n runs INSTEAD of seq_sample + seq_run_* when the shapes allow it
+  // (the first launch of each samples the batch itself: plan_sample fills its replay view)
+  std::vector<Launch> seq_chain_critic, seq_chain_policy;
+  bool chain_on = false;
   bool tail_fused = false;
   int n_actor_fwd = 0;                       // leading launches of seq_actor_fb that are the actor's forward pass
   const float* plan_rows = nullptr;
@@ -1462,6 +1478,17 @@ int plan_agent(td3_agent* a, long long batch) {
   alloc_bwd(ws, c, c.q, g_crit, B, sc_c, true);
   alloc_bwd(ws, c, c.q, g_q1, B, sc_q1, false);
   alloc_bwd(ws, c, c.actor, g_actor, B, sc_a, true);
+  // layer-fused chains (chain.cuh): dZ of every layer at once (the weight-gradient stage runs after the whole chain),
+  // per-tile flags / loss terms, launch epoch and completion counter
+  const int ch_tiles = (B + kChRows - 1) / kChRows;
+  float* ch_cz[TD3_MAX_LINEAR] = {};
+  float* ch_az[TD3_MAX_LINEAR] = {};
+  if (!enc) {
+    for (int l = 0; l + 1 < c.q.n_linear; ++l) ch_cz[l] = ws.take((long long)nA * nq * B * c.q.dims[l + 1]);
+    for (int l = 0; l < c.actor.n_linear; ++l) ch_az[l] = ws.take((long long)nA * B * c.actor.dims[l + 1]);
+  }
+  unsigned int* ch_sync = reinterpret_cast<unsigned int*>(ws.take(64 + (long long)nA * ch_tiles * nq, "chain_sync"));
+  float* ch_loss_part = ws.take(2LL * nA * ch_tiles * nq, "chain_loss_terms");
   a->ws_floats = ws.used;
   if (!ws.base) return TD3_OK;   // sizing pass only
 
@@ -1844,11 +1871,284 @@ int plan_agent(td3_agent* a, long long batch) {
     }
     for (; (int)ai < a->n_actor_fwd; ++ai) v_tp.push_back(a->seq_actor_fb[ai]);
   }
+
+  // ---- layer-fused chains (chain.cuh), opt-in: TD3_CHAIN=1 ----
+  // Plain MLPs of the featured variant in TF32 mode: the row-local part of the update is ONE launch (per policy_freq
+  // phase), the weight gradients of layers >= 1 are one tensor-core stage, the first layer's gradient + the optimiser
+  // are the apply launch: 3 launches for a critic-only update, 6 for a policy update.  Correct (the whole GPU suite
+  // passes with it on) but MEASURED SLOWER than the stage-per-layer graph on B200 (cfg2: 120 / 260 us per critic-only /
+  // policy update against 53 / 104 us; 8- and 16-agent populations: on par): one CTA per 64-row tile streams every
+  // layer's full weight matrix through a 3-slot ring, and at ~2 k cycles of L2 round trip per slot that is ~25 B/clk per
+  // SM -- a 400 x 300 layer takes 23 k cycles where the stage kernel spreads it over 20-130 SMs (DESIGN.md section 9,
+  // profiles/r02b_chain_*).  Kept as the measured record of that design and as a second implementation the parity
+  // tests cross-check; not on the default path.
+  std::vector<Launch> v_ch_cdw, v_ch_adw;
+  Launch ch_A, ch_Apol, ch_P;
+  bool chain = false;
+  {
+    auto widths_ok = [&](const td3_net_layout& n) {
+      if (n.n_linear < 2 || n.n_linear - 1 > kChMaxMask) return false;
+      for (int l = 1; l < n.n_linear; ++l)
+        if ((n.dims[l] & 3) || n.dims[l] > kChMaxW || n.dims[l] < 8) return false;
+      if ((n.n_floats & 3) != 0) return false;
+      for (int l = 1; l < n.n_linear; ++l)
+        if (n.w_off[l] & 3) return false;
+      return true;
+    };
+    chain = fuse_tail && tf && !enc && !ln && !wn && qw == 1 && nq >= 1 && nq <= 2 && S + A <= 32 && A <= 8 &&
+            widths_ok(c.q) && widths_ok(c.actor) && a->global_batch == 0 && a->batch_offset == 0 && a->sh_c != nullptr &&
+            encode_tiled_fn() != nullptr && getenv("TD3_CHAIN") && !getenv("TD3_NO_CHAIN");
+  }
+  if (chain) {
+    EncodeTiledFn encf = encode_tiled_fn();
+    bool ok = true;
+    // 3-D tensor map over the weight matrix at `w` ([rows][cols] fp32, row-major) of `n_nets` networks `stride` floats apart
+    auto add_map = [&](Launch& L, int& n_maps, const float* w, long long stride, int n_nets, int rows, int cols, bool mn, int nb) {
+      if (n_maps >= kChMaxMaps || !aligned16(w) || (cols & 3) || (stride & 3)) { ok = false; return 0; }
+      CUtensorMap m;
+      cuuint64_t gdim[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)n_nets};
+      cuuint64_t gstride[2] = {(cuuint64_t)cols * 4, (cuuint64_t)std::max<long long>(stride, 4) * 4};
+      cuuint32_t box[3] = {32, mn ? 32u : (cuuint32_t)nb, 1}, estr[3] = {1, 1, 1};
+      CUresult r = encf(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(w), gdim, gstride, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, mn ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) { ok = false; return 0; }
+      static_assert(sizeof(CUtensorMap) == sizeof(TensorMapBlob), "tensor map blob size");
+      memcpy(&L.chain.maps[n_maps], &m, sizeof(m));
+      return n_maps++;
+    };
+    struct Fam { const float* P; const float* Psh; long long go, gi; int z_o, z_i, n_nets; long long stride; };
+    const Fam f_at{a->actor.target, a->sh_at, an, 0, 1, 0, nA, an};
+    const Fam f_a{a->actor.params, a->sh_a, an, 0, 1, 0, nA, an};
+    const Fam f_ct{a->critic.target, a->sh_ct, qn * nq, qn, nq, 1, nA * nq, qn};
+    const Fam f_c{a->critic.params, a->sh_c, qn * nq, qn, nq, 1, nA * nq, qn};
+    const Fam f_q1{a->critic.params, a->sh_c, qn * nq, 0, nq, 0, nA * nq, qn};
+    int slot_need = 4096, maxw = 32;
+    auto blocks = [&](ChainStep& st) {
+      st.n_blk = (st.N + 255) / 256;
+      st.nb = (int)round_up((st.N + st.n_blk - 1) / st.n_blk, 8);
+      const bool mn = st.b_mode == CB_TMA_MN || st.b_mode == CB_MANUAL_MN;
+      if (st.b_mode == CB_MANUAL_MN) { st.n_blk = 1; st.nb = (int)round_up(st.N, 8); }
+      st.blk_bytes = mn ? (st.b_mode == CB_MANUAL_MN ? 4096 : ((st.nb + 31) / 32) * 4096) : st.nb * 128;
+      slot_need = std::max(slot_need, (int)round_up(st.blk_bytes, 1024));
+      maxw = std::max(maxw, std::max(st.a_x0 ? 32 : st.K, st.N));
+    };
+    auto base_step = [&](const Fam& f) {
+      ChainStep st;
+      memset(&st, 0, sizeof(st));
+      st.P = f.P; st.Psh = f.Psh; st.p_go = f.go; st.p_gi = f.gi; st.z_o = f.z_o; st.z_i = f.z_i;
+      st.bias_off = -1; st.mask_w = st.mask_r = -1; st.map = -1;
+      return st;
+    };
+    // forward through linear layer l of `n` (hidden layers: ReLU; the actor's output layer: tanh)
+    auto fwd_step = [&](Launch& L, int& n_maps, const td3_net_layout& n, const Fam& f, int l, bool out_layer) {
+      ChainStep st = base_step(f);
+      st.K = n.dims[l]; st.N = n.dims[l + 1];
+      st.w_off = n.w_off[l]; st.bias_off = n.b_off[l];
+      st.epi = out_layer ? CE_ACTOR_OUT : CE_HIDDEN;
+      if (l == 0) { st.b_mode = CB_MANUAL_K; st.a_x0 = 1; st.ld_w = n.dims[0]; }
+      else st.b_mode = CB_TMA_K;
+      blocks(st);
+      if (l > 0) st.map = add_map(L, n_maps, f.Psh + n.w_off[l], f.stride, f.n_nets, n.dims[l + 1], n.dims[l], false, st.nb);
+      return st;
+    };
+    // backward through linear layer l >= 1: d(in) = dZ_l . W_l, gated by the ReLU of hidden layer l - 1
+    auto bwd_step = [&](Launch& L, int& n_maps, const td3_net_layout& n, const Fam& f, int l) {
+      ChainStep st = base_step(f);
+      st.K = n.dims[l + 1]; st.N = n.dims[l];
+      st.w_off = n.w_off[l];
+      st.epi = CE_BWD_MASK; st.b_mode = CB_TMA_MN;
+      blocks(st);
+      st.map = add_map(L, n_maps, f.Psh + n.w_off[l], f.stride, f.n_nets, n.dims[l + 1], n.dims[l], true, st.nb);
+      return st;
+    };
+    auto push = [&](Launch& L, int& n_steps, const ChainStep& st) {
+      if (n_steps >= kChMaxSteps) { ok = false; return; }
+      L.chain.steps[n_steps++] = st;
+    };
+    auto common = [&](Launch& L) {
+      L = Launch{};
+      L.kind = Launch::CHAIN;
+      ChainParams& P = L.chain;
+      memset(&P, 0, sizeof(P));
+      P.batch = B; P.n_agents = nA; P.tiles = ch_tiles; P.S = S; P.A = A; P.n_q = nq; P.ld_q = ld_q; P.ld_tanh = A;
+      P.xq = a->xq; P.xq_go = a->xq_go; P.xq2 = a->xq2; P.xq2_go = a->xq_go; P.xpi = a->xpi; P.xpi_go = a->xpi_go;
+      P.r = a->r; P.nd = a->nd; P.r_go = B;
+      P.tanh_y = a->tanh_y; P.tanh_go = (long long)B * A;
+      P.q = a->q; P.tq = a->tq; P.dq = a->dq; P.q_gi = B; P.q_go = (long long)B * nq;
+      P.y = a->y; P.y_go = B; P.q_pi = a->q_pi; P.qpi_go = B;
+      P.lp_go = (long long)ch_tiles * nq;
+      P.loss = a->state_f32;
+      P.flags = ch_sync + 64; P.flag_go = (long long)ch_tiles * nq;
+      P.epoch = ch_sync; P.done = ch_sync + 1;
+      P.discount = c.discount; P.inv_norm = 1.f / (float)(batch * qw);
+      P.max_action = c.max_action; P.clamp_action = c.clamp_target_action ? c.max_action : 0.f;
+      P.prof = getenv("TD3_CHAIN_PROF") ? a->prof_dev : nullptr;
+    };
+    const int Lq_ = c.q.n_linear;
+    // critic-side launch; with_actor: the online actor's forward pass rides along (policy steps)
+    auto build_A = [&](Launch& L, bool with_actor) {
+      common(L);
+      ChainParams& P = L.chain;
+      P.loss_part = ch_loss_part;
+      P.fin_mode = 0;
+      P.tick = AdamTick{a->state_u64, 0, 0, c.lr_critic, c.beta1, c.beta2};
+      P.host_status = a->host_status_live ? a->host_status : nullptr; P.seq = head_seq;
+      int n_steps = 0, n_maps = 0, n_roles = 0, first = 0;
+      auto begin_role = [&](int kind, int inner) {
+        P.role_kind[n_roles] = kind; P.role_inner[n_roles] = inner; P.role_first[n_roles] = first; P.role_step0[n_roles] = n_steps;
+      };
+      auto end_role = [&](int inner) {
+        P.role_nsteps[n_roles] = n_steps - P.role_step0[n_roles];
+        first += nA * inner * ch_tiles;
+        ++n_roles;
+        P.role_first[n_roles] = first;
+      };
+      // TARGET: target actor, then target critic twin t on [s', a']
+      begin_role(CR_TARGET, nq);
+      for (int l = 0; l + 1 < La; ++l) push(L, n_steps, fwd_step(L, n_maps, c.actor, f_at, l, false));
+      { ChainStep st = fwd_step(L, n_maps, c.actor, f_at, La - 1, true); st.flavour = 0; push(L, n_steps, st); }
+      for (int l = 0; l + 1 < Lq_; ++l) {
+        ChainStep st = fwd_step(L, n_maps, c.q, f_ct, l, false);
+        if (l == Lq_ - 2) { st.post = CP_TQ; st.head_w_off = c.q.w_off[Lq_ - 1]; st.head_b_off = c.q.b_off[Lq_ - 1]; }
+        push(L, n_steps, st);
+      }
+      end_role(nq);
+      if (with_actor) {
+        begin_role(CR_ACTOR, 1);
+        for (int l = 0; l + 1 < La; ++l) {
+          ChainStep st = fwd_step(L, n_maps, c.actor, f_a, l, false);
+          st.out = pa.r[l]; st.out_go = pa.h_go[l]; st.out_gi = pa.h_gi[l]; st.ld_out = c.actor.dims[l + 1];
+          push(L, n_steps, st);
+        }
+        { ChainStep st = fwd_step(L, n_maps, c.actor, f_a, La - 1, true); st.flavour = 1; push(L, n_steps, st); }
+        end_role(1);
+      }
+      // CRITIC: online critic twin t forward, loss gradient, dX chain
+      begin_role(CR_CRITIC, nq);
+      for (int l = 0; l + 1 < Lq_; ++l) {
+        ChainStep st = fwd_step(L, n_maps, c.q, f_c, l, false);
+        st.out = cc.r[l]; st.out_go = cc.h_go[l]; st.out_gi = cc.h_gi[l]; st.ld_out = c.q.dims[l + 1];
+        st.mask_w = l;
+        if (l == Lq_ - 2) {
+          st.post = CP_CRITIC; st.head_w_off = c.q.w_off[Lq_ - 1]; st.head_b_off = c.q.b_off[Lq_ - 1];
+          st.out2 = ch_cz[l]; st.out2_gi = (long long)B * c.q.dims[l + 1]; st.out2_go = st.out2_gi * nq;
+        }
+        push(L, n_steps, st);
+      }
+      for (int l = Lq_ - 2; l >= 1; --l) {
+        ChainStep st = bwd_step(L, n_maps, c.q, f_c, l);
+        st.mask_r = l - 1;
+        st.out = ch_cz[l - 1]; st.out_gi = (long long)B * c.q.dims[l]; st.out_go = st.out_gi * nq; st.ld_out = c.q.dims[l];
+        push(L, n_steps, st);
+      }
+      end_role(nq);
+      P.n_roles = n_roles; P.n_ctas = first;
+    };
+    // policy launch: Q1(s, pi(s)) with the stepped critic, -mean, backward to the action and through the actor
+    auto build_P = [&](Launch& L) {
+      common(L);
+      ChainParams& P = L.chain;
+      P.loss_part = ch_loss_part + (long long)nA * ch_tiles * nq;
+      P.fin_mode = 1;
+      if (P.prof) P.prof += 4 * 48;
+      P.tick = AdamTick{a->state_u64, 1, 0, c.lr_actor, c.beta1, c.beta2};
+      int n_steps = 0, n_maps = 0;
+      P.role_kind[0] = CR_POLICY; P.role_inner[0] = 1; P.role_first[0] = 0; P.role_step0[0] = 0;
+      for (int l = 0; l + 1 < Lq_; ++l) {
+        ChainStep st = fwd_step(L, n_maps, c.q, f_q1, l, false);
+        st.mask_w = l;
+        if (l == Lq_ - 2) { st.post = CP_Q1; st.head_w_off = c.q.w_off[Lq_ - 1]; st.head_b_off = c.q.b_off[Lq_ - 1]; st.ld_out = c.q.dims[l + 1]; }
+        push(L, n_steps, st);
+      }
+      for (int l = Lq_ - 2; l >= 1; --l) {
+        ChainStep st = bwd_step(L, n_maps, c.q, f_q1, l);
+        st.mask_r = l - 1;
+        push(L, n_steps, st);
+      }
+      {   // d([s, a]) = dZ_0 . W_0, the action columns through max_action * tanh
+        ChainStep st = base_step(f_q1);
+        st.K = c.q.dims[1]; st.N = c.q.dims[0]; st.w_off = c.q.w_off[0]; st.ld_w = c.q.dims[0];
+        st.b_mode = CB_MANUAL_MN; st.epi = CE_DX_TANH;
+        st.out = ch_az[La - 1]; st.out_go = (long long)B * A; st.ld_out = A;
+        blocks(st);
+        push(L, n_steps, st);
+      }
+      {   // through the actor's output layer: K = A
+        ChainStep st = bwd_step(L, n_maps, c.actor, f_a, La - 1);
+        st.gmask = pa.r[La - 2]; st.gmask_go = pa.h_go[La - 2]; st.gmask_gi = 0;
+        st.out = ch_az[La - 2]; st.out_go = (long long)B * c.actor.dims[La - 1]; st.ld_out = c.actor.dims[La - 1];
+        push(L, n_steps, st);
+      }
+      for (int l = La - 2; l >= 1; --l) {
+        ChainStep st = bwd_step(L, n_maps, c.actor, f_a, l);
+        st.gmask = pa.r[l - 1]; st.gmask_go = pa.h_go[l - 1]; st.gmask_gi = 0;
+        st.out = ch_az[l - 1]; st.out_go = (long long)B * c.actor.dims[l]; st.ld_out = c.actor.dims[l];
+        push(L, n_steps, st);
+      }
+      P.role_nsteps[0] = n_steps;
+      P.role_first[1] = nA * ch_tiles;
+      P.n_roles = 1; P.n_ctas = nA * ch_tiles;
+    };
+    build_A(ch_A, false);
+    build_A(ch_Apol, true);
+    build_P(ch_P);
+    // shared-memory geometry (the same for the three launches: the worst case of all steps)
+    const int act_bytes = kChRows * 128 * ((maxw + 31) / 32);
+    const int n_mask = std::max(Lq_ - 1, 1);
+    const int fixed = kChainSmemFixed + act_bytes + n_mask * kChMaskBytes;
+    const int n_slots = std::min(kChMaxSlots, (kChainSmemMax - fixed) / slot_need);
+    if (n_slots < 2) ok = false;
+    for (Launch* L : {&ch_A, &ch_Apol, &ch_P}) {
+      L->chain.act_bytes = act_bytes; L->chain.slot_bytes = slot_need; L->chain.n_slots = n_slots; L->chain.n_mask = n_mask;
+      L->smem_bytes = fixed + n_slots * slot_need;
+      for (int i = 0; i < kChMaxSteps; ++i) {        // small column blocks: several 32-step chunks per ring-slot use
+        ChainStep& st = L->chain.steps[i];
+        if (st.K <= 0) continue;
+        const int nch = (st.K + 31) / 32;
+        st.cps = (st.n_blk > 1 || st.b_mode == CB_MANUAL_K) ? 1 : std::max(1, std::min(nch, slot_need / st.blk_bytes));
+      }
+    }
+    // weight gradients of layers >= 1 (dW_l = dZ_l^T . H_{l-1}, db_l = column sums of dZ_l): one stage per family
+    auto dw_stage = [&](std::vector<Launch>& seq, const td3_net_layout& n, GradRef G, GroupShape gs, const PassBuf& pb,
+                        float* const* dzs, const float* dz_top, int ld_top, long long top_go, long long top_gi, int n_inner) {
+      ProblemList stage;
+      for (int l = n.n_linear - 1; l >= 1; --l) {
+        const int K = n.dims[l], N = n.dims[l + 1];
+        const bool top = l == n.n_linear - 1;
+        const float* dz = top ? dz_top : dzs[l];
+        const int ld_dz = top ? ld_top : N;
+        const long long dz_gi = top ? top_gi : (long long)B * N, dz_go = top ? top_go : (long long)B * N * n_inner;
+        Problem p = make_gemm(N, K, B, dz, ld_dz, false, pb.r[l - 1], K, false, G.base + n.w_off[l], K, EPI_STORE);
+        set_groups(p, dz_go, dz_gi, pb.h_go[l - 1], pb.h_gi[l - 1], G.go, G.gi);
+        finalize_problem(p, gs);
+        if (p.use_tc) {
+          Problem cs = blank_problem(PK_COLSUM);
+          cs.N = N; cs.K = B; cs.A = dz; cs.lda = ld_dz; cs.a_go = dz_go; cs.a_gi = dz_gi;
+          cs.C = G.base + n.b_off[l]; cs.c_go = G.go; cs.c_gi = G.gi;
+          finalize_problem(cs, gs);
+          stage.push_back(p);
+          stage.push_back(cs);
+        } else {
+          p.aux1 = G.base + n.b_off[l]; p.aux1_go = G.go; p.aux1_gi = G.gi;
+          finalize_problem(p, gs);
+          stage.push_back(p);
+        }
+      }
+      emit_stage(seq, stage);
+    };
+    dw_stage(v_ch_cdw, c.q, Gc, g_crit, cc, ch_cz, a->dq, qw, (long long)B * qw * nq, (long long)B * qw, nq);
+    dw_stage(v_ch_adw, c.actor, Ga, g_actor, pa, ch_az, ch_az[La - 1], A, (long long)B * A, 0, 1);
+    if (!ok) chain = false;
+    cudaMemset(ch_sync, 0, (size_t)(64 + (long long)nA * ch_tiles * nq) * sizeof(unsigned int));
+  }
+  a->chain_on = chain;
+  a->seq_chain_critic.clear(); a->seq_chain_policy.clear();
   // TMA descriptors of every tensor-core operand (pointers are fixed from here on: torch owns the buffers).  Merged
   // sequences get their own: merging stages can change a launch's cluster size and with it the A-panel box.
   if (g_tc_mode) {
     std::vector<CUtensorMap> host;
-    if (!attach_tensor_maps({&a->seq_target, &a->seq_critic_fb, &a->seq_actor_fb, &a->seq_policy_mid, &v_cb, &v_abf, &v_tp},
+    if (!attach_tensor_maps({&a->seq_target, &a->seq_critic_fb, &a->seq_actor_fb, &a->seq_policy_mid, &v_cb, &v_abf, &v_tp, &v_ch_cdw, &v_ch_adw},
                             a->tmaps_dev, host))
       return fail(TD3_ERR_CUDA, "cuTensorMapEncodeTiled failed for a tensor-core operand (or more than %d maps needed)", kMaxTensorMaps);
     if (!host.empty())
@@ -1892,6 +2192,21 @@ int plan_agent(td3_agent* a, long long batch) {
     append(a->seq_run_policy, a->seq_actor_fb, (size_t)a->n_actor_fwd, n_actor_pre_bwd);
     append(a->seq_run_policy, v_abf);
     a->seq_run_policy.push_back(apply_a);
+    if (chain) {
+      // the apply launches of the chains read the first-layer dZ the chains wrote
+      Launch apc = apply_c, apa = apply_a;
+      apc.dw.dz = ch_cz[0]; apc.dw.ld_dz = c.q.dims[1]; apc.dw.dz_gi = (long long)B * c.q.dims[1]; apc.dw.dz_go = apc.dw.dz_gi * nq;
+      apa.dw.dz = ch_az[0]; apa.dw.ld_dz = c.actor.dims[1]; apa.dw.dz_gi = 0; apa.dw.dz_go = (long long)B * c.actor.dims[1];
+      a->seq_chain_critic.push_back(ch_A);
+      append(a->seq_chain_critic, v_ch_cdw);
+      a->seq_chain_critic.push_back(apc);
+      a->seq_chain_policy.push_back(ch_Apol);
+      append(a->seq_chain_policy, v_ch_cdw);
+      a->seq_chain_policy.push_back(apc);
+      a->seq_chain_policy.push_back(ch_P);
+      append(a->seq_chain_policy, v_ch_adw);
+      a->seq_chain_policy.push_back(apa);
+    }
   } else {
     append(a->seq_run_critic, a->seq_target);
     append(a->seq_run_critic, a->seq_critic_fb);
@@ -1973,6 +2288,9 @@ int plan_sample(td3_agent* a, const td3_replay_view* rb, int rng_mode) {
   }
   if (n > kMaxSeg) return fail(TD3_ERR_INVALID, "too many gather segments (%d)", n);
   G.n_seg = n;
+  // the chain launches sample their rows themselves (chain.cuh): same view, same index / noise source
+  for (auto* seq : {&a->seq_chain_critic, &a->seq_chain_policy})
+    if (!seq->empty()) (*seq)[0].chain.g = G;
   const long long jobs = (long long)nA * B;
   L.grid_x = (int)((jobs + 7) / 8);
   L.grid_y = rb->row_floats > 2048 ? (int)std::min<long long>(32, (rb->row_floats + 2047) / 2048) : 1;
@@ -2186,8 +2504,9 @@ int capture(td3_agent* a, bool with_actor, cudaGraphExec_t* out, long long* n_no
   if (!a->cap_stream) CUDA_TRY(cudaStreamCreateWithFlags(&a->cap_stream, cudaStreamNonBlocking));
   cudaStream_t s = a->cap_stream;
   CUDA_TRY(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-  int rc = run_seq(a->seq_sample, s);
-  if (rc == TD3_OK) rc = run_seq(with_actor ? a->seq_run_policy : a->seq_run_critic, s);
+  int rc = a->chain_on ? TD3_OK : run_seq(a->seq_sample, s);
+  if (rc == TD3_OK) rc = run_seq(a->chain_on ? (with_actor ? a->seq_chain_policy : a->seq_chain_critic)
+                                             : (with_actor ? a->seq_run_policy : a->seq_run_critic), s);
   cudaError_t e = cudaStreamEndCapture(s, &graph);
   *n_nodes = g_launches.load() - launches_before;            // captured, not executed: move to per-replay accounting
   g_launches.fetch_sub(*n_nodes, std::memory_order_relaxed);
@@ -2421,6 +2740,7 @@ int td3_agent_bind_host_status(td3_agent* a, void* host_words) {
 }
 
 int td3_agent_host_status_live(const td3_agent* a) { return a && a->host_status_live ? 1 : 0; }
+int td3_agent_chain_active(const td3_agent* a) { return a && a->chain_on ? 1 : 0; }
 
 int td3_dp_bind_peers(td3_agent* a, int32_t world, int32_t rank, float* const* critic_grad_peers, float* const* actor_grad_peers,
                       uint32_t* const* flag_peers) {
@@ -2614,8 +2934,12 @@ int td3_train_n(td3_agent* a, const td3_replay_view* rb, int64_t total_it, int32
       CUDA_TRY(cudaGraphLaunch(policy_step ? a->graphs.with_actor : a->graphs.critic_only, s));
       g_launches.fetch_add(policy_step ? a->graphs.nodes_with_actor : a->graphs.nodes_critic_only, std::memory_order_relaxed);
     } else {
-      rc = run_seq(a->seq_sample, s);
-      if (rc == TD3_OK) rc = run_seq(policy_step ? a->seq_run_policy : a->seq_run_critic, s);
+      if (a->chain_on) {
+        rc = run_seq(policy_step ? a->seq_chain_policy : a->seq_chain_critic, s);
+      } else {
+        rc = run_seq(a->seq_sample, s);
+        if (rc == TD3_OK) rc = run_seq(policy_step ? a->seq_run_policy : a->seq_run_critic, s);
+      }
       if (rc != TD3_OK) return rc;
     }
   }
@@ -2639,8 +2963,13 @@ int td3_debug_prefix_times(td3_agent* a, const td3_replay_view* rb, int32_t with
   rc = sync_rb_size(a, rb, s);
   if (rc == TD3_OK) rc = ensure_shadows(a, s);
   if (rc != TD3_OK) return rc;
-  std::vector<Launch> all = a->seq_sample;
-  for (const Launch& L : (with_actor ? a->seq_run_policy : a->seq_run_critic)) all.push_back(L);
+  std::vector<Launch> all;
+  if (a->chain_on) {
+    all = with_actor ? a->seq_chain_policy : a->seq_chain_critic;
+  } else {
+    all = a->seq_sample;
+    for (const Launch& L : (with_actor ? a->seq_run_policy : a->seq_run_critic)) all.push_back(L);
+  }
   const int n = (int)std::min<size_t>(all.size(), (size_t)cap);
   const long long launches_before = g_launches.load();
   cudaEvent_t e0, e1;

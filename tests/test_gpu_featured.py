@@ -252,21 +252,26 @@ def test_ragged_batch_and_small_dims_through_the_fused_path():
 
 
 @pytest.mark.parametrize("precision", ["fp32", "tf32"])
-def test_persistent_kernel_many_updates_per_launch_is_bit_identical_to_plain_launches(precision):
+def test_persistent_kernel_many_updates_per_launch_is_bit_identical_to_plain_launches(precision, monkeypatch):
     """the persistent kernel runs `iterations` updates inside ONE cooperative launch; the first stage
     of an update (the front sampling kernel) reads parameters the previous update's optimiser stage writes, so the
     inter-update barrier must stay.  60 updates in one launch against 60 updates as plain stage-by-stage launches, same
-    Philox key: every parameter bit-identical (a race would show up as run-to-run differences long before that)."""
+    Philox key: every parameter bit-identical (a race would show up as run-to-run differences long before that).
+    With TD3_CHAIN=1 the TF32 launch sequence would be the layer-fused chain (chain.cuh), a different program from the
+    stage program the persistent kernel walks: the persistent kernel is always compared with the stage-by-stage
+    launches (TD3_NO_CHAIN), and the graph with the plain launches of whatever sequence is the default."""
     outs = {}
-    for mode in ("launches", "persistent", "graph"):
+    for mode in ("launches", "persistent", "graph", "launches_stage_program"):
+        if mode == "launches_stage_program":
+            monkeypatch.setenv("TD3_NO_CHAIN", "1")
         _, _, ours, rb = make_featured(actor_widths=(400, 300), q_widths=(400, 300), rows=4096, lr=1e-3, precision=precision)
-        ours.exec_mode = mode
+        ours.exec_mode = "launches" if mode == "launches_stage_program" else mode
         ours.train(rb, 256, iterations=60)
         torch.cuda.synchronize()
         outs[mode] = {k: {n: t.detach().clone() for n, t in getattr(ours, k).state_dict().items()}
                       for k in ("actor", "critic", "actor_target", "critic_target")}
         assert int(ours._state[1].item()) == 60 and int(ours._state[2].item()) == 30
-    for mode in ("persistent", "graph"):
-        for k, sd in outs["launches"].items():
+    for mode, ref in (("persistent", "launches_stage_program"), ("graph", "launches")):
+        for k, sd in outs[ref].items():
             for n, t in sd.items():
-                assert torch.equal(t, outs[mode][k][n]), f"{mode} vs launches: {k}.{n} differs (max |d| {(t - outs[mode][k][n]).abs().max().item():.3e})"
+                assert torch.equal(t, outs[mode][k][n]), f"{mode} vs {ref}: {k}.{n} differs (max |d| {(t - outs[mode][k][n]).abs().max().item():.3e})"

@@ -205,3 +205,22 @@ def test_params_changed_rebuilds_the_tf32_copies():
     ora2.train(orb, 256, indices=idx, noise=nz)
     ours.train(rb, 256, indices=idx, noise=nz)
     assert _q_err(ours, ora2) <= TOL_Q
+
+
+@pytest.mark.parametrize("cfg", ["cfg2_400_300", "cfg3_fork", "ragged_small"])
+def test_layer_fused_chain_kernels_meet_the_same_tolerances(cfg, monkeypatch):
+    """chain.cuh (opt-in, TD3_CHAIN=1): sampling, target actor + noise, twin target critics, Bellman target, online
+    critics, loss gradient and the whole dX chain in ONE launch per phase (M64 tcgen05 tiles, activations on chip, ReLU
+    masks in shared memory, tq hand-over between CTAs through release / acquire flags).  Same oracle, same tolerances as
+    the default stage-per-layer path; the ragged case has a batch that is not a multiple of the 64-row tile, widths
+    that are not multiples of 32 and a policy update every step."""
+    monkeypatch.setenv("TD3_CHAIN", "1")
+    if cfg == "ragged_small":
+        ora, orb, ours, rb = make_featured(S=5, A=2, rows=300, norm=None, actor_widths=(40, 24), q_widths=(44, 20), lr=1e-4,
+                                           precision="tf32", policy_freq=1)
+        _one_cycle(ora, orb, ours, rb, B=37, A=2, rows=300, label="chain " + cfg)
+    else:
+        aw, qw = ((400, 300), (400, 300)) if cfg.startswith("cfg2") else ((500, 400, 300), (500, 400, 200))
+        ora, orb, ours, rb = make_featured(norm=None, actor_widths=aw, q_widths=qw, rows=2048, lr=1e-4, precision="tf32")
+        _one_cycle(ora, orb, ours, rb, B=256, A=6, rows=2048, label="chain " + cfg)
+    assert ours.chain_active()
