@@ -165,6 +165,28 @@ int adam_polyak_step(float* params, const float* grad, float* exp_avg, float* ex
 int td3_gemm(int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, int32_t a_rc, const float* B, int64_t ldb,
              int32_t b_rc, float* C, int64_t ldc, const float* bias, int32_t relu, int32_t use_tc, void* stream);
 
+/* ---- particle-set encoder on caller buffers (TD3_particles.py:29-32, 53-58 / 104-109) ------------------------------
+ * The encoder both particle networks share: conv1 = Conv2d(1, enc_hidden, (1, D)) == a per-particle linear layer
+ * D -> enc_hidden, ReLU, conv2 = Conv1d(enc_hidden, enc_out, 1) == per-particle linear enc_hidden -> enc_out, ReLU,
+ * AvgPool2d((1, N)) over the particles, ReLU.  particles is [batch * n_particles, particle_dim] (row = one particle),
+ * the weights are the reference modules' tensors viewed as [enc_hidden, D] and [enc_out, enc_hidden].
+ * set_encoder_fwd writes pooled[b, 0:enc_out] (row stride ld_pooled) and, when the pointers are given, the activations
+ * h1 [rows, enc_hidden] and h2 [rows, enc_out] a backward pass needs.  use_tc = 1 runs the fused tcgen05 kernel
+ * (csrc/enc.cuh: both layers and the pooling partial sums in one persistent launch, TF32 operands, fp32 accumulation; needs
+ * enc_hidden = 256, enc_out = 128, D <= 7, n_particles % 128 == 0, else TD3_ERR_UNSUPPORTED); use_tc = 0 the strict-fp32
+ * tiles.  set_encoder_bwd turns d(loss)/d(pooled) into the gradients of conv1 / conv2 (what autograd produces for the
+ * reference's backward pass through _encode); it reads the h1 / h2 / pooled a forward call stored.
+ * workspace: at least set_encoder_workspace_floats(...) floats of device memory, contents undefined afterwards. */
+int64_t set_encoder_workspace_floats(int64_t batch, int64_t n_particles, int64_t particle_dim, int64_t enc_hidden, int64_t enc_out);
+int set_encoder_fwd(const float* particles, int64_t batch, int64_t n_particles, int64_t particle_dim, int64_t enc_hidden,
+                    int64_t enc_out, const float* conv1_w, const float* conv1_b, const float* conv2_w, const float* conv2_b,
+                    float* pooled, int64_t ld_pooled, float* h1, float* h2, float* workspace, int64_t workspace_floats,
+                    int32_t use_tc, void* stream);
+int set_encoder_bwd(const float* particles, int64_t batch, int64_t n_particles, int64_t particle_dim, int64_t enc_hidden,
+                    int64_t enc_out, const float* conv2_w, const float* h1, const float* h2, const float* pooled, int64_t ld_pooled,
+                    const float* d_pooled, int64_t ld_d_pooled, float* g_conv1_w, float* g_conv1_b, float* g_conv2_w,
+                    float* g_conv2_b, float* workspace, int64_t workspace_floats, int32_t use_tc, void* stream);
+
 /* ---- agent ------------------------------------------------------------------------- */
 int td3_agent_create(const td3_agent_config* cfg, td3_agent** out);
 int td3_agent_destroy(td3_agent* agent);

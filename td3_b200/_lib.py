@@ -76,6 +76,10 @@ SIGNATURES = {
     "rb_sample_indices": (C.c_int, [_P(ReplayView), _vp, _i64, _i32, _P(_i64), _P(_i64), _P(_vp), _P(_i64), _vp]),
     "rb_philox_indices": (C.c_int, [_vp, _i64, _i64, _u64, _u64, _u64, _vp]),
     "adam_polyak_step": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _f64, _f64, _f64, _f64, _f64, _vp]),
+    "set_encoder_workspace_floats": (_i64, [_i64, _i64, _i64, _i64, _i64]),
+    "set_encoder_fwd": (C.c_int, [_vp, _i64, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _i32, _vp]),
+    "set_encoder_bwd": (C.c_int, [_vp, _i64, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i64,
+                                  _i32, _vp]),
     "td3_gemm": (C.c_int, [_i64, _i64, _i64, _vp, _i64, _i32, _vp, _i64, _i32, _vp, _i64, _vp, _i32, _i32, _vp]),
     "td3_agent_create": (C.c_int, [_P(AgentConfig), _P(_vp)]),
     "td3_agent_destroy": (C.c_int, [_vp]),

@@ -926,6 +926,121 @@ int choose_ksplit(int tiles, int groups, int K) {
   return std::max(1, std::min(std::min(want, cap), 128));
 }
 
+// ------------------------------------------------------------------------------------
+// Backward pass of the particle-set encoder (TD3_particles.py:53-58 under autograd): from the gradient w.r.t. the pooled
+// features to the gradients of conv1 / conv2.  Used by build_backward and by the set_encoder_bwd export.
+// ------------------------------------------------------------------------------------
+struct EncBwdArgs {
+  int B = 0, n_particles = 0, D = 0, H = 0, O = 0;
+  const float* dpool = nullptr; int ld_dpool = 0; long long dpool_go = 0, dpool_gi = 0;     // d(loss)/d(pooled) [B, >= O]
+  const float* pooled = nullptr; int ld_pooled = 0; long long pooled_go = 0, pooled_gi = 0; // relu(mean) (the outer ReLU's gate)
+  const float* h1 = nullptr; const float* h2 = nullptr; long long h1_go = 0, h1_gi = 0, h2_go = 0, h2_gi = 0;
+  const float* P = nullptr; long long P_go = 0;
+  float* dh2 = nullptr; float* dh1 = nullptr; long long dh2_go = 0, dh2_gi = 0, dh1_go = 0, dh1_gi = 0;
+  float* part = nullptr; long long part_go = 0, part_gi = 0;                                 // split-K partials
+  const float* W2 = nullptr; const float* W2_tc = nullptr; long long w_go = 0, w_gi = 0;
+  float* gW1 = nullptr; float* gb1 = nullptr; float* gW2 = nullptr; float* gb2 = nullptr; long long g_go = 0, g_gi = 0;
+};
+
+std::vector<ProblemList> enc_backward_stages(const EncBwdArgs& e, GroupShape gs) {
+  std::vector<ProblemList> st;
+  const int groups = gs.n_outer * gs.n_inner;
+  const int tf = g_tc_mode ? 1 : 0;
+  const int B = e.B;
+  {
+      const int rows = B * e.n_particles;
+      const int H = e.H, O = e.O, D = e.D;
+      // dH2 = dpool/N gated by both ReLUs (:56-57)
+      Problem pbk = blank_problem(PK_POOL_BWD);
+      pbk.M = B; pbk.N = O; pbk.K = e.n_particles;
+      pbk.A = e.dpool; pbk.lda = e.ld_dpool; pbk.a_go = e.dpool_go; pbk.a_gi = e.dpool_gi;
+      pbk.aux0 = const_cast<float*>(e.pooled); pbk.ldaux = e.ld_pooled; pbk.aux0_go = e.pooled_go; pbk.aux0_gi = e.pooled_gi;
+      pbk.aux1 = const_cast<float*>(e.h2); pbk.ldb = O; pbk.aux1_go = e.h2_go; pbk.aux1_gi = e.h2_gi;
+      pbk.C = e.dh2; pbk.ldc = O; pbk.c_go = e.dh2_go; pbk.c_gi = e.dh2_gi;
+      pbk.rn_out = tf;
+      finalize_problem(pbk, gs);
+      st.push_back({pbk});
+      // conv2: dW2 = dH2^T H1 (split-K over B*N), dH1 = (dH2 W2) * (H1 > 0)
+      const int tiles2 = ((O + 31) / 32) * ((H + 31) / 32);
+      // tensor-core dW2: many short slices (64 chunks each) so that the long reduction balances against the dX tiles of
+      // the same stage under the static tile -> CTA assignment
+      const int ks2 = g_tc_mode ? std::max(1, std::min(128, rows / 2048)) : choose_ksplit(tiles2, groups, rows);
+      Problem dw2 = make_gemm(O, H, rows, e.dh2, O, false, e.h1, H, false, ks2 > 1 ? e.part : e.gW2, H,
+                              EPI_STORE);
+      dw2.ksplit = ks2; dw2.c_split = (long long)O * H;
+      set_groups(dw2, e.dh2_go, e.dh2_gi, e.h1_go, e.h1_gi, ks2 > 1 ? e.part_go : e.g_go, ks2 > 1 ? e.part_gi : e.g_gi);
+      finalize_problem(dw2, gs);
+      Problem cs2 = blank_problem(PK_COLSUM);
+      const bool dw2_tc = dw2.use_tc;
+      if (dw2_tc) {
+        cs2.N = O; cs2.K = rows; cs2.ksplit = ks2; cs2.c_split = O;
+        cs2.A = e.dh2; cs2.lda = O; cs2.a_go = e.dh2_go; cs2.a_gi = e.dh2_gi;
+        cs2.C = ks2 > 1 ? e.part + (long long)ks2 * O * H : e.gb2;
+        cs2.c_go = ks2 > 1 ? e.part_go : e.g_go; cs2.c_gi = ks2 > 1 ? e.part_gi : e.g_gi;
+        finalize_problem(cs2, gs);
+      } else {
+        dw2.aux1 = ks2 > 1 ? e.part + (long long)ks2 * O * H : e.gb2;
+        dw2.aux1_go = ks2 > 1 ? e.part_go : e.g_go; dw2.aux1_gi = ks2 > 1 ? e.part_gi : e.g_gi;
+        finalize_problem(dw2, gs);
+      }
+      Problem dx2 = make_gemm(rows, H, O, e.dh2, O, true, e.W2, H, false, e.dh1, H, EPI_RELU_MASK);
+      set_groups(dx2, e.dh2_go, e.dh2_gi, e.w_go, e.w_gi, e.dh1_go, e.dh1_gi);
+      dx2.aux0 = const_cast<float*>(e.h1); dx2.ldaux = H; dx2.aux0_go = e.h1_go; dx2.aux0_gi = e.h1_gi;
+      if (e.W2_tc) { dx2.B = e.W2_tc; dx2.B_master = e.W2; }
+      dx2.rn_out = tf;
+      finalize_problem(dx2, gs);
+      if (dw2_tc) st.push_back({dw2, dx2, cs2});
+      else st.push_back({dw2, dx2});
+      ProblemList s3;
+      if (ks2 > 1) {
+        Problem r1 = blank_problem(PK_REDUCE_SPLITS);
+        r1.M = O * H; r1.K = ks2; r1.c_split = (long long)O * H;
+        r1.A = e.part; r1.a_go = e.part_go; r1.a_gi = e.part_gi;
+        r1.C = e.gW2; r1.c_go = e.g_go; r1.c_gi = e.g_gi;
+        finalize_problem(r1, gs);
+        s3.push_back(r1);
+        Problem r2 = blank_problem(PK_REDUCE_SPLITS);
+        r2.M = O; r2.K = ks2; r2.c_split = O;
+        r2.A = e.part + (long long)ks2 * O * H; r2.a_go = e.part_go; r2.a_gi = e.part_gi;
+        r2.C = e.gb2; r2.c_go = e.g_go; r2.c_gi = e.g_gi;
+        finalize_problem(r2, gs);
+        s3.push_back(r2);
+      }
+      // conv1: dW1 = dH1^T P (split-K), second half of the partial buffer
+      const int tiles1 = ((H + 31) / 32) * ((D + 31) / 32);
+      // the small-K tile reads dH1 once, coalesced: give every SM a couple of row slices
+      const int ks1 = (D <= 8 && H <= kStageThreads) ? std::max(1, std::min(128, rows / 512)) : choose_ksplit(tiles1, groups, rows);
+      float* part1 = e.part + (long long)ks2 * (O * H + O);
+      Problem dw1 = make_gemm(H, D, rows, e.dh1, H, false, e.P, D, false, ks1 > 1 ? part1 : e.gW1, D,
+                              EPI_STORE);
+      dw1.ksplit = ks1; dw1.c_split = (long long)H * D;
+      set_groups(dw1, e.dh1_go, e.dh1_gi, e.P_go, 0, ks1 > 1 ? e.part_go : e.g_go, ks1 > 1 ? e.part_gi : e.g_gi);
+      dw1.aux1 = ks1 > 1 ? part1 + (long long)ks1 * H * D : e.gb1;
+      dw1.aux1_go = ks1 > 1 ? e.part_go : e.g_go; dw1.aux1_gi = ks1 > 1 ? e.part_gi : e.g_gi;
+      if (D <= 8 && H <= kStageThreads) dw1.kind = PK_SMALLK_DW;
+      finalize_problem(dw1, gs);
+      s3.push_back(dw1);
+      st.push_back(s3);
+      if (ks1 > 1) {
+        ProblemList s4;
+        Problem r1 = blank_problem(PK_REDUCE_SPLITS);
+        r1.M = H * D; r1.K = ks1; r1.c_split = (long long)H * D;
+        r1.A = part1; r1.a_go = e.part_go; r1.a_gi = e.part_gi;
+        r1.C = e.gW1; r1.c_go = e.g_go; r1.c_gi = e.g_gi;
+        finalize_problem(r1, gs);
+        s4.push_back(r1);
+        Problem r2 = blank_problem(PK_REDUCE_SPLITS);
+        r2.M = H; r2.K = ks1; r2.c_split = H;
+        r2.A = part1 + (long long)ks1 * H * D; r2.a_go = e.part_go; r2.a_gi = e.part_gi;
+        r2.C = e.gb1; r2.c_go = e.g_go; r2.c_gi = e.g_gi;
+        finalize_problem(r2, gs);
+        s4.push_back(r2);
+        st.push_back(s4);
+      }
+  }
+  return st;
+}
+
 std::vector<ProblemList> build_backward(const td3_agent_config& cfg, const td3_net_layout& net, ParamRef W, GradRef G,
                                         GroupShape gs, int B, const PassBuf& pb, const float* dout, int ld_dout,
                                         long long dout_go, long long dout_gi, bool want_dw, const Dx0Spec& dx0,
@@ -1085,95 +1200,18 @@ std::vector<ProblemList> build_backward(const td3_agent_config& cfg, const td3_n
       st.push_back(s2);
     }
     if (need_enc_bwd) {
-      const int rows = B * cfg.n_particles;
-      const int H = net.enc_hidden, O = net.enc_out, D = cfg.particle_dim;
-      // dH2 = dpool/N gated by both ReLUs (:56-57)
-      Problem pbk = blank_problem(PK_POOL_BWD);
-      pbk.M = B; pbk.N = O; pbk.K = cfg.n_particles;
-      pbk.A = sc.dx0_full; pbk.lda = pb.ld0; pbk.a_go = sc.dx0_full_go; pbk.a_gi = sc.dx0_full_gi;
-      pbk.aux0 = pb.x0; pbk.ldaux = pb.ld0; pbk.aux0_go = pb.x0_go; pbk.aux0_gi = pb.x0_gi;
-      pbk.aux1 = pb.h2; pbk.ldb = O; pbk.aux1_go = pb.h2_go; pbk.aux1_gi = pb.h2_gi;
-      pbk.C = sc.dh2; pbk.ldc = O; pbk.c_go = sc.dh2_go; pbk.c_gi = sc.dh2_gi;
-      pbk.rn_out = tf;
-      finalize_problem(pbk, gs);
-      st.push_back({pbk});
-      // conv2: dW2 = dH2^T H1 (split-K over B*N), dH1 = (dH2 W2) * (H1 > 0)
-      const int tiles2 = ((O + 31) / 32) * ((H + 31) / 32);
-      // tensor-core dW2: many short slices (64 chunks each) so that the long reduction balances against the dX tiles of
-      // the same stage under the static tile -> CTA assignment
-      const int ks2 = g_tc_mode ? std::max(1, std::min(128, rows / 2048)) : choose_ksplit(tiles2, groups, rows);
-      Problem dw2 = make_gemm(O, H, rows, sc.dh2, O, false, pb.h1, H, false, ks2 > 1 ? sc.part : G.base + net.c2w_off, H,
-                              EPI_STORE);
-      dw2.ksplit = ks2; dw2.c_split = (long long)O * H;
-      set_groups(dw2, sc.dh2_go, sc.dh2_gi, pb.h1_go, pb.h1_gi, ks2 > 1 ? sc.part_go : G.go, ks2 > 1 ? sc.part_gi : G.gi);
-      finalize_problem(dw2, gs);
-      Problem cs2 = blank_problem(PK_COLSUM);
-      const bool dw2_tc = dw2.use_tc;
-      if (dw2_tc) {
-        cs2.N = O; cs2.K = rows; cs2.ksplit = ks2; cs2.c_split = O;
-        cs2.A = sc.dh2; cs2.lda = O; cs2.a_go = sc.dh2_go; cs2.a_gi = sc.dh2_gi;
-        cs2.C = ks2 > 1 ? sc.part + (long long)ks2 * O * H : G.base + net.c2b_off;
-        cs2.c_go = ks2 > 1 ? sc.part_go : G.go; cs2.c_gi = ks2 > 1 ? sc.part_gi : G.gi;
-        finalize_problem(cs2, gs);
-      } else {
-        dw2.aux1 = ks2 > 1 ? sc.part + (long long)ks2 * O * H : G.base + net.c2b_off;
-        dw2.aux1_go = ks2 > 1 ? sc.part_go : G.go; dw2.aux1_gi = ks2 > 1 ? sc.part_gi : G.gi;
-        finalize_problem(dw2, gs);
-      }
-      Problem dx2 = make_gemm(rows, H, O, sc.dh2, O, true, W.base + net.c2w_off, H, false, sc.dh1, H, EPI_RELU_MASK);
-      set_groups(dx2, sc.dh2_go, sc.dh2_gi, W.go, W.gi, sc.dh1_go, sc.dh1_gi);
-      dx2.aux0 = pb.h1; dx2.ldaux = H; dx2.aux0_go = pb.h1_go; dx2.aux0_gi = pb.h1_gi;
-      weight_operand(dx2, W, net.c2w_off);
-      dx2.rn_out = tf;
-      finalize_problem(dx2, gs);
-      if (dw2_tc) st.push_back({dw2, dx2, cs2});
-      else st.push_back({dw2, dx2});
-      ProblemList s3;
-      if (ks2 > 1) {
-        Problem r1 = blank_problem(PK_REDUCE_SPLITS);
-        r1.M = O * H; r1.K = ks2; r1.c_split = (long long)O * H;
-        r1.A = sc.part; r1.a_go = sc.part_go; r1.a_gi = sc.part_gi;
-        r1.C = G.base + net.c2w_off; r1.c_go = G.go; r1.c_gi = G.gi;
-        finalize_problem(r1, gs);
-        s3.push_back(r1);
-        Problem r2 = blank_problem(PK_REDUCE_SPLITS);
-        r2.M = O; r2.K = ks2; r2.c_split = O;
-        r2.A = sc.part + (long long)ks2 * O * H; r2.a_go = sc.part_go; r2.a_gi = sc.part_gi;
-        r2.C = G.base + net.c2b_off; r2.c_go = G.go; r2.c_gi = G.gi;
-        finalize_problem(r2, gs);
-        s3.push_back(r2);
-      }
-      // conv1: dW1 = dH1^T P (split-K), second half of the partial buffer
-      const int tiles1 = ((H + 31) / 32) * ((D + 31) / 32);
-      // the small-K tile reads dH1 once, coalesced: give every SM a couple of row slices
-      const int ks1 = (D <= 8 && H <= kStageThreads) ? std::max(1, std::min(128, rows / 512)) : choose_ksplit(tiles1, groups, rows);
-      float* part1 = sc.part + (long long)ks2 * (O * H + O);
-      Problem dw1 = make_gemm(H, D, rows, sc.dh1, H, false, pb.P, D, false, ks1 > 1 ? part1 : G.base + net.c1w_off, D,
-                              EPI_STORE);
-      dw1.ksplit = ks1; dw1.c_split = (long long)H * D;
-      set_groups(dw1, sc.dh1_go, sc.dh1_gi, pb.P_go, 0, ks1 > 1 ? sc.part_go : G.go, ks1 > 1 ? sc.part_gi : G.gi);
-      dw1.aux1 = ks1 > 1 ? part1 + (long long)ks1 * H * D : G.base + net.c1b_off;
-      dw1.aux1_go = ks1 > 1 ? sc.part_go : G.go; dw1.aux1_gi = ks1 > 1 ? sc.part_gi : G.gi;
-      if (D <= 8 && H <= kStageThreads) dw1.kind = PK_SMALLK_DW;
-      finalize_problem(dw1, gs);
-      s3.push_back(dw1);
-      st.push_back(s3);
-      if (ks1 > 1) {
-        ProblemList s4;
-        Problem r1 = blank_problem(PK_REDUCE_SPLITS);
-        r1.M = H * D; r1.K = ks1; r1.c_split = (long long)H * D;
-        r1.A = part1; r1.a_go = sc.part_go; r1.a_gi = sc.part_gi;
-        r1.C = G.base + net.c1w_off; r1.c_go = G.go; r1.c_gi = G.gi;
-        finalize_problem(r1, gs);
-        s4.push_back(r1);
-        Problem r2 = blank_problem(PK_REDUCE_SPLITS);
-        r2.M = H; r2.K = ks1; r2.c_split = H;
-        r2.A = part1 + (long long)ks1 * H * D; r2.a_go = sc.part_go; r2.a_gi = sc.part_gi;
-        r2.C = G.base + net.c1b_off; r2.c_go = G.go; r2.c_gi = G.gi;
-        finalize_problem(r2, gs);
-        s4.push_back(r2);
-        st.push_back(s4);
-      }
+      EncBwdArgs e;
+      e.B = B; e.n_particles = cfg.n_particles; e.D = cfg.particle_dim; e.H = net.enc_hidden; e.O = net.enc_out;
+      e.dpool = sc.dx0_full; e.ld_dpool = pb.ld0; e.dpool_go = sc.dx0_full_go; e.dpool_gi = sc.dx0_full_gi;
+      e.pooled = pb.x0; e.ld_pooled = pb.ld0; e.pooled_go = pb.x0_go; e.pooled_gi = pb.x0_gi;
+      e.h1 = pb.h1; e.h1_go = pb.h1_go; e.h1_gi = pb.h1_gi; e.h2 = pb.h2; e.h2_go = pb.h2_go; e.h2_gi = pb.h2_gi;
+      e.P = pb.P; e.P_go = pb.P_go;
+      e.dh2 = sc.dh2; e.dh2_go = sc.dh2_go; e.dh2_gi = sc.dh2_gi; e.dh1 = sc.dh1; e.dh1_go = sc.dh1_go; e.dh1_gi = sc.dh1_gi;
+      e.part = sc.part; e.part_go = sc.part_go; e.part_gi = sc.part_gi;
+      e.W2 = W.base + net.c2w_off; e.W2_tc = W.tc ? W.tc + net.c2w_off : nullptr; e.w_go = W.go; e.w_gi = W.gi;
+      e.gW1 = G.base + net.c1w_off; e.gb1 = G.base + net.c1b_off; e.gW2 = G.base + net.c2w_off; e.gb2 = G.base + net.c2b_off;
+      e.g_go = G.go; e.g_gi = G.gi;
+      for (auto& s2 : enc_backward_stages(e, gs)) st.push_back(s2);
     }
   }
   return st;
@@ -2677,6 +2715,116 @@ int td3_gemm(int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, int32
       CUDA_TRY(cudaMemcpyAsync(scratch, host.data(), host.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice, (cudaStream_t)stream));
   }
   return run_seq(seq, (cudaStream_t)stream);
+}
+
+// ---- the particle-set encoder on caller buffers (set_encoder_fwd / set_encoder_bwd) ----------------------
+namespace {
+int run_problem_stages(std::vector<ProblemList>& stages, bool any_tc, cudaStream_t s) {
+  std::vector<Launch> seq;
+  for (auto& st : stages) {
+    int rc = emit_stage(seq, st);
+    if (rc != TD3_OK) return rc;
+  }
+  if (any_tc) {
+    static CUtensorMap* scratch = nullptr;      // calls on one stream are ordered; concurrent streams / devices must not share it
+    if (!scratch) CUDA_TRY(cudaMalloc(&scratch, 32 * sizeof(CUtensorMap)));
+    std::vector<CUtensorMap> host;
+    if (!attach_tensor_maps({&seq}, scratch, host) || host.size() > 32) return fail(TD3_ERR_CUDA, "cuTensorMapEncodeTiled failed");
+    if (!host.empty())
+      CUDA_TRY(cudaMemcpyAsync(scratch, host.data(), host.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice, s));
+  }
+  return run_seq(seq, s);
+}
+}  // namespace
+
+int64_t set_encoder_workspace_floats(int64_t batch, int64_t n_particles, int64_t particle_dim, int64_t enc_hidden, int64_t enc_out) {
+  const long long rows = batch * n_particles;
+  return rows * (enc_hidden + enc_out) + 128 * (enc_out * enc_hidden + enc_out) + 128 * (enc_hidden * particle_dim + enc_hidden) +
+         (rows / kEncTile + 1) * enc_out + 1024;
+}
+
+int set_encoder_fwd(const float* particles, int64_t batch, int64_t n_particles, int64_t particle_dim, int64_t enc_hidden,
+                    int64_t enc_out, const float* conv1_w, const float* conv1_b, const float* conv2_w, const float* conv2_b,
+                    float* pooled, int64_t ld_pooled, float* h1, float* h2, float* workspace, int64_t workspace_floats,
+                    int32_t use_tc, void* stream) {
+  if (!particles || !conv1_w || !conv1_b || !conv2_w || !conv2_b || !pooled || !workspace || batch <= 0 || n_particles <= 0 ||
+      particle_dim <= 0 || enc_hidden <= 0 || enc_out <= 0 || enc_out > 256 || ld_pooled < enc_out)
+    return fail(TD3_ERR_INVALID, "set_encoder_fwd: bad arguments");
+  if (workspace_floats < set_encoder_workspace_floats(batch, n_particles, particle_dim, enc_hidden, enc_out))
+    return fail(TD3_ERR_INVALID, "set_encoder_fwd: workspace too small (see set_encoder_workspace_floats)");
+  const int B = (int)batch, N = (int)n_particles, D = (int)particle_dim, H = (int)enc_hidden, O = (int)enc_out;
+  const long long rows = (long long)B * N;
+  const GroupShape gs{1, 1};
+  g_tc_mode = use_tc ? 1 : 0;
+  g_cluster_mode = 0;
+  cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, 0);
+  float* h1w = h1 ? h1 : workspace;
+  float* h2w = h2 ? h2 : workspace + rows * H;
+  float* part = workspace + rows * (H + O);
+  std::vector<ProblemList> st;
+  if (use_tc) {
+    if (H != kEncH || O != kEncO || D > 7 || rows % kEncTile != 0 || N % kEncTile != 0 || !encode_tiled_fn() || !aligned16(conv2_w))
+      return fail(TD3_ERR_UNSUPPORTED, "set_encoder_fwd(use_tc): the fused tcgen05 encoder needs 256 / 128 channels, particle_dim <= 7 and "
+                                       "n_particles a multiple of 128");
+    Problem ef = blank_problem(PK_ENC_FUSED);
+    ef.M = (int)rows; ef.K = D; ef.N = N;
+    ef.A = particles;
+    ef.B = conv1_w; ef.bias = conv1_b;
+    ef.aux0 = const_cast<float*>(conv2_w); ef.aux1 = const_cast<float*>(conv2_b);
+    ef.aux2 = h1; ef.aux3 = h2;
+    ef.C = part;
+    finalize_problem(ef, gs);
+    st.push_back({ef});
+    Problem pl = blank_problem(PK_POOL_FWD);
+    pl.M = B; pl.N = O; pl.K = N / kEncTile;
+    pl.A = part; pl.lda = O;
+    pl.C = pooled; pl.ldc = (int)ld_pooled;
+    finalize_problem(pl, gs);
+    st.push_back({pl});
+  } else {
+    Problem e1 = make_gemm((int)rows, H, D, particles, D, true, conv1_w, D, true, h1w, H, EPI_BIAS_RELU);
+    e1.bias = conv1_b;
+    if (D <= 8) e1.kind = PK_SMALLK_FWD;
+    finalize_problem(e1, gs);
+    st.push_back({e1});
+    Problem e2 = make_gemm((int)rows, O, H, h1w, H, true, conv2_w, H, true, h2w, O, EPI_BIAS_RELU);
+    e2.bias = conv2_b;
+    finalize_problem(e2, gs);
+    st.push_back({e2});
+    Problem pl = blank_problem(PK_POOL_FWD);
+    pl.M = B; pl.N = O; pl.K = N;
+    pl.A = h2w; pl.lda = O;
+    pl.C = pooled; pl.ldc = (int)ld_pooled;
+    finalize_problem(pl, gs);
+    st.push_back({pl});
+  }
+  return run_problem_stages(st, false, (cudaStream_t)stream);
+}
+
+int set_encoder_bwd(const float* particles, int64_t batch, int64_t n_particles, int64_t particle_dim, int64_t enc_hidden,
+                    int64_t enc_out, const float* conv2_w, const float* h1, const float* h2, const float* pooled, int64_t ld_pooled,
+                    const float* d_pooled, int64_t ld_d_pooled, float* g_conv1_w, float* g_conv1_b, float* g_conv2_w,
+                    float* g_conv2_b, float* workspace, int64_t workspace_floats, int32_t use_tc, void* stream) {
+  if (!particles || !conv2_w || !h1 || !h2 || !pooled || !d_pooled || !g_conv1_w || !g_conv1_b || !g_conv2_w || !g_conv2_b ||
+      !workspace || batch <= 0 || n_particles <= 0 || particle_dim <= 0 || enc_hidden <= 0 || enc_out <= 0)
+    return fail(TD3_ERR_INVALID, "set_encoder_bwd: bad arguments");
+  if (workspace_floats < set_encoder_workspace_floats(batch, n_particles, particle_dim, enc_hidden, enc_out))
+    return fail(TD3_ERR_INVALID, "set_encoder_bwd: workspace too small (see set_encoder_workspace_floats)");
+  const long long rows = batch * n_particles;
+  g_tc_mode = use_tc ? 1 : 0;
+  g_cluster_mode = 0;
+  cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, 0);
+  EncBwdArgs e;
+  e.B = (int)batch; e.n_particles = (int)n_particles; e.D = (int)particle_dim; e.H = (int)enc_hidden; e.O = (int)enc_out;
+  e.dpool = d_pooled; e.ld_dpool = (int)ld_d_pooled;
+  e.pooled = pooled; e.ld_pooled = (int)ld_pooled;
+  e.h1 = h1; e.h2 = h2; e.P = particles;
+  e.dh1 = workspace; e.dh2 = workspace + rows * enc_hidden;
+  e.part = workspace + rows * (enc_hidden + enc_out);
+  e.W2 = conv2_w;
+  e.gW1 = g_conv1_w; e.gb1 = g_conv1_b; e.gW2 = g_conv2_w; e.gb2 = g_conv2_b;
+  std::vector<ProblemList> st = enc_backward_stages(e, GroupShape{1, 1});
+  return run_problem_stages(st, use_tc != 0, (cudaStream_t)stream);
 }
 
 int td3_agent_create(const td3_agent_config* cfg, td3_agent** out) {

@@ -1,0 +1,95 @@
+"""The particle-set encoder in isolation, through the C ABI (set_encoder_fwd / set_encoder_bwd), against the
+oracle's _encode (TD3_particles.py:29-32, 53-58 restated in oracle/td3_oracle.py:_SetEncoderMixin) and torch autograd:
+
+  use_tc = 0   strict fp32 tiles: pooled features rel 1e-5, gradients rel 1e-4 (summation order over B*N particles)
+  use_tc = 1   the fused tcgen05 kernel (csrc/enc.cuh, K6): TF32 operands, fp32 accumulation; pooled features
+               |d| <= 2e-3 * max(1, |x|) (SURVEY 8d's TF32 bound), gradients rel 2e-2 / cosine >= 0.999 (ReLU masks computed in
+               TF32 flip for pre-activations within ~1e-4 of zero: tests/test_gpu_tf32.py header)
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import td3_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+class _Enc(torch.nn.Module, O._SetEncoderMixin):
+    def __init__(self, n, d):
+        super().__init__()
+        self._build_encoder((O.Space(4), O.Space(n, d)))
+
+
+def _run(B, N, D, use_tc, seed=0):
+    from td3_b200 import _lib
+    lib = _lib.require_cuda()
+    torch.manual_seed(seed)
+    enc = _Enc(N, D)
+    parts = torch.randn(B, N, D)
+    pooled_ref = enc._encode(parts)                                   # [B, 128]
+    gen = torch.Generator().manual_seed(seed + 1)
+    d_pooled = torch.randn(B, O.ENC_OUT, generator=gen)
+    pooled_ref.backward(d_pooled)
+    H, E = O.ENC_HIDDEN, O.ENC_OUT
+    w1 = enc.conv1.weight.detach().reshape(H, D).contiguous().cuda()
+    b1 = enc.conv1.bias.detach().contiguous().cuda()
+    w2 = enc.conv2.weight.detach().reshape(E, H).contiguous().cuda()
+    b2 = enc.conv2.bias.detach().contiguous().cuda()
+    P = parts.reshape(B * N, D).contiguous().cuda()
+    rows = B * N
+    ws_n = int(lib.set_encoder_workspace_floats(B, N, D, H, E))
+    ws = torch.empty(ws_n, device="cuda")
+    ld = E + 4                                                        # the trunk input is wider than the pooled block
+    pooled = torch.full((B, ld), float("nan"), device="cuda")
+    h1 = torch.empty(rows, H, device="cuda")
+    h2 = torch.empty(rows, E, device="cuda")
+    _lib.check(lib.set_encoder_fwd(P.data_ptr(), B, N, D, H, E, w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(),
+                                   pooled.data_ptr(), ld, h1.data_ptr(), h2.data_ptr(), ws.data_ptr(), ws_n, int(use_tc),
+                                   _lib.stream_ptr()))
+    dp = torch.zeros(B, ld, device="cuda")
+    dp[:, :E] = d_pooled.cuda()
+    g = {k: torch.full_like(v, float("nan")) for k, v in dict(w1=w1, b1=b1, w2=w2, b2=b2).items()}
+    _lib.check(lib.set_encoder_bwd(P.data_ptr(), B, N, D, H, E, w2.data_ptr(), h1.data_ptr(), h2.data_ptr(), pooled.data_ptr(), ld,
+                                   dp.data_ptr(), ld, g["w1"].data_ptr(), g["b1"].data_ptr(), g["w2"].data_ptr(),
+                                   g["b2"].data_ptr(), ws.data_ptr(), ws_n, int(use_tc), _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    assert torch.isnan(pooled[:, E:]).all()                           # nothing written past the pooled block
+    want = {"w1": enc.conv1.weight.grad.reshape(H, D), "b1": enc.conv1.bias.grad, "w2": enc.conv2.weight.grad.reshape(E, H),
+            "b2": enc.conv2.bias.grad}
+    return pooled[:, :E].cpu(), pooled_ref.detach(), {k: v.cpu() for k, v in g.items()}, want
+
+
+@pytest.mark.parametrize("B,N,D", [(4, 128, 6), (3, 64, 6), (2, 200, 3)])
+def test_encoder_fp32_tiles_match_the_oracle(B, N, D):
+    got, want, g, gw = _run(B, N, D, use_tc=False)
+    rel = float((got - want).abs().max() / want.abs().max())
+    assert rel <= 1e-5, rel
+    for k in g:
+        r = float((g[k].double() - gw[k].double()).norm() / gw[k].double().norm())
+        assert r <= 1e-4, (k, r)
+
+
+@pytest.mark.parametrize("B,N,D", [(4, 128, 6), (16, 1024, 6), (2, 256, 3)])
+def test_fused_tcgen05_encoder_meets_the_tf32_bound(B, N, D):
+    got, want, g, gw = _run(B, N, D, use_tc=True)
+    err = float(((got - want).abs() / want.abs().clamp(min=1.0)).max())
+    print(f"[enc tf32 B={B} N={N} D={D}] pooled |d| {err:.2e}")
+    assert err <= 2e-3, err
+    for k in g:
+        a, b = g[k].double().reshape(-1), gw[k].double().reshape(-1)
+        r = float((a - b).norm() / b.norm())
+        cos = float(torch.dot(a, b) / (a.norm() * b.norm()))
+        print(f"   grad {k}: rel {r:.2e} cos {cos:.6f}")
+        assert r <= 2e-2 and cos >= 0.999, (k, r, cos)
+
+
+def test_fused_encoder_refuses_shapes_it_does_not_cover():
+    from td3_b200 import _lib
+    lib = _lib.require_cuda()
+    x = torch.zeros(1024, device="cuda")
+    rc = lib.set_encoder_fwd(x.data_ptr(), 1, 100, 6, 256, 128, x.data_ptr(), x.data_ptr(), x.data_ptr(), x.data_ptr(), x.data_ptr(),
+                             128, None, None, x.data_ptr(), 10 ** 9, 1, _lib.stream_ptr())
+    assert rc != 0 and b"128" in lib.td3_last_error()
