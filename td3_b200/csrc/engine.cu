@@ -130,7 +130,8 @@ int run_launch(const Launch& L, cudaStream_t s) {
       if (rc != TD3_OK) return rc;
       // fp32-only stages need the FFMA tile's buffers only: a small footprint lets the successor's CTAs co-reside
       if (L.stage.any_tc)
-        e = launch_pdl(stage_kernel<true>, dim3(L.stage.total_tiles), dim3(kStageThreads), kDynSmemBytes, s, L.stage, L.stage.cluster);
+        e = launch_pdl(stage_kernel<true>, dim3(L.stage.total_tiles), dim3(kStageThreads), L.stage.small_ring ? kDynSmemBytesSmall : kDynSmemBytes, s,
+                       L.stage, L.stage.cluster);
       else e = launch_pdl(stage_kernel<false>, dim3(L.stage.total_tiles), dim3(kStageThreads), kSmemBytes + 1024, s, L.stage);
       break;
     }
@@ -511,6 +512,8 @@ void layout_stage(Launch& L) {
   S.total_tiles = tiles;
   S.any_tc = any_tc ? 1 : 0;
   S.cluster = c;
+  // many tiles per SM (particle-encoder backward, batch-8192 data-parallel update): half the ring, two CTAs per SM
+  S.small_ring = (any_tc && c == 1 && tiles >= 4 * g_sm_count && !getenv("TD3_NO_SMALL_RING")) ? 1 : 0;
 }
 
 // the fused set-encoder forward of one pass (enc.cuh) as a launch: the problem record carries

@@ -17,6 +17,8 @@ namespace td3 {
 // dynamic shared memory of both kernels: 1 KB alignment slack + the tensor-core operand ring.  The FFMA tile's
 // cp.async ring, epilogue tile and bias strip (kSmemBytes) alias the start of the same region.
 constexpr int kDynSmemBytes = 1024 + kTcRingBytes + 512;   // + bias strip of the TC epilogue
+constexpr int kDynSmemBytesSmall = 1024 + kTcSlots * kTcSub + 512;   // small ring (StageParams::small_ring): two CTAs per SM
+static_assert(kSmemBytes <= kTcSlots * kTcSub, "FFMA tile buffers must fit inside the small TC ring");
 static_assert(kSmemBytes <= kTcRingBytes, "FFMA tile buffers must fit inside the TC ring");
 
 __device__ __forceinline__ unsigned char* aligned_smem(unsigned char* raw) {
@@ -59,14 +61,14 @@ __device__ __forceinline__ void run_stage_tile(const StageParams& S, int tile_gl
 
 // stage-per-launch form (phase-by-phase API, CUDA-graph mode, B=small inference)
 template <bool kTc>
-__global__ void __launch_bounds__(kStageThreads, 1) stage_kernel(const __grid_constant__ StageParams S) {
+__global__ void __launch_bounds__(kStageThreads, 2) stage_kernel(const __grid_constant__ StageParams S) {
   extern __shared__ unsigned char smem_raw[];
   __shared__ TcState tc;
   unsigned char* ring = aligned_smem(smem_raw);
   pdl_launch_dependents();
   const int cluster = S.cluster;
   if constexpr (kTc) {
-    if (S.any_tc) tc_setup(&tc, cluster > 1 ? cluster : 1);   // TMEM allocation + mbarrier init overlap the previous stage's tail
+    if (S.any_tc) tc_setup(&tc, cluster > 1 ? cluster : 1, S.small_ring ? 1 : kTcGroup);   // TMEM allocation + mbarrier init overlap the previous stage's tail
     if (cluster > 1) cluster_sync_all();     // every peer's barriers exist before anybody multicasts into its shared memory
   }
   pdl_wait();                                // the previous stage's outputs are complete and visible from here on

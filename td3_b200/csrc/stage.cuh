@@ -80,6 +80,8 @@ struct StageParams {
   int n_problems;
   int total_tiles;
   int any_tc, cluster;            // some problem runs on the tensor cores (TMEM must be allocated); cluster size of the launch
+  int small_ring, pad_sr;         // 1: many-tile launch -> one chunk per ring slot (96 KB instead of 192 KB): two CTAs per SM, so one
+                                  //    tile's epilogue overlaps the other's operand loads and MMAs
   Problem p[kMaxProblemsPerStage];
   TensorMapBlob maps[kStageMaps];
 };

@@ -55,6 +55,7 @@ struct TcState {                                    // lives in shared memory, o
   unsigned int tma_chunk_count;                     // chunks staged so far (full/empty barrier phases)
   unsigned int tile_count;                          // TC tiles finished so far (done_bar phase)
   int prof_stage;                                   // >= 0: record clock64 stamps of this CTA's tiles (debug builds)
+  int group;                                        // chunks per pipeline stage of this launch: kTcGroup, or 1 (small ring: two CTAs per SM)
 };
 
 __device__ __forceinline__ unsigned int smem_u32(const void* p) { return (unsigned int)__cvta_generic_to_shared(p); }
@@ -124,7 +125,7 @@ __device__ __forceinline__ void tma_load_2d_mc_u32(unsigned int dst, const void*
 
 // called by all threads of the CTA once, before the first TC tile.  cluster = CTAs that share (multicast) the A panel:
 // a slot is free again only when the MMAs of ALL of them have finished reading it.
-__device__ __forceinline__ void tc_setup(TcState* st, int cluster = 1) {
+__device__ __forceinline__ void tc_setup(TcState* st, int cluster = 1, int group = kTcGroup) {
   if (threadIdx.x == 0) {
     for (int i = 0; i < kTcMaxSlots; ++i) {
       mbar_init(&st->full_bar[i], 1);
@@ -135,6 +136,7 @@ __device__ __forceinline__ void tc_setup(TcState* st, int cluster = 1) {
     st->tma_chunk_count = 0;
     st->prof_stage = -1;
     st->tile_count = 0;
+    st->group = group;
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   __syncthreads();                                  // barriers exist: the producer warp may start loading operands
@@ -395,9 +397,11 @@ __device__ __forceinline__ void gemm_tile_tc(const Problem& P, int tile, unsigne
   const unsigned int a_kstep = arc ? 32 : 1024, b_kstep = brc ? 32 : 1024;
 
   const unsigned int tile_no = st->tile_count;
+  const int grp = st->group;                                      // chunks per ring slot (barrier round trip)
+  const int ring_bytes = kTcSlots * grp * kTcSub;
   // bias strip of this tile -> shared memory (read by every row's epilogue; a global load there would sit on the
   // critical path once per 4-column iteration)
-  float* bias_s = reinterpret_cast<float*>(ring + kTcRingBytes);
+  float* bias_s = reinterpret_cast<float*>(ring + ring_bytes);
   if (P.bias && tid >= 64 && tid < 64 + NT) {
     const float* bias = P.bias + go * P.bias_go + gi * P.bias_gi;
     const int j = j0 + tid - 64;
@@ -413,8 +417,8 @@ __device__ __forceinline__ void gemm_tile_tc(const Problem& P, int tile, unsigne
                                    : reinterpret_cast<const unsigned char*>(P.tmapB) + (size_t)g * 128;
     const unsigned int bytes = 16384u + (arc ? 0u : 0u) + (brc ? (unsigned)NT * 128u : (unsigned)((NT + 31) >> 5) * 4096u);
     TCP(1);
-    const unsigned int n_slots = kTcSlots, slot_bytes = kTcSlotBytes;
-    const int n_stages = (n_chunks + kTcGroup - 1) / kTcGroup;
+    const unsigned int n_slots = kTcSlots, slot_bytes = (unsigned)(grp * kTcSub);
+    const int n_stages = (n_chunks + grp - 1) / grp;
     if (tid == 0) asm volatile("prefetch.tensormap [%0];\n" ::"l"(mapA) : "memory");
     if (tid == 32) asm volatile("prefetch.tensormap [%0];\n" ::"l"(mapB) : "memory");
     const int csz = P.tc_cluster > 1 ? P.tc_cluster : 1;
@@ -441,11 +445,11 @@ __device__ __forceinline__ void gemm_tile_tc(const Problem& P, int tile, unsigne
       unsigned int sa0 = ring_u + slot * sbytes, fb = fb0 + slot * 8, eb = eb0 + slot * 8;
       const unsigned short mask = (unsigned short)((1u << ucsz) - 1u);
       const int a_rows = 128 / ucsz;
-      const int nst = TD3_UNI(n_stages);
+      const int nst = TD3_UNI(n_stages), ugrp = TD3_UNI(grp);
 #pragma unroll 1
       for (int c = 0; c < nst; ++c) {
         if (use > 0) mbar_wait_u32(eb, (use - 1) & 1);                     // every CTA of the cluster is done with the slot
-        const int nsub = min(kTcGroup, nch - c * kTcGroup);
+        const int nsub = min(ugrp, nch - c * ugrp);
         if (elect_one()) {
           asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(fb), "r"(ubytes * nsub) : "memory");
 #pragma unroll 1
@@ -472,7 +476,7 @@ __device__ __forceinline__ void gemm_tile_tc(const Problem& P, int tile, unsigne
           }
         }
         __syncwarp();
-        kc += kTcGroup * 32; sa0 += sbytes; fb += 8; eb += 8;
+        kc += ugrp * 32; sa0 += sbytes; fb += 8; eb += 8;
         if (++slot == nsl) { slot = 0; ++use; sa0 = ring_u; fb = fb0; eb = eb0; }
       }
       TCP(2);
@@ -490,13 +494,13 @@ __device__ __forceinline__ void gemm_tile_tc(const Problem& P, int tile, unsigne
       unsigned int slot = tch % nsl, use = tch / nsl;
       unsigned int sa = ring_u + slot * sbytes, fb = fb0 + slot * 8, eb = eb0 + slot * 8;
       const unsigned short mask = (unsigned short)((1u << ucsz) - 1u);
-      const int nst = TD3_UNI(n_stages);
+      const int nst = TD3_UNI(n_stages), ugrp = TD3_UNI(grp);
 #pragma unroll 1
       for (int c = 0; c < nst; ++c) {
         mbar_wait_u32(fb, use & 1);
         if (c == 0) TCP(1);
         asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-        const int nsub = min(kTcGroup, nch - c * kTcGroup);
+        const int nsub = min(ugrp, nch - c * ugrp);
         if (elect_one()) {
           const unsigned int a_lo = a_lo0 | (sa >> 4), b_lo = b_lo0 | ((sa + 16384) >> 4);
           tc_mma(utmem, ((unsigned long long)a_hi << 32) | a_lo, ((unsigned long long)b_hi << 32) | b_lo, uidesc, c > 0 ? 1u : 0u);
@@ -559,7 +563,7 @@ __device__ __forceinline__ void gemm_tile_tc(const Problem& P, int tile, unsigne
   }
 #endif
   if (tid == 0) {
-    st->tma_chunk_count += (unsigned)max((n_chunks + kTcGroup - 1) / kTcGroup, 0);
+    st->tma_chunk_count += (unsigned)max((n_chunks + grp - 1) / grp, 0);
     if (n_chunks > 0) st->tile_count = tile_no + 1;
   }
   __syncthreads();

@@ -79,8 +79,10 @@ def _head_grad_err(family, module):
     return float((g - w).norm() / w.norm()), float(torch.dot(g, w) / (g.norm() * w.norm()))
 
 
-def _one_cycle(ora, orb, ours, rb, B, A, rows, label):
-    """update 1 (critic only) and update 2 (policy step) of a policy_freq = 2 cycle"""
+def _one_cycle(ora, orb, ours, rb, B, A, rows, label, check_critic_grad=True):
+    """update 1 (critic only) and update 2 (policy step) of a policy_freq = 2 cycle.  check_critic_grad = False: the agent
+    runs a policy step every update; the oracle's critic .grad then also holds what actor_loss.backward() accumulated
+    into Q1 (the reference never zeroes it in between, TD3_featured.py:159-163) -- nothing the update uses."""
     rs = np.random.RandomState(5)
     idx = rs.randint(0, rows, size=B)
     nz = rs.standard_normal((B, A)).astype(np.float32)
@@ -103,8 +105,9 @@ def _one_cycle(ora, orb, ours, rb, B, A, rows, label):
           f"actor grad rel {rel_a:.2e} cos {cos_a:.7f}")
     assert dq <= TOL_Q and dq2 <= TOL_Q2, (dq, dq2)
     assert dl <= TOL_LOSS and dal <= TOL_LOSS, (dl, dal)
-    assert rel_h <= TOL_GRAD and cos_h >= MIN_COS, (rel_h, cos_h)
-    assert rel_c <= TOL_GRAD_FAMILY and cos_c >= MIN_COS_FAMILY, (rel_c, cos_c)
+    if check_critic_grad:
+        assert rel_h <= TOL_GRAD and cos_h >= MIN_COS, (rel_h, cos_h)
+        assert rel_c <= TOL_GRAD_FAMILY and cos_c >= MIN_COS_FAMILY, (rel_c, cos_c)
     assert rel_a <= TOL_GRAD_FAMILY and cos_a >= MIN_COS_FAMILY, (rel_a, cos_a)
 
 
@@ -218,7 +221,7 @@ def test_layer_fused_chain_kernels_meet_the_same_tolerances(cfg, monkeypatch):
     if cfg == "ragged_small":
         ora, orb, ours, rb = make_featured(S=5, A=2, rows=300, norm=None, actor_widths=(40, 24), q_widths=(44, 20), lr=1e-4,
                                            precision="tf32", policy_freq=1)
-        _one_cycle(ora, orb, ours, rb, B=37, A=2, rows=300, label="chain " + cfg)
+        _one_cycle(ora, orb, ours, rb, B=37, A=2, rows=300, label="chain " + cfg, check_critic_grad=False)
     else:
         aw, qw = ((400, 300), (400, 300)) if cfg.startswith("cfg2") else ((500, 400, 300), (500, 400, 200))
         ora, orb, ours, rb = make_featured(norm=None, actor_widths=aw, q_widths=qw, rows=2048, lr=1e-4, precision="tf32")
