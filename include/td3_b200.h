@@ -132,6 +132,10 @@ const char* td3_last_error(void);
 /* SM count / name of the current device; fails (TD3_ERR_CUDA) when no sm_100 device is present. */
 int td3_device_info(int* sm_count, int* cc_major, int* cc_minor, char* name, int name_len);
 
+/* The stand-alone entry points below (rb_sample_indices, td3_gemm, set_encoder_*) keep small scratch allocations per
+ * device (the device current at the call).  Calls on one stream are ordered; two streams of the same device must not
+ * run the same stand-alone entry point concurrently.  Agents (td3_agent_*) own all their memory and have no such limit. */
+
 /* ---- replay buffer (my_replay_buffer.py) ------------------------------------------ */
 /* add(): copy n packed fp32 rows from (pinned) host memory into rows[ptr .. ptr+n) with
  * ring wrap-around.  Replaces ReplayBuffer_*.add (my_replay_buffer.py:46-56,109-117); the

@@ -143,6 +143,15 @@ class TD3_base(object):
         self._seq_expected = 0
         self._status_live = bool(self._lib.td3_agent_host_status_live(self._handle))
 
+    def _forward_chunks(self, B: int):
+        """Row ranges for a forward pass over B caller rows that never re-plans an agent that already trains: the planned
+        batch is kept (a re-plan re-captures the update graphs and resets the host-status sequence) and larger inputs go
+        through in slices of it.  An agent without a plan gets one for B rows."""
+        if self._planned_batch <= 0:
+            self._ensure_plan(B)
+        step = self._planned_batch
+        return [(lo, min(B, lo + step)) for lo in range(0, B, step)]
+
     def _region(self, name: str) -> torch.Tensor:
         off, n = C.c_int64(), C.c_int64()
         _lib.check(self._lib.td3_agent_region(self._handle, name.encode(), C.byref(off), C.byref(n)))
@@ -170,6 +179,8 @@ class TD3_base(object):
         view = self._rb_view(replay_buffer)
         if view.size <= 0:
             raise ValueError("high <= 0")        # what np.random.randint(0, 0) raises (my_replay_buffer.py:59,120)
+        if getattr(self, "_dp_owner", None) is not None:
+            raise RuntimeError("this agent is driven by DataParallelTD3 (global batch, gradient sums): call its train()")
         self._ensure_plan(batch_size)
         s = _lib.stream_ptr()
         injected = indices is not None or noise is not None or self.rng == "host"

@@ -118,20 +118,23 @@ class TD3(TD3_base):
     def _actor_forward(self, which, state, particles=None, agent=0):
         state = state.to(self._device, torch.float32).contiguous()
         B = state.shape[0]
-        self._ensure_plan(max(B, self._planned_batch))
         out = torch.empty(B, self._cfg.action_dim, device=self._device)
-        _lib.check(self._lib.td3_actor_forward(self._handle, which, int(agent), state.data_ptr(), None, B, out.data_ptr(),
-                                               _lib.stream_ptr()))
+        for lo, hi in self._forward_chunks(B):
+            _lib.check(self._lib.td3_actor_forward(self._handle, which, int(agent), state[lo:hi].data_ptr(), None, hi - lo,
+                                                   out[lo:hi].data_ptr(), _lib.stream_ptr()))
         return out
 
     def _critic_forward(self, which, state, action, particles=None, agent=0):
         state = state.to(self._device, torch.float32).contiguous()
         action = action.to(self._device, torch.float32).contiguous()
         B = state.shape[0]
-        self._ensure_plan(max(B, self._planned_batch))
-        out = torch.empty(self._cfg.n_q, B, 1, device=self._device)
-        _lib.check(self._lib.td3_critic_forward(self._handle, which, int(agent), state.data_ptr(), None, action.data_ptr(), B,
-                                                out.data_ptr(), _lib.stream_ptr()))
+        outs = []
+        for lo, hi in self._forward_chunks(B):
+            o = torch.empty(self._cfg.n_q, hi - lo, 1, device=self._device)
+            _lib.check(self._lib.td3_critic_forward(self._handle, which, int(agent), state[lo:hi].data_ptr(), None,
+                                                    action[lo:hi].data_ptr(), hi - lo, o.data_ptr(), _lib.stream_ptr()))
+            outs.append(o)
+        out = outs[0] if len(outs) == 1 else torch.cat(outs, dim=1)
         return [out[i] for i in range(self._cfg.n_q)]
 
     # ------------------------------------------------------------------ the hot path (TD3_featured.py:123-171)

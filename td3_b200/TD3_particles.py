@@ -91,10 +91,10 @@ class TD3(TD3_base):
         feats = feats.to(self._device, torch.float32).contiguous()
         particles = particles.to(self._device, torch.float32).contiguous()
         B = feats.shape[0]
-        self._ensure_plan(max(B, self._planned_batch))
         out = torch.empty(B, self._cfg.action_dim, device=self._device)
-        _lib.check(self._lib.td3_actor_forward(self._handle, which, int(agent), feats.data_ptr(), particles.data_ptr(), B,
-                                               out.data_ptr(), _lib.stream_ptr()))
+        for lo, hi in self._forward_chunks(B):
+            _lib.check(self._lib.td3_actor_forward(self._handle, which, int(agent), feats[lo:hi].data_ptr(),
+                                                   particles[lo:hi].data_ptr(), hi - lo, out[lo:hi].data_ptr(), _lib.stream_ptr()))
         return out
 
     def _critic_forward(self, which, feats, action, particles, agent=0):
@@ -102,10 +102,14 @@ class TD3(TD3_base):
         action = action.to(self._device, torch.float32).contiguous()
         particles = particles.to(self._device, torch.float32).contiguous()
         B = feats.shape[0]
-        self._ensure_plan(max(B, self._planned_batch))
-        out = torch.empty(self._cfg.n_q, B, self._cfg.action_dim, device=self._device)
-        _lib.check(self._lib.td3_critic_forward(self._handle, which, int(agent), feats.data_ptr(), particles.data_ptr(),
-                                                action.data_ptr(), B, out.data_ptr(), _lib.stream_ptr()))
+        outs = []
+        for lo, hi in self._forward_chunks(B):
+            o = torch.empty(self._cfg.n_q, hi - lo, self._cfg.action_dim, device=self._device)
+            _lib.check(self._lib.td3_critic_forward(self._handle, which, int(agent), feats[lo:hi].data_ptr(),
+                                                    particles[lo:hi].data_ptr(), action[lo:hi].data_ptr(), hi - lo, o.data_ptr(),
+                                                    _lib.stream_ptr()))
+            outs.append(o)
+        out = outs[0] if len(outs) == 1 else torch.cat(outs, dim=1)
         return [out[i] for i in range(self._cfg.n_q)]
 
     # ------------------------------------------------------------------ the hot path (TD3_particles.py:167-207)

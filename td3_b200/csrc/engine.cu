@@ -16,6 +16,7 @@
 #include <cstring>
 #include <ctime>
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -56,6 +57,26 @@ int fail(int code, const char* fmt, ...) {
 
 inline long long round_up(long long v, long long m) { return (v + m - 1) / m * m; }
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// Per-device scratch allocations of the stand-alone entry points (rb_sample_indices, td3_gemm, set_encoder_*): keyed by
+// (current device, slot), grown on demand, never shared between devices.  Calls on one stream are ordered; concurrent
+// streams of one device must not use the same entry point at the same time (stated in td3_b200.h).
+void* device_scratch(int slot, size_t bytes, bool zero = false) {
+  static std::map<std::pair<int, int>, std::pair<void*, size_t>> pool;
+  static std::mutex mu;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+  std::lock_guard<std::mutex> lock(mu);
+  auto& e = pool[{dev, slot}];
+  if (e.second < bytes) {
+    if (e.first) { cudaDeviceSynchronize(); cudaFree(e.first); }
+    e.first = nullptr; e.second = 0;
+    if (cudaMalloc(&e.first, bytes) != cudaSuccess) return nullptr;
+    e.second = bytes;
+    if (zero) cudaMemset(e.first, 0, bytes);
+  }
+  return e.first;
+}
 
 // ------------------------------------------------------------------------------------
 // launch list
@@ -513,7 +534,11 @@ void layout_stage(Launch& L) {
   S.any_tc = any_tc ? 1 : 0;
   S.cluster = c;
   // many tiles per SM (particle-encoder backward, batch-8192 data-parallel update): half the ring, two CTAs per SM
-  S.small_ring = (any_tc && c == 1 && tiles >= 4 * g_sm_count && !getenv("TD3_NO_SMALL_RING")) ? 1 : 0;
+  {
+    const char* thr = getenv("TD3_SMALL_RING_TILES");       // tiles per SM from which the small ring is used (tuning knob)
+    const double per_sm = thr ? atof(thr) : 1.5;
+    S.small_ring = (any_tc && c == 1 && tiles >= per_sm * g_sm_count && !getenv("TD3_NO_SMALL_RING")) ? 1 : 0;
+  }
 }
 
 // the fused set-encoder forward of one pass (enc.cuh) as a launch: the problem record carries
@@ -2633,18 +2658,9 @@ int rb_sample_indices(const td3_replay_view* rb, const int64_t* idx_dev, int64_t
                       const int64_t* seg_len, float* const* dst, const int64_t* dst_ld, void* stream) {
   if (!rb || !rb->rows || !idx_dev || batch <= 0 || n_seg <= 0 || n_seg > kMaxSeg)
     return fail(TD3_ERR_INVALID, "rb_sample_indices: bad arguments");
-  static unsigned long long* zero_step = nullptr;
-  if (!zero_step) {
-    CUDA_TRY(cudaMalloc(&zero_step, sizeof(unsigned long long)));
-    CUDA_TRY(cudaMemset(zero_step, 0, sizeof(unsigned long long)));
-  }
-  static long long* idx_scratch = nullptr;
-  static int64_t idx_cap = 0;
-  if (idx_cap < batch) {
-    if (idx_scratch) cudaFree(idx_scratch);
-    CUDA_TRY(cudaMalloc(&idx_scratch, batch * sizeof(long long)));
-    idx_cap = batch;
-  }
+  unsigned long long* zero_step = static_cast<unsigned long long*>(device_scratch(0, sizeof(unsigned long long), true));
+  long long* idx_scratch = static_cast<long long*>(device_scratch(1, (size_t)batch * sizeof(long long)));
+  if (!zero_step || !idx_scratch) return fail(TD3_ERR_CUDA, "rb_sample_indices: scratch allocation failed");
   Launch L;
   L.kind = Launch::GATHER;
   GatherParams& G = L.gather;
@@ -2708,8 +2724,8 @@ int td3_gemm(int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, int32
   std::vector<Launch> seq;
   emit_stage(seq, {p});
   if (use_tc) {
-    static CUtensorMap* scratch = nullptr;      // two maps; calls on one stream are ordered, concurrent streams must not share it
-    if (!scratch) CUDA_TRY(cudaMalloc(&scratch, 8 * sizeof(CUtensorMap)));
+    CUtensorMap* scratch = static_cast<CUtensorMap*>(device_scratch(2, 8 * sizeof(CUtensorMap)));
+    if (!scratch) return fail(TD3_ERR_CUDA, "td3_gemm: scratch allocation failed");
     std::vector<CUtensorMap> host;
     if (!p.use_tc)
       return fail(TD3_ERR_UNSUPPORTED, "td3_gemm: operands are not eligible for the tcgen05 tile (TMA needs 16-byte aligned rows; K >= 64)");
@@ -2729,8 +2745,8 @@ int run_problem_stages(std::vector<ProblemList>& stages, bool any_tc, cudaStream
     if (rc != TD3_OK) return rc;
   }
   if (any_tc) {
-    static CUtensorMap* scratch = nullptr;      // calls on one stream are ordered; concurrent streams / devices must not share it
-    if (!scratch) CUDA_TRY(cudaMalloc(&scratch, 32 * sizeof(CUtensorMap)));
+    CUtensorMap* scratch = static_cast<CUtensorMap*>(device_scratch(3, 32 * sizeof(CUtensorMap)));
+    if (!scratch) return fail(TD3_ERR_CUDA, "set_encoder: scratch allocation failed");
     std::vector<CUtensorMap> host;
     if (!attach_tensor_maps({&seq}, scratch, host) || host.size() > 32) return fail(TD3_ERR_CUDA, "cuTensorMapEncodeTiled failed");
     if (!host.empty())

@@ -49,6 +49,7 @@ class DataParallelTD3(object):
         if not dist.is_initialized():
             raise RuntimeError("torch.distributed is not initialised")
         self.agent, self.group = agent, process_group
+        agent._dp_owner = self           # the agent's own train() now refuses (its plan carries a global batch / shard offset)
         self.world, self.rank = dist.get_world_size(process_group), dist.get_rank(process_group)
         self._configured = None
         self.communicate = True          # False: skip the reduction (timing of the compute alone; replicas diverge)
