@@ -411,7 +411,7 @@ void finalize_problem(Problem& p, GroupShape gs) {
       p.tiles_per_group = p.ksplit;
       break;
     case PK_POOL_BWD:
-      p.tiles_per_group = (int)(((long long)p.M * p.K + 63) / 64);
+      p.tiles_per_group = (int)(((long long)p.M * p.K + kPoolBwdRows - 1) / kPoolBwdRows);
       break;
     case PK_REDUCE_SPLITS:
       p.tiles_per_group = (p.M + 1023) / 1024;

@@ -566,8 +566,9 @@ __device__ __forceinline__ void pool_fwd_tile(const Problem& P, int tile, float*
 // dH2[(b*K+n), c] = (A[b,c] / K) * (aux0[b,c] > 0) * (aux1[(b*K+n), c] > 0)
 //   A = d(pool out) [M, lda], aux0 = pool out [M, ldaux], aux1 = h2 [M*K, N] (ld = ldb), C = dH2 [M*K, ldc]
 //   tile = 8 particle rows x all channels
+constexpr int kPoolBwdRows = 256;    // rows per tile: 128 KB read + 128 KB written per CTA (64-row tiles spent their time being launched)
 __device__ __forceinline__ void pool_bwd_tile(const Problem& P, int tile) {
-  // tile = 64 particle rows of one sample; a thread owns 4 channels (16-byte accesses) and walks the rows
+  // tile = kPoolBwdRows particle rows; a thread owns 4 channels (16-byte accesses) and walks the rows
   const int g = tile / P.tiles_per_group;
   const int t = tile - g * P.tiles_per_group;
   long long go, gi;
@@ -575,7 +576,7 @@ __device__ __forceinline__ void pool_bwd_tile(const Problem& P, int tile) {
   const int N4 = P.N >> 2;
   const int lanes = max(1, kStageThreads / N4);
   const int c4 = threadIdx.x % N4, rl = threadIdx.x / N4;
-  const long long row0 = (long long)t * 64;
+  const long long row0 = (long long)t * kPoolBwdRows;
   if (rl >= lanes) return;
   const float* dpb = P.A + go * P.a_go + gi * P.a_gi + c4 * 4;
   const float* poolb = P.aux0 + go * P.aux0_go + gi * P.aux0_gi + c4 * 4;
@@ -585,7 +586,7 @@ __device__ __forceinline__ void pool_bwd_tile(const Problem& P, int tile) {
   const float* h2 = P.aux1 + go * P.aux1_go + gi * P.aux1_gi + c4 * 4;
   float* out = P.C + go * P.c_go + gi * P.c_gi + c4 * 4;
 #pragma unroll 8
-  for (int r = rl; r < 64; r += lanes) {
+  for (int r = rl; r < kPoolBwdRows; r += lanes) {
     const long long row = row0 + r;
     if (row >= (long long)P.M * P.K) break;
     const int b = (int)(row / P.K);                         // a tile may straddle samples when 64 does not divide N
@@ -664,6 +665,7 @@ __device__ __forceinline__ void smallk_fwd_tile(const Problem& P, int tile, floa
 // Weight gradient of the same layer: dW1[c, d] = sum_r dH1[r, c] P[r, d], db1[c] = sum_r dH1[r, c], reduction over the
 // B*N particles split over `ksplit` CTAs (partials at C + ks*c_split and aux1 + ks*M, reduced by PK_REDUCE_SPLITS).
 //   A = dH1 [K rows, lda] (M = channels), B = P [K rows, ldb] (N = D <= 8 columns)
+constexpr int kSmallkDwRows = 1024;   // particle rows staged per pass (32 KB of shared memory, columns D..7 zero)
 __device__ __forceinline__ void smallk_dw_tile(const Problem& P, int tile, float* smem) {
   const int g = tile / P.tiles_per_group;
   const int ks = tile - g * P.tiles_per_group;
@@ -680,9 +682,10 @@ __device__ __forceinline__ void smallk_dw_tile(const Problem& P, int tile, float
 #pragma unroll
   for (int d = 0; d < 8; ++d) acc[d] = 0.f;
   const int c = threadIdx.x;            // channel (M <= 256)
+  for (int e = threadIdx.x; e < kSmallkDwRows * 8; e += kStageThreads) smem[e] = 0.f;      // columns D..7 stay zero
 #pragma unroll 1
-  for (int rb = r_begin; rb < r_end; rb += 128) {
-    const int nr = min(128, r_end - rb);
+  for (int rb = r_begin; rb < r_end; rb += kSmallkDwRows) {
+    const int nr = min(kSmallkDwRows, r_end - rb);
     __syncthreads();
     for (int e = threadIdx.x; e < nr * D; e += kStageThreads) {
       const int r = e / D, d = e - r * D;
@@ -690,13 +693,19 @@ __device__ __forceinline__ void smallk_dw_tile(const Problem& P, int tile, float
     }
     __syncthreads();
     if (c < P.M) {
-#pragma unroll 16
-      for (int r = 0; r < nr; ++r) {
-        const float a = A[(size_t)(rb + r) * P.lda + c];
-        accb += a;
+      const float* ap = A + (size_t)rb * P.lda + c;
+#pragma unroll 1
+      for (int r0 = 0; r0 < nr; r0 += 32) {
+        float a[32];
 #pragma unroll
-        for (int d = 0; d < 8; ++d)
-          if (d < D) acc[d] = fmaf(a, smem[r * 8 + d], acc[d]);
+        for (int u = 0; u < 32; ++u) a[u] = r0 + u < nr ? ap[(size_t)(r0 + u) * P.lda] : 0.f;     // 32 rows in flight per thread
+#pragma unroll
+        for (int u = 0; u < 32; ++u) {
+          accb += a[u];
+          const float4 p0 = *reinterpret_cast<const float4*>(smem + (r0 + u) * 8), p1 = *reinterpret_cast<const float4*>(smem + (r0 + u) * 8 + 4);
+          acc[0] = fmaf(a[u], p0.x, acc[0]); acc[1] = fmaf(a[u], p0.y, acc[1]); acc[2] = fmaf(a[u], p0.z, acc[2]); acc[3] = fmaf(a[u], p0.w, acc[3]);
+          acc[4] = fmaf(a[u], p1.x, acc[4]); acc[5] = fmaf(a[u], p1.y, acc[5]); acc[6] = fmaf(a[u], p1.z, acc[6]); acc[7] = fmaf(a[u], p1.w, acc[7]);
+        }
       }
     }
   }
@@ -721,10 +730,24 @@ __device__ __forceinline__ void colsum_tile(const Problem& P, int tile, float* s
   const int per = (P.K + P.ksplit - 1) / P.ksplit;
   const int r0 = ks * per, r1 = min(P.K, r0 + per);
   const float* a = P.A + go * P.a_go + gi * P.a_gi;
+  // 16 rows in flight per thread, four independent partial sums (fixed order): with long reductions (the particle
+  // encoder's bias gradients: 2048 rows per slice) a 4-deep dependent chain of loads was a fifth of the whole stage
   float s = 0.f;
   if (j < P.N) {
-#pragma unroll 4
-    for (int r = r0 + rl; r < r1; r += 8) s += a[(size_t)r * P.lda + j];
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    const float* ap = a + (size_t)(r0 + rl) * P.lda + j;
+    const size_t step = (size_t)8 * P.lda;
+    int n = (r1 - r0 - rl + 7) / 8;
+#pragma unroll 1
+    for (; n >= 16; n -= 16, ap += 16 * step) {
+      float v[16];
+#pragma unroll
+      for (int u = 0; u < 16; ++u) v[u] = ap[u * step];
+#pragma unroll
+      for (int u = 0; u < 16; ++u) acc[u & 3] += v[u];
+    }
+    for (int u = 0; u < n; ++u) acc[u & 3] += ap[u * step];
+    s = (acc[0] + acc[1]) + (acc[2] + acc[3]);
   }
   smem[rl * 32 + lane] = s;
   __syncthreads();

@@ -339,11 +339,19 @@ __device__ __forceinline__ void tc_epilogue_cols(const Problem& P, float* __rest
     tc_load_aux_group<16>(P, aux0, aux_read, x_vec, row_ok, i, j0 + jw, ax);
     if (have_acc) mbar_wait_u32(done_bar, done_parity);
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    // the auxiliary operand (ReLU mask / tanh / noise) of group jc + 1 is requested before group jc is processed: on the
+    // many-tile stages it comes from HBM, and one DRAM round trip per 16 columns was most of a tile's time
 #pragma unroll 1
     for (int jc = 0; jc < half; jc += 16) {
-      if (jc > 0) tc_load_aux_group<16>(P, aux0, aux_read, x_vec, row_ok, i, j0 + jw + jc, ax);
+      float ax_next[16];
+      const bool more = jc + 16 < half;
+      if (more) tc_load_aux_group<16>(P, aux0, aux_read, x_vec, row_ok, i, j0 + jw + jc + 16, ax_next);
       tc_epilogue_group<EPI, 16>(P, C, aux0, bias_s, has_bias, c_vec, row_ok, have_acc, i, j0 + jw + jc, jw + jc,
                                  tmem_lane + (unsigned)(jw + jc), ax);
+      if (more) {
+#pragma unroll
+        for (int q = 0; q < 16; ++q) ax[q] = ax_next[q];
+      }
     }
   } else {   // NT = 16: eight columns per warp half
     float ax[8];
