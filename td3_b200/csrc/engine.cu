@@ -107,6 +107,7 @@ int ensure_kernel_attrs() {
   if (done) return TD3_OK;
   CUDA_TRY(cudaFuncSetAttribute(head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
   CUDA_TRY(cudaFuncSetAttribute(front_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFrontSmemBytes));
+  CUDA_TRY(cudaFuncSetAttribute(front_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFrontWideSmemBytes));
   CUDA_TRY(cudaFuncSetAttribute(enc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kEncSmemBytes));
   CUDA_TRY(cudaFuncSetAttribute(chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmemMax));
   CUDA_TRY(cudaFuncSetAttribute(stage_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynSmemBytes));
@@ -198,7 +199,10 @@ int run_launch(const Launch& L, cudaStream_t s) {
     case Launch::FRONT: {
       int rc = ensure_kernel_attrs();
       if (rc != TD3_OK) return rc;
-      e = launch_pdl(front_kernel, dim3(L.grid_x), dim3(256), (size_t)front_smem_bytes(L.front.rows_per_tile, L.front.head != 0), s, L.front);
+      if (L.front.job_groups > 0)
+        e = launch_pdl(front_wide_kernel, dim3(L.grid_x), dim3(256), (size_t)front_wide_smem_bytes(L.front.rows_per_tile, L.front.head != 0, L.front.w_window), s, L.front);
+      else
+        e = launch_pdl(front_kernel, dim3(L.grid_x), dim3(256), (size_t)front_smem_bytes(L.front.rows_per_tile, L.front.head != 0), s, L.front);
       break;
     }
     case Launch::DPSYNC:
@@ -1341,9 +1345,13 @@ FrontNet front_first_layer(const td3_net_layout& net, ParamRef W, int n_inner, c
 // job table + grid of a front launch
 void front_finish(Launch& L, int B, int nA) {
   FrontParams& F = L.front;
-  // thousands of rows (a population, or a large data-parallel batch): 32-row tiles amortise the weight block; one agent
-  // at batch 256 keeps 8-row tiles (more CTAs in flight on a path that is pure latency)
-  F.rows_per_tile = (long long)nA * B >= 1024 && !getenv("TD3_FRONT_ROWS8") ? kFrontRowsWide : kFrontRows;
+  // thousands of rows (a population, or a large data-parallel batch): the row-block-major kernel (front_wide_body), one
+  // tile per (agent, row block, group of jobs); one agent at batch 256 keeps (8 rows, one job) tiles -- more CTAs in
+  // flight on a path that is pure latency
+  const bool many = (long long)nA * B >= 1024 && !getenv("TD3_FRONT_ROWS8");
+  const bool wide = many && !getenv("TD3_NO_FRONT_WIDE");
+  F.rows_per_tile = many ? kFrontRowsWide : kFrontRows;
+  if (wide && (long long)nA * ((B + 15) / 16) <= 2 * 148) F.rows_per_tile = 16;
   F.batch = B; F.n_agents = nA; F.row_blocks = (B + F.rows_per_tile - 1) / F.rows_per_tile;
   int jobs = 0;
   for (int i = 0; i < F.n_nets; ++i) {
@@ -1353,7 +1361,29 @@ void front_finish(Launch& L, int B, int nA) {
   }
   F.jobs = jobs;
   L.kind = Launch::FRONT;
-  L.grid_x = nA * F.row_blocks * jobs;
+  if (wide) {
+    // a tile = (agent, row block, group of (network, twin) units); the groups' weight matrices sit in shared memory all
+    // at once when they fit (a tile then waits for memory once)
+    std::vector<int> unit_floats;
+    for (int i = 0; i < F.n_nets; ++i)
+      for (int t = 0; t < F.net[i].n_inner; ++t) unit_floats.push_back(front_unit_floats(F.net[i].N, F.net[i].K));
+    const int units = (int)unit_floats.size();
+    int g = 1;
+    while (g < units && (long long)nA * F.row_blocks * g < 128) ++g;
+    F.job_groups = g; F.units = units;
+    int window = 0;
+    for (int jg = 0; jg < g; ++jg) {
+      int need = 0;
+      for (int u = units * jg / g; u < units * (jg + 1) / g; ++u) need += unit_floats[u];
+      window = std::max(window, need);
+    }
+    const int cap = kFrontWideSmemBytes / 4 - front_wide_smem_floats_fixed(F.rows_per_tile, F.head != 0);
+    F.w_window = std::max(std::min(window, cap), *std::max_element(unit_floats.begin(), unit_floats.end()));
+    L.grid_x = nA * F.row_blocks * g;
+  } else {
+    F.job_groups = 0;
+    L.grid_x = nA * F.row_blocks * jobs;
+  }
 }
 
 // ---- weight normalisation (misc.cuh: wn_body) ----

@@ -20,6 +20,7 @@ constexpr int kDynSmemBytes = 1024 + kTcRingBytes + 512;   // + bias strip of th
 constexpr int kDynSmemBytesSmall = 1024 + kTcSlots * kTcSub + 512;   // small ring (StageParams::small_ring): two CTAs per SM
 static_assert(kSmemBytes <= kTcSlots * kTcSub, "FFMA tile buffers must fit inside the small TC ring");
 static_assert(kSmemBytes <= kTcRingBytes, "FFMA tile buffers must fit inside the TC ring");
+static_assert(kFrontWideSmemBytes <= kTcRingBytes && kFrontSmemBytes <= kTcRingBytes, "front tiles must fit inside the TC ring");
 
 __device__ __forceinline__ unsigned char* aligned_smem(unsigned char* raw) {
   const unsigned int a = smem_u32(raw);
@@ -185,7 +186,8 @@ __global__ void __launch_bounds__(kStageThreads, 1) persistent_update_kernel(con
         } else if (R.kind == SK_WN) {
           wn_body(R.u.w, tile);
         } else if (R.kind == SK_FRONT) {
-          front_body(R.u.f, tile, reinterpret_cast<float*>(ring));
+          if (R.u.f.job_groups > 0) front_wide_body(R.u.f, tile, reinterpret_cast<float*>(ring));
+          else front_body(R.u.f, tile, reinterpret_cast<float*>(ring));
         } else if (R.kind == SK_APPLY) {
           __syncthreads();
           dw_adam_body(R.u.d, R.ew, tile, reinterpret_cast<float*>(ring));
