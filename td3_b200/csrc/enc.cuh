@@ -53,6 +53,11 @@ struct EncParams {
   float* h1; long long h1_go, h1_gi;                 // optional [rows, 256] (nullptr: not stored)
   float* h2; long long h2_go, h2_gi;                 // optional [rows, 128]
   float* part; long long part_go, part_gi;           // [rows / 128, 128] partial means
+  // optional ReLU bitmaps for the fused backward (encbwd.cuh), one block of 16 * rows words per group:
+  //   bits2  [rows][4]          bit o % 32 of word o / 32      = h2[p, o] > 0
+  //   bits2T [rows / 128][128][4]   bit p % 32 of word p / 32  = h2[tile * 128 + p, o] > 0      (+ 4 * rows words)
+  //   bits1T [rows / 128][256][4]   the same for h1[., c] > 0                                   (+ 8 * rows words)
+  unsigned int* bits; long long bits_go, bits_gi;
   int rows, D, n_inner, n_groups, tiles_per_group, pad;
   TensorMapBlob w2_map[kEncMaxGroups];               // W2 [128, 256] of every group (box 32 k x 128 rows, 128-byte swizzle)
 };
@@ -154,6 +159,7 @@ __global__ void __launch_bounds__(kEncThreads, 1) enc_fwd_kernel(const __grid_co
       asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
       const long long row = (long long)rt * kEncTile + e * 32 + lane;
       float* h2row = E.h2 ? E.h2 + (long long)go * E.h2_go + (long long)gi * E.h2_gi + row * kEncO : nullptr;
+      unsigned int* bits2 = E.bits ? E.bits + (long long)go * E.bits_go + (long long)gi * E.bits_gi : nullptr;
 #pragma unroll 1
       for (int pass = 0; pass < 4; ++pass) {
         unsigned int r[32];
@@ -164,6 +170,18 @@ __global__ void __launch_bounds__(kEncThreads, 1) enc_fwd_kernel(const __grid_co
         if (h2row) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(h2row + pass * 32 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        }
+        if (bits2) {                                                // sign bits of this thread's particle, and -- transposed by
+          unsigned int nat = 0, mine = 0;                           // ballots -- of the warp's 32 particles for channel pass * 32 + lane
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const bool on = v[j] > 0.f;
+            nat |= on ? (1u << j) : 0u;
+            const unsigned int bal = __ballot_sync(0xffffffffu, on);
+            if (lane == j) mine = bal;
+          }
+          bits2[row * 4 + pass] = nat;
+          bits2[(long long)E.rows * 4 + ((long long)rt * kEncO + pass * 32 + lane) * 4 + e] = mine;
         }
         part_s[e * kEncO + pass * 32 + lane] = enc_colsum32(v, lane);
       }
@@ -227,6 +245,7 @@ __global__ void __launch_bounds__(kEncThreads, 1) enc_fwd_kernel(const __grid_co
       mbar_wait(&h1_full, tcount & 1u);
       asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
       float* h1g = E.h1 ? E.h1 + (long long)go * E.h1_go + (long long)gi * E.h1_gi + ((long long)rt * kEncTile + row) * kEncH : nullptr;
+      unsigned int* bits1T = E.bits ? E.bits + (long long)go * E.bits_go + (long long)gi * E.bits_gi + (long long)E.rows * 8 : nullptr;
 #pragma unroll 1
       for (int q = 0; q < 4; ++q, ++qcount) {
         const unsigned int buf = qcount & 1u, use = qcount >> 1;
@@ -245,6 +264,15 @@ __global__ void __launch_bounds__(kEncThreads, 1) enc_fwd_kernel(const __grid_co
         asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");      // generic-proxy stores -> visible to the tensor core
         __syncwarp();
         if (lane == 0) enc_arrive(&a_full[buf]);
+        if (bits1T) {                                               // h1 > 0 of the warp's 32 particles, per hidden channel
+          unsigned int mine = 0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const unsigned int bal = __ballot_sync(0xffffffffu, v[j] > 0.f);
+            if (lane == j) mine = bal;
+          }
+          bits1T[((long long)rt * kEncH + chunk * 32 + lane) * 4 + lq] = mine;
+        }
         if (h1g) {
 #pragma unroll
           for (int j = 0; j < 8; ++j)

@@ -28,6 +28,7 @@
 #include "persist.cuh"
 #include "infer.cuh"
 #include "enc.cuh"
+#include "encbwd.cuh"
 #include "chain.cuh"
 
 using namespace td3;
@@ -82,10 +83,11 @@ void* device_scratch(int slot, size_t bytes, bool zero = false) {
 // launch list
 // ------------------------------------------------------------------------------------
 struct Launch {
-  enum Kind { STAGE, GATHER, LOSS, EW, TICK, HEAD, WN, FRONT, DPSYNC, ENC, CHAIN } kind = STAGE;
+  enum Kind { STAGE, GATHER, LOSS, EW, TICK, HEAD, WN, FRONT, DPSYNC, ENC, CHAIN, ENCBWD_W2, ENCBWD_X } kind = STAGE;
   ChainParams chain{};
   DpSyncParams dpsync{};
   EncParams enc{};
+  EncBwdParams encb{};
   HeadParams head{};
   WnParams wn{};
   FrontParams front{};
@@ -109,6 +111,8 @@ int ensure_kernel_attrs() {
   CUDA_TRY(cudaFuncSetAttribute(front_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFrontSmemBytes));
   CUDA_TRY(cudaFuncSetAttribute(front_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFrontWideSmemBytes));
   CUDA_TRY(cudaFuncSetAttribute(enc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kEncSmemBytes));
+  CUDA_TRY(cudaFuncSetAttribute(enc_bwd_w2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kEbW2SmemBytes));
+  CUDA_TRY(cudaFuncSetAttribute(enc_bwd_x_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kEbXSmemBytes));
   CUDA_TRY(cudaFuncSetAttribute(chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmemMax));
   CUDA_TRY(cudaFuncSetAttribute(stage_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynSmemBytes));
   CUDA_TRY(cudaFuncSetAttribute(stage_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynSmemBytes));
@@ -200,7 +204,7 @@ int run_launch(const Launch& L, cudaStream_t s) {
       int rc = ensure_kernel_attrs();
       if (rc != TD3_OK) return rc;
       if (L.front.job_groups > 0)
-        e = launch_pdl(front_wide_kernel, dim3(L.grid_x), dim3(256), (size_t)front_wide_smem_bytes(L.front.rows_per_tile, L.front.head != 0, L.front.w_window), s, L.front);
+        e = launch_pdl(front_wide_kernel, dim3(L.grid_x), dim3(kFrontWideThreads), (size_t)front_wide_smem_bytes(L.front.rows_per_tile, L.front.head != 0, L.front.w_window), s, L.front);
       else
         e = launch_pdl(front_kernel, dim3(L.grid_x), dim3(256), (size_t)front_smem_bytes(L.front.rows_per_tile, L.front.head != 0), s, L.front);
       break;
@@ -213,6 +217,18 @@ int run_launch(const Launch& L, cudaStream_t s) {
       int rc = ensure_kernel_attrs();
       if (rc != TD3_OK) return rc;
       e = launch_pdl(enc_fwd_kernel, dim3(L.grid_x), dim3(kEncThreads), (size_t)kEncSmemBytes, s, L.enc);
+      break;
+    }
+    case Launch::ENCBWD_W2: {
+      int rc = ensure_kernel_attrs();
+      if (rc != TD3_OK) return rc;
+      e = launch_pdl(enc_bwd_w2_kernel, dim3(L.grid_x), dim3(kEbThreads), (size_t)kEbW2SmemBytes, s, L.encb);
+      break;
+    }
+    case Launch::ENCBWD_X: {
+      int rc = ensure_kernel_attrs();
+      if (rc != TD3_OK) return rc;
+      e = launch_pdl(enc_bwd_x_kernel, dim3(L.grid_x), dim3(kEbThreads), (size_t)kEbXSmemBytes, s, L.encb);
       break;
     }
     case Launch::CHAIN: {
@@ -424,6 +440,8 @@ void finalize_problem(Problem& p, GroupShape gs) {
       p.tiles_per_group = 1;
       break;
     case PK_ENC_FUSED:
+    case PK_ENC_BWD_W2:
+    case PK_ENC_BWD_X:
       p.tiles_per_group = p.M / kEncTile;
       break;
   }
@@ -563,6 +581,8 @@ bool make_enc_launch(const Problem& p, Launch& L) {
   E.h1 = p.aux2; E.h1_go = p.aux2_go; E.h1_gi = p.aux2_gi;
   E.h2 = p.aux3; E.h2_go = p.aux3_go; E.h2_gi = p.aux3_gi;
   E.part = p.C; E.part_go = p.c_go; E.part_gi = p.c_gi;
+  E.bits = reinterpret_cast<unsigned int*>(const_cast<void*>(p.tmapA)); E.bits_go = p.aux2_go; E.bits_gi = p.aux2_gi;   // (see build_forward)
+  if (E.bits) { E.h1 = nullptr; E.h2 = nullptr; }
   E.rows = p.M; E.D = p.K; E.n_inner = n_inner; E.n_groups = groups; E.tiles_per_group = p.tiles_per_group;
   for (int o = 0; o < n_outer; ++o)
     for (int i = 0; i < n_inner; ++i) {
@@ -580,6 +600,29 @@ bool make_enc_launch(const Problem& p, Launch& L) {
   return true;
 }
 
+// the fused set-encoder backward (encbwd.cuh) as a launch: the problem record carries
+//   A = particles, B / bias = conv1 weight / bias, aux0 = conv2 weight (TF32 shadow), aux1 / lda = d(pooled), aux2 / ldb = pooled,
+//   tmapA = bitmaps (strides in aux3_go / aux3_gi), C = split-K partials, M = rows, K = D, N = particles per sample,
+//   ksplit = CTAs per group (per channel half for the X kernel), c_split = offset of the kernel's region in the partial buffer
+Launch make_enc_bwd_launch(const Problem& p) {
+  Launch L;
+  L.kind = p.kind == PK_ENC_BWD_W2 ? Launch::ENCBWD_W2 : Launch::ENCBWD_X;
+  EncBwdParams& E = L.encb;
+  memset(&E, 0, sizeof(E));
+  const int groups = p.tile_count / std::max(1, p.tiles_per_group);
+  E.P = p.A; E.p_go = p.a_go;
+  E.W1 = p.B; E.b1 = p.bias; E.W2 = p.aux0; E.w_go = p.b_go; E.w_gi = p.b_gi;
+  E.dpool = p.aux1; E.ld_dpool = p.lda; E.dpool_go = p.aux1_go; E.dpool_gi = p.aux1_gi;
+  E.pooled = p.aux2; E.ld_pooled = p.ldb; E.pooled_go = p.aux2_go; E.pooled_gi = p.aux2_gi;
+  E.bits = reinterpret_cast<const unsigned int*>(p.tmapA); E.bits_go = p.aux3_go; E.bits_gi = p.aux3_gi;
+  E.part = p.C + p.c_split; E.part_go = p.c_go; E.part_gi = p.c_gi;
+  E.rows = p.M; E.D = p.K; E.n_particles = p.N; E.n_inner = std::max(1, p.groups_inner); E.n_groups = groups;
+  E.tiles_per_group = p.tiles_per_group; E.ks = p.ksplit;
+  E.inv_n = 1.f / (float)p.N;
+  L.grid_x = groups * p.ksplit * (p.kind == PK_ENC_BWD_X ? 2 : 1);
+  return L;
+}
+
 int emit_stage(std::vector<Launch>& seq, const ProblemList& probs_in) {
   ProblemList probs;
   for (const Problem& p : probs_in) {
@@ -587,6 +630,8 @@ int emit_stage(std::vector<Launch>& seq, const ProblemList& probs_in) {
       Launch L;
       if (!make_enc_launch(p, L)) return fail(TD3_ERR_CUDA, "fused set-encoder: tensor map for conv2 could not be encoded");
       seq.push_back(L);
+    } else if (p.kind == PK_ENC_BWD_W2 || p.kind == PK_ENC_BWD_X) {
+      seq.push_back(make_enc_bwd_launch(p));
     } else {
       probs.push_back(p);
     }
@@ -671,6 +716,7 @@ struct PassBuf {
   float* h1 = nullptr; float* h2 = nullptr;           // encoder activations
   long long h1_go = 0, h1_gi = 0, h2_go = 0, h2_gi = 0;
   float* part = nullptr; long long part_go = 0, part_gi = 0;   // fused encoder: partial means [rows / 128, enc_out]
+  unsigned int* enc_bits = nullptr; long long bits_go = 0, bits_gi = 0;   // ReLU bitmaps instead of h1 / h2 (fused backward, encbwd.cuh)
   bool keep_enc_acts = true;                          // false: nothing reads h1 / h2 after the forward pass (target networks, Q1)
 };
 
@@ -797,6 +843,13 @@ void set_groups(Problem& p, long long a_go, long long a_gi, long long b_go, long
   p.a_go = a_go; p.a_gi = a_gi; p.b_go = b_go; p.b_gi = b_gi; p.c_go = c_go; p.c_gi = c_gi;
 }
 
+// K6 (enc.cuh / encbwd.cuh) applies: TF32 mode, the reference's 256 / 128 encoder widths, whole 128-particle tiles per sample
+bool enc_fusable(const td3_agent_config& cfg, const td3_net_layout& net, GroupShape gs, int B) {
+  return cfg.variant == TD3_VARIANT_PARTICLES && g_tc_mode && net.enc_hidden == kEncH && net.enc_out == kEncO &&
+         cfg.particle_dim <= 7 && ((long long)B * cfg.n_particles) % kEncTile == 0 && cfg.n_particles % kEncTile == 0 &&
+         gs.n_outer * gs.n_inner <= kEncMaxGroups && encode_tiled_fn() != nullptr && !getenv("TD3_NO_ENC_FUSION");
+}
+
 std::vector<ProblemList> build_forward(const td3_agent_config& cfg, const td3_net_layout& net, ParamRef W, GroupShape gs,
                                        int B, const PassBuf& pb, const OutSpec& out, int pool_dups = 1,
                                        long long pool_dup_stride = 0, bool skip_last = false, bool skip_first = false) {
@@ -810,10 +863,7 @@ std::vector<ProblemList> build_forward(const td3_agent_config& cfg, const td3_ne
   // producer (stage.cuh: Problem::rn_out), and weights come from the rounded shadows (ParamRef::tc)
   const int tf = g_tc_mode ? 1 : 0;
   // K6 (enc.cuh): layer 1 -> layer 2 on tcgen05 -> partial pooling in ONE persistent launch, activations on chip
-  const bool fuse_enc = enc && tf && net.enc_hidden == kEncH && net.enc_out == kEncO && cfg.particle_dim <= 7 &&
-                        ((long long)B * cfg.n_particles) % kEncTile == 0 && cfg.n_particles % kEncTile == 0 &&
-                        gs.n_outer * gs.n_inner <= kEncMaxGroups && pb.part && encode_tiled_fn() != nullptr &&
-                        !getenv("TD3_NO_ENC_FUSION");
+  const bool fuse_enc = enc_fusable(cfg, net, gs, B) && pb.part;
   if (fuse_enc) {
     const int rows = B * cfg.n_particles;
     Problem ef = blank_problem(PK_ENC_FUSED);
@@ -823,7 +873,9 @@ std::vector<ProblemList> build_forward(const td3_agent_config& cfg, const td3_ne
     ef.bias = W.base + net.c1b_off; ef.bias_go = W.go; ef.bias_gi = W.gi;
     ef.aux0 = const_cast<float*>((W.tc ? W.tc : W.base) + net.c2w_off); ef.aux0_go = W.go; ef.aux0_gi = W.gi;
     ef.aux1 = const_cast<float*>(W.base + net.c2b_off); ef.aux1_go = W.go; ef.aux1_gi = W.gi;
-    if (pb.keep_enc_acts) {
+    if (pb.keep_enc_acts && pb.enc_bits) {            // the backward pass recomputes from bitmaps: no activation stores
+      ef.tmapA = pb.enc_bits; ef.aux2_go = pb.bits_go; ef.aux2_gi = pb.bits_gi;
+    } else if (pb.keep_enc_acts) {
       ef.aux2 = pb.h1; ef.aux2_go = pb.h1_go; ef.aux2_gi = pb.h1_gi;
       ef.aux3 = pb.h2; ef.aux3_go = pb.h2_go; ef.aux3_gi = pb.h2_gi;
     }
@@ -962,6 +1014,8 @@ int choose_ksplit(int tiles, int groups, int K) {
 // Backward pass of the particle-set encoder (TD3_particles.py:53-58 under autograd): from the gradient w.r.t. the pooled
 // features to the gradients of conv1 / conv2.  Used by build_backward and by the set_encoder_bwd export.
 // ------------------------------------------------------------------------------------
+constexpr int kEncPartials = 148;      // split-K partials the encoder-backward buffers hold per group (one per CTA at most)
+
 struct EncBwdArgs {
   int B = 0, n_particles = 0, D = 0, H = 0, O = 0;
   const float* dpool = nullptr; int ld_dpool = 0; long long dpool_go = 0, dpool_gi = 0;     // d(loss)/d(pooled) [B, >= O]
@@ -972,6 +1026,8 @@ struct EncBwdArgs {
   float* part = nullptr; long long part_go = 0, part_gi = 0;                                 // split-K partials
   const float* W2 = nullptr; const float* W2_tc = nullptr; long long w_go = 0, w_gi = 0;
   float* gW1 = nullptr; float* gb1 = nullptr; float* gW2 = nullptr; float* gb2 = nullptr; long long g_go = 0, g_gi = 0;
+  const unsigned int* bits = nullptr; long long bits_go = 0, bits_gi = 0;   // ReLU bitmaps of the forward pass: fused backward
+  const float* W1 = nullptr; const float* b1 = nullptr;
 };
 
 std::vector<ProblemList> enc_backward_stages(const EncBwdArgs& e, GroupShape gs) {
@@ -979,6 +1035,41 @@ std::vector<ProblemList> enc_backward_stages(const EncBwdArgs& e, GroupShape gs)
   const int groups = gs.n_outer * gs.n_inner;
   const int tf = g_tc_mode ? 1 : 0;
   const int B = e.B;
+  if (e.bits) {
+    // fused backward (encbwd.cuh): two persistent tcgen05 launches leave per-CTA partials, one stage reduces them
+    const int rows = B * e.n_particles, H = e.H, O = e.O, D = e.D;
+    const int tiles = rows / kEncTile;
+    const int ks2 = std::max(1, std::min(tiles, std::min(kEncPartials, g_sm_count / std::max(1, groups))));
+    const int ks1 = std::max(1, std::min(tiles, std::min(kEncPartials, g_sm_count / std::max(1, 2 * groups))));
+    auto fused = [&](int kind, int ks, long long part_ofs) {
+      Problem p = blank_problem(kind);
+      p.M = rows; p.K = D; p.N = e.n_particles;
+      p.A = e.P; p.a_go = e.P_go;
+      p.B = e.W1; p.bias = e.b1; p.b_go = e.w_go; p.b_gi = e.w_gi;
+      p.aux0 = const_cast<float*>(e.W2_tc ? e.W2_tc : e.W2);
+      p.aux1 = const_cast<float*>(e.dpool); p.lda = e.ld_dpool; p.aux1_go = e.dpool_go; p.aux1_gi = e.dpool_gi;
+      p.aux2 = const_cast<float*>(e.pooled); p.ldb = e.ld_pooled; p.aux2_go = e.pooled_go; p.aux2_gi = e.pooled_gi;
+      p.tmapA = e.bits; p.aux3_go = e.bits_go; p.aux3_gi = e.bits_gi;
+      p.C = e.part; p.c_go = e.part_go; p.c_gi = e.part_gi; p.c_split = part_ofs;
+      p.ksplit = ks;
+      finalize_problem(p, gs);
+      return p;
+    };
+    st.push_back({fused(PK_ENC_BWD_W2, ks2, 0)});
+    float* part1 = e.part + (long long)ks2 * (O * H + O);
+    st.push_back({fused(PK_ENC_BWD_X, ks1, (long long)ks2 * (O * H + O))});
+    auto reduce = [&](const float* src, int n, int ks, float* dst) {
+      Problem r = blank_problem(PK_REDUCE_SPLITS);
+      r.M = n; r.K = ks; r.c_split = n;
+      r.A = src; r.a_go = e.part_go; r.a_gi = e.part_gi;
+      r.C = dst; r.c_go = e.g_go; r.c_gi = e.g_gi;
+      finalize_problem(r, gs);
+      return r;
+    };
+    st.push_back({reduce(e.part, O * H, ks2, e.gW2), reduce(e.part + (long long)ks2 * O * H, O, ks2, e.gb2),
+                  reduce(part1, H * D, ks1, e.gW1), reduce(part1 + (long long)ks1 * H * D, H, ks1, e.gb1)});
+    return st;
+  }
   {
       const int rows = B * e.n_particles;
       const int H = e.H, O = e.O, D = e.D;
@@ -1243,6 +1334,8 @@ std::vector<ProblemList> build_backward(const td3_agent_config& cfg, const td3_n
       e.W2 = W.base + net.c2w_off; e.W2_tc = W.tc ? W.tc + net.c2w_off : nullptr; e.w_go = W.go; e.w_gi = W.gi;
       e.gW1 = G.base + net.c1w_off; e.gb1 = G.base + net.c1b_off; e.gW2 = G.base + net.c2w_off; e.gb2 = G.base + net.c2b_off;
       e.g_go = G.go; e.g_gi = G.gi;
+      e.bits = pb.enc_bits; e.bits_go = pb.bits_go; e.bits_gi = pb.bits_gi;
+      e.W1 = W.base + net.c1w_off; e.b1 = W.base + net.c1b_off;
       for (auto& s2 : enc_backward_stages(e, gs)) st.push_back(s2);
     }
   }
@@ -1252,7 +1345,7 @@ std::vector<ProblemList> build_backward(const td3_agent_config& cfg, const td3_n
 long long partial_floats(const td3_agent_config& cfg, const td3_net_layout& net, int B) {
   if (cfg.variant != TD3_VARIANT_PARTICLES) return 1;
   const long long H = net.enc_hidden, O = net.enc_out, D = cfg.particle_dim;
-  return 128 * (O * H + O) + 128 * (H * D + H);
+  return kEncPartials * (O * H + O) + kEncPartials * (H * D + H);
 }
 
 // allocate the activations of a pass
@@ -1284,7 +1377,12 @@ void alloc_pass(Bump& ws, const td3_agent_config& cfg, const td3_net_layout& net
       pb.rstd[l] = ws.take((long long)groups * B);
     }
   }
-  if (enc && need_enc_acts) {
+  if (enc && need_enc_acts && enc_fusable(cfg, net, gs, B) && !getenv("TD3_NO_ENC_BWD_FUSION")) {
+    // fused backward: 64 bytes of ReLU bitmaps per particle instead of the 1.5 KB of h1 / h2
+    const long long rows = (long long)B * cfg.n_particles;
+    pb.bits_gi = rows * 16; pb.bits_go = pb.bits_gi * gs.n_inner;
+    pb.enc_bits = reinterpret_cast<unsigned int*>(ws.take((long long)groups * rows * 16));
+  } else if (enc && need_enc_acts) {
     const long long rows = (long long)B * cfg.n_particles;
     pb.h1_gi = rows * net.enc_hidden; pb.h1_go = pb.h1_gi * gs.n_inner;
     pb.h2_gi = rows * net.enc_out; pb.h2_go = pb.h2_gi * gs.n_inner;
@@ -1310,7 +1408,11 @@ void alloc_bwd(Bump& ws, const td3_agent_config& cfg, const td3_net_layout& net,
   const long long ld0 = round_up(net.dims[0], 4);
   sc.dx0_full_gi = B * ld0; sc.dx0_full_go = sc.dx0_full_gi * gs.n_inner;
   sc.dx0_full = ws.take(groups * B * ld0);
-  if (cfg.variant == TD3_VARIANT_PARTICLES && enc_bwd) {
+  if (cfg.variant == TD3_VARIANT_PARTICLES && enc_bwd && enc_fusable(cfg, net, gs, B) && !getenv("TD3_NO_ENC_BWD_FUSION")) {
+    sc.part_cap = partial_floats(cfg, net, B);      // fused backward (encbwd.cuh): no dH2 / dH1 in memory, only the partials
+    sc.part_gi = sc.part_cap; sc.part_go = sc.part_cap * gs.n_inner;
+    sc.part = ws.take(groups * sc.part_cap);
+  } else if (cfg.variant == TD3_VARIANT_PARTICLES && enc_bwd) {
     const long long rows = (long long)B * cfg.n_particles;
     sc.dh2_gi = rows * net.enc_out; sc.dh2_go = sc.dh2_gi * gs.n_inner;
     sc.dh1_gi = rows * net.enc_hidden; sc.dh1_go = sc.dh1_gi * gs.n_inner;

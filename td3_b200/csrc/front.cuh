@@ -532,9 +532,9 @@ __device__ __forceinline__ void front_wide_body(const FrontParams& P, int tile, 
   }
 
   // ---- phase 3: the tile's units, a window of weight matrices at a time (normally all of them at once).
-  // thread = output columns c, c + 128, ...; R / 2 rows each ----
-  const int c = tid & (kFrontCols - 1), half = tid >> 7;
-  const int rbeg = half * (R / 2), rows = min(nrows - rbeg, R / 2);
+  // thread = output columns c, c + 128, ... of the rows of its 128-thread part ----
+  const int c = tid & (kFrontCols - 1), part = tid >> 7, rpp = R / (nthr >> 7);      // rows per 128-thread part
+  const int rbeg = part * rpp, rows = min(nrows - rbeg, rpp);
   int chunk_lo = unit_lo;
 #pragma unroll 1
   while (true) {
@@ -547,7 +547,7 @@ __device__ __forceinline__ void front_wide_body(const FrontParams& P, int tile, 
       const float* wsb = ws + woff;
       const float* bsb = N.bias ? wsb + ((Nn * K + 3) & ~3) : nullptr;
       woff += front_unit_floats(Nn, K);
-      if (half < 2 && rows > 0) {
+      if (rows > 0) {
         const long long o0 = (long long)agent * N.out_go + (long long)U.inner * N.out_gi + (long long)(r0 + rbeg) * ldo;
         const float* xr0 = xn + (U.ni * R + rbeg) * kFrontMaxK;
         if (N.mask)
@@ -568,7 +568,8 @@ __device__ __forceinline__ void front_wide_body(const FrontParams& P, int tile, 
   }
 }
 
-__global__ void __launch_bounds__(256, 2) front_wide_kernel(const __grid_constant__ FrontParams P) {
+constexpr int kFrontWideThreads = 512;
+__global__ void __launch_bounds__(kFrontWideThreads, 1) front_wide_kernel(const __grid_constant__ FrontParams P) {
   extern __shared__ __align__(16) float front_smem[];
   pdl_launch_dependents();
   pdl_wait();

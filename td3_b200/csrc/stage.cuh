@@ -28,7 +28,9 @@ enum ProblemKind : int {
   PK_COLSUM = 8,        // C[j] = sum_i A[i,j]    (bias gradient next to a tensor-core dW)
   PK_SMALLK_FWD = 9,    // C[i,j] = relu(bias[j] + sum_{d<K} A[i,d] B[j,d]), K <= 8   (particle encoder layer 1: HBM-write bound)
   PK_SMALLK_DW = 10,    // C[j,d] = sum_i A[i,j] B[i,d], aux1[j] = sum_i A[i,j], N <= 8, reduction split over CTAs
-  PK_ENC_FUSED = 11     // host-side planning only: the fused set-encoder forward (enc.cuh), emitted as a launch of its own
+  PK_ENC_FUSED = 11,    // host-side planning only: the fused set-encoder forward (enc.cuh), emitted as a launch of its own
+  PK_ENC_BWD_W2 = 12,   // host-side planning only: fused set-encoder backward (encbwd.cuh), conv2 weight / bias gradient
+  PK_ENC_BWD_X = 13     //                          ... and d(hidden) -> conv1 weight / bias gradient
 };
 
 enum Epilogue : int {

@@ -11,7 +11,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench
 from td3_b200 import _lib
 
-KINDS = {0: "stage", 1: "gather", 2: "loss", 3: "adam/apply", 4: "tick", 5: "head", 6: "wn", 7: "front", 8: "dpsync", 9: "enc", 10: "chain"}
+KINDS = {0: "stage", 1: "gather", 2: "loss", 3: "adam/apply", 4: "tick", 5: "head", 6: "wn", 7: "front", 8: "dpsync", 9: "enc", 10: "chain", 11: "encbwd_w2", 12: "encbwd_x"}
 
 
 def main():
