@@ -191,6 +191,21 @@ int set_encoder_bwd(const float* particles, int64_t batch, int64_t n_particles, 
                     const float* d_pooled, int64_t ld_d_pooled, float* g_conv1_w, float* g_conv1_b, float* g_conv2_w,
                     float* g_conv2_b, float* workspace, int64_t workspace_floats, int32_t use_tc, void* stream);
 
+/* The fused forward / backward pair of the same encoder (csrc/enc.cuh + csrc/encbwd.cuh; enc_hidden = 256, enc_out = 128,
+ * D <= 7, n_particles % 128 == 0, TF32 operands, fp32 accumulation).  Instead of h1 / h2 (1.5 KB per particle) the forward
+ * keeps relu_bits: 16 * batch * n_particles uint32 words of ReLU sign bits (4 words per particle for h2, the same bits
+ * transposed per 128-particle tile, and 8 words per particle for h1, transposed).  set_encoder_bwd_fused recomputes h1
+ * from the particles and produces the same four gradients as set_encoder_bwd in two persistent tcgen05 launches plus a
+ * fixed-order reduction of per-CTA partials (deterministic).  This is what TD3_particles.train runs in TF32 mode
+ * (TD3_particles.py:167-224 under autograd through :53-58). */
+int set_encoder_fwd_bits(const float* particles, int64_t batch, int64_t n_particles, int64_t particle_dim, const float* conv1_w,
+                         const float* conv1_b, const float* conv2_w, const float* conv2_b, float* pooled, int64_t ld_pooled,
+                         uint32_t* relu_bits, float* workspace, int64_t workspace_floats, void* stream);
+int set_encoder_bwd_fused(const float* particles, int64_t batch, int64_t n_particles, int64_t particle_dim, const float* conv1_w,
+                          const float* conv1_b, const float* conv2_w, const uint32_t* relu_bits, const float* pooled,
+                          int64_t ld_pooled, const float* d_pooled, int64_t ld_d_pooled, float* g_conv1_w, float* g_conv1_b,
+                          float* g_conv2_w, float* g_conv2_b, float* workspace, int64_t workspace_floats, void* stream);
+
 /* ---- agent ------------------------------------------------------------------------- */
 int td3_agent_create(const td3_agent_config* cfg, td3_agent** out);
 int td3_agent_destroy(td3_agent* agent);

@@ -80,6 +80,9 @@ SIGNATURES = {
     "set_encoder_fwd": (C.c_int, [_vp, _i64, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _i32, _vp]),
     "set_encoder_bwd": (C.c_int, [_vp, _i64, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i64,
                                   _i32, _vp]),
+    "set_encoder_fwd_bits": (C.c_int, [_vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _i64, _vp]),
+    "set_encoder_bwd_fused": (C.c_int, [_vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp,
+                                        _i64, _vp]),
     "td3_gemm": (C.c_int, [_i64, _i64, _i64, _vp, _i64, _i32, _vp, _i64, _i32, _vp, _i64, _vp, _i32, _i32, _vp]),
     "td3_agent_create": (C.c_int, [_P(AgentConfig), _P(_vp)]),
     "td3_agent_destroy": (C.c_int, [_vp]),

@@ -2890,8 +2890,8 @@ int run_problem_stages(std::vector<ProblemList>& stages, bool any_tc, cudaStream
 
 int64_t set_encoder_workspace_floats(int64_t batch, int64_t n_particles, int64_t particle_dim, int64_t enc_hidden, int64_t enc_out) {
   const long long rows = batch * n_particles;
-  return rows * (enc_hidden + enc_out) + 128 * (enc_out * enc_hidden + enc_out) + 128 * (enc_hidden * particle_dim + enc_hidden) +
-         (rows / kEncTile + 1) * enc_out + 1024;
+  return rows * (enc_hidden + enc_out) + kEncPartials * (enc_out * enc_hidden + enc_out) +
+         kEncPartials * (enc_hidden * particle_dim + enc_hidden) + (rows / kEncTile + 1) * enc_out + 1024;
 }
 
 int set_encoder_fwd(const float* particles, int64_t batch, int64_t n_particles, int64_t particle_dim, int64_t enc_hidden,
@@ -2976,6 +2976,76 @@ int set_encoder_bwd(const float* particles, int64_t batch, int64_t n_particles, 
   e.gW1 = g_conv1_w; e.gb1 = g_conv1_b; e.gW2 = g_conv2_w; e.gb2 = g_conv2_b;
   std::vector<ProblemList> st = enc_backward_stages(e, GroupShape{1, 1});
   return run_problem_stages(st, use_tc != 0, (cudaStream_t)stream);
+}
+
+// The fused pair (enc.cuh / encbwd.cuh): the forward keeps 64 bytes of ReLU bitmaps per particle instead of h1 / h2, the
+// backward recomputes from the particles and those bitmaps.
+static bool enc_fused_shape_ok(int64_t batch, int64_t n_particles, int64_t particle_dim, const float* conv2_w) {
+  return particle_dim >= 1 && particle_dim <= 7 && n_particles % kEncTile == 0 && batch >= 1 && encode_tiled_fn() != nullptr &&
+         aligned16(conv2_w) && batch * n_particles < (1ll << 31);
+}
+
+int set_encoder_fwd_bits(const float* particles, int64_t batch, int64_t n_particles, int64_t particle_dim, const float* conv1_w,
+                         const float* conv1_b, const float* conv2_w, const float* conv2_b, float* pooled, int64_t ld_pooled,
+                         uint32_t* relu_bits, float* workspace, int64_t workspace_floats, void* stream) {
+  if (!particles || !conv1_w || !conv1_b || !conv2_w || !conv2_b || !pooled || !relu_bits || !workspace || ld_pooled < kEncO)
+    return fail(TD3_ERR_INVALID, "set_encoder_fwd_bits: bad arguments");
+  if (!enc_fused_shape_ok(batch, n_particles, particle_dim, conv2_w))
+    return fail(TD3_ERR_UNSUPPORTED, "set_encoder_fwd_bits: the fused tcgen05 encoder needs particle_dim <= 7 and n_particles a multiple of 128");
+  if (workspace_floats < set_encoder_workspace_floats(batch, n_particles, particle_dim, kEncH, kEncO))
+    return fail(TD3_ERR_INVALID, "set_encoder_fwd_bits: workspace too small (see set_encoder_workspace_floats)");
+  const int B = (int)batch, N = (int)n_particles, D = (int)particle_dim;
+  const long long rows = (long long)B * N;
+  const GroupShape gs{1, 1};
+  g_tc_mode = 1;
+  g_cluster_mode = 0;
+  cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, 0);
+  float* part = workspace + rows * (kEncH + kEncO);
+  std::vector<ProblemList> st;
+  Problem ef = blank_problem(PK_ENC_FUSED);
+  ef.M = (int)rows; ef.K = D; ef.N = N;
+  ef.A = particles;
+  ef.B = conv1_w; ef.bias = conv1_b;
+  ef.aux0 = const_cast<float*>(conv2_w); ef.aux1 = const_cast<float*>(conv2_b);
+  ef.tmapA = relu_bits;
+  ef.C = part;
+  finalize_problem(ef, gs);
+  st.push_back({ef});
+  Problem pl = blank_problem(PK_POOL_FWD);
+  pl.M = B; pl.N = kEncO; pl.K = N / kEncTile;
+  pl.A = part; pl.lda = kEncO;
+  pl.C = pooled; pl.ldc = (int)ld_pooled;
+  finalize_problem(pl, gs);
+  st.push_back({pl});
+  return run_problem_stages(st, false, (cudaStream_t)stream);
+}
+
+int set_encoder_bwd_fused(const float* particles, int64_t batch, int64_t n_particles, int64_t particle_dim, const float* conv1_w,
+                          const float* conv1_b, const float* conv2_w, const uint32_t* relu_bits, const float* pooled,
+                          int64_t ld_pooled, const float* d_pooled, int64_t ld_d_pooled, float* g_conv1_w, float* g_conv1_b,
+                          float* g_conv2_w, float* g_conv2_b, float* workspace, int64_t workspace_floats, void* stream) {
+  if (!particles || !conv1_w || !conv1_b || !conv2_w || !relu_bits || !pooled || !d_pooled || !g_conv1_w || !g_conv1_b || !g_conv2_w ||
+      !g_conv2_b || !workspace)
+    return fail(TD3_ERR_INVALID, "set_encoder_bwd_fused: bad arguments");
+  if (!enc_fused_shape_ok(batch, n_particles, particle_dim, conv2_w))
+    return fail(TD3_ERR_UNSUPPORTED, "set_encoder_bwd_fused: needs particle_dim <= 7 and n_particles a multiple of 128");
+  if (workspace_floats < set_encoder_workspace_floats(batch, n_particles, particle_dim, kEncH, kEncO))
+    return fail(TD3_ERR_INVALID, "set_encoder_bwd_fused: workspace too small (see set_encoder_workspace_floats)");
+  const long long rows = batch * n_particles;
+  g_tc_mode = 1;
+  g_cluster_mode = 0;
+  cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, 0);
+  EncBwdArgs e;
+  e.B = (int)batch; e.n_particles = (int)n_particles; e.D = (int)particle_dim; e.H = kEncH; e.O = kEncO;
+  e.dpool = d_pooled; e.ld_dpool = (int)ld_d_pooled;
+  e.pooled = pooled; e.ld_pooled = (int)ld_pooled;
+  e.P = particles;
+  e.part = workspace + rows * (kEncH + kEncO);
+  e.W2 = conv2_w; e.W1 = conv1_w; e.b1 = conv1_b;
+  e.bits = relu_bits;
+  e.gW1 = g_conv1_w; e.gb1 = g_conv1_b; e.gW2 = g_conv2_w; e.gb2 = g_conv2_b;
+  std::vector<ProblemList> st = enc_backward_stages(e, GroupShape{1, 1});
+  return run_problem_stages(st, false, (cudaStream_t)stream);
 }
 
 int td3_agent_create(const td3_agent_config* cfg, td3_agent** out) {
