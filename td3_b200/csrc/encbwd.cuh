@@ -35,7 +35,8 @@
 
 namespace td3 {
 
-constexpr int kEbThreads = 9 * 32;                                 // 8 worker warps + the MMA warp
+constexpr int kEbThreads = 9 * 32;                                 // dW2 kernel: 8 worker warps + the MMA warp
+constexpr int kEbXThreads = 13 * 32;                               // dX kernel: 4 builder + 8 epilogue warps + the MMA warp
 constexpr int kEbChunk128 = 128 * 128, kEbChunk256 = 256 * 128, kEbChunk16 = 16 * 128;   // bytes of a [rows][32 fp32] K-major chunk
 constexpr int kEbW2SmemBytes = 1024 + 4 * kEbChunk256 + 4 * kEbChunk128 + kEncW1Bytes + 2 * kEncPBytes + 256;
 constexpr int kEbXSmemBytes = 1024 + 3 * 4 * kEbChunk128 + 2 * 4 * kEbChunk16 + 2 * 128 * 4 + 256;
@@ -251,9 +252,9 @@ __global__ void __launch_bounds__(kEbThreads, 1) enc_bwd_w2_kernel(const __grid_
 // ---------------------------------------------------------------------------------------------------------------------
 // dz2 -> dh1 -> dz1 -> dW1 / db1, one half of the hidden channels per CTA
 // ---------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kEbThreads, 1) enc_bwd_x_kernel(const __grid_constant__ EncBwdParams E) {
+__global__ void __launch_bounds__(kEbXThreads, 1) enc_bwd_x_kernel(const __grid_constant__ EncBwdParams E) {
   extern __shared__ unsigned char eb_smem_raw[];
-  __shared__ unsigned long long dz2_full, dz2_empty, dh1_full[2], dh1_empty[2], dz1_full, dz1_empty, pt_empty[2], done_bar;
+  __shared__ unsigned long long dz2_full, dz2_empty, dh1_full[2], dh1_empty[2], dz1_full, dz1_empty, pt_full[2], pt_empty[2], done_bar;
   __shared__ unsigned int tmem_base_s;
   unsigned char* base = eb_smem_raw + ((1024u - (smem_u32(eb_smem_raw) & 1023u)) & 1023u);
   unsigned char* W2T = base;                                        // 4 chunks x [128 c][32 o]   (this CTA's half of the channels)
@@ -265,11 +266,11 @@ __global__ void __launch_bounds__(kEbThreads, 1) enc_bwd_x_kernel(const __grid_c
 
   if (tid == 0) {
     mbar_init(&dz2_full, 4); mbar_init(&dz2_empty, 1);
-    mbar_init(&dz1_full, 4); mbar_init(&dz1_empty, 1); mbar_init(&done_bar, 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(&dh1_full[i], 1); mbar_init(&dh1_empty[i], 4); mbar_init(&pt_empty[i], 1); }
+    mbar_init(&dz1_full, 8); mbar_init(&dz1_empty, 1); mbar_init(&done_bar, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&dh1_full[i], 1); mbar_init(&dh1_empty[i], 8); mbar_init(&pt_empty[i], 1); mbar_init(&pt_full[i], 4); }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
-  if (warp == 8) {
+  if (warp == kEbXThreads / 32 - 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_base_s)), "r"(512u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
@@ -300,23 +301,27 @@ __global__ void __launch_bounds__(kEbThreads, 1) enc_bwd_x_kernel(const __grid_c
 
   if (warp < 4) {
     // ------------------------------------------------------------------ builders: thread = particle p of the tile
+    // The builder is the head of the tile's dependency chain (dz2 -> dh1 MMAs -> epilogue -> dW1 MMAs): its global reads
+    // are issued one tile ahead and consumed at the top of the next iteration, so their latency stays off the chain.
     const int p = tid;
+    auto sample_of = [&](int t) { return (int)(((long long)(k + t * E.ks) * kEncTile) / E.n_particles); };
+    const long long gofs_dp = (long long)go * E.dpool_go + (long long)gi * E.dpool_gi + p;
+    const long long gofs_pl = (long long)go * E.pooled_go + (long long)gi * E.pooled_gi + p;
+    float dp_n = E.dpool[gofs_dp + (long long)sample_of(0) * E.ld_dpool];
+    float pl_n = E.pooled[gofs_pl + (long long)sample_of(0) * E.ld_pooled];
+    uint4 bw_n = __ldg(reinterpret_cast<const uint4*>(bits2 + ((long long)k * kEncTile + p) * 4));
     for (int t = 0; t < n_my; ++t) {
       const unsigned int ut = (unsigned)t;
-      const int rt = k + t * E.ks;
-      const int b = (int)(((long long)rt * kEncTile) / E.n_particles);
       float* gsb = gs + (ut & 1u) * 128;
-      gsb[p] = eb_pool_grad(E, go, gi, b, p);                       // (thread index doubles as the output channel here)
-      const uint4 bw = __ldg(reinterpret_cast<const uint4*>(bits2 + ((long long)rt * kEncTile + p) * 4));
-      const float* Pg = E.P + (long long)go * E.p_go + ((long long)rt * kEncTile + p) * D;
-      float ph[8], plo[8];
-#pragma unroll
-      for (int d = 0; d < 8; ++d) {
-        const float x = d < D ? __ldg(Pg + d) : 0.f;
-        ph[d] = rn_tf32(x);
-        plo[d] = rn_tf32(x - ph[d]);
-      }
+      gsb[p] = rn_tf32(pl_n > 0.f ? dp_n * E.inv_n : 0.f);          // g[b, o = p]  (thread index doubles as the output channel here)
+      const uint4 bw = bw_n;
       enc_named_barrier(3, 128);                                    // gs of this tile complete (the other buffer is two tiles old)
+      if (t + 1 < n_my) {
+        const int rt1 = k + (t + 1) * E.ks;
+        dp_n = E.dpool[gofs_dp + (long long)sample_of(t + 1) * E.ld_dpool];
+        pl_n = E.pooled[gofs_pl + (long long)sample_of(t + 1) * E.ld_pooled];
+        bw_n = __ldg(reinterpret_cast<const uint4*>(bits2 + ((long long)rt1 * kEncTile + p) * 4));
+      }
       if (t > 0) mbar_wait(&dz2_empty, (ut - 1u) & 1u);             // the previous tile's dh1 MMAs have read DZ2
       const unsigned int ww[4] = {bw.x, bw.y, bw.z, bw.w};
 #pragma unroll
@@ -332,40 +337,68 @@ __global__ void __launch_bounds__(kEbThreads, 1) enc_bwd_x_kernel(const __grid_c
         }
         eb_store_row(DZ2 + ch * kEbChunk128, p, v);
       }
-      if (t >= 2) mbar_wait(&pt_empty[ut & 1u], ((ut >> 1) - 1u) & 1u);   // the dW1 MMAs of two tiles ago have read this PT buffer
-      unsigned char* pt = PT + (ut & 1u) * 4 * kEbChunk16 + (p >> 5) * kEbChunk16;
-#pragma unroll
-      for (int d = 0; d < 8; ++d)
-        if (d < D) {
-          *reinterpret_cast<float*>(pt + eb_elem(d, p)) = ph[d];
-          *reinterpret_cast<float*>(pt + eb_elem(8 + d, p)) = plo[d];
-        }
       asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
       __syncwarp();
       if (lane == 0) enc_arrive(&dz2_full);
     }
-  } else if (warp < 8) {
-    // ------------------------------------------------------------------ epilogue: thread = hidden channel h * 128 + c == TMEM lane c
-    const int e = warp - 4, c = e * 32 + lane;
+  } else if (warp < 12) {
+    // ------------------------------------------------------------------ epilogue: thread = hidden channel h * 128 + c == TMEM lane c;
+    // the two warps of a lane quarter take two of the four 32-particle passes each (one warp per scheduler cannot hide
+    // the latency of its own instruction stream: two can)
+    const int e = warp & 3, hi2 = (warp - 4) >> 2, c = e * 32 + lane;
     float db1 = 0.f;
+    // the second warp of each lane quarter also stages the particle coordinates of the tile (B operand of the dW1 MMAs: rows
+    // d = P_hi, 8 + d = P_lo; thread = particle c), read one tile ahead
+    float pn[8];
+#pragma unroll
+    for (int d = 0; d < 8; ++d) pn[d] = 0.f;
+    if (hi2 == 1) {
+      const float* Pg = E.P + (long long)go * E.p_go + ((long long)k * kEncTile + c) * D;
+#pragma unroll
+      for (int d = 0; d < 8; ++d)
+        if (d < D) pn[d] = __ldg(Pg + d);
+    }
     for (int t = 0; t < n_my; ++t) {
       const unsigned int ut = (unsigned)t, buf = ut & 1u;
       const int rt = k + t * E.ks;
-      const uint4 bw = __ldg(reinterpret_cast<const uint4*>(bits1T + ((long long)rt * kEncH + h * 128 + c) * 4));
+      if (hi2 == 1) {
+        if (t >= 2) mbar_wait(&pt_empty[ut & 1u], ((ut >> 1) - 1u) & 1u);   // the dW1 MMAs of two tiles ago have read this PT buffer
+        unsigned char* pt = PT + (ut & 1u) * 4 * kEbChunk16 + (c >> 5) * kEbChunk16;
+#pragma unroll
+        for (int d = 0; d < 8; ++d)
+          if (d < D) {
+            const float ph = rn_tf32(pn[d]);
+            *reinterpret_cast<float*>(pt + eb_elem(d, c)) = ph;
+            *reinterpret_cast<float*>(pt + eb_elem(8 + d, c)) = rn_tf32(pn[d] - ph);
+          }
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+        __syncwarp();
+        if (lane == 0) enc_arrive(&pt_full[ut & 1u]);
+        if (t + 1 < n_my) {
+          const float* Pg = E.P + (long long)go * E.p_go + ((long long)(rt + E.ks) * kEncTile + c) * D;
+#pragma unroll
+          for (int d = 0; d < 8; ++d)
+            if (d < D) pn[d] = __ldg(Pg + d);
+        }
+      }
+      const uint2 bw = __ldg(reinterpret_cast<const uint2*>(bits1T + ((long long)rt * kEncH + h * 128 + c) * 4 + 2 * hi2));
       mbar_wait(&dh1_full[buf], (ut >> 1) & 1u);
       asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
       if (t > 0) mbar_wait(&dz1_empty, (ut - 1u) & 1u);             // the previous tile's dW1 MMAs have read DZ1T
-#pragma unroll 1
-      for (int pass = 0; pass < 4; ++pass) {
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        const int pass = 2 * hi2 + cc;
         unsigned int r[32];
         enc_tmem_ld32(tmem + buf * 128u + (unsigned)(pass * 32) + (((unsigned)e * 32u) << 16), r);
-        const unsigned int w = pass == 0 ? bw.x : pass == 1 ? bw.y : pass == 2 ? bw.z : bw.w;
+        const unsigned int w = cc == 0 ? bw.x : bw.y;
         float v[32];
+        float s4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
           v[i] = (w >> i) & 1u ? rn_tf32(__uint_as_float(r[i])) : 0.f;
-          db1 += v[i];
+          s4[i & 3] += v[i];
         }
+        db1 += (s4[0] + s4[1]) + (s4[2] + s4[3]);
         eb_store_row(DZ1T + pass * kEbChunk128, c, v);
       }
       asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
@@ -373,15 +406,18 @@ __global__ void __launch_bounds__(kEbThreads, 1) enc_bwd_x_kernel(const __grid_c
       __syncwarp();
       if (lane == 0) { enc_arrive(&dh1_empty[buf]); enc_arrive(&dz1_full); }
     }
+    // the two warps of a lane quarter hold disjoint particle ranges of the same channel: summed in fixed order
     mbar_wait(&done_bar, 0);
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-    {
+    if (hi2 == 1) gs[c] = db1;                                      // (gs is free: every build has been consumed)
+    enc_named_barrier(4, 256);
+    if (hi2 == 0) {
       unsigned int r[16];
       eb_tmem_ld16(tmem + 256u + (((unsigned)e * 32u) << 16), r);
       float* pw = E.part + (long long)go * E.part_go + (long long)gi * E.part_gi;     // (the host passes this kernel's region)
       float* dst = pw + (long long)k * (kEncH * D) + (long long)(h * 128 + c) * D;
       for (int d = 0; d < D; ++d) dst[d] = __uint_as_float(r[d]) + __uint_as_float(r[8 + d]);
-      pw[(long long)E.ks * (kEncH * D) + (long long)k * kEncH + h * 128 + c] = db1;
+      pw[(long long)E.ks * (kEncH * D) + (long long)k * kEncH + h * 128 + c] = db1 + gs[c];
     }
   } else {
     // ------------------------------------------------------------------ MMA warp
@@ -415,6 +451,7 @@ __global__ void __launch_bounds__(kEbThreads, 1) enc_bwd_x_kernel(const __grid_c
       const unsigned int ut = (unsigned)t;
       if (t + 1 < n_my) issue_dx(ut + 1u);
       mbar_wait(&dz1_full, ut & 1u);
+      mbar_wait(&pt_full[ut & 1u], (ut >> 1) & 1u);
       asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
       if (elect_one()) {
 #pragma unroll
@@ -435,7 +472,7 @@ __global__ void __launch_bounds__(kEbThreads, 1) enc_bwd_x_kernel(const __grid_c
   }
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
   __syncthreads();
-  if (warp == 8) {
+  if (warp == kEbXThreads / 32 - 1) {
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "r"(512u) : "memory");
   }

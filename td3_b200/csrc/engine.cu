@@ -228,7 +228,7 @@ int run_launch(const Launch& L, cudaStream_t s) {
     case Launch::ENCBWD_X: {
       int rc = ensure_kernel_attrs();
       if (rc != TD3_OK) return rc;
-      e = launch_pdl(enc_bwd_x_kernel, dim3(L.grid_x), dim3(kEbThreads), (size_t)kEbXSmemBytes, s, L.encb);
+      e = launch_pdl(enc_bwd_x_kernel, dim3(L.grid_x), dim3(kEbXThreads), (size_t)kEbXSmemBytes, s, L.encb);
       break;
     }
     case Launch::CHAIN: {
@@ -434,7 +434,7 @@ void finalize_problem(Problem& p, GroupShape gs) {
       p.tiles_per_group = (int)(((long long)p.M * p.K + kPoolBwdRows - 1) / kPoolBwdRows);
       break;
     case PK_REDUCE_SPLITS:
-      p.tiles_per_group = (p.M + 1023) / 1024;
+      p.tiles_per_group = (p.M + kReduceTile - 1) / kReduceTile;
       break;
     case PK_NEG_MEAN:
       p.tiles_per_group = 1;

@@ -608,7 +608,9 @@ __device__ __forceinline__ void pool_bwd_tile(const Problem& P, int tile) {
   }
 }
 
-// C[e] = sum_s A[s*c_split + e] for e in tile of 1024 elements (M = element count, K = splits)
+// C[e] = sum_s A[s*c_split + e] for e in tile of kReduceTile elements (M = element count, K = splits); a thread sums its
+// elements' partials in split order (fixed: deterministic) with the loads of eight splits in flight
+constexpr int kReduceTile = 512;
 __device__ __forceinline__ void reduce_splits_tile(const Problem& P, int tile) {
   const int g = tile / P.tiles_per_group;
   const int t = tile - g * P.tiles_per_group;
@@ -616,16 +618,21 @@ __device__ __forceinline__ void reduce_splits_tile(const Problem& P, int tile) {
   group_ptrs(P, g, go, gi);
   const float* part = P.A + go * P.a_go + gi * P.a_gi;
   float* out = P.C + go * P.c_go + gi * P.c_gi;
+  constexpr int kPer = kReduceTile / kStageThreads;
+  const int e0 = t * kReduceTile + threadIdx.x;
+  float s[kPer];
 #pragma unroll
-  for (int u = 0; u < 4; ++u) {
-    const int e = t * 1024 + u * 256 + threadIdx.x;
-    if (e < P.M) {
-      float s = 0.f;
-      #pragma unroll 4
-      for (int k = 0; k < P.K; ++k) s += part[(long long)k * P.c_split + e];
-      out[e] = s;
-    }
+  for (int u = 0; u < kPer; ++u) s[u] = 0.f;
+  const float* p = part + e0;
+#pragma unroll 8
+  for (int k = 0; k < P.K; ++k, p += P.c_split) {
+#pragma unroll
+    for (int u = 0; u < kPer; ++u)
+      if (e0 + u * kStageThreads < P.M) s[u] += p[u * kStageThreads];
   }
+#pragma unroll
+  for (int u = 0; u < kPer; ++u)
+    if (e0 + u * kStageThreads < P.M) out[e0 + u * kStageThreads] = s[u];
 }
 
 // Particle-encoder layer 1 (TD3_particles.py:29,54: Conv2d(1,256,(1,D)) == a D -> 256 linear layer per particle).  The
