@@ -107,6 +107,16 @@ def stage_gflop_per_cycle(w):
     return (critic * pf + actor) / 1e9
 
 
+def encoder_gflop_per_cycle(w):
+    """GFLOP of the particle-set encoder passes in one policy_freq cycle (the E / Eb terms of algorithmic_per_update)."""
+    pf, B = HYPER["policy_freq"], w["B"]
+    E = w["N"] * w["D"] * 256 + w["N"] * 256 * 128
+    Eb = w["N"] * w["D"] * 256 + 2 * w["N"] * 256 * 128
+    critic = 2 * B * (E + 2 * E + 2 * E + 2 * Eb)          # target actor, target critics, critics forward, critics backward
+    actor = 2 * B * (E + E + Eb)                           # actor forward, Q1 forward, actor backward
+    return (critic * pf + actor) / 1e9
+
+
 def measured_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -553,7 +563,7 @@ def main():
         import ctypes as C
         from td3_b200 import _lib as L_
         view = agent._rb_view(rb)
-        tot_us, stage_us, n_stage, n_all = 0.0, 0.0, 0, 0
+        tot_us, stage_us, n_stage, n_all, enc_us, n_enc = 0.0, 0.0, 0, 0, 0.0, 0
         for with_actor in (0, 1):                      # one policy_freq = 2 cycle: a critic-only and a policy update
             us, kinds, n = (C.c_float * 128)(), (C.c_int32 * 128)(), C.c_int32()
             L_.check(lib.td3_debug_prefix_times(agent._handle, C.byref(view), with_actor, 200, us, kinds, 128, C.byref(n)))
@@ -562,10 +572,13 @@ def main():
                 if kinds[k] == 0:
                     stage_us += us[k] - prev
                     n_stage += 1
+                elif kinds[k] in (9, 11, 12):          # K6: fused set-encoder forward / backward launches (enc.cuh, encbwd.cuh)
+                    enc_us += us[k] - prev
+                    n_enc += 1
                 prev = us[k]
             tot_us += us[n.value - 1]
             n_all += n.value
-        stage_info = dict(stage_us=stage_us, cycle_us=tot_us, n_stage=n_stage, n_all=n_all)
+        stage_info = dict(stage_us=stage_us, cycle_us=tot_us, n_stage=n_stage, n_all=n_all, enc_us=enc_us, n_enc=n_enc)
         torch.cuda.synchronize()
 
     # ---------------- population: several independent agents per GPU in lock-step ----------------
@@ -770,7 +783,22 @@ def main():
         note = ("single-agent MLP updates are bound by the dependency chain of 7-14 launches (cold code, first-operand "
                 "latency, a K loop that is bound by the ~50-cycle issue rate of tcgen05.mma from one thread plus barrier rounds), not by HBM or tensor throughput "
                 "(SURVEY.md 8d, DESIGN.md 5); fractions are reported against the floors anyway")
-        if stage_info and stage_info["n_stage"] > 0:
+        if stage_info and stage_info["n_enc"] > 0:
+            # particles: the dominant kernels are the fused set-encoder launches.  Algorithmic flops = the encoder terms of
+            # SURVEY 8d's formula (forward E per pass, backward Eb per pass with an encoder gradient); the h1 recomputation
+            # of the backward kernels and the padded K = 8 layer 1 are NOT counted.
+            eg = encoder_gflop_per_cycle(w)
+            ach = eg * 1e9 / (stage_info["enc_us"] * 1e-6) / 1e12
+            line["roofline"] = {
+                "bound": "tensor", "achieved": ach, "peak": tf32_peak, "unit": "TFLOP/s", "frac": ach / tf32_peak, "traffic": traffic,
+                "kernel": "td3::enc_fwd_kernel + td3::enc_bwd_w2_kernel + td3::enc_bwd_x_kernel (K6: fused particle-set encoder, tcgen05 kind::tf32)",
+                "launches_per_cycle": stage_info["n_enc"], "us_per_launch": stage_info["enc_us"] / stage_info["n_enc"],
+                "share_of_update_time": stage_info["enc_us"] / stage_info["cycle_us"],
+                "algorithmic_gflop_per_launch": eg / stage_info["n_enc"],
+                "how": "CUDA events around graph replays of the first k launches of a critic-only and a policy update, "
+                       "k = 1..n (td3_debug_prefix_times, on the replay stream); a launch's duration = prefix(k) - prefix(k-1)",
+                "peak_source": tf32_src, "whole_update": whole, "note": "cfg4 is tensor-bound: whole_update carries the update-level fraction"}
+        elif stage_info and stage_info["n_stage"] > 0:
             # dominant kernel: td3::stage_kernel<true>, the tcgen05 TF32 GEMM stages (hidden-layer contractions of all
             # passes).  Algorithmic flops = every contraction of the cycle that is not a first layer (front / apply
             # kernels) or an output head (head / front kernels).

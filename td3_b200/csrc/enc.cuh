@@ -77,6 +77,18 @@ __device__ __forceinline__ float enc_colsum32(float (&v)[32], int lane) {
   return v[0];
 }
 
+// 32 x 32 bit-matrix transpose across a warp: lane i holds row i (bit j = column j); returns column `lane` (bit i = row i).
+// Five butterfly steps swap the off-diagonal blocks of size 16, 8, 4, 2, 1: 5 shuffles instead of 32 ballots.
+__device__ __forceinline__ unsigned int enc_transpose32(unsigned int x, int lane) {
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    const unsigned int m = s == 16 ? 0x0000ffffu : s == 8 ? 0x00ff00ffu : s == 4 ? 0x0f0f0f0fu : s == 2 ? 0x33333333u : 0x55555555u;
+    const unsigned int y = __shfl_xor_sync(0xffffffffu, x, s);
+    x = (lane & s) ? (((y & ~m) >> s) | (x & ~m)) : ((x & m) | ((y & m) << s));
+  }
+  return x;
+}
+
 __device__ __forceinline__ void enc_named_barrier(int id, int threads) {
   asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(threads) : "memory");
 }
@@ -97,6 +109,20 @@ __device__ __forceinline__ void enc_tmem_ld32(unsigned int taddr, unsigned int (
       : "memory");
   asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
 }
+
+// the same load without the wait: the caller overlaps it with other work and calls enc_tmem_wait before reading r
+__device__ __forceinline__ void enc_tmem_ld32_issue(unsigned int taddr, unsigned int (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, "
+      "%18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void enc_tmem_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
 
 __global__ void __launch_bounds__(kEncThreads, 1) enc_fwd_kernel(const __grid_constant__ EncParams E) {
   extern __shared__ unsigned char enc_smem_raw[];
@@ -171,17 +197,12 @@ __global__ void __launch_bounds__(kEncThreads, 1) enc_fwd_kernel(const __grid_co
 #pragma unroll
           for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(h2row + pass * 32 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
         }
-        if (bits2) {                                                // sign bits of this thread's particle, and -- transposed by
-          unsigned int nat = 0, mine = 0;                           // ballots -- of the warp's 32 particles for channel pass * 32 + lane
+        if (bits2) {                                                // sign bits of this thread's particle, and -- transposed across
+          unsigned int nat = 0;                                     // the warp -- of its 32 particles for channel pass * 32 + lane
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const bool on = v[j] > 0.f;
-            nat |= on ? (1u << j) : 0u;
-            const unsigned int bal = __ballot_sync(0xffffffffu, on);
-            if (lane == j) mine = bal;
-          }
+          for (int j = 0; j < 32; ++j) nat |= v[j] > 0.f ? (1u << j) : 0u;
           bits2[row * 4 + pass] = nat;
-          bits2[(long long)E.rows * 4 + ((long long)rt * kEncO + pass * 32 + lane) * 4 + e] = mine;
+          bits2[(long long)E.rows * 4 + ((long long)rt * kEncO + pass * 32 + lane) * 4 + e] = enc_transpose32(nat, lane);
         }
         part_s[e * kEncO + pass * 32 + lane] = enc_colsum32(v, lane);
       }
@@ -254,7 +275,7 @@ __global__ void __launch_bounds__(kEncThreads, 1) enc_fwd_kernel(const __grid_co
         enc_tmem_ld32(tmem + 256u + (unsigned)(chunk * 32) + (((unsigned)lq * 32u) << 16), r);
         float v[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = rn_tf32(fmaxf(__uint_as_float(r[j]), 0.f));
+        for (int j = 0; j < 32; ++j) v[j] = rn_tf32_finite(fmaxf(__uint_as_float(r[j]), 0.f));
         if (use > 0) mbar_wait(&a_empty[buf], (use - 1u) & 1u);     // the MMAs that read this buffer have completed
         // operand layout: chunk = 32 reduction columns; row r at r * 128 B, 16-byte granule j at (j ^ (r & 7))
         unsigned char* arow = As + buf * kEncQuarterBytes + half * kEncChunk + row * 128;
@@ -265,13 +286,10 @@ __global__ void __launch_bounds__(kEncThreads, 1) enc_fwd_kernel(const __grid_co
         __syncwarp();
         if (lane == 0) enc_arrive(&a_full[buf]);
         if (bits1T) {                                               // h1 > 0 of the warp's 32 particles, per hidden channel
-          unsigned int mine = 0;
+          unsigned int nat = 0;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const unsigned int bal = __ballot_sync(0xffffffffu, v[j] > 0.f);
-            if (lane == j) mine = bal;
-          }
-          bits1T[((long long)rt * kEncH + chunk * 32 + lane) * 4 + lq] = mine;
+          for (int j = 0; j < 32; ++j) nat |= v[j] > 0.f ? (1u << j) : 0u;
+          bits1T[((long long)rt * kEncH + chunk * 32 + lane) * 4 + lq] = enc_transpose32(nat, lane);
         }
         if (h1g) {
 #pragma unroll

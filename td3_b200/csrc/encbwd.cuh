@@ -169,14 +169,22 @@ __global__ void __launch_bounds__(kEbThreads, 1) enc_bwd_w2_kernel(const __grid_
       }
       mbar_wait(&h1_full, (unsigned)t & 1u);
       asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-#pragma unroll 1
-      for (int pass = 0; pass < 4; ++pass) {
-        unsigned int r[32];
-        enc_tmem_ld32(tmem + (unsigned)(half * 128 + pass * 32) + (((unsigned)lq * 32u) << 16), r);
+      // the four 32-particle passes, two at a time: the TMEM read of the second is in flight while the first is converted
+      // and stored
+      const unsigned int z1_addr = tmem + (unsigned)(half * 128) + (((unsigned)lq * 32u) << 16);
+#pragma unroll
+      for (int pp = 0; pp < 2; ++pp) {
+        unsigned int ra[32], rb[32];
+        enc_tmem_ld32_issue(z1_addr + (unsigned)(pp * 64), ra);
+        enc_tmem_ld32_issue(z1_addr + (unsigned)(pp * 64 + 32), rb);
+        enc_tmem_wait();
         float v[32];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = rn_tf32(fmaxf(__uint_as_float(r[i]), 0.f));
-        eb_store_row(H1T + pass * kEbChunk256, c, v);
+        for (int i = 0; i < 32; ++i) v[i] = rn_tf32_finite(fmaxf(__uint_as_float(ra[i]), 0.f));
+        eb_store_row(H1T + (2 * pp) * kEbChunk256, c, v);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = rn_tf32_finite(fmaxf(__uint_as_float(rb[i]), 0.f));
+        eb_store_row(H1T + (2 * pp + 1) * kEbChunk256, c, v);
       }
       asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
       asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
@@ -395,7 +403,7 @@ __global__ void __launch_bounds__(kEbXThreads, 1) enc_bwd_x_kernel(const __grid_
         float s4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          v[i] = (w >> i) & 1u ? rn_tf32(__uint_as_float(r[i])) : 0.f;
+          v[i] = (w >> i) & 1u ? rn_tf32_finite(__uint_as_float(r[i])) : 0.f;
           s4[i & 3] += v[i];
         }
         db1 += (s4[0] + s4[1]) + (s4[2] + s4[3]);

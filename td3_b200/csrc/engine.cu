@@ -329,7 +329,7 @@ bool encode_operand_maps(const Problem& p, bool is_a, int n_outer, int n_inner, 
   return true;
 }
 
-constexpr int kMaxTensorMaps = 1024;
+constexpr int kMaxTensorMaps = 8192;    // (128 bytes each; a 64-agent population needs ~2500)
 
 // Give every tensor-core problem of `seqs` its maps; `dev_maps` is the device array they will be copied to.
 bool attach_tensor_maps(std::initializer_list<std::vector<Launch>*> seqs, CUtensorMap* dev_maps, std::vector<CUtensorMap>& host) {

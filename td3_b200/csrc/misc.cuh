@@ -21,6 +21,10 @@ __device__ __forceinline__ float rn_tf32(float x) {
   return __uint_as_float(u);
 }
 
+// The same rounding as two integer instructions, for inner loops whose inputs are finite: add half an ulp of the 10-bit
+// mantissa to the magnitude, drop the low 13 bits (ptxas expands cvt.rna.tf32 to exactly this plus an |x| < inf guard).
+__device__ __forceinline__ float rn_tf32_finite(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u); }
+
 // ------------------------------------------------------------------------------------
 // Philox4x32-10 (Salmon et al., SC'11).  Counter-based: every draw is a pure function of
 // (seed, stream, step, element), so a captured CUDA graph replays correctly from a
