@@ -160,6 +160,46 @@ def test_fused_backward_is_deterministic():
         assert torch.equal(a[k], b[k]), k
 
 
+def test_fused_pair_stress_many_tiles_per_cta_bit_identical_replays():
+    """The kernels' cross-warp protocols (mbarrier phases over a CTA's run of tiles, TMEM / shared-memory buffer reuse,
+    per-CTA partials) at the real cfg4 shape -- 2048 tiles, ~14 per CTA in the dW2 kernel and ~28 per CTA in the dX
+    kernel -- and at shapes whose tile count does not divide the CTA count: 40 replays must be bit-identical (a lost
+    barrier phase or a buffer reused too early shows up as a changed low bit long before it breaks a tolerance)."""
+    from td3_b200 import _lib
+    lib = _lib.require_cuda()
+    H, E = O.ENC_HIDDEN, O.ENC_OUT
+    for (B, N, D) in [(256, 1024, 6), (37, 384, 5), (149, 128, 7)]:
+        torch.manual_seed(B)
+        rows = B * N
+        P = torch.randn(rows, D, device="cuda")
+        w1 = (torch.randn(H, D, device="cuda") * 0.4).contiguous()
+        b1 = torch.randn(H, device="cuda") * 0.1
+        w2 = (torch.randn(E, H, device="cuda") * 0.06).contiguous()
+        b2 = torch.randn(E, device="cuda") * 0.1
+        ws_n = int(lib.set_encoder_workspace_floats(B, N, D, H, E))
+        ws = torch.empty(ws_n, device="cuda")
+        pooled = torch.zeros(B, E, device="cuda")
+        bits = torch.zeros(16 * rows, dtype=torch.int32, device="cuda")
+        dp = torch.randn(B, E, device="cuda")
+        first = None
+        for it in range(40):
+            g = [torch.full_like(t, float("nan")) for t in (w1, b1, w2, b2)]
+            bits.zero_()
+            _lib.check(lib.set_encoder_fwd_bits(P.data_ptr(), B, N, D, w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(),
+                                                pooled.data_ptr(), E, bits.data_ptr(), ws.data_ptr(), ws_n, _lib.stream_ptr()))
+            _lib.check(lib.set_encoder_bwd_fused(P.data_ptr(), B, N, D, w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), bits.data_ptr(),
+                                                 pooled.data_ptr(), E, dp.data_ptr(), E, g[0].data_ptr(), g[1].data_ptr(),
+                                                 g[2].data_ptr(), g[3].data_ptr(), ws.data_ptr(), ws_n, _lib.stream_ptr()))
+            torch.cuda.synchronize()
+            snap = [t.clone() for t in g] + [pooled.clone(), bits.clone()]
+            assert all(torch.isfinite(t).all() for t in snap[:5])
+            if first is None:
+                first = snap
+            else:
+                for a, b in zip(first, snap):
+                    assert torch.equal(a, b), (B, N, D, it)
+
+
 def test_fused_encoder_refuses_shapes_it_does_not_cover():
     from td3_b200 import _lib
     lib = _lib.require_cuda()
