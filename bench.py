@@ -23,6 +23,9 @@ batch 256, 1M-row device-resident replay buffer, one agent per GPU.
   torch_eager_gpu  the oracle port of the reference with its networks on the GPU (eager PyTorch): a comparator.
   population  8 independent agents per GPU in lock-step (BASELINE config 5) + the HBM-side roofline of its
          optimiser launch.
+  particles_cfg4  (default workload, rank 0) BASELINE config 4 -- TD3_particles, 1024 particles, batch 256 -- timed the same
+         way (device-resident graph replays) with the fused set-encoder launches' share and their algorithmic TFLOP/s
+         against the TF32 peak measured in this run; `--workload cfg4` gives the full line for it.
   --impl reference times the CPU oracle port of the reference (oracle/td3_oracle.py, torch CPU ops --
          /root/reference is not present on the GPU box) on the host cores with the same config.
 With N > 1 (torchrun) every rank runs an independent agent/seed on its own GPU (weak scaling, no
@@ -676,6 +679,49 @@ def main():
         del wa, wrb
         torch.cuda.empty_cache()
 
+    # ---------------- BASELINE config 4 (particles, N = 1024, batch 256): the tensor-bound workload, on rank 0 ----------------
+    # the driver runs this file with the default workload only; the particle variant's number (fused set-encoder forward and
+    # backward, csrc/enc.cuh + encbwd.cuh) rides along as a key.  `python bench.py --workload cfg4` is the full line.
+    cfg4 = None
+    if rank == 0 and args.workload == "cfg2" and args.precision == "tf32" and args.exec_mode == "graph":
+        try:
+            import ctypes as C
+            from td3_b200 import _lib as L_
+            w4 = WORKLOADS["cfg4"]
+            a4, rb4 = build_ours(w4, seed=400)
+            a4.train(rb4, w4["B"], iterations=10)
+            torch.cuda.synchronize()
+            n4 = max(20, min(K, 100))
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record()
+            a4.train(rb4, w4["B"], iterations=n4)
+            c1.record()
+            torch.cuda.synchronize()
+            ms4 = c0.elapsed_time(c1) / n4
+            view4 = a4._rb_view(rb4)
+            enc_us, n_enc, cyc_us = 0.0, 0, 0.0
+            for with_actor in (0, 1):
+                us, kinds, n = (C.c_float * 128)(), (C.c_int32 * 128)(), C.c_int32()
+                L_.check(lib.td3_debug_prefix_times(a4._handle, C.byref(view4), with_actor, 20, us, kinds, 128, C.byref(n)))
+                prev = 0.0
+                for k in range(n.value):
+                    if kinds[k] in (9, 11, 12):
+                        enc_us += us[k] - prev
+                        n_enc += 1
+                    prev = us[k]
+                cyc_us += us[n.value - 1]
+            gf4, mb4 = algorithmic_per_update(w4)
+            cfg4 = {"workload": "cfg4: TD3_particles F=8 N=1024 D=6 A=3, batch 256, 8192-row buffer (1.6 GB of particle sets)",
+                    "value": 1000.0 / ms4, "unit": "updates/s (this rank)", "ms_per_step": ms4, "steps": n4,
+                    "algorithmic_gflop_per_update": gf4,
+                    "encoder_kernels": {"us_per_cycle": enc_us, "launches_per_cycle": n_enc, "share_of_update_time": enc_us / max(cyc_us, 1e-9),
+                                        "algorithmic_gflop_per_cycle": encoder_gflop_per_cycle(w4),
+                                        "kernel": "td3::enc_fwd_kernel + enc_bwd_w2_kernel + enc_bwd_x_kernel (tcgen05 kind::tf32)"}}
+            del a4, rb4
+        except Exception as exc:                              # a side measurement, never a reason to lose the bench line
+            cfg4 = {"unavailable": repr(exc)[:300]}
+        torch.cuda.empty_cache()
+
     # ---------------- B = 1 latency of select_action / eval_q (the calls main.py makes every env step) ----------------
     b1 = None
     if rank == 0 and args.workload == "cfg2":
@@ -742,6 +788,11 @@ def main():
         line["b1_latency"] = b1
     if wide:
         line["wide_state"] = wide
+    if cfg4:
+        if "encoder_kernels" in cfg4:     # against the TF32 peak measured in this run
+            ek = cfg4["encoder_kernels"]
+            ek["achieved_tflops"] = ek["algorithmic_gflop_per_cycle"] * 1e9 / (ek["us_per_cycle"] * 1e-6) / 1e12
+        line["particles_cfg4"] = cfg4
     if dp_line:
         line["dp_critic"] = dp_line
     if n_pop > 1 and pop_ms > 0:
@@ -759,6 +810,11 @@ def main():
                     f"{peaks['bf16_sustained'] / 2.0:.1f})") if tf32_measured else peaks["source"] + " (bf16 sustained / 2 for kind::tf32)"
         if args.precision == "fp32":
             tf32_peak, tf32_src = FFMA_PEAK_TFLOPS, "fp32 FFMA peak: 148 SMs x 128 lanes x 2 flop x 1.965 GHz"
+        if "particles_cfg4" in line and "encoder_kernels" in line["particles_cfg4"]:
+            ek = line["particles_cfg4"]["encoder_kernels"]
+            ek.update({"bound": "tensor", "peak_tflops": tf32_peak, "frac": ek["achieved_tflops"] / tf32_peak, "peak_source": tf32_src})
+            line["particles_cfg4"]["whole_update_frac_of_tf32_peak"] = (line["particles_cfg4"]["algorithmic_gflop_per_update"] * 1e9 /
+                                                                        (line["particles_cfg4"]["ms_per_step"] * 1e-3) / 1e12 / tf32_peak)
         try:
             line["hbm_kernels"] = hbm_kernel_rooflines(peaks)
         except Exception as exc:

@@ -2547,7 +2547,9 @@ int append_records(std::vector<StageRec>& prog, const std::vector<Launch>& seq, 
       case Launch::FRONT:
         r.kind = SK_FRONT; r.u.f = L.front; r.main_tiles = L.grid_x;
         break;
-      default: break;
+      default:     // kernels with their own persistent CTA structure (fused set-encoder, chain) or host-side protocols (DP flags)
+        return fail(TD3_ERR_UNSUPPORTED, "exec_mode persistent cannot run this plan (fused set-encoder / chain / data-parallel "
+                                         "launches are kernels of their own): use exec_mode graph or launches");
     }
     prog.push_back(r);
   }
@@ -2559,8 +2561,10 @@ int build_programs(td3_agent* a, cudaStream_t s) {
   std::vector<StageRec> pc, pp;
   AdamTick pend{};
   // the same sequences the CUDA graphs replay (tail-fused where the plan allows it)
-  for (auto* seq : {&a->seq_sample, &a->seq_run_critic}) append_records(pc, *seq, &pend);
-  for (auto* seq : {&a->seq_sample, &a->seq_run_policy}) append_records(pp, *seq, &pend);
+  for (auto* seq : {&a->seq_sample, &a->seq_run_critic})
+    if (int rc = append_records(pc, *seq, &pend)) return rc;
+  for (auto* seq : {&a->seq_sample, &a->seq_run_policy})
+    if (int rc = append_records(pp, *seq, &pend)) return rc;
   if (pc.empty() || pp.empty() || (int)pc.size() > kMaxProgStages || (int)pp.size() > kMaxProgStages)
     return fail(TD3_ERR_STATE, "persistent program has %zu / %zu stages (max %d)", pc.size(), pp.size(), kMaxProgStages);
   // When the first stage of an update is a plain gather it touches nothing the optimiser stage before it writes (the
