@@ -176,6 +176,26 @@ def test_particles_cycle_tf32(norm, cdq):
     _one_cycle(ora, orb, ours, rb, B=128, A=3, rows=256, label=f"particles norm={norm} CDQ={cdq}")
 
 
+def test_particles_trajectory_40_updates_tf32():
+    """A TD3_particles trajectory through the fused set-encoder forward / backward (enc.cuh, encbwd.cuh): 40 updates at
+    256 particles, batch 64; the conv1 / conv2 parameters are part of every compared state_dict.  Same bounds as the
+    featured N = 200 trajectory, scaled to the update count."""
+    ora, orb, ours, rb = make_particles(F=8, N=256, D=6, A=3, rows=256, lr=1e-4, precision="tf32")
+    rs = np.random.RandomState(5)
+    worst_l = 0.0
+    for t in range(40):
+        idx = rs.randint(0, 256, size=64)
+        nz = rs.standard_normal((64, 3)).astype(np.float32)
+        ora.train(orb, 64, indices=idx, noise=nz)
+        ours.train(rb, 64, indices=idx, noise=nz)
+        if t % 10 == 9:
+            got, want = float(ours.last_critic_loss[0].item()), ora.trace["critic_loss"]
+            worst_l = max(worst_l, abs(got - want) / abs(want))
+    worst = compare_nets(ours, ora, tol_rel=1e-2, max_abs=40 * 1e-4, label="tf32 particles N=40", abs_floor=1e-4 * 40)
+    print(f"[tf32 particles 40 updates] loss curve within {worst_l:.2e}; worst parameter tensor {worst}")
+    assert worst_l <= 2e-2
+
+
 def test_particles_policy_freq_3_fp32():
     """SURVEY T3 cell that round 1 left out: particles x policy_freq = 3 (strict fp32 against the oracle)."""
     ora, orb, ours, rb = make_particles(F=8, N=64, D=6, A=3, rows=128, lr=1e-3, precision="fp32", policy_freq=3)
