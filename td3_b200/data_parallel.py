@@ -49,7 +49,8 @@ class DataParallelTD3(object):
         if not dist.is_initialized():
             raise RuntimeError("torch.distributed is not initialised")
         self.agent, self.group = agent, process_group
-        agent._dp_owner = self           # the agent's own train() now refuses (its plan carries a global batch / shard offset)
+        agent._dp_owner = True           # the agent's own train() now refuses (its plan carries a global batch / shard offset);
+                                         # a flag, not a back-reference: a cycle would keep the symmetric-memory buffers alive past `del`
         self.world, self.rank = dist.get_world_size(process_group), dist.get_rank(process_group)
         self._configured = None
         self.communicate = True          # False: skip the reduction (timing of the compute alone; replicas diverge)

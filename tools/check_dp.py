@@ -82,4 +82,24 @@ for mode in ("p2p", "nccl"):
                           "reductions_per_update": "1 x critic gradient (1.04 MB) + 0.5 x actor gradient (0.52 MB)"}))
     dist.barrier()
     del dp, a, rb
-dist.destroy_process_group()
+if os.environ.get("CHECK_DP_TRACE"):
+    print(f"[rank {rank}] all checks done, tearing down", file=sys.stderr, flush=True)
+# Teardown.  The agents and their driver reference each other (agent._dp_owner <-> dp.agent), so `del` alone leaves the
+# symmetric-memory gradient buffers alive until the cycle collector runs; with them alive destroy_process_group() has
+# been seen to wait forever on a 2-GPU box.  Collect first, and never let a stuck teardown turn a finished check into
+# a hung process: every result line has been printed by now.
+import gc, threading
+gc.collect()
+torch.cuda.synchronize()
+if os.environ.get("CHECK_DP_TRACE"):
+    print(f"[rank {rank}] device idle", file=sys.stderr, flush=True)
+dist.barrier()
+th = threading.Thread(target=dist.destroy_process_group, daemon=True)
+th.start()
+th.join(30.0)
+if os.environ.get("CHECK_DP_TRACE"):
+    print(f"[rank {rank}] process group {'destroyed' if not th.is_alive() else 'teardown still waiting after 30 s: leaving'}",
+          file=sys.stderr, flush=True)
+sys.stdout.flush()
+sys.stderr.flush()
+os._exit(0)
