@@ -39,7 +39,7 @@ constexpr int kEbThreads = 9 * 32;                                 // dW2 kernel
 constexpr int kEbXThreads = 13 * 32;                               // dX kernel: 4 builder + 8 epilogue warps + the MMA warp
 constexpr int kEbChunk128 = 128 * 128, kEbChunk256 = 256 * 128, kEbChunk16 = 16 * 128;   // bytes of a [rows][32 fp32] K-major chunk
 constexpr int kEbW2SmemBytes = 1024 + 4 * kEbChunk256 + 4 * kEbChunk128 + kEncW1Bytes + 2 * kEncPBytes + 256;
-constexpr int kEbXSmemBytes = 1024 + 3 * 4 * kEbChunk128 + 2 * 4 * kEbChunk16 + 2 * 128 * 4 + 256;
+constexpr int kEbXSmemBytes = 1024 + 3 * 4 * kEbChunk128 + 2 * 4 * kEbChunk16 + 2 * 128 * 4 + 256;    // W2^T half + two dz2 buffers + particles + g
 
 struct EncBwdParams {
   const float* P; long long p_go;                     // particles [rows, D] of outer group o at P + o * p_go
@@ -63,6 +63,34 @@ __device__ __forceinline__ void eb_store_row(unsigned char* chunk, int row, cons
 }
 // byte offset of element (row, k) inside such a chunk
 __device__ __forceinline__ int eb_elem(int row, int k) { return row * 128 + ((((k & 31) >> 2) ^ (row & 7)) << 4) + (k & 3) * 4; }
+
+// TMEM columns of the dX kernel: [0, 256) the two dh1^T accumulators, [256, 384) dz1^T (A operand of the dW1 MMAs, written
+// by the epilogue warps with tcgen05.st: it never touches shared memory), [384, 400) the dW1 accumulator
+constexpr unsigned int kEbXDz1Col = 256u, kEbXDw1Col = 384u;
+
+// 32 consecutive columns of this thread's TMEM lane <- registers
+__device__ __forceinline__ void eb_tmem_st32(unsigned int taddr, const float (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, "
+      "%19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};\n" ::"r"(taddr),
+      "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]), "f"(v[8]), "f"(v[9]), "f"(v[10]), "f"(v[11]),
+      "f"(v[12]), "f"(v[13]), "f"(v[14]), "f"(v[15]), "f"(v[16]), "f"(v[17]), "f"(v[18]), "f"(v[19]), "f"(v[20]), "f"(v[21]), "f"(v[22]),
+      "f"(v[23]), "f"(v[24]), "f"(v[25]), "f"(v[26]), "f"(v[27]), "f"(v[28]), "f"(v[29]), "f"(v[30]), "f"(v[31])
+      : "memory");
+}
+
+// tcgen05.mma with the A operand in tensor memory (lane = row, column = reduction index) and B from a shared-memory descriptor
+__device__ __forceinline__ void tc_mma_ts(unsigned int tmem_d, unsigned int tmem_a, unsigned long long db, unsigned int idesc,
+                                          unsigned int accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 
 __device__ __forceinline__ void eb_tmem_ld16(unsigned int taddr, unsigned int (&r)[16]) {
   asm volatile(
@@ -262,20 +290,19 @@ __global__ void __launch_bounds__(kEbThreads, 1) enc_bwd_w2_kernel(const __grid_
 // ---------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kEbXThreads, 1) enc_bwd_x_kernel(const __grid_constant__ EncBwdParams E) {
   extern __shared__ unsigned char eb_smem_raw[];
-  __shared__ unsigned long long dz2_full, dz2_empty, dh1_full[2], dh1_empty[2], dz1_full, dz1_empty, pt_full[2], pt_empty[2], done_bar;
+  __shared__ unsigned long long dz2_full[2], dz2_empty[2], dh1_full[2], dh1_empty[2], dz1_full, dz1_empty, pt_full[2], pt_empty[2], done_bar;
   __shared__ unsigned int tmem_base_s;
   unsigned char* base = eb_smem_raw + ((1024u - (smem_u32(eb_smem_raw) & 1023u)) & 1023u);
   unsigned char* W2T = base;                                        // 4 chunks x [128 c][32 o]   (this CTA's half of the channels)
-  unsigned char* DZ2 = W2T + 4 * kEbChunk128;                       // 4 chunks x [128 p][32 o]
-  unsigned char* DZ1T = DZ2 + 4 * kEbChunk128;                      // 4 chunks x [128 c][32 p]
-  unsigned char* PT = DZ1T + 4 * kEbChunk128;                       // 2 x 4 chunks x [16 d][32 p]: rows d < D = P_hi, 8 + d = P_lo
+  unsigned char* DZ2 = W2T + 4 * kEbChunk128;                       // 2 buffers x 4 chunks x [128 p][32 o]
+  unsigned char* PT = DZ2 + 2 * 4 * kEbChunk128;                       // 2 x 4 chunks x [16 d][32 p]: rows d < D = P_hi, 8 + d = P_lo
   float* gs = reinterpret_cast<float*>(PT + 2 * 4 * kEbChunk16);    // 2 x [128]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (tid == 0) {
-    mbar_init(&dz2_full, 4); mbar_init(&dz2_empty, 1);
     mbar_init(&dz1_full, 8); mbar_init(&dz1_empty, 1); mbar_init(&done_bar, 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(&dh1_full[i], 1); mbar_init(&dh1_empty[i], 8); mbar_init(&pt_empty[i], 1); mbar_init(&pt_full[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&dh1_full[i], 1); mbar_init(&dh1_empty[i], 8); mbar_init(&pt_empty[i], 1); mbar_init(&pt_full[i], 4);
+                                  mbar_init(&dz2_full[i], 4); mbar_init(&dz2_empty[i], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   if (warp == kEbXThreads / 32 - 1) {
@@ -330,7 +357,8 @@ __global__ void __launch_bounds__(kEbXThreads, 1) enc_bwd_x_kernel(const __grid_
         pl_n = E.pooled[gofs_pl + (long long)sample_of(t + 1) * E.ld_pooled];
         bw_n = __ldg(reinterpret_cast<const uint4*>(bits2 + ((long long)rt1 * kEncTile + p) * 4));
       }
-      if (t > 0) mbar_wait(&dz2_empty, (ut - 1u) & 1u);             // the previous tile's dh1 MMAs have read DZ2
+      if (t >= 2) mbar_wait(&dz2_empty[ut & 1u], ((ut >> 1) - 1u) & 1u);   // the dh1 MMAs of two tiles ago have read this DZ2 buffer
+      unsigned char* dzb = DZ2 + (ut & 1u) * 4 * kEbChunk128;
       const unsigned int ww[4] = {bw.x, bw.y, bw.z, bw.w};
 #pragma unroll
       for (int ch = 0; ch < 4; ++ch) {
@@ -343,11 +371,11 @@ __global__ void __launch_bounds__(kEbXThreads, 1) enc_bwd_x_kernel(const __grid_
           v[4 * i4 + 2] = (ww[ch] >> (4 * i4 + 2)) & 1u ? g4.z : 0.f;
           v[4 * i4 + 3] = (ww[ch] >> (4 * i4 + 3)) & 1u ? g4.w : 0.f;
         }
-        eb_store_row(DZ2 + ch * kEbChunk128, p, v);
+        eb_store_row(dzb + ch * kEbChunk128, p, v);
       }
       asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
       __syncwarp();
-      if (lane == 0) enc_arrive(&dz2_full);
+      if (lane == 0) enc_arrive(&dz2_full[ut & 1u]);
     }
   } else if (warp < 12) {
     // ------------------------------------------------------------------ epilogue: thread = hidden channel h * 128 + c == TMEM lane c;
@@ -392,7 +420,8 @@ __global__ void __launch_bounds__(kEbXThreads, 1) enc_bwd_x_kernel(const __grid_
       const uint2 bw = __ldg(reinterpret_cast<const uint2*>(bits1T + ((long long)rt * kEncH + h * 128 + c) * 4 + 2 * hi2));
       mbar_wait(&dh1_full[buf], (ut >> 1) & 1u);
       asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-      if (t > 0) mbar_wait(&dz1_empty, (ut - 1u) & 1u);             // the previous tile's dW1 MMAs have read DZ1T
+      if (t > 0) mbar_wait(&dz1_empty, (ut - 1u) & 1u);             // the previous tile's dW1 MMAs have read dz1^T
+      asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
 #pragma unroll
       for (int cc = 0; cc < 2; ++cc) {
         const int pass = 2 * hi2 + cc;
@@ -407,10 +436,10 @@ __global__ void __launch_bounds__(kEbXThreads, 1) enc_bwd_x_kernel(const __grid_
           s4[i & 3] += v[i];
         }
         db1 += (s4[0] + s4[1]) + (s4[2] + s4[3]);
-        eb_store_row(DZ1T + pass * kEbChunk128, c, v);
+        eb_tmem_st32(tmem + kEbXDz1Col + (unsigned)(pass * 32) + (((unsigned)e * 32u) << 16), v);   // row c of dz1^T: the A operand, in TMEM
       }
+      asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
       asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
-      asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
       __syncwarp();
       if (lane == 0) { enc_arrive(&dh1_empty[buf]); enc_arrive(&dz1_full); }
     }
@@ -421,7 +450,7 @@ __global__ void __launch_bounds__(kEbXThreads, 1) enc_bwd_x_kernel(const __grid_
     enc_named_barrier(4, 256);
     if (hi2 == 0) {
       unsigned int r[16];
-      eb_tmem_ld16(tmem + 256u + (((unsigned)e * 32u) << 16), r);
+      eb_tmem_ld16(tmem + kEbXDw1Col + (((unsigned)e * 32u) << 16), r);
       float* pw = E.part + (long long)go * E.part_go + (long long)gi * E.part_gi;     // (the host passes this kernel's region)
       float* dst = pw + (long long)k * (kEncH * D) + (long long)(h * 128 + c) * D;
       for (int d = 0; d < D; ++d) dst[d] = __uint_as_float(r[d]) + __uint_as_float(r[8 + d]);
@@ -434,22 +463,21 @@ __global__ void __launch_bounds__(kEbXThreads, 1) enc_bwd_x_kernel(const __grid_
     const unsigned int lo0 = (16u >> 4) << 16;
     const unsigned int w2t = __shfl_sync(0xffffffffu, smem_u32(W2T), 0);
     const unsigned int dz2 = __shfl_sync(0xffffffffu, smem_u32(DZ2), 0);
-    const unsigned int dz1t = __shfl_sync(0xffffffffu, smem_u32(DZ1T), 0);
     const unsigned int ptb = __shfl_sync(0xffffffffu, smem_u32(PT), 0);
     auto issue_dx = [&](unsigned int u) {       // dh1^T[c, p] = sum_o W2^T[c, o] dz2[p, o] of tile u
-      mbar_wait(&dz2_full, u & 1u);
+      mbar_wait(&dz2_full[u & 1u], (u >> 1) & 1u);
       if (u >= 2) mbar_wait(&dh1_empty[u & 1u], ((u >> 1) - 1u) & 1u);
       asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
       if (elect_one()) {
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch) {
-          const unsigned int a_lo = lo0 | ((w2t + ch * kEbChunk128) >> 4), b_lo = lo0 | ((dz2 + ch * kEbChunk128) >> 4);
+          const unsigned int a_lo = lo0 | ((w2t + ch * kEbChunk128) >> 4), b_lo = lo0 | ((dz2 + (u & 1u) * 4 * kEbChunk128 + ch * kEbChunk128) >> 4);
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk)
             tc_mma(tmem + (u & 1u) * 128u, ((unsigned long long)hi << 32) | (a_lo + kk * 2), ((unsigned long long)hi << 32) | (b_lo + kk * 2),
                    idesc_x, (ch | kk) != 0 ? 1u : 0u);
         }
-        tc_commit(&dz2_empty);
+        tc_commit(&dz2_empty[u & 1u]);
         tc_commit(&dh1_full[u & 1u]);
       }
       __syncwarp();
@@ -464,12 +492,11 @@ __global__ void __launch_bounds__(kEbXThreads, 1) enc_bwd_x_kernel(const __grid_
       if (elect_one()) {
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch) {
-          const unsigned int a_lo = lo0 | ((dz1t + ch * kEbChunk128) >> 4);
           const unsigned int b_lo = lo0 | ((ptb + (ut & 1u) * 4 * kEbChunk16 + ch * kEbChunk16) >> 4);
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk)
-            tc_mma(tmem + 256u, ((unsigned long long)hi << 32) | (a_lo + kk * 2), ((unsigned long long)hi << 32) | (b_lo + kk * 2), idesc_w,
-                   (ut | (unsigned)ch | (unsigned)kk) != 0 ? 1u : 0u);
+          for (int kk = 0; kk < 4; ++kk)      // A = 8 columns (particles) of dz1^T straight from tensor memory
+            tc_mma_ts(tmem + kEbXDw1Col, tmem + kEbXDz1Col + (unsigned)(ch * 32 + kk * 8), ((unsigned long long)hi << 32) | (b_lo + kk * 2), idesc_w,
+                      (ut | (unsigned)ch | (unsigned)kk) != 0 ? 1u : 0u);
         }
         tc_commit(&dz1_empty);
         tc_commit(&pt_empty[ut & 1u]);
