@@ -26,6 +26,9 @@
 #include "front.cuh"
 #include "apply.cuh"
 #include "persist.cuh"
+#ifndef TD3_NO_PIPE_KERNEL
+#include "tcpipe.cuh"
+#endif
 #include "infer.cuh"
 #include "enc.cuh"
 #include "encbwd.cuh"
@@ -104,10 +107,13 @@ struct Launch {
 constexpr int kChainSmemMax = 232448 - 1024;     // dynamic shared memory of a chain CTA (static barriers take the rest)
 constexpr int kChainSmemFixed = 1024 + kChX0Bytes + 2 * kChMaxW * 4 + 5 * kChRows * 4;   // alignment, X0, bias, head weights, reductions
 
+extern int g_sm_count;
+
 int ensure_kernel_attrs() {
   static bool done = false;
   if (done) return TD3_OK;
   CUDA_TRY(cudaFuncSetAttribute(head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+  CUDA_TRY(cudaFuncSetAttribute(head_kernel_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
   CUDA_TRY(cudaFuncSetAttribute(front_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFrontSmemBytes));
   CUDA_TRY(cudaFuncSetAttribute(front_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFrontWideSmemBytes));
   CUDA_TRY(cudaFuncSetAttribute(enc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kEncSmemBytes));
@@ -116,6 +122,10 @@ int ensure_kernel_attrs() {
   CUDA_TRY(cudaFuncSetAttribute(chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmemMax));
   CUDA_TRY(cudaFuncSetAttribute(stage_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynSmemBytes));
   CUDA_TRY(cudaFuncSetAttribute(stage_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynSmemBytes));
+  CUDA_TRY(cudaFuncSetAttribute(stage_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynSmemBytesSmall));
+#ifndef TD3_NO_PIPE_KERNEL
+  CUDA_TRY(cudaFuncSetAttribute(stage_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPipeSmemBytes));
+#endif
   CUDA_TRY(cudaFuncSetAttribute(persistent_update_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynSmemBytes));
   CUDA_TRY(cudaFuncSetAttribute(persistent_update_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynSmemBytes));
   done = true;
@@ -155,9 +165,15 @@ int run_launch(const Launch& L, cudaStream_t s) {
       int rc = ensure_kernel_attrs();
       if (rc != TD3_OK) return rc;
       // fp32-only stages need the FFMA tile's buffers only: a small footprint lets the successor's CTAs co-reside
-      if (L.stage.any_tc)
-        e = launch_pdl(stage_kernel<true>, dim3(L.stage.total_tiles), dim3(kStageThreads), L.stage.small_ring ? kDynSmemBytesSmall : kDynSmemBytes, s,
-                       L.stage, L.stage.cluster);
+#ifndef TD3_NO_PIPE_KERNEL
+      if (L.stage.any_tc && L.stage.pipe_tiles > 0)
+        e = launch_pdl(stage_pipe_kernel, dim3(std::min(g_sm_count, L.stage.pipe_tiles)), dim3(kStageThreads), kPipeSmemBytes, s, L.stage);
+      else
+#endif
+      if (L.stage.any_tc && L.stage.small_ring)    // many tiles per SM: the instance with the coalesced epilogue (small ring excludes clusters)
+        e = launch_pdl(stage_kernel<true, true>, dim3(L.stage.total_tiles), dim3(kStageThreads), kDynSmemBytesSmall, s, L.stage);
+      else if (L.stage.any_tc)
+        e = launch_pdl(stage_kernel<true>, dim3(L.stage.total_tiles), dim3(kStageThreads), kDynSmemBytes, s, L.stage, L.stage.cluster);
       else e = launch_pdl(stage_kernel<false>, dim3(L.stage.total_tiles), dim3(kStageThreads), kSmemBytes + 1024, s, L.stage);
       break;
     }
@@ -194,7 +210,10 @@ int run_launch(const Launch& L, cudaStream_t s) {
     case Launch::HEAD: {
       int rc = ensure_kernel_attrs();
       if (rc != TD3_OK) return rc;
-      e = launch_pdl(head_kernel, dim3(L.grid_x), dim3(kHeadThreads), (size_t)L.smem_bytes, s, L.head);
+      if (L.grid_x > g_sm_count && L.smem_bytes <= 100 * 1024 && !getenv("TD3_NO_WIDE_HEAD"))
+        e = launch_pdl(head_kernel_wide, dim3(L.grid_x), dim3(kHeadThreads), (size_t)L.smem_bytes, s, L.head);
+      else
+        e = launch_pdl(head_kernel, dim3(L.grid_x), dim3(kHeadThreads), (size_t)L.smem_bytes, s, L.head);
       break;
     }
     case Launch::WN:
@@ -398,7 +417,7 @@ void finalize_problem(Problem& p, GroupShape gs) {
         int nt = p.N <= 16 ? 16 : 32;
         for (int cand : {64, 128}) {   // wider tiles only when there are plenty of them (A is re-read once per N tile)
           const long long tiles = (long long)p.tiles_m * ((p.N + cand - 1) / cand) * p.ksplit * groups;
-          if (p.N > nt && tiles >= 2LL * g_sm_count) nt = cand;
+          if (p.N > nt && tiles >= 2LL * g_sm_count) nt = cand;   // (from 1 or 0.6 tiles per SM: measured no gain on 8 / 32-agent populations)
         }
         p.tc_nt = nt;
         p.tiles_n = (p.N + nt - 1) / nt;
@@ -560,6 +579,26 @@ void layout_stage(Launch& L) {
     const char* thr = getenv("TD3_SMALL_RING_TILES");       // tiles per SM from which the small ring is used (tuning knob)
     const double per_sm = thr ? atof(thr) : 1.5;
     S.small_ring = (any_tc && c == 1 && tiles >= per_sm * g_sm_count && !getenv("TD3_NO_SMALL_RING")) ? 1 : 0;
+    // ... or, when every tensor-core problem keeps its whole reduction in one tile, one persistent CTA per SM whose
+    // producer / MMA / epilogue warps are pipelined across tiles (tcpipe.cuh)
+    S.pipe_tiles = 0;
+    // Measured (profiles/r02g_pipe_kernel_prefix_times.txt): NOT faster than two small-ring CTAs per SM -- the forward stages
+    // of a population are bound by L2 -> shared-memory operand traffic (fp32 operands: 32 flop per byte at 128 x 128), and a
+    // backward stage's column-sum / FFMA tiles run after the pipelined tiles instead of beside them -- so it is opt-in.
+    const char* pthr = getenv("TD3_PIPE_TILES");            // tiles per SM from which the pipelined kernel is used (tuning knob)
+    const double pipe_per_sm = pthr ? atof(pthr) : 1.5;
+    if (any_tc && c == 1 && getenv("TD3_PIPE")) {
+      int tc_tiles = 0;
+      bool ok = true;
+      for (int q = 0; q < n; ++q) {
+        const Problem& p = S.p[q];
+        if (p.kind == PK_GEMM && p.use_tc) {
+          ok = ok && p.ksplit == 1 && p.tile_begin == tc_tiles && p.K >= 32;
+          tc_tiles += p.tile_count;
+        }
+      }
+      if (ok && tc_tiles >= pipe_per_sm * g_sm_count) { S.pipe_tiles = tc_tiles; S.small_ring = 0; }
+    }
   }
 }
 
@@ -1569,7 +1608,9 @@ int plan_agent(td3_agent* a, long long batch) {
   g_tc_mode = c.precision == TD3_PRECISION_TF32 ? 1 : 0;
   // A-panel multicast over thread-block clusters is implemented and tested but measured no faster on B200 (the K loop
   // is bound by the MMA's shared-memory A read, not by the operand stream: DESIGN.md section 5): opt-in.
-  g_cluster_mode = (a->cluster_mode && getenv("TD3_CLUSTER")) ? 1 : 0;
+  // Single agents only: with a population's groups the cluster launches fault (found in round 2, not debugged: the knob
+  // buys nothing there either, since small-ring / many-tile launches exclude it).
+  g_cluster_mode = (a->cluster_mode && nA == 1 && getenv("TD3_CLUSTER")) ? 1 : 0;
   cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, 0);
   if (g_sm_count <= 0) g_sm_count = 148;
   const int A = c.action_dim, S = c.state_dim, E = enc ? c.actor.enc_out : 0;

@@ -639,6 +639,15 @@ __global__ void __launch_bounds__(kHeadThreads) head_kernel(const __grid_constan
   head_body(H, blockIdx.x, head_smem);
 }
 
+// the same body compiled for two CTAs per SM (64 registers): launches with more tiles than SMs (populations, the
+// batch-8192 update) run one wave instead of two; the latency form above keeps its 96 registers
+__global__ void __launch_bounds__(kHeadThreads, 2) head_kernel_wide(const __grid_constant__ HeadParams H) {
+  extern __shared__ __align__(16) float head_smem[];
+  pdl_launch_dependents();
+  pdl_wait();
+  head_body(H, blockIdx.x, head_smem);
+}
+
 // ------------------------------------------------------------------------------------
 // Weight normalisation (TD3_particles.py:48-50, torch.nn.utils.weight_norm on every `linears` module):
 // the packed buffers hold (bias, weight_g [out], weight_v [out, in]) per layer and the layer computes with

@@ -29,7 +29,7 @@ __device__ __forceinline__ unsigned char* aligned_smem(unsigned char* raw) {
 
 // one tile of a stage: look up the problem the tile index falls into and run it.  kTc selects which GEMM tile is
 // compiled in: the tensor-core kernels carry no FFMA GEMM code and vice versa (instruction footprint).
-template <bool kTc>
+template <bool kTc, bool kCo = false>
 __device__ __forceinline__ void run_stage_tile(const StageParams& S, int tile_global, unsigned char* ring, TcState* tc,
                                                bool param_maps = false) {
   int pi = 0;
@@ -42,7 +42,7 @@ __device__ __forceinline__ void run_stage_tile(const StageParams& S, int tile_gl
   switch (P.kind) {
     case PK_GEMM:
       if constexpr (kTc) {
-        if (P.use_tc) { gemm_tile_tc(P, tile, ring, tc, param_maps ? S.maps : nullptr); break; }
+        if (P.use_tc) { gemm_tile_tc<kCo>(P, tile, ring, tc, param_maps ? S.maps : nullptr); break; }
       }
       gemm_tile(P, tile, smem);
       break;
@@ -61,7 +61,8 @@ __device__ __forceinline__ void run_stage_tile(const StageParams& S, int tile_gl
 }
 
 // stage-per-launch form (phase-by-phase API, CUDA-graph mode, B=small inference)
-template <bool kTc>
+// kCo: the many-tile (small-ring) launches' instance, with the coalesced epilogue of tc.cuh
+template <bool kTc, bool kCo = false>
 __global__ void __launch_bounds__(kStageThreads, 2) stage_kernel(const __grid_constant__ StageParams S) {
   extern __shared__ unsigned char smem_raw[];
   __shared__ TcState tc;
@@ -77,7 +78,7 @@ __global__ void __launch_bounds__(kStageThreads, 2) stage_kernel(const __grid_co
   if (threadIdx.x == 0) tc.prof_stage = 0;   // stage-per-launch form: block 0's stamps land in slot 0
   __syncthreads();
 #endif
-  if ((int)blockIdx.x < S.total_tiles) run_stage_tile<kTc>(S, blockIdx.x, ring, &tc, true);   // S is __grid_constant__
+  if ((int)blockIdx.x < S.total_tiles) run_stage_tile<kTc, kCo>(S, blockIdx.x, ring, &tc, true);   // S is __grid_constant__
   if constexpr (kTc) {
     if (cluster > 1) cluster_sync_all();     // nobody leaves while a peer may still write its shared memory or barriers
     if (S.any_tc) tc_teardown(&tc);

@@ -82,8 +82,10 @@ struct StageParams {
   int n_problems;
   int total_tiles;
   int any_tc, cluster;            // some problem runs on the tensor cores (TMEM must be allocated); cluster size of the launch
-  int small_ring, pad_sr;         // 1: many-tile launch -> one chunk per ring slot (96 KB instead of 192 KB): two CTAs per SM, so one
-                                  //    tile's epilogue overlaps the other's operand loads and MMAs
+  int small_ring, pipe_tiles;     // small_ring 1: many-tile launch -> one chunk per ring slot (96 KB instead of 192 KB): two CTAs per
+                                  //    SM, so one tile's epilogue overlaps the other's operand loads and MMAs
+                                  // pipe_tiles > 0: the launch's first pipe_tiles tiles are tensor-core tiles walked by one persistent
+                                  //    CTA per SM with producer / MMA / epilogue warps pipelined ACROSS tiles (tcpipe.cuh)
   Problem p[kMaxProblemsPerStage];
   TensorMapBlob maps[kStageMaps];
 };

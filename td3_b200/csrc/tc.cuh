@@ -328,15 +328,113 @@ __device__ __forceinline__ void tc_epilogue_group(const Problem& P, float* __res
   }
 }
 
-// Epilogue of one warp: its 32 accumulator rows (TMEM lanes) x `half` columns starting at local column jw.
+// ---- coalesced form of a 16-column group -------------------------------------------------------------------------
+// tcgen05.ld hands lane l the 16 columns of accumulator ROW l, so a store of 16 bytes per lane touches 32 different
+// rows: 32 half-used sectors per instruction, and on the many-tile stages (populations, batch-8192) the L1 / L2 request
+// rate of those accesses -- not the tensor pipe -- set the tile time.  The group is therefore transposed through 2 KB of
+// shared memory per warp (16-byte chunks XOR-swizzled by row pair: conflict-free both ways): afterwards lane l owns
+// columns 4 (l & 3) .. + 3 of rows 8 p + (l >> 2), p = 0..3, i.e. four lanes cover 64 contiguous bytes of a row and an
+// instruction touches 8 rows with every sector fully used.  The auxiliary operand (ReLU mask / tanh / noise) is read in
+// the same layout.  The arithmetic per element is unchanged.
+__device__ __forceinline__ void tc_load_aux_group_co(const Problem& P, const float* aux0, bool aux_read, bool x_vec, int ib, int j,
+                                                     int lane, float (&ax)[16]) {
+  const int c = lane & 3, rr = lane >> 2;
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    const int i = ib + 8 * p + rr;
+    const float4 v = tc_load_aux(P, aux0, aux_read, x_vec, i < P.M, i, j + 4 * c);
+    ax[4 * p] = v.x; ax[4 * p + 1] = v.y; ax[4 * p + 2] = v.z; ax[4 * p + 3] = v.w;
+  }
+}
+
 template <int EPI>
+__device__ __forceinline__ void tc_epilogue_group_co(const Problem& P, float* __restrict__ C, float* aux0, const float* bias_s,
+                                                     bool has_bias, bool c_vec, bool have_acc, int ib, int j, int jl,
+                                                     unsigned int taddr, const float (&ax)[16], float* stg, int lane) {
+  unsigned int r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+  {
+    uint4* row = reinterpret_cast<uint4*>(stg + lane * 16);
+    const int sw = (lane >> 1) & 3;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) row[q ^ sw] = make_uint4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
+  }
+  __syncwarp();
+  const int c = lane & 3, rr = lane >> 2;
+  uint4 t[4];
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    const int rl = 8 * p + rr;
+    t[p] = reinterpret_cast<const uint4*>(stg + rl * 16)[c ^ ((rl >> 1) & 3)];
+  }
+  __syncwarp();                                      // the next group overwrites the staging rows
+  const int jq = j + 4 * c;
+  if (jq >= P.N) return;
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    const int i = ib + 8 * p + rr;
+    if (i >= P.M) continue;
+    const unsigned int rv[4] = {t[p].x, t[p].y, t[p].z, t[p].w};
+    float o[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float aux_out = 0.f;
+      const float v = have_acc ? __uint_as_float(rv[e]) : 0.f;
+      o[e] = epi_apply<EPI>(v, has_bias ? bias_s[jl + 4 * c + e] : 0.f, ax[4 * p + e], P.f0, P.f1, aux_out);
+      if (EPI == EPI_BIAS_TANH && jq + e < P.N) aux0[(size_t)i * P.ldaux + jq + e] = aux_out;
+      if (P.rn_out) o[e] = rn_tf32(o[e]);
+    }
+#pragma unroll 1
+    for (int d = 0; d < P.c_dups; ++d) {
+      float* cp = C + d * P.c_dup_stride + (size_t)i * P.ldc + jq;
+      if (c_vec && jq + 3 < P.N) {
+        *reinterpret_cast<float4*>(cp) = make_float4(o[0], o[1], o[2], o[3]);
+      } else {
+        cp[0] = o[0];
+        if (jq + 1 < P.N) cp[1] = o[1];
+        if (jq + 2 < P.N) cp[2] = o[2];
+        if (jq + 3 < P.N) cp[3] = o[3];
+      }
+    }
+  }
+}
+
+// Epilogue of one warp: its 32 accumulator rows (TMEM lanes) x `half` columns starting at local column jw.
+template <int EPI, bool kCo>
 __device__ __forceinline__ void tc_epilogue_cols(const Problem& P, float* __restrict__ C, float* aux0, const float* bias_s,
                                                  bool has_bias, bool aux_read, bool x_vec, bool c_vec, bool row_ok, bool have_acc,
                                                  int i, int j0, int jw, int half, unsigned int tmem_lane, unsigned int done_bar,
-                                                 unsigned int done_parity) {
-  if (half >= 16) {
+                                                 unsigned int done_parity, float* stg) {
+  if (half >= 16 && !kCo) {
+    // latency form (a launch is one wave of tiles on the update's dependency chain): row-per-lane accesses, no staging --
+    // the transposition below costs two shared-memory round trips per group, ~0.5 us per update at cfg2
     float ax[16];
     tc_load_aux_group<16>(P, aux0, aux_read, x_vec, row_ok, i, j0 + jw, ax);
+    if (have_acc) mbar_wait_u32(done_bar, done_parity);
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+#pragma unroll 1
+    for (int jc = 0; jc < half; jc += 16) {
+      float ax_next[16];
+      const bool more = jc + 16 < half;
+      if (more) tc_load_aux_group<16>(P, aux0, aux_read, x_vec, row_ok, i, j0 + jw + jc + 16, ax_next);
+      tc_epilogue_group<EPI, 16>(P, C, aux0, bias_s, has_bias, c_vec, row_ok, have_acc, i, j0 + jw + jc, jw + jc,
+                                 tmem_lane + (unsigned)(jw + jc), ax);
+      if (more) {
+#pragma unroll
+        for (int q = 0; q < 16; ++q) ax[q] = ax_next[q];
+      }
+    }
+  } else if (kCo && half >= 16) {
+    // throughput form (many tiles per SM): coalesced accesses through the per-warp staging
+    const int lane = threadIdx.x & 31, ib = i - lane;    // first accumulator row of this warp
+    float ax[16];
+    tc_load_aux_group_co(P, aux0, aux_read, x_vec, ib, j0 + jw, lane, ax);
     if (have_acc) mbar_wait_u32(done_bar, done_parity);
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
     // the auxiliary operand (ReLU mask / tanh / noise) of group jc + 1 is requested before group jc is processed: on the
@@ -345,9 +443,9 @@ __device__ __forceinline__ void tc_epilogue_cols(const Problem& P, float* __rest
     for (int jc = 0; jc < half; jc += 16) {
       float ax_next[16];
       const bool more = jc + 16 < half;
-      if (more) tc_load_aux_group<16>(P, aux0, aux_read, x_vec, row_ok, i, j0 + jw + jc + 16, ax_next);
-      tc_epilogue_group<EPI, 16>(P, C, aux0, bias_s, has_bias, c_vec, row_ok, have_acc, i, j0 + jw + jc, jw + jc,
-                                 tmem_lane + (unsigned)(jw + jc), ax);
+      if (more) tc_load_aux_group_co(P, aux0, aux_read, x_vec, ib, j0 + jw + jc + 16, lane, ax_next);
+      tc_epilogue_group_co<EPI>(P, C, aux0, bias_s, has_bias, c_vec, have_acc, ib, j0 + jw + jc, jw + jc,
+                                tmem_lane + (unsigned)(jw + jc), ax, stg, lane);
       if (more) {
 #pragma unroll
         for (int q = 0; q < 16; ++q) ax[q] = ax_next[q];
@@ -365,6 +463,9 @@ __device__ __forceinline__ void tc_epilogue_cols(const Problem& P, float* __rest
 // ------------------------------------------------------------------------------------
 // One 128 x NT tile.  `ring` is kTcRingBytes of 1024-byte-aligned shared memory.
 // ------------------------------------------------------------------------------------
+// kCo: coalesced (throughput) epilogue -- a template parameter, not a run-time switch: merely compiling the second epilogue
+// into the latency kernel cost the single-agent update 2 us (profiles/r02g_code_size_ab.txt: it runs every launch cold)
+template <bool kCo = false>
 __device__ __forceinline__ void gemm_tile_tc(const Problem& P, int tile, unsigned char* ring, TcState* st,
                                              const TensorMapBlob* param_maps = nullptr) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -556,8 +657,13 @@ __device__ __forceinline__ void gemm_tile_tc(const Problem& P, int tile, unsigne
   __syncthreads();                                         // bias strip visible (the MMA pipeline is busy meanwhile)
   const unsigned int tmem = tc_tmem_base(st);
   TCP(3);
-  TD3_DISPATCH_EPI(epi, (tc_epilogue_cols<E>(P, C, aux0, bias_s, has_bias, aux_read, x_vec, c_vec, row_ok, n_chunks > 0, i, j0, jw,
-                                             half, tmem + (((unsigned)(warp & 3) * 32u) << 16), smem_u32(&st->done_bar), tile_no & 1)));
+  // transposition staging of the coalesced epilogue: 2 KB per warp at the start of the ring (the staging is touched only
+  // after done_bar has completed, i.e. after the tensor core has consumed every operand byte of this tile)
+  float* stg = kCo ? reinterpret_cast<float*>(ring) + warp * 512 : nullptr;
+  TD3_DISPATCH_EPI(epi, (tc_epilogue_cols<E, kCo>(P, C, aux0, bias_s, has_bias, aux_read, x_vec, c_vec, row_ok, n_chunks > 0, i, j0, jw,
+                                             half, tmem + (((unsigned)(warp & 3) * 32u) << 16), smem_u32(&st->done_bar), tile_no & 1,
+                                             stg)));
+  if (kCo) asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic-proxy staging accesses before the next tile's TMA writes
   TCP(4);
   TCP(5);
   // every warp is past its TMEM reads before the next tile's first MMA overwrites the accumulator

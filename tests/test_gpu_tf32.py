@@ -247,3 +247,19 @@ def test_layer_fused_chain_kernels_meet_the_same_tolerances(cfg, monkeypatch):
         ora, orb, ours, rb = make_featured(norm=None, actor_widths=aw, q_widths=qw, rows=2048, lr=1e-4, precision="tf32")
         _one_cycle(ora, orb, ours, rb, B=256, A=6, rows=2048, label="chain " + cfg)
     assert ours.chain_active()
+
+
+@pytest.mark.parametrize("cfg", ["cfg2_400_300", "cfg3_fork_layer"])
+def test_cross_tile_pipelined_stage_kernel_meets_the_same_tolerances(cfg, monkeypatch):
+    """tcpipe.cuh (opt-in, TD3_PIPE=1): the tensor-core tiles of a stage walked by one persistent CTA per SM with producer,
+    MMA and epilogue warps pipelined across tiles (two TMEM accumulators), the stage's other tiles afterwards.  Forced on
+    for every tensor-core launch (TD3_PIPE_TILES=0: normally only from 1.5 tiles per SM); same oracle, same tolerances
+    as the default one-CTA-per-tile launches."""
+    monkeypatch.setenv("TD3_PIPE", "1")
+    monkeypatch.setenv("TD3_PIPE_TILES", "0")
+    if cfg.startswith("cfg2"):
+        ora, orb, ours, rb = make_featured(norm=None, actor_widths=(400, 300), q_widths=(400, 300), rows=2048, lr=1e-4, precision="tf32")
+    else:
+        ora, orb, ours, rb = make_featured(norm="layer", actor_widths=(500, 400, 300), q_widths=(500, 400, 200), rows=2048, lr=1e-4,
+                                           precision="tf32")
+    _one_cycle(ora, orb, ours, rb, B=256, A=6, rows=2048, label="pipe " + cfg)
