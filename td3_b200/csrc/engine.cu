@@ -123,6 +123,7 @@ int ensure_kernel_attrs() {
   CUDA_TRY(cudaFuncSetAttribute(stage_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynSmemBytes));
   CUDA_TRY(cudaFuncSetAttribute(stage_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynSmemBytes));
   CUDA_TRY(cudaFuncSetAttribute(stage_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynSmemBytesSmall));
+  CUDA_TRY(cudaFuncSetAttribute(stage_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynSmemBytes));
 #ifndef TD3_NO_PIPE_KERNEL
   CUDA_TRY(cudaFuncSetAttribute(stage_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPipeSmemBytes));
 #endif
@@ -157,8 +158,53 @@ cudaError_t launch_pdl(Kernel k, dim3 grid, dim3 block, size_t smem, cudaStream_
   return cudaLaunchKernelEx(&cfg, k, p);
 }
 
+// A fork of the graph being captured on `s`: work launched on g_fork.side after fork_begin() depends only on what `s` held
+// at that point; fork_join() makes `s` wait for it again (run_launch before any launch that is not a plain stage,
+// run_seq / the capture sites at their end: a capture must not end with unjoined work).
+struct ForkState {
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  bool pending = false;
+};
+thread_local ForkState g_fork;
+
+// stream + events of the fork, created outside any capture (capture(), the prefix timer and every eager head launch call this)
+static int fork_ensure() {
+  if (g_fork.side) return TD3_OK;
+  cudaStream_t st = nullptr;
+  if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) return TD3_ERR_CUDA;
+  if (cudaEventCreateWithFlags(&g_fork.ev_fork, cudaEventDisableTiming) != cudaSuccess) return TD3_ERR_CUDA;
+  if (cudaEventCreateWithFlags(&g_fork.ev_join, cudaEventDisableTiming) != cudaSuccess) return TD3_ERR_CUDA;
+  g_fork.side = st;
+  return TD3_OK;
+}
+
+static int fork_begin(cudaStream_t s) {
+  if (!g_fork.side || g_fork.pending) return TD3_ERR_STATE;   // no fork: the caller launches behind the head instead
+  if (cudaEventRecord(g_fork.ev_fork, s) != cudaSuccess) return TD3_ERR_CUDA;
+  if (cudaStreamWaitEvent(g_fork.side, g_fork.ev_fork, 0) != cudaSuccess) return TD3_ERR_CUDA;
+  g_fork.pending = true;
+  return TD3_OK;
+}
+
+static cudaError_t fork_join(cudaStream_t s) {
+  if (!g_fork.pending) return cudaSuccess;
+  g_fork.pending = false;
+  return cudaStreamWaitEvent(s, g_fork.ev_join, 0);
+}
+
+static bool stage_all_tc(const StageParams& S) {
+  for (int q = 0; q < S.n_problems; ++q)
+    if (!(S.p[q].kind == PK_GEMM && S.p[q].use_tc)) return false;
+  return S.n_problems > 0;
+}
+
 int run_launch(const Launch& L, cudaStream_t s) {
   cudaError_t e = cudaSuccess;
+  if (L.kind != Launch::STAGE) {
+    e = fork_join(s);
+    if (e != cudaSuccess) return fail(TD3_ERR_CUDA, "fork_join: %s", cudaGetErrorString(e));
+  }
   switch (L.kind) {
     case Launch::STAGE: {
       if (L.stage.total_tiles <= 0) return TD3_OK;
@@ -172,6 +218,8 @@ int run_launch(const Launch& L, cudaStream_t s) {
 #endif
       if (L.stage.any_tc && L.stage.small_ring)    // many tiles per SM: the instance with the coalesced epilogue (small ring excludes clusters)
         e = launch_pdl(stage_kernel<true, true>, dim3(L.stage.total_tiles), dim3(kStageThreads), kDynSmemBytesSmall, s, L.stage);
+      else if (L.stage.any_tc && stage_all_tc(L.stage) && !getenv("TD3_NO_LEAN"))
+        e = launch_pdl(stage_kernel<true, false, true>, dim3(L.stage.total_tiles), dim3(kStageThreads), kDynSmemBytes, s, L.stage, L.stage.cluster);
       else if (L.stage.any_tc)
         e = launch_pdl(stage_kernel<true>, dim3(L.stage.total_tiles), dim3(kStageThreads), kDynSmemBytes, s, L.stage, L.stage.cluster);
       else e = launch_pdl(stage_kernel<false>, dim3(L.stage.total_tiles), dim3(kStageThreads), kSmemBytes + 1024, s, L.stage);
@@ -214,6 +262,20 @@ int run_launch(const Launch& L, cudaStream_t s) {
         e = launch_pdl(head_kernel_wide, dim3(L.grid_x), dim3(kHeadThreads), (size_t)L.smem_bytes, s, L.head);
       else
         e = launch_pdl(head_kernel, dim3(L.grid_x), dim3(kHeadThreads), (size_t)L.smem_bytes, s, L.head);
+      if (e == cudaSuccess && L.head.defer_finish) {
+        // loss / host mirror / optimiser tick: beside the next stage when the stream is being captured (a fork of the
+        // graph, joined by fork_join() before the next launch that is not a plain stage), behind the head otherwise
+        const int n_agents = L.grid_x / std::max(1, L.head.n_cta);
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        cudaStreamIsCapturing(s, &cs);
+        cudaStream_t fs = s;
+        if (cs != cudaStreamCaptureStatusActive) fork_ensure();
+        else if (fork_begin(s) == TD3_OK) fs = g_fork.side;
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        head_finish_kernel<<<n_agents, 32, 0, fs>>>(L.head);
+        e = cudaGetLastError();
+        if (fs != s && e == cudaSuccess) e = cudaEventRecord(g_fork.ev_join, fs);
+      }
       break;
     }
     case Launch::WN:
@@ -1864,6 +1926,7 @@ int plan_agent(td3_agent* a, long long batch) {
       H.part = head_part; H.part_go = head_part_go; H.counter = head_counter; H.loss = a->state_f32;
       H.batch = B; H.w = wq_last; H.qw = qw; H.n_q = nq; H.ldh = wq_last; H.lddz = wq_last; H.n_cta = head_ctas;
       H.mode = 0; H.relu_mask = ln ? 0 : 1; H.skip_dw = head_dw_in_stage ? 1 : 0;
+      H.defer_finish = (head_dw_in_stage && !getenv("TD3_NO_DEFER_FINISH")) ? 1 : 0;
       H.rn_out = tf ? 1 : 0;
       H.discount = c.discount; H.inv_norm = inv_norm; H.tick = tick;
       H.host_status = a->host_status_live ? a->host_status : nullptr; H.seq = head_seq;
@@ -1962,6 +2025,7 @@ int plan_agent(td3_agent* a, long long batch) {
       H.part = head_part + nA * head_part_go; H.part_go = head_part_go; H.counter = head_counter + nA; H.loss = a->state_f32 + nA;
       H.batch = B; H.w = wq_last; H.qw = qw; H.n_q = 1; H.ldh = wq_last; H.lddz = wq_last; H.n_cta = head_ctas;
       H.mode = 1; H.relu_mask = ln ? 0 : 1;
+      H.defer_finish = getenv("TD3_NO_DEFER_FINISH") ? 0 : 1;
       H.rn_out = tf ? 1 : 0;
       H.inv_norm = 1.f / (float)((a->global_batch > 0 ? a->global_batch : batch) * qw);
       H.tick = AdamTick{a->state_u64, 1, 0, c.lr_actor, c.beta1, c.beta2};
@@ -2581,6 +2645,7 @@ int append_records(std::vector<StageRec>& prog, const std::vector<Launch>& seq, 
         break;
       case Launch::HEAD:
         r.kind = SK_HEAD; r.u.h = L.head; r.main_tiles = L.grid_x;
+        r.u.h.defer_finish = 0;                 // inside the persistent kernel the last CTA finishes
         break;
       case Launch::WN:
         r.kind = SK_WN; r.u.w = L.wn; r.main_tiles = L.grid_x;
@@ -2683,6 +2748,7 @@ int run_seq(const std::vector<Launch>& seq, cudaStream_t s) {
     int rc = run_launch(L, s);
     if (rc != TD3_OK) return rc;
   }
+  if (fork_join(s) != cudaSuccess) return fail(TD3_ERR_CUDA, "fork_join at the end of a launch sequence failed");
   return TD3_OK;
 }
 
@@ -2746,6 +2812,7 @@ int capture(td3_agent* a, bool with_actor, cudaGraphExec_t* out, long long* n_no
   const long long launches_before = g_launches.load();
   if (!a->cap_stream) CUDA_TRY(cudaStreamCreateWithFlags(&a->cap_stream, cudaStreamNonBlocking));
   cudaStream_t s = a->cap_stream;
+  fork_ensure();
   CUDA_TRY(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
   int rc = a->chain_on ? TD3_OK : run_seq(a->seq_sample, s);
   if (rc == TD3_OK) rc = run_seq(a->chain_on ? (with_actor ? a->seq_chain_policy : a->seq_chain_critic)
@@ -3389,11 +3456,13 @@ int td3_debug_prefix_times(td3_agent* a, const td3_replay_view* rb, int32_t with
   cudaEvent_t e0, e1;
   CUDA_TRY(cudaEventCreate(&e0));
   CUDA_TRY(cudaEventCreate(&e1));
+  fork_ensure();
   for (int k = 1; k <= n; ++k) {
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t exec = nullptr;
     CUDA_TRY(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
     for (int i = 0; i < k && rc == TD3_OK; ++i) rc = run_launch(all[i], s);
+    fork_join(s);
     cudaError_t e = cudaStreamEndCapture(s, &graph);
     if (rc != TD3_OK || e != cudaSuccess) return rc != TD3_OK ? rc : fail(TD3_ERR_CUDA, "prefix capture: %s", cudaGetErrorString(e));
     CUDA_TRY(cudaGraphInstantiate(&exec, graph, 0));

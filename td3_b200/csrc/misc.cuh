@@ -387,6 +387,8 @@ struct HeadParams {
   float* loss;                                // loss[agent]
   int batch, w, qw, n_q, ldh, lddz, n_cta, mode, relu_mask;
   int skip_dw;                                // 1: dW/db of the head are a GEMM problem of the next stage (from dq and h)
+  int defer_finish;                           // 1: the CTAs leave after storing their loss partial; head_finish_kernel -- off the update's
+                                              //    dependency chain, beside the next stage -- sums them and does the bookkeeping
   int rn_out;                                 // dz / dq stored rounded to nearest TF32 (operands of tensor-core contractions)
   float discount, inv_norm;
   AdamTick tick;                              // critic optimiser tick + sampling step (mode 0), done by the finishing CTA
@@ -396,6 +398,35 @@ struct HeadParams {
   unsigned long long* host_status;
   unsigned int* seq;
 };
+
+// The launch's loss from the CTAs' partials (fixed order), the host mirror of it, the optimiser tick: one warp per agent.
+// Run by the last CTA to arrive (head_body_t) or, with HeadParams::defer_finish, by head_finish_kernel.
+__device__ __forceinline__ void head_finish_warp(const HeadParams& H, int agent, const float* lpart, int lane) {
+  const bool critic = H.mode == 0;
+  float t = 0.f;
+  for (int c2 = lane; c2 < ((H.n_cta + 31) & ~31); c2 += 32) {
+    float v = c2 < H.n_cta ? __ldcg(lpart + c2) : 0.f;
+    // fixed-order tree over the 32 lanes, then accumulate the groups of 32 CTAs in order
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    t += v;
+  }
+  if (lane == 0) {
+    H.loss[agent] = critic ? t * H.inv_norm : -t * H.inv_norm;
+    if (critic && H.host_status) {
+      const unsigned int sq = H.seq[agent] + 1u;
+      H.seq[agent] = sq;
+      const unsigned long long word = ((unsigned long long)sq << 32) | (unsigned long long)__float_as_uint(t * H.inv_norm);
+      // plain posted store: no system-scope fence here (it would hold the chain for a PCIe round trip); the word
+      // is a single aligned 8-byte write, and the end of the kernel flushes it at the latest
+      *reinterpret_cast<volatile unsigned long long*>(H.host_status + agent) = word;
+    }
+    if (agent == 0 && H.tick.state) {
+      if (critic) H.tick.state[0] += 1;          // sampling step (Philox counter)
+      adam_tick(H.tick);
+    }
+  }
+}
 
 // One warp per (batch row, twin): every global load of the pair is issued before anything is consumed -- the kernel
 // sits on a dependency chain, so the length of one warp's instruction stream, not throughput, is what the update
@@ -569,6 +600,7 @@ __device__ __forceinline__ void head_body_t(const HeadParams& H, int tile, float
     for (int wv = 0; wv < pairs; ++wv) t += lred[wv];
     lpart[cb] = t;
   }
+  if (H.defer_finish) return;                 // (never together with want_dw: host)
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
@@ -596,31 +628,7 @@ __device__ __forceinline__ void head_body_t(const HeadParams& H, int tile, float
       else H.gb[agent * H.g_go + g * H.g_gi + (o - qw * w)] = sacc;
     }
   }
-  if (threadIdx.x < 32) {
-    float t = 0.f;
-    for (int c2 = lane; c2 < ((H.n_cta + 31) & ~31); c2 += 32) {
-      float v = c2 < H.n_cta ? __ldcg(lpart + c2) : 0.f;
-      // fixed-order tree over the 32 lanes, then accumulate the groups of 32 CTAs in order
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      t += v;
-    }
-    if (lane == 0) {
-      H.loss[agent] = critic ? t * H.inv_norm : -t * H.inv_norm;
-      if (critic && H.host_status) {
-        const unsigned int sq = H.seq[agent] + 1u;
-        H.seq[agent] = sq;
-        const unsigned long long word = ((unsigned long long)sq << 32) | (unsigned long long)__float_as_uint(t * H.inv_norm);
-        // plain posted store: no system-scope fence here (it would hold the chain for a PCIe round trip); the word
-        // is a single aligned 8-byte write, and the end of the kernel flushes it at the latest
-        *reinterpret_cast<volatile unsigned long long*>(H.host_status + agent) = word;
-      }
-      if (agent == 0 && H.tick.state) {
-        if (critic) H.tick.state[0] += 1;          // sampling step (Philox counter)
-        adam_tick(H.tick);
-      }
-    }
-  }
+  if (threadIdx.x < 32) head_finish_warp(H, agent, lpart, lane);
 }
 
 __device__ __forceinline__ void head_body(const HeadParams& H, int tile, float* smem) {
@@ -646,6 +654,16 @@ __global__ void __launch_bounds__(kHeadThreads, 2) head_kernel_wide(const __grid
   pdl_launch_dependents();
   pdl_wait();
   head_body(H, blockIdx.x, head_smem);
+}
+
+// HeadParams::defer_finish: what the last CTA of the head launch would do, as a launch of its own that the graph runs
+// BESIDE the backward stage (a fork in the captured graph, joined before the optimiser launch that reads the tick's
+// scalars): the fence + atomic + partial read-back + bookkeeping tail (~2 us) leaves the update's dependency chain.
+__global__ void __launch_bounds__(32) head_finish_kernel(const __grid_constant__ HeadParams H) {
+  const int agent = blockIdx.x;
+  const int per_g = H.qw * H.w + H.qw;
+  const float* lpart = H.part + agent * H.part_go + (size_t)H.n_cta * H.n_q * per_g;
+  head_finish_warp(H, agent, lpart, threadIdx.x & 31);
 }
 
 // ------------------------------------------------------------------------------------

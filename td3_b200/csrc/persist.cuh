@@ -29,7 +29,7 @@ __device__ __forceinline__ unsigned char* aligned_smem(unsigned char* raw) {
 
 // one tile of a stage: look up the problem the tile index falls into and run it.  kTc selects which GEMM tile is
 // compiled in: the tensor-core kernels carry no FFMA GEMM code and vice versa (instruction footprint).
-template <bool kTc, bool kCo = false>
+template <bool kTc, bool kCo = false, bool kLean = false>
 __device__ __forceinline__ void run_stage_tile(const StageParams& S, int tile_global, unsigned char* ring, TcState* tc,
                                                bool param_maps = false) {
   int pi = 0;
@@ -38,6 +38,10 @@ __device__ __forceinline__ void run_stage_tile(const StageParams& S, int tile_gl
     if (q < S.n_problems && tile_global >= S.p[q].tile_begin) pi = q;
   const Problem& P = S.p[pi];
   const int tile = tile_global - P.tile_begin;
+  if constexpr (kLean) {                      // every problem of the launch is a tensor-core GEMM (host: StageParams::all_tc)
+    gemm_tile_tc<kCo>(P, tile, ring, tc, param_maps ? S.maps : nullptr);
+    return;
+  }
   float* smem = reinterpret_cast<float*>(ring);
   switch (P.kind) {
     case PK_GEMM:
@@ -62,7 +66,8 @@ __device__ __forceinline__ void run_stage_tile(const StageParams& S, int tile_gl
 
 // stage-per-launch form (phase-by-phase API, CUDA-graph mode, B=small inference)
 // kCo: the many-tile (small-ring) launches' instance, with the coalesced epilogue of tc.cuh
-template <bool kTc, bool kCo = false>
+// kLean: the launch holds tensor-core GEMM problems only -- an instance without the other tile kinds' code
+template <bool kTc, bool kCo = false, bool kLean = false>
 __global__ void __launch_bounds__(kStageThreads, 2) stage_kernel(const __grid_constant__ StageParams S) {
   extern __shared__ unsigned char smem_raw[];
   __shared__ TcState tc;
@@ -78,7 +83,7 @@ __global__ void __launch_bounds__(kStageThreads, 2) stage_kernel(const __grid_co
   if (threadIdx.x == 0) tc.prof_stage = 0;   // stage-per-launch form: block 0's stamps land in slot 0
   __syncthreads();
 #endif
-  if ((int)blockIdx.x < S.total_tiles) run_stage_tile<kTc, kCo>(S, blockIdx.x, ring, &tc, true);   // S is __grid_constant__
+  if ((int)blockIdx.x < S.total_tiles) run_stage_tile<kTc, kCo, kLean>(S, blockIdx.x, ring, &tc, true);   // S is __grid_constant__
   if constexpr (kTc) {
     if (cluster > 1) cluster_sync_all();     // nobody leaves while a peer may still write its shared memory or barriers
     if (S.any_tc) tc_teardown(&tc);
