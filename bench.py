@@ -832,7 +832,7 @@ def main():
         except Exception:
             pass
         kernel = {"persistent": "td3::persistent_update_kernel (one cooperative launch = all K updates; per-update figures)",
-                  "graph": "whole update = 7 (critic-only) / 14 (policy) graph nodes (per-update figures)",
+                  "graph": "whole update = 7 (critic-only) / 14 (policy) dependent graph nodes + 1 / 2 head_finish nodes on a fork beside the backward stage (per-update figures)",
                   "launches": "td3::stage_kernel launches (per-update figures)"}[args.exec_mode]
         whole = {"bound": bound, "achieved": achieved, "peak": peak, "unit": unit, "frac": achieved / peak,
                  "us_per_update": t_update_us, "hbm_floor_us": hbm_floor_us, "tensor_floor_us": tensor_floor_us, "kernel": kernel}
