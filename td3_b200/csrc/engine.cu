@@ -165,22 +165,36 @@ struct ForkState {
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool pending = false;
+  int dev = -1;                 // device the stream and events belong to
 };
 thread_local ForkState g_fork;
 
-// stream + events of the fork, created outside any capture (capture(), the prefix timer and every eager head launch call this)
+// stream + events of the fork for the CURRENT device, created outside any capture (capture(), the prefix timer and every
+// eager head launch call this); a thread that moves to another device gets new ones on its next eager launch
 static int fork_ensure() {
-  if (g_fork.side) return TD3_OK;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return TD3_ERR_CUDA;
+  if (g_fork.side && g_fork.dev == dev) return TD3_OK;
+  if (g_fork.pending) return TD3_ERR_STATE;
+  if (g_fork.side) {            // (destroying another device's handles is legal from any device)
+    cudaStreamDestroy(g_fork.side);
+    cudaEventDestroy(g_fork.ev_fork);
+    cudaEventDestroy(g_fork.ev_join);
+    g_fork = ForkState{};
+  }
   cudaStream_t st = nullptr;
   if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) return TD3_ERR_CUDA;
   if (cudaEventCreateWithFlags(&g_fork.ev_fork, cudaEventDisableTiming) != cudaSuccess) return TD3_ERR_CUDA;
   if (cudaEventCreateWithFlags(&g_fork.ev_join, cudaEventDisableTiming) != cudaSuccess) return TD3_ERR_CUDA;
   g_fork.side = st;
+  g_fork.dev = dev;
   return TD3_OK;
 }
 
 static int fork_begin(cudaStream_t s) {
-  if (!g_fork.side || g_fork.pending) return TD3_ERR_STATE;   // no fork: the caller launches behind the head instead
+  int dev = -1;
+  cudaGetDevice(&dev);
+  if (!g_fork.side || g_fork.pending || g_fork.dev != dev) return TD3_ERR_STATE;   // no fork: the caller launches behind the head instead
   if (cudaEventRecord(g_fork.ev_fork, s) != cudaSuccess) return TD3_ERR_CUDA;
   if (cudaStreamWaitEvent(g_fork.side, g_fork.ev_fork, 0) != cudaSuccess) return TD3_ERR_CUDA;
   g_fork.pending = true;
